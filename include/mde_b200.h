@@ -1,0 +1,184 @@
+/*
+ * mde_b200.h -- C ABI of libmde_b200.so, the B200 (sm_100a) replacement for the TensorRT engine
+ * path of yester31/Monocular_Depth_Estimation_TRT.
+ *
+ * What each group replaces in the reference (paths relative to the reference checkout):
+ *
+ *   mde_engine_*    the tensorrt.ICudaEngine that core/common.py:141-312 `get_engine` builds or
+ *                   loads, and the engine surface core/common_runtime.py:136-171 touches
+ *                   (num_io_tensors, get_tensor_name/shape/dtype/mode).  "Build" here is
+ *                   weights + description -> packed device weights; there is no ONNX and no
+ *                   multi-minute tactic search.
+ *   mde_context_*   the tensorrt.IExecutionContext used by core/common_runtime.py:268-275
+ *                   `do_inference` (set_tensor_address, execute_async_v3) and
+ *                   models/depth_anything_v2/onnx2trt.py:99-100 (set_input_shape).
+ *   mde_k_*         single-kernel entry points, the test surface for tests/ -m gpu.
+ *
+ * Conventions: every function returns 0 on success and a non-zero code otherwise;
+ * mde_last_error() returns a thread-local message for the last failure (the Python shim raises
+ * RuntimeError with it, like core/common_runtime.py:41-56 `cuda_call`).  No exceptions cross the
+ * ABI.  All pointers named d_* are device pointers owned by the caller; `stream` is a
+ * cudaStream_t passed as void*.  mde_context_enqueue never allocates and never synchronises.
+ * There is no CPU fallback anywhere: without a B200 every compute entry point fails.
+ */
+#ifndef MDE_B200_H
+#define MDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDE_ABI_VERSION 1
+
+/* operand precision of the tensor-core path (accumulation is always fp32) */
+#define MDE_FP16 0
+#define MDE_BF16 1
+
+/* input binding */
+#define MDE_INPUT_F32_NCHW 0 /* the reference's contract: float32 [B,3,H,W] from core/preprocess.py */
+#define MDE_INPUT_U8_HWC 1   /* uint8 [B,src_h,src_w,3] source images; resize+normalise+im2col fused on the GPU */
+
+/* tensor dtypes reported by mde_engine_io_dtype */
+#define MDE_DT_F32 0
+#define MDE_DT_U8 1
+
+/* error codes */
+#define MDE_OK 0
+#define MDE_ERR_INVALID 1  /* bad argument / unsupported configuration */
+#define MDE_ERR_CUDA 2     /* a CUDA call failed (no device, launch failure, ...) */
+#define MDE_ERR_STATE 3    /* call order violated (e.g. enqueue before all addresses are set) */
+#define MDE_ERR_IO 4       /* weights file unreadable / malformed */
+#define MDE_ERR_MISSING 5  /* a required weight tensor was not provided */
+
+typedef struct mde_engine mde_engine;
+typedef struct mde_context mde_context;
+
+/* DINOv2 ViT encoder + DPT head (Depth Anything V2 family).  Mirrors the constructor arguments at
+ * models/depth_anything_v2/infer.py:55-62 and infer_metric.py:53-65. */
+typedef struct mde_engine_desc {
+  int32_t struct_size;     /* sizeof(mde_engine_desc), for ABI evolution */
+  int32_t embed_dim;       /* 384 / 768 / 1024 */
+  int32_t depth;           /* 12 / 12 / 24 */
+  int32_t num_heads;       /* 6 / 12 / 16 (head dim must be 64) */
+  int32_t patch_size;      /* 14 */
+  int32_t features;        /* 64 / 128 / 256 */
+  int32_t out_channels[4]; /* e.g. 256,512,1024,1024 */
+  int32_t taps[4];         /* block indices whose outputs feed the head, e.g. 4,11,17,23 */
+  int32_t input_h, input_w;/* model input size, multiples of patch_size */
+  int32_t batch;           /* images per enqueue */
+  int32_t precision;       /* MDE_FP16 | MDE_BF16 */
+  int32_t input_mode;      /* MDE_INPUT_* */
+  int32_t max_src_h, max_src_w; /* MDE_INPUT_U8_HWC: largest source image the input binding must hold */
+  int32_t swap_rb;         /* MDE_INPUT_U8_HWC: source is BGR (cv2.imread), network wants RGB */
+  double norm_mean[3];     /* MDE_INPUT_U8_HWC: (v/255 - mean)/std, evaluated in double like */
+  double norm_std[3];      /*   core/preprocess.py:294-328 with float64 dtypes */
+  float max_depth;         /* > 0: metric head, sigmoid * max_depth;  <= 0: relative head, ReLU */
+  int32_t device;          /* CUDA device ordinal */
+} mde_engine_desc;
+
+const char* mde_last_error(void);
+int mde_abi_version(void);
+
+/* ---- engine ------------------------------------------------------------------------------ */
+int mde_engine_create(const mde_engine_desc* desc, mde_engine** out);
+/* Provide one tensor of the upstream state dict (key names as in depth_anything_v2_*.pth), fp32,
+ * host memory, C-contiguous.  Copied; the caller may free `data` on return. */
+int mde_engine_set_weight(mde_engine* e, const char* name, const float* data, int32_t ndim, const int64_t* dims);
+/* Read every tensor from a .mdew file (see monocular_depth_estimation_trt_b200/weights.py). */
+int mde_engine_load_weights(mde_engine* e, const char* path);
+/* Check that every required tensor is present, pack to the kernels' layouts, upload.  Needs the GPU. */
+int mde_engine_finalize(mde_engine* e);
+void mde_engine_destroy(mde_engine* e);
+
+int mde_engine_num_io(const mde_engine* e);
+const char* mde_engine_io_name(const mde_engine* e, int32_t i);
+/* dims[] receives up to 8 extents, *ndim their count (maximum extents for the uint8 input). */
+int mde_engine_io_shape(const mde_engine* e, int32_t i, int32_t* ndim, int64_t* dims);
+int mde_engine_io_dtype(const mde_engine* e, int32_t i); /* MDE_DT_* or -1 */
+int mde_engine_io_is_input(const mde_engine* e, int32_t i); /* 1 input, 0 output, -1 bad index */
+/* bytes of device workspace a context of this engine allocates */
+int64_t mde_engine_workspace_bytes(const mde_engine* e);
+
+/* ---- execution context -------------------------------------------------------------------- */
+int mde_context_create(mde_engine* e, mde_context** out);
+void mde_context_destroy(mde_context* c);
+int mde_context_set_tensor_address(mde_context* c, const char* name, void* d_ptr);
+/* MDE_INPUT_U8_HWC only: actual source size of this batch, dims = {B, src_h, src_w, 3}. */
+int mde_context_set_input_shape(mde_context* c, const char* name, int32_t ndim, const int64_t* dims);
+/* Launch one forward of the whole batch on `stream`.  Asynchronous. */
+int mde_context_enqueue(mde_context* c, void* stream);
+/* Number of kernels one enqueue launches (bench.py's gpu_launches). */
+int mde_context_launches_per_enqueue(const mde_context* c);
+/* Intermediate tensors for the per-stage parity gates: "cols", "x" (residual stream after the
+ * last block), "tap0".."tap3", "path_1", "r0".."r3".  Valid after enqueue + stream sync.
+ * dtype: 0 = fp32, 1 = 16-bit in the engine's precision. */
+int mde_context_get_buffer(mde_context* c, const char* name, void** d_ptr, int64_t* bytes, int32_t* dtype);
+/* Snapshot the fp32 residual stream after block `block` into an internal buffer during enqueue
+ * (-1 disables).  Read it back with mde_context_get_buffer(c, "x_snapshot", ...). */
+int mde_context_snapshot_block(mde_context* c, int32_t block);
+
+/* ---- single kernels (test surface) ---------------------------------------------------------- */
+
+/* Kernel (1): uint8 HWC -> cv2-exact bilinear resize -> normalise -> patch im2col.
+ * d_cols: [B*(dst_h/patch)*(dst_w/patch)][kpad] 16-bit (may be NULL); d_nchw: float32 [B,3,dst_h,dst_w]
+ * (may be NULL).  kpad >= 3*patch*patch, multiple of 64. */
+int mde_k_preprocess_u8(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
+                        int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
+                        const double* mean3, const double* std3, void* d_cols, float* d_nchw, void* stream);
+int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int32_t h, int32_t w, int32_t patch,
+                     int32_t kpad, void* d_cols, void* stream);
+
+/* Epilogue of the tensor-core GEMM / conv:  v = acc + bias; v = act(v); v *= gamma; v += pos;
+ * v += res1 + res2; x = (accumulate_x ? x : 0) + v; out = v; out_relu = relu(v). */
+typedef struct mde_epilogue {
+  const float* d_bias;   /* [N] or NULL */
+  const float* d_gamma;  /* [N] or NULL */
+  int32_t act;           /* 0 none, 1 GELU(erf), 2 ReLU */
+  float* d_x;            /* fp32 [rows][ld_out] or NULL */
+  int32_t accumulate_x;
+  const void* d_res1;    /* 16-bit [rows][ld_out] or NULL */
+  const void* d_res2;
+  void* d_out;           /* 16-bit [rows][ld_out] or NULL */
+  void* d_out_relu;
+  int32_t ld_out;
+  /* token remap (patch embed): row b*T+t -> b*(T+1)+1+t, plus pos[(1+t)][:] */
+  int32_t tokens;        /* 0 = off */
+  const float* d_pos;
+  /* pixel shuffle (ConvTranspose2d with kernel == stride == s): A rows are (b,y,x) of an HxW map,
+   * N = s*s*cout, column (ky*s+kx)*cout + o goes to pixel (s*y+ky, s*x+kx), channel o */
+  int32_t shuffle_s, shuffle_cout, shuffle_h, shuffle_w; /* shuffle_s == 0: off */
+  /* fused depth head (N == 32): z = sum_n relu(v_n) * head_w[n] + head_b;
+   * head_out[row] = head_scale > 0 ? head_scale*sigmoid(z) : relu(z) */
+  const float* d_head_w;
+  float head_b, head_scale;
+  float* d_head_out;
+} mde_epilogue;
+
+/* D[M,N] = A[M,K] * B[N,K]^T.  A: 16-bit row-major, pitch lda elements; B: 16-bit row-major, pitch ldb.
+ * lda, ldb multiples of 8; N multiple of 8. */
+int mde_k_gemm(int32_t precision, const void* d_a, int64_t m, int32_t k, int32_t lda, const void* d_b, int32_t n,
+               int32_t ldb, const mde_epilogue* ep, void* stream);
+/* 3x3 / stride 1 / pad 1 convolution, NHWC.  d_in: [B][H][W][cin] 16-bit (cin multiple of 8);
+ * d_w: [cout][9*cin_pad] 16-bit with cin_pad = cin rounded up to 64 and K index = (ky*3+kx)*cin_pad + c. */
+int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h, int32_t w, int32_t cin,
+                  const void* d_w, int32_t cout, const mde_epilogue* ep, void* stream);
+/* softmax(Q K^T / 8) V over [B*ntok][3*D] packed q|k|v rows, head dim 64 -> [B*ntok][D]. */
+int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                    void* stream);
+/* LayerNorm of fp32 rows -> 16-bit.  drop_cls != 0: rows are [B][ntok]; token 0 of each image is
+ * skipped and the output is dense [B][ntok-1]. */
+int mde_k_layernorm(int32_t precision, const float* d_x, const float* d_w, const float* d_b, void* d_out,
+                    int64_t rows, int32_t dim, float eps, int32_t drop_cls, int32_t ntok, void* stream);
+/* bilinear, align_corners=True, NHWC 16-bit, c multiple of 8 */
+int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t hi, int32_t wi, int32_t ho,
+                   int32_t wo, int32_t c, void* stream);
+/* 3x3 / stride 2 / pad 1 gather: NHWC -> [(b,oy,ox)][tap*c + ch] */
+int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t h, int32_t w, int32_t c,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDE_B200_H */

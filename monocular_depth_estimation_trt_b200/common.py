@@ -1,0 +1,150 @@
+"""`get_engine` for the B200 runtime -- drop-in for the reference's core/common.py:141-312.
+
+The reference parses an ONNX file and lets TensorRT search tactics for minutes, then caches the
+serialized plan next to a fingerprint.  Here "build" is: read the exported weights (.mdew, see
+weights.py), describe the engine (encoder, input size, precision, batch), pack the weights into the
+kernels' layouts and upload them.  That takes seconds, so nothing heavy is cached; what *is* kept is
+the reference's bookkeeping, because its tooling reads it:
+
+  <engine>.engine        a small JSON stub describing what was built (stands in for the plan file
+                         that core/build_conditions.stamp() sizes and dates)
+  <engine>.fingerprint   sha256(weights) + runtime ABI + options + GPU name (core/common.py:92-117)
+  engine_staleness()     same decision table as core/common.py:120-138
+
+Everything core/common_runtime.py exports is re-exported, as core/common.py:43 does.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from typing import Optional, Sequence, Tuple
+
+from . import _lib, weights as W
+from .common_runtime import *          # noqa: F401,F403  (mirrors `from core.common_runtime import *`)
+from .common_runtime import allocate_buffers, do_inference, free_buffers  # noqa: F401  explicit for linters
+from .engine import Engine, ExecutionContext, TensorIOMode, make_desc   # noqa: F401
+
+
+def GiB(val):
+    return val * 1 << 30
+
+
+def _gpu_name() -> Optional[str]:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.get_device_name(0)
+    except Exception:
+        pass
+    return None
+
+
+def _engine_fingerprint(model_file_path, precision, workspace_gib, opt_level,
+                        obey_precision_constraints, dynamic_input_shapes, batch=1, input_mode="f32_nchw"):
+    """What an engine was built from, so a stale stub is not trusted."""
+    parts = [
+        W.file_sha256(model_file_path),
+        f"mde_b200_abi={_lib.load().mde_abi_version()}",
+        f"precision={precision}",
+        f"workspace={workspace_gib}",
+        f"opt_level={opt_level}",
+        f"obey_precision={obey_precision_constraints}",
+        f"dynamic={dynamic_input_shapes}",
+        f"batch={batch}",
+        f"input_mode={input_mode}",
+    ]
+    gpu = _gpu_name()
+    if gpu:
+        parts.append(f"gpu={gpu}")
+    return "\n".join(parts)
+
+
+def engine_staleness(engine_file_path, fingerprint_path, fingerprint, model_exists):
+    """Why the recorded engine cannot be trusted, or None if it can (core/common.py:120-138)."""
+    if not os.path.exists(engine_file_path):
+        return "no engine file"
+    if not model_exists or fingerprint is None:
+        return None
+    if not os.path.exists(fingerprint_path):
+        return "no fingerprint recorded"
+    with open(fingerprint_path, encoding="utf-8") as f:
+        return None if f.read() == fingerprint else "weights or build options changed"
+
+
+def get_engine(
+    onnx_file_path,
+    engine_file_path="",
+    precision="fp16",
+    dynamic_input_shapes=None,
+    workspace_gib=2,
+    opt_level=None,
+    obey_precision_constraints=False,
+    check_fingerprint=True,
+    *,
+    batch: int = 1,
+    input_mode: str = "f32_nchw",
+    max_src_hw: Tuple[int, int] = (0, 0),
+    swap_rb: bool = True,
+    device: int = 0,
+) -> Engine:
+    """Build the engine for the exported model at `onnx_file_path` (an .mdew file here).
+
+    Positional arguments keep the reference's order and meaning.  `precision` is "fp16" (the
+    reference's build target) or "bf16"; "fp32" is refused -- the B200 path is a 16-bit
+    tensor-core path with fp32 accumulation and will not silently run something else.
+    `dynamic_input_shapes` must be None: engines are static, as every engine the reference ships
+    (models/depth_anything_v2/onnx2trt.py:67 "dynamic = False  # fail...(False only)").
+    `workspace_gib`, `opt_level` and `obey_precision_constraints` only enter the fingerprint.
+    Keyword-only extras: `batch` (images per execute), `input_mode` ("f32_nchw" = the reference's
+    float32 contract fed by core/preprocess.py; "u8_hwc" = raw source frames, preprocessing fused
+    on the GPU), `max_src_hw` for the latter.
+    """
+    model_path = os.fspath(onnx_file_path)
+    if not os.path.exists(model_path):
+        raise FileNotFoundError(f"[MDET] model file {model_path} not found.")
+    if dynamic_input_shapes is not None:
+        raise ValueError("[MDET] dynamic input shapes are not supported: engines are static")
+
+    begin = time.time()
+    meta = W.read_meta(model_path)
+    desc = make_desc(meta, precision=precision, batch=batch, input_mode=input_mode,
+                     max_src_hw=max_src_hw, swap_rb=swap_rb, device=device)
+
+    fingerprint = None
+    fingerprint_path = os.path.splitext(engine_file_path)[0] + ".fingerprint" if engine_file_path else ""
+    if check_fingerprint:
+        fingerprint = _engine_fingerprint(model_path, precision, workspace_gib, opt_level,
+                                          obey_precision_constraints, dynamic_input_shapes, batch, input_mode)
+    if engine_file_path:
+        stale = engine_staleness(engine_file_path, fingerprint_path, fingerprint, True)
+        if stale is None:
+            print(f"[MDET] Engine record is current ({engine_file_path})")
+        elif os.path.exists(engine_file_path):
+            print(f"[MDET] Rebuilding engine - {stale}")
+    print(f"[MDET] Build engine ({engine_file_path or model_path})")
+
+    engine = Engine(desc, meta)
+    try:
+        engine.load_weights_file(model_path)
+        engine.finalize()
+    except Exception:
+        engine.close()
+        raise
+    for i in range(engine.num_io_tensors):
+        name = engine.get_tensor_name(i)
+        kind = "input" if engine.get_tensor_mode(name) == TensorIOMode.INPUT else "output"
+        print(f"[MDET] {kind}({i}) name: {name}, shape= {engine.get_tensor_shape(name)}")
+
+    if engine_file_path:
+        os.makedirs(os.path.dirname(engine_file_path) or ".", exist_ok=True)
+        with open(engine_file_path, "w", encoding="utf-8") as f:
+            json.dump({"backend": "mde_b200", "abi": _lib.load().mde_abi_version(), "meta": meta,
+                       "precision": precision, "batch": batch, "input_mode": input_mode,
+                       "workspace_bytes": engine.workspace_bytes}, f, indent=2)
+        if fingerprint is not None:
+            with open(fingerprint_path, "w", encoding="utf-8") as f:
+                f.write(fingerprint)
+    dur = time.time() - begin
+    print(f"[MDET] Engine build done! ({dur:.2f} [sec])")
+    return engine

@@ -1,0 +1,292 @@
+// Memory-bound kernels of the path: fused uint8 resize + normalise + patch im2col (kernel 1 of
+// north_star), float32-NCHW im2col (the reference's input contract), warp-shuffle LayerNorm,
+// bilinear (align_corners=True) NHWC upsampling, the stride-2 3x3 im2col gather and the cls row.
+#pragma once
+#include "ptx.cuh"
+
+namespace mde {
+
+// ---------------------------------------------------------------------------------------------
+// Kernel (1): HWC uint8 source (any size) -> cv2.resize(INTER_LINEAR) semantics on uint8 ->
+// float64-derived normalisation LUT -> patch im2col rows [(b, gy, gx)][c*p*p + ky*p + kx] (16-bit),
+// optionally also the float32 NCHW tensor core/preprocess.py produces (for bit-exact parity tests).
+//
+// Restates OpenCV's 8-bit bilinear path (11-bit fixed-point coefficients; see oracle/preprocess_np.py
+// for the line-by-line statement and SURVEY section 8 a-1): coordinates in double, fractional part in
+// float, coefficients rint(f * 2048) as int16, horizontal pass un-shifted, vertical pass
+// (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+// ---------------------------------------------------------------------------------------------
+struct PreprocParams {
+  const uint8_t* src;       // [B][src_h][src_w][3] (batch stride src_batch_stride bytes)
+  long long src_batch_stride;
+  int src_h, src_w;
+  int dst_h, dst_w;         // model input size (multiples of patch)
+  int patch;                // 14 or 16
+  int kpad;                 // im2col row pitch in elements (>= 3*patch*patch, multiple of 64)
+  int swap_rb;              // source is BGR (cv2.imread) -> RGB
+  const float* lut;         // [3][256] float32: (v/255 - mean_c)/std_c evaluated in float64
+  void* cols;               // [B*gh*gw][kpad] 16-bit, or null
+  float* nchw;              // [B][3][dst_h][dst_w] float32, or null
+  int exact2x;              // cv2 switches INTER_LINEAR to INTER_AREA when both scales are exactly 2
+};
+
+__device__ __forceinline__ void cv_linear_coeff(int d, double scale, int src_size, int& s0, short& a0, short& a1,
+                                                bool clamp_coeff) {
+  // *_rn intrinsics: never contracted into an FMA, so the rounding sequence is the CPU's
+  float f = __double2float_rn(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(d), 0.5), scale), 0.5));
+  int s = static_cast<int>(floorf(f));
+  f = __fsub_rn(f, static_cast<float>(s));
+  if (clamp_coeff) {               // x axis: coefficients collapse at the borders
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src_size - 1) { f = 0.f; s = src_size - 1; }
+  }
+  s0 = s;
+  a0 = static_cast<short>(__float2int_rn((1.f - f) * 2048.f));
+  a1 = static_cast<short>(__float2int_rn(f * 2048.f));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const PreprocParams p) {
+  extern __shared__ __align__(16) uint8_t pp_smem[];
+  const int gw = p.dst_w / p.patch;
+  const int gy = blockIdx.x, b = blockIdx.y;
+  // smem: xofs[dst_w] int, xa[dst_w][2] short, tile[gw][kpad] T
+  int* xofs = reinterpret_cast<int*>(pp_smem);
+  short* xa = reinterpret_cast<short*>(xofs + p.dst_w);
+  T* tile = reinterpret_cast<T*>(pp_smem + ((p.dst_w * 8 + 15) & ~15));
+  const double inv_x = static_cast<double>(p.dst_w) / p.src_w, inv_y = static_cast<double>(p.dst_h) / p.src_h;
+  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+
+  for (int dx = threadIdx.x; dx < p.dst_w; dx += blockDim.x) {
+    int s0; short a0, a1;
+    cv_linear_coeff(dx, scale_x, p.src_w, s0, a0, a1, true);
+    xofs[dx] = s0; xa[2 * dx] = a0; xa[2 * dx + 1] = a1;
+  }
+  if (p.cols) {
+    const int k_real = 3 * p.patch * p.patch;
+    const int padw = p.kpad - k_real;
+    for (int i = threadIdx.x; i < gw * padw; i += blockDim.x)
+      tile[(i / padw) * p.kpad + k_real + i % padw] = F16Traits<T>::from_f(0.f);
+  }
+  __syncthreads();
+
+  const uint8_t* src = p.src + static_cast<long long>(b) * p.src_batch_stride;
+  const long long row_bytes = static_cast<long long>(p.src_w) * 3;
+  const int pp2 = p.patch * p.patch;
+  for (int i = threadIdx.x; i < p.patch * p.dst_w; i += blockDim.x) {
+    const int ky = i / p.dst_w, dx = i % p.dst_w;
+    const int dy = gy * p.patch + ky;
+    int out[3];
+    if (p.exact2x) {
+      const uint8_t* r0 = src + static_cast<long long>(2 * dy) * row_bytes + 6 * dx;
+      const uint8_t* r1 = r0 + row_bytes;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[c] = (r0[c] + r0[c + 3] + r1[c] + r1[c + 3] + 2) >> 2;
+    } else {
+      int sy; short b0, b1;
+      cv_linear_coeff(dy, scale_y, p.src_h, sy, b0, b1, false);
+      const int y0 = min(max(sy, 0), p.src_h - 1), y1 = min(max(sy + 1, 0), p.src_h - 1);
+      const int sx = xofs[dx];
+      const int sx1 = min(sx + 1, p.src_w - 1);    // coefficient is 0 whenever this clamp acts
+      const int a0 = xa[2 * dx], a1 = xa[2 * dx + 1];
+      const uint8_t* r0 = src + y0 * row_bytes;
+      const uint8_t* r1 = src + y1 * row_bytes;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+        const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+        out[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      }
+    }
+    const int gx = dx / p.patch, kx = dx % p.patch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = p.swap_rb ? 2 - c : c;               // output channel c reads source channel cs
+      const float v = __ldg(p.lut + c * 256 + out[cs]);
+      if (p.cols) tile[gx * p.kpad + c * pp2 + ky * p.patch + kx] = F16Traits<T>::from_f(v);
+      if (p.nchw) p.nchw[((static_cast<long long>(b) * 3 + c) * p.dst_h + dy) * p.dst_w + dx] = v;
+    }
+  }
+  if (p.cols) {
+    __syncthreads();
+    // one patch row = gw consecutive im2col rows = one contiguous block: 16-byte coalesced stores
+    const int n16 = gw * p.kpad / 8;
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(p.cols) +
+                                          (static_cast<long long>(b) * (p.dst_h / p.patch) + gy) * gw * p.kpad);
+    const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = s4[i];
+  }
+}
+
+// float32 NCHW [B,3,H,W] (what core/preprocess.py emits) -> the same im2col rows.
+struct Im2colParams {
+  const float* nchw;
+  void* cols;
+  int H, W, patch, kpad;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_f32_kernel(const Im2colParams p) {
+  extern __shared__ __align__(16) uint8_t ic_smem[];
+  T* tile = reinterpret_cast<T*>(ic_smem);
+  const int gw = p.W / p.patch, gh = p.H / p.patch;
+  const int gy = blockIdx.x, b = blockIdx.y;
+  const int pp2 = p.patch * p.patch, k_real = 3 * pp2, padw = p.kpad - k_real;
+  for (int i = threadIdx.x; i < gw * padw; i += blockDim.x)
+    tile[(i / padw) * p.kpad + k_real + i % padw] = F16Traits<T>::from_f(0.f);
+  const int per_c = p.patch * p.W;
+  for (int i = threadIdx.x; i < 3 * per_c; i += blockDim.x) {
+    const int c = i / per_c, rem = i % per_c, ky = rem / p.W, x = rem % p.W;
+    const float v = p.nchw[((static_cast<long long>(b) * 3 + c) * p.H + gy * p.patch + ky) * p.W + x];
+    tile[(x / p.patch) * p.kpad + c * pp2 + ky * p.patch + x % p.patch] = F16Traits<T>::from_f(v);
+  }
+  __syncthreads();
+  const int n16 = gw * p.kpad / 8;
+  uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(p.cols) + (static_cast<long long>(b) * gh + gy) * gw * p.kpad);
+  const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = s4[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim of the fp32 residual stream, one warp per row, statistics in fp32
+// (two-pass on registers), 16-bit output.  drop_cls: rows are [B][ntok] tokens; the cls row (0) of
+// every image is skipped and the output is the dense [B][ntok-1] patch grid (the DPT taps).
+// ---------------------------------------------------------------------------------------------
+struct LayerNormParams {
+  const float* x;      // [rows][D]
+  const float* w;
+  const float* b;
+  void* out;           // 16-bit
+  long long rows;
+  int D;               // multiple of 128, <= 1024
+  float eps;
+  int drop_cls;
+  int ntok;
+};
+template <typename T, int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p) {
+  constexpr int V = D / 128;   // float4 per lane
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  long long orow = row;
+  if (p.drop_cls) {
+    const long long b = row / p.ntok;
+    const int t = static_cast<int>(row % p.ntok);
+    if (t == 0) return;
+    orow = b * (p.ntok - 1) + (t - 1);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(p.x + row * D);
+  float4 v[V];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[lane + i * 32];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / D) + p.eps);
+  T* out = static_cast<T*>(p.out) + orow * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + i * 32) * 4;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.b + c));
+    uint2 u;
+    u.x = F16Traits<T>::pack2((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y);
+    u.y = F16Traits<T>::pack2((v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+    *reinterpret_cast<uint2*>(out + c) = u;
+  }
+}
+
+// x[b][0][:] = cls + pos[0]   (the patch-embed GEMM epilogue writes rows 1..T)
+__global__ void cls_row_kernel(float* x, const float* cls, const float* pos, int ntok, int D) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) x[static_cast<long long>(b) * ntok * D + i] = cls[i] + pos[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners=True, NHWC 16-bit, 8 channels (16 bytes) per thread.
+// Matches torch.nn.functional.interpolate: src = dst * (in-1)/(out-1), lerp in fp32.
+// ---------------------------------------------------------------------------------------------
+struct BilinearParams {
+  const void* in;   // [B][Hi][Wi][C]
+  void* out;        // [B][Ho][Wo][C]
+  int B, Hi, Wi, Ho, Wo, C;
+  float sy, sx;     // (Hi-1)/(Ho-1), (Wi-1)/(Wo-1)
+};
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const BilinearParams p) {
+  using Tr = F16Traits<T>;
+  const int cv = p.C / 8;
+  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    long long pix = i / cv;
+    const int x = static_cast<int>(pix % p.Wo); pix /= p.Wo;
+    const int y = static_cast<int>(pix % p.Ho);
+    const int b = static_cast<int>(pix / p.Ho);
+    const float fy = y * p.sy, fx = x * p.sx;
+    const int y0 = min(static_cast<int>(fy), p.Hi - 1), x0 = min(static_cast<int>(fx), p.Wi - 1);
+    const int y1 = min(y0 + 1, p.Hi - 1), x1 = min(x0 + 1, p.Wi - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const T* base = static_cast<const T*>(p.in) + static_cast<long long>(b) * p.Hi * p.Wi * p.C + c * 8;
+    const uint4 q00 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * p.Wi + x0) * p.C);
+    const uint4 q01 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * p.Wi + x1) * p.C);
+    const uint4 q10 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * p.Wi + x0) * p.C);
+    const uint4 q11 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * p.Wi + x1) * p.C);
+    const uint32_t* a = &q00.x; const uint32_t* bb = &q01.x; const uint32_t* cc = &q10.x; const uint32_t* d = &q11.x;
+    uint4 r; uint32_t* ro = &r.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 v00 = Tr::unpack2(a[k]), v01 = Tr::unpack2(bb[k]), v10 = Tr::unpack2(cc[k]), v11 = Tr::unpack2(d[k]);
+      const float tx0 = v00.x + wx * (v01.x - v00.x), tx1 = v00.y + wx * (v01.y - v00.y);
+      const float bx0 = v10.x + wx * (v11.x - v10.x), bx1 = v10.y + wx * (v11.y - v10.y);
+      ro[k] = Tr::pack2(tx0 + wy * (bx0 - tx0), tx1 + wy * (bx1 - tx1));
+    }
+    *reinterpret_cast<uint4*>(static_cast<T*>(p.out) + ((static_cast<long long>(b) * p.Ho + y) * p.Wo + x) * p.C + c * 8) = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 / stride 2 / pad 1 gather: NHWC [B][H][W][C] -> rows [(b, oy, ox)][tap*C + c] for a plain GEMM
+// (resize_layers[3]: 37x37 -> 19x19; 0.5 % of the FLOPs, not worth a strided tensor map).
+// ---------------------------------------------------------------------------------------------
+struct Im2colS2Params {
+  const void* in;
+  void* out;
+  int B, H, W, C, Ho, Wo;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const Im2colS2Params p) {
+  const int cv = p.C / 8;
+  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * 9 * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    long long r = i / cv;
+    const int tap = static_cast<int>(r % 9); r /= 9;
+    const int ox = static_cast<int>(r % p.Wo); r /= p.Wo;
+    const int oy = static_cast<int>(r % p.Ho);
+    const int b = static_cast<int>(r / p.Ho);
+    const int y = 2 * oy + tap / 3 - 1, x = 2 * ox + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < p.H && x >= 0 && x < p.W)
+      v = *reinterpret_cast<const uint4*>(static_cast<const T*>(p.in) +
+                                          ((static_cast<long long>(b) * p.H + y) * p.W + x) * p.C + c * 8);
+    *reinterpret_cast<uint4*>(static_cast<T*>(p.out) +
+                              (((static_cast<long long>(b) * p.Ho + oy) * p.Wo + ox) * 9 + tap) * p.C + c * 8) = v;
+  }
+}
+
+}  // namespace mde

@@ -1,0 +1,64 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, the driver entry point for
+// tensor-map encoding, GEMM/conv op construction and kernel launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/mde_b200.h"
+#include "gemm.cuh"
+
+namespace mde {
+
+int fail(int code, const char* fmt, ...);
+void clear_error();
+
+#define MDE_CUDA_TRY(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) return ::mde::fail(MDE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define MDE_TRY(expr)            \
+  do {                           \
+    int r__ = (expr);            \
+    if (r__ != MDE_OK) return r__; \
+  } while (0)
+
+int num_sms();   // SM count of the current device (cached), 0 on failure
+
+// One tensor-core GEMM / implicit-GEMM conv launch, fully described at plan-build time.
+struct GemmOp {
+  alignas(64) CUtensorMap map_a;
+  alignas(64) CUtensorMap map_b;
+  GemmParams p;
+  int block_n;
+  int precision;
+  int grid;
+};
+
+// D[M,N] = A[M,K] B[N,K]^T
+int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k, int lda, const void* d_b, int n,
+                 int ldb, const mde_epilogue* ep);
+// 3x3 s1 p1 NHWC conv, weights [cout][9*cin_pad]
+int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, int w, int cin, const void* d_w,
+                 int cout, const mde_epilogue* ep);
+int launch_gemm(const GemmOp& op, cudaStream_t stream);
+
+int launch_attention(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);
+int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,
+                     int dim, float eps, int drop_cls, int ntok, cudaStream_t s);
+int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int hi, int wi, int ho, int wo, int c,
+                    cudaStream_t s);
+int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s);
+int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int w, int patch, int kpad, void* d_cols,
+                      cudaStream_t s);
+int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batch_stride, int batch, int src_h,
+                         int src_w, int dst_h, int dst_w, int patch, int kpad, int swap_rb, const float* d_lut,
+                         void* d_cols, float* d_nchw, cudaStream_t s);
+int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, int batch, int ntok, int dim, cudaStream_t s);
+// (v/255 - mean)/std in double, rounded once to float32: 3 x 256 entries (core/preprocess.py:294-328,337-342)
+void build_norm_lut(const double* mean3, const double* std3, float* lut768);
+
+}  // namespace mde

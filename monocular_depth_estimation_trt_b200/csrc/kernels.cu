@@ -1,0 +1,455 @@
+// Kernel instantiations, launchers and the single-kernel C-ABI entry points (mde_k_*).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "attention_mma.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "host_common.h"
+
+namespace mde {
+
+// ------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+void clear_error() { g_last_error.clear(); }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+int num_sms() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached = n;
+  }
+  return cached;
+}
+
+// ------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MDE_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p)
+      return fail(MDE_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cached = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *fn = cached;
+  return MDE_OK;
+}
+
+static int encode_map(CUtensorMap* map, int precision, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn enc;
+  MDE_TRY(get_encode(&enc));
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapDataType dt = precision == MDE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MDE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,...] box [%u,%u,...]",
+                static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+  return MDE_OK;
+}
+
+static int pick_block_n(int n) {
+  // smallest padded N wins; ties go to the wider tile (fewer A re-reads, longer MMA bursts)
+  const int cands[4] = {256, 128, 64, 32};
+  int best = 32;
+  long long best_pad = 1LL << 60;
+  for (int bn : cands) {
+    const long long pad = static_cast<long long>((n + bn - 1) / bn) * bn;
+    if (pad < best_pad) { best_pad = pad; best = bn; }
+  }
+  return best;
+}
+
+static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_out_unused) {
+  (void)rows_out_unused;
+  p.row_map = ROW_IDENTITY;
+  p.tokens = 0; p.shuffle_s = 0; p.shuffle_cout = 0;
+  p.act = ep->act;
+  p.ld_out = ep->ld_out;
+  p.accumulate_x = ep->accumulate_x;
+  p.bias = ep->d_bias; p.gamma = ep->d_gamma; p.pos = ep->d_pos;
+  p.x = ep->d_x; p.res1 = ep->d_res1; p.res2 = ep->d_res2; p.out = ep->d_out; p.out_relu = ep->d_out_relu;
+  p.head_w = ep->d_head_w; p.head_b = ep->head_b;
+  p.head_scale = ep->head_scale > 0.f ? ep->head_scale : -1.f;
+  p.head_out = ep->d_head_out;
+  if (ep->ld_out % 8 != 0 && !ep->d_head_w) return fail(MDE_ERR_INVALID, "ld_out must be a multiple of 8");
+  if (ep->act < 0 || ep->act > 2) return fail(MDE_ERR_INVALID, "unknown activation %d", ep->act);
+  return MDE_OK;
+}
+
+int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k, int lda, const void* d_b, int n,
+                 int ldb, const mde_epilogue* ep) {
+  if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
+  if (m <= 0 || n <= 0 || k <= 0) return fail(MDE_ERR_INVALID, "gemm: empty problem m=%lld n=%d k=%d", m, n, k);
+  if (lda % 8 || ldb % 8 || n % 8) return fail(MDE_ERR_INVALID, "gemm: lda, ldb and n must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b)) & 15)
+    return fail(MDE_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  memset(&op->p, 0, sizeof(op->p));
+  GemmParams& p = op->p;
+  MDE_TRY(fill_epilogue(p, ep, m));
+  p.M = static_cast<int>(m); p.N = n; p.K = k;
+  if (m > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "gemm: m too large");
+  p.num_k_blocks = (k + 63) / 64;
+  op->block_n = ep->d_head_w ? 32 : pick_block_n(n);
+  if (ep->d_head_w && n != 32) return fail(MDE_ERR_INVALID, "fused depth head needs n == 32");
+  p.m_tiles = static_cast<int>((m + 127) / 128);
+  p.n_tiles = (n + op->block_n - 1) / op->block_n;
+  p.conv = 0;
+  if (ep->tokens > 0) {
+    p.row_map = ROW_TOKENS; p.tokens = ep->tokens;
+    if (m % ep->tokens) return fail(MDE_ERR_INVALID, "gemm: m not a multiple of tokens");
+  } else if (ep->shuffle_s > 0) {
+    p.row_map = ROW_SHUFFLE; p.shuffle_s = ep->shuffle_s; p.shuffle_cout = ep->shuffle_cout;
+    p.H = ep->shuffle_h; p.W = ep->shuffle_w;
+    if (n != ep->shuffle_s * ep->shuffle_s * ep->shuffle_cout || ep->shuffle_cout % 8 ||
+        m % (static_cast<long long>(p.H) * p.W))
+      return fail(MDE_ERR_INVALID, "gemm: inconsistent pixel-shuffle description");
+  }
+  op->precision = precision;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(m)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(lda) * 2};
+    cuuint32_t box[2] = {64, 128};
+    MDE_TRY(encode_map(&op->map_a, precision, d_a, 2, dims, str, box));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(n)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(ldb) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n)};
+    MDE_TRY(encode_map(&op->map_b, precision, d_b, 2, dims, str, box));
+  }
+  const int sms = num_sms();
+  if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
+  op->grid = std::min(sms, p.m_tiles * p.n_tiles);
+  return MDE_OK;
+}
+
+int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, int w, int cin, const void* d_w,
+                 int cout, const mde_epilogue* ep) {
+  if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
+  if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return fail(MDE_ERR_INVALID, "conv: empty problem");
+  if (cin % 8 || cout % 8) return fail(MDE_ERR_INVALID, "conv: cin and cout must be multiples of 8");
+  if (ep->tokens > 0 || ep->shuffle_s > 0) return fail(MDE_ERR_INVALID, "conv: row remaps are GEMM-only");
+  memset(&op->p, 0, sizeof(op->p));
+  GemmParams& p = op->p;
+  MDE_TRY(fill_epilogue(p, ep, 0));
+  const int cin_pad = (cin + 63) / 64 * 64;
+  p.M = batch * h * w; p.N = cout; p.K = 9 * cin_pad;
+  p.num_k_blocks = 9 * (cin_pad / 64);
+  p.cin_blocks = cin_pad / 64;
+  p.conv = 1; p.row_map = ROW_CONV; p.H = h; p.W = w;
+  // spatial tile of <= 128 output pixels: maximise useful pixels per tile
+  double best_eff = -1.0;
+  for (int tw = 1; tw <= 128 && tw <= 256; ++tw) {
+    const int th = 128 / tw;
+    if (th < 1) break;
+    if (th > 256) continue;
+    const int tx = (w + tw - 1) / tw, ty = (h + th - 1) / th;
+    const double eff = static_cast<double>(h) * w / (static_cast<double>(tx) * ty * 128.0);
+    // prefer wide tiles on ties: longer contiguous runs per TMA box row
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && tw > p.tile_w)) {
+      best_eff = eff; p.tile_w = tw; p.tile_h = th; p.tiles_x = tx; p.tiles_y = ty;
+    }
+  }
+  op->block_n = ep->d_head_w ? 32 : pick_block_n(cout);
+  if (ep->d_head_w && cout != 32) return fail(MDE_ERR_INVALID, "fused depth head needs cout == 32");
+  p.m_tiles = batch * p.tiles_x * p.tiles_y;
+  p.n_tiles = (cout + op->block_n - 1) / op->block_n;
+  op->precision = precision;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                          static_cast<cuuint64_t>(batch)};
+    cuuint64_t str[3] = {static_cast<cuuint64_t>(cin) * 2, static_cast<cuuint64_t>(w) * cin * 2,
+                         static_cast<cuuint64_t>(h) * w * cin * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.tile_w), static_cast<cuuint32_t>(p.tile_h), 1};
+    MDE_TRY(encode_map(&op->map_a, precision, d_in, 4, dims, str, box));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(9 * cin_pad), static_cast<cuuint64_t>(cout)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(9 * cin_pad) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n)};
+    MDE_TRY(encode_map(&op->map_b, precision, d_w, 2, dims, str, box));
+  }
+  const int sms = num_sms();
+  if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
+  op->grid = std::min(sms, p.m_tiles * p.n_tiles);
+  return MDE_OK;
+}
+
+template <int BN, typename T>
+static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<BN, T>;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<op.grid, 256, GemmCfg<BN>::kSmemBytes, s>>>(op.map_a, op.map_b, op.p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+template <typename T>
+static int launch_gemm_bn(const GemmOp& op, cudaStream_t s) {
+  switch (op.block_n) {
+    case 256: return launch_gemm_t<256, T>(op, s);
+    case 128: return launch_gemm_t<128, T>(op, s);
+    case 64: return launch_gemm_t<64, T>(op, s);
+    case 32: return launch_gemm_t<32, T>(op, s);
+  }
+  return fail(MDE_ERR_INVALID, "unsupported BLOCK_N %d", op.block_n);
+}
+
+int launch_gemm(const GemmOp& op, cudaStream_t s) {
+  return op.precision == MDE_BF16 ? launch_gemm_bn<__nv_bfloat16>(op, s) : launch_gemm_bn<__half>(op, s);
+}
+
+// ------------------------------------------------------------------------------------------- other launchers
+template <typename T>
+static int launch_attention_t(const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = attention_mma_kernel<T>;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.qkv = d_qkv; p.out = d_out; p.ntok = ntok; p.heads = heads; p.D = heads * 64;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  dim3 grid((ntok + kAttnBlockQ - 1) / kAttnBlockQ, heads, batch);
+  kern<<<grid, 256, kAttnSmemBytes, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+int launch_attention(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s) {
+  if (batch <= 0 || ntok <= 0 || heads <= 0) return fail(MDE_ERR_INVALID, "attention: empty problem");
+  if (batch > 65535 || heads > 65535) return fail(MDE_ERR_INVALID, "attention: batch/heads exceed grid limits");
+  return precision == MDE_BF16 ? launch_attention_t<__nv_bfloat16>(d_qkv, d_out, batch, ntok, heads, s)
+                               : launch_attention_t<__half>(d_qkv, d_out, batch, ntok, heads, s);
+}
+
+template <typename T>
+static int launch_layernorm_t(const LayerNormParams& p, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>((p.rows + 7) / 8);
+  switch (p.D) {
+    case 384: layernorm_kernel<T, 384><<<grid, 256, 0, s>>>(p); break;
+    case 768: layernorm_kernel<T, 768><<<grid, 256, 0, s>>>(p); break;
+    case 1024: layernorm_kernel<T, 1024><<<grid, 256, 0, s>>>(p); break;
+    case 128: layernorm_kernel<T, 128><<<grid, 256, 0, s>>>(p); break;
+    case 1536: layernorm_kernel<T, 1536><<<grid, 256, 0, s>>>(p); break;
+    default: return fail(MDE_ERR_INVALID, "layernorm: unsupported width %d", p.D);
+  }
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,
+                     int dim, float eps, int drop_cls, int ntok, cudaStream_t s) {
+  if (rows <= 0) return fail(MDE_ERR_INVALID, "layernorm: no rows");
+  if (drop_cls && (ntok < 2 || rows % ntok)) return fail(MDE_ERR_INVALID, "layernorm: rows not a multiple of ntok");
+  LayerNormParams p;
+  p.x = d_x; p.w = d_w; p.b = d_b; p.out = d_out; p.rows = rows; p.D = dim; p.eps = eps; p.drop_cls = drop_cls; p.ntok = ntok;
+  return precision == MDE_BF16 ? launch_layernorm_t<__nv_bfloat16>(p, s) : launch_layernorm_t<__half>(p, s);
+}
+
+static unsigned grid_for(long long total, int per_block) {
+  const long long blocks = (total + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(std::max(1, num_sms())) * 16;
+  return static_cast<unsigned>(std::max(1LL, std::min(blocks, cap)));
+}
+
+int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int hi, int wi, int ho, int wo, int c,
+                    cudaStream_t s) {
+  if (c % 8) return fail(MDE_ERR_INVALID, "bilinear: channels must be a multiple of 8");
+  if (batch <= 0 || hi <= 0 || wi <= 0 || ho <= 0 || wo <= 0) return fail(MDE_ERR_INVALID, "bilinear: empty problem");
+  BilinearParams p;
+  p.in = d_in; p.out = d_out; p.B = batch; p.Hi = hi; p.Wi = wi; p.Ho = ho; p.Wo = wo; p.C = c;
+  p.sy = ho > 1 ? static_cast<float>(hi - 1) / static_cast<float>(ho - 1) : 0.f;
+  p.sx = wo > 1 ? static_cast<float>(wi - 1) / static_cast<float>(wo - 1) : 0.f;
+  const long long total = static_cast<long long>(batch) * ho * wo * (c / 8);
+  if (precision == MDE_BF16) bilinear_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(p);
+  else bilinear_nhwc_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s) {
+  if (c % 8) return fail(MDE_ERR_INVALID, "im2col_s2: channels must be a multiple of 8");
+  Im2colS2Params p;
+  p.in = d_in; p.out = d_out; p.B = batch; p.H = h; p.W = w; p.C = c;
+  p.Ho = (h - 1) / 2 + 1; p.Wo = (w - 1) / 2 + 1;
+  const long long total = static_cast<long long>(batch) * p.Ho * p.Wo * 9 * (c / 8);
+  if (precision == MDE_BF16) im2col_s2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(p);
+  else im2col_s2_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+static int check_patch_geometry(int h, int w, int patch, int kpad) {
+  if (patch <= 0 || h % patch || w % patch) return fail(MDE_ERR_INVALID, "input size %dx%d is not a multiple of patch %d", h, w, patch);
+  if (kpad % 64 || kpad < 3 * patch * patch) return fail(MDE_ERR_INVALID, "kpad %d must be a multiple of 64 and >= %d", kpad, 3 * patch * patch);
+  return MDE_OK;
+}
+
+int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int w, int patch, int kpad, void* d_cols,
+                      cudaStream_t s) {
+  MDE_TRY(check_patch_geometry(h, w, patch, kpad));
+  Im2colParams p;
+  p.nchw = d_nchw; p.cols = d_cols; p.H = h; p.W = w; p.patch = patch; p.kpad = kpad;
+  const int smem = (w / patch) * kpad * 2;
+  dim3 grid(h / patch, batch);
+  if (precision == MDE_BF16) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(im2col_f32_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    im2col_f32_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
+  } else {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(im2col_f32_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    im2col_f32_kernel<__half><<<grid, 256, smem, s>>>(p);
+  }
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+void build_norm_lut(const double* mean3, const double* std3, float* lut768) {
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) {
+      volatile double x = static_cast<double>(v) / 255.0;   // volatile: no fused/reassociated evaluation
+      volatile double y = x - mean3[c];
+      volatile double z = y / std3[c];
+      lut768[c * 256 + v] = static_cast<float>(z);
+    }
+}
+
+int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batch_stride, int batch, int src_h,
+                         int src_w, int dst_h, int dst_w, int patch, int kpad, int swap_rb, const float* d_lut,
+                         void* d_cols, float* d_nchw, cudaStream_t s) {
+  MDE_TRY(check_patch_geometry(dst_h, dst_w, patch, kpad));
+  if (src_h < 1 || src_w < 1) return fail(MDE_ERR_INVALID, "preprocess: empty source image");
+  PreprocParams p;
+  p.src = d_src; p.src_batch_stride = src_batch_stride; p.src_h = src_h; p.src_w = src_w;
+  p.dst_h = dst_h; p.dst_w = dst_w; p.patch = patch; p.kpad = kpad; p.swap_rb = swap_rb; p.lut = d_lut;
+  p.cols = d_cols; p.nchw = d_nchw;
+  p.exact2x = (src_w == 2 * dst_w && src_h == 2 * dst_h) ? 1 : 0;
+  const int smem = ((dst_w * 8 + 15) & ~15) + (d_cols ? (dst_w / patch) * kpad * 2 : 0);
+  dim3 grid(dst_h / patch, batch);
+  if (precision == MDE_BF16) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(preprocess_u8_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    preprocess_u8_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
+  } else {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(preprocess_u8_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    preprocess_u8_kernel<__half><<<grid, 256, smem, s>>>(p);
+  }
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, int batch, int ntok, int dim, cudaStream_t s) {
+  cls_row_kernel<<<batch, 256, 0, s>>>(d_x, d_cls, d_pos, ntok, dim);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+}  // namespace mde
+
+// =============================================================================================== C ABI
+using namespace mde;
+
+extern "C" {
+
+const char* mde_last_error(void) { return mde::last_error_cstr(); }
+int mde_abi_version(void) { return MDE_ABI_VERSION; }
+
+int mde_k_gemm(int32_t precision, const void* d_a, int64_t m, int32_t k, int32_t lda, const void* d_b, int32_t n,
+               int32_t ldb, const mde_epilogue* ep, void* stream) {
+  clear_error();
+  if (!ep) return fail(MDE_ERR_INVALID, "epilogue description is required");
+  GemmOp op;
+  MDE_TRY(make_gemm_op(&op, precision, d_a, m, k, lda, d_b, n, ldb, ep));
+  return launch_gemm(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h, int32_t w, int32_t cin,
+                  const void* d_w, int32_t cout, const mde_epilogue* ep, void* stream) {
+  clear_error();
+  if (!ep) return fail(MDE_ERR_INVALID, "epilogue description is required");
+  GemmOp op;
+  MDE_TRY(make_conv_op(&op, precision, d_in, batch, h, w, cin, d_w, cout, ep));
+  return launch_gemm(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                    void* stream) {
+  clear_error();
+  return launch_attention(precision, d_qkv, d_out, batch, ntok, heads, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_layernorm(int32_t precision, const float* d_x, const float* d_w, const float* d_b, void* d_out,
+                    int64_t rows, int32_t dim, float eps, int32_t drop_cls, int32_t ntok, void* stream) {
+  clear_error();
+  return launch_layernorm(precision, d_x, d_w, d_b, d_out, rows, dim, eps, drop_cls, ntok,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t hi, int32_t wi, int32_t ho,
+                   int32_t wo, int32_t c, void* stream) {
+  clear_error();
+  return launch_bilinear(precision, d_in, d_out, batch, hi, wi, ho, wo, c, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t h, int32_t w, int32_t c,
+                    void* stream) {
+  clear_error();
+  return launch_im2col_s2(precision, d_in, d_out, batch, h, w, c, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int32_t h, int32_t w, int32_t patch,
+                     int32_t kpad, void* d_cols, void* stream) {
+  clear_error();
+  return launch_im2col_f32(precision, d_nchw, batch, h, w, patch, kpad, d_cols, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_preprocess_u8(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
+                        int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
+                        const double* mean3, const double* std3, void* d_cols, float* d_nchw, void* stream) {
+  clear_error();
+  if (!mean3 || !std3) return fail(MDE_ERR_INVALID, "mean/std are required");
+  float lut[768];
+  build_norm_lut(mean3, std3, lut);
+  float* d_lut = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MDE_CUDA_TRY(cudaMalloc(&d_lut, sizeof(lut)));
+  cudaError_t e = cudaMemcpyAsync(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, s);
+  int rc = MDE_OK;
+  if (e != cudaSuccess) rc = fail(MDE_ERR_CUDA, "LUT upload: %s", cudaGetErrorString(e));
+  if (rc == MDE_OK)
+    rc = launch_preprocess_u8(precision, d_src, static_cast<long long>(src_h) * src_w * 3, batch, src_h, src_w, dst_h,
+                              dst_w, patch, kpad, swap_rb, d_lut, d_cols, d_nchw, s);
+  cudaStreamSynchronize(s);   // test entry point: the temporary LUT must outlive the kernel
+  cudaFree(d_lut);
+  return rc;
+}
+
+}  // extern "C"

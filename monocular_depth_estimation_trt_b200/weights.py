@@ -1,0 +1,133 @@
+"""Weights container for the B200 runtime: the artefact of the "export" stage.
+
+In the reference `run.py export <model>` runs models/<name>/onnx_export.py in the model's own
+environment and leaves an ONNX file that `run.py build` hands to TensorRT
+(run.py:40-44, models/depth_anything_v2/onnx_export.py:24-65).  Here export leaves an `.mdew`
+file instead: the upstream state dict (key names untouched, fp32) plus a JSON description of the
+architecture and the input size.  Build (`core.common.get_engine` replacement) needs nothing
+else -- in particular not the upstream package, keeping the reference's environment separation
+(run.py:9-15).
+
+Layout:  b"MDEW0001" | u32 meta_len | meta JSON (utf-8) | u32 count |
+         count x { u32 name_len | name | u32 ndim | i64 dims[ndim] | f32 data[] }
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import math
+import struct
+from typing import Dict, Mapping, Tuple
+
+import numpy as np
+
+MAGIC = b"MDEW0001"
+
+# models/depth_anything_v2/infer.py:55-60 -- the three released encoder sizes, plus the DINOv2
+# widths/depths/head counts and tap indices that go with them (reports/profile/*.json layer lists).
+ENCODERS = {
+    "vits": dict(embed_dim=384, depth=12, num_heads=6, features=64,
+                 out_channels=[48, 96, 192, 384], taps=[2, 5, 8, 11]),
+    "vitb": dict(embed_dim=768, depth=12, num_heads=12, features=128,
+                 out_channels=[96, 192, 384, 768], taps=[2, 5, 8, 11]),
+    "vitl": dict(embed_dim=1024, depth=24, num_heads=16, features=256,
+                 out_channels=[256, 512, 1024, 1024], taps=[4, 11, 17, 23]),
+}
+
+
+def describe(encoder: str, input_h: int = 518, input_w: int = 518, max_depth: float | None = 20.0,
+             patch_size: int = 14) -> dict:
+    """The architecture description stored next to the tensors."""
+    if encoder not in ENCODERS:
+        raise KeyError(f"unknown encoder {encoder!r}; available: {sorted(ENCODERS)}")
+    if input_h % patch_size or input_w % patch_size:
+        raise ValueError(f"input size {input_h}x{input_w} is not a multiple of the patch size {patch_size}")
+    meta = dict(ENCODERS[encoder])
+    meta.update(family="depth_anything_v2", encoder=encoder, patch_size=patch_size,
+                input_h=int(input_h), input_w=int(input_w),
+                max_depth=None if max_depth is None else float(max_depth))
+    return meta
+
+
+def resize_pos_embed(pos_embed: np.ndarray, gh: int, gw: int) -> np.ndarray:
+    """DINOv2's position-embedding rule for a grid other than the trained square one: bicubic
+    resize of the patch part with scale (g + 0.1) / m, cls part untouched.  At the trained grid
+    (37 x 37 for 518 / 14) the table is used as is."""
+    n = pos_embed.shape[1] - 1
+    m = int(round(math.sqrt(n)))
+    if gh * gw == n and gh == gw:
+        return np.ascontiguousarray(pos_embed, dtype=np.float32)
+    import torch
+    import torch.nn.functional as F
+    pe = torch.from_numpy(np.asarray(pos_embed, dtype=np.float32))
+    d = pe.shape[-1]
+    patch = F.interpolate(pe[:, 1:].reshape(1, m, m, d).permute(0, 3, 1, 2),
+                          scale_factor=((gh + 0.1) / m, (gw + 0.1) / m), mode="bicubic", antialias=False)
+    if tuple(patch.shape[-2:]) != (gh, gw):
+        raise ValueError(f"position embedding resize produced {tuple(patch.shape[-2:])}, wanted {(gh, gw)}")
+    patch = patch.permute(0, 2, 3, 1).reshape(1, gh * gw, d)
+    return torch.cat([pe[:, :1], patch], dim=1).contiguous().numpy()
+
+
+def _as_numpy(v) -> np.ndarray:
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().float().numpy()
+    return np.ascontiguousarray(v, dtype=np.float32)
+
+
+def save(path: str, state_dict: Mapping[str, object], meta: dict) -> str:
+    """Write an .mdew file; returns the sha256 of its bytes."""
+    h = hashlib.sha256()
+    with open(path, "wb") as f:
+        def w(b: bytes):
+            f.write(b)
+            h.update(b)
+        mj = json.dumps(meta, sort_keys=True).encode("utf-8")
+        w(MAGIC)
+        w(struct.pack("<I", len(mj)))
+        w(mj)
+        items = [(k, _as_numpy(v)) for k, v in state_dict.items()]
+        w(struct.pack("<I", len(items)))
+        for name, arr in items:
+            nb = name.encode("utf-8")
+            w(struct.pack("<I", len(nb)))
+            w(nb)
+            w(struct.pack("<I", arr.ndim))
+            w(struct.pack(f"<{arr.ndim}q", *arr.shape))
+            w(arr.tobytes())
+    return h.hexdigest()
+
+
+def read_meta(path: str) -> dict:
+    with open(path, "rb") as f:
+        if f.read(8) != MAGIC:
+            raise ValueError(f"[MDET] {path} is not an MDEW0001 weights file")
+        (n,) = struct.unpack("<I", f.read(4))
+        return json.loads(f.read(n).decode("utf-8"))
+
+
+def load(path: str) -> Tuple[Dict[str, np.ndarray], dict]:
+    """Read an .mdew file back (tests and tools; the engine reads the file natively)."""
+    out: Dict[str, np.ndarray] = {}
+    with open(path, "rb") as f:
+        if f.read(8) != MAGIC:
+            raise ValueError(f"[MDET] {path} is not an MDEW0001 weights file")
+        (n,) = struct.unpack("<I", f.read(4))
+        meta = json.loads(f.read(n).decode("utf-8"))
+        (count,) = struct.unpack("<I", f.read(4))
+        for _ in range(count):
+            (ln,) = struct.unpack("<I", f.read(4))
+            name = f.read(ln).decode("utf-8")
+            (nd,) = struct.unpack("<I", f.read(4))
+            dims = struct.unpack(f"<{nd}q", f.read(8 * nd))
+            cnt = int(np.prod(dims)) if nd else 1
+            out[name] = np.frombuffer(f.read(4 * cnt), dtype="<f4").reshape(dims).copy()
+    return out, meta
+
+
+def file_sha256(path: str) -> str:
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
