@@ -1,0 +1,67 @@
+"""Generate tests/golden/*.npz.  Run in the survey/build container, where /root/reference exists:
+
+    python oracle/make_golden.py
+
+preprocess_golden.npz  outputs of the REFERENCE module itself (imported from /root/reference:
+                       core.preprocess.preprocess_for(img, 'depth_anything_v2', size)) on the
+                       reference's synthetic-input convention (tests/test_preprocess.py:47-51):
+                       full tensors at small target sizes, sha256 of the float32 bytes at 518x518.
+dav2_vits_golden.npz   the oracle's own ViT-S 518x518 batch-1 forward (BASELINE config 1) with the
+                       seeded, calibrated init: a 7x-strided subsample of the depth map and summary
+                       statistics.  It pins the oracle against drift between hosts; the oracle
+                       itself is pinned against transformers' DepthAnything in
+                       tests/test_oracle_model.py.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SOURCES = [(480, 640), (720, 1280), (500, 500), (1036, 1036), (300, 777)]
+SMALL_TARGETS = [(70, 84), (56, 56)]
+
+
+def synthetic(seed, h, w):
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sys.path.insert(0, "/root/reference")
+    from core import preprocess as ref   # the reference module, unmodified
+
+    blob = {}
+    for i, (h, w) in enumerate(SOURCES):
+        img = synthetic(i, h, w)
+        for (th, tw) in SMALL_TARGETS:
+            t, _ = ref.preprocess_for(img, "depth_anything_v2", (th, tw))
+            blob[f"full_seed{i}_{h}x{w}_to_{th}x{tw}"] = t
+        t, _ = ref.preprocess_for(img, "depth_anything_v2", (518, 518))
+        digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+        blob[f"sha_seed{i}_{h}x{w}_to_518x518"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), **blob)
+    print("wrote preprocess_golden.npz", len(blob), "entries")
+
+    import torch
+    from oracle import dav2_torch as O
+    from oracle import preprocess_np as P
+    torch.manual_seed(0)
+    x = torch.from_numpy(P.preprocess_stretch_imagenet(synthetic(0, 480, 640), 518, 518))
+    sd = O.init_state_dict("vits", seed=0)
+    m, s = O.calibrate_head(sd, x, "vits")
+    d = O.forward(sd, x, "vits", max_depth=20.0)[0].numpy()
+    np.savez_compressed(os.path.join(OUT, "dav2_vits_golden.npz"),
+                        depth_stride7=d[::7, ::7].astype(np.float32),
+                        stats=np.array([d.min(), d.max(), d.mean(), d.std(), m, s], dtype=np.float64))
+    print("wrote dav2_vits_golden.npz", d.shape, d.min(), d.max(), d.mean(), d.std(), "precalib", m, s)
+
+
+if __name__ == "__main__":
+    main()

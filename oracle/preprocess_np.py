@@ -1,0 +1,104 @@
+"""ORACLE (test infrastructure, never shipped, never on the product path).
+
+numpy restatement of the reference's host preprocessing for the stretch + ImageNet family
+(Depth Anything V2/V3, Distill Any Depth): /root/reference/core/preprocess.py:412-430
+`preprocess` with MODELS['depth_anything_v2'] (:463-468):
+
+    cvtColor BGR->RGB (:420) -> resize_stretch = cv2.resize(INTER_LINEAR) on uint8 (:144-154)
+    -> scale: uint8 -> float64 / 255.0 (:294-305) -> post_resize keep_ratio: identity at the built
+    size (:465-467; tests/test_preprocess.py:175-188) -> standardize (x - mean)/std in float64
+    (:308-328) -> to_nchw: contiguous float32 (:337-342)
+
+cv2's 8-bit bilinear is itself a third-party algorithm (OpenCV 4.13, modules/imgproc/src/
+resize.cpp: `resizeGeneric_`/`HResizeLinear`/`VResizeLinear` with INTER_RESIZE_COEF_BITS = 11);
+`resize_linear_u8` restates it in integer arithmetic and is pinned against the cv2 build in this
+image by tests/test_oracle_preprocess.py (bit-exact on every shape pair tried), and the whole
+pipeline is pinned against the reference module itself (imported from /root/reference where that
+exists) and against tests/golden/preprocess_*.npz.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # core/preprocess.py:39-40
+IMAGENET_STD = (0.229, 0.224, 0.225)
+COEF_SCALE = 2048                       # 1 << INTER_RESIZE_COEF_BITS
+
+
+def _coeffs(dst: int, src: int, clamp: bool):
+    """Per destination index: source index and the two int16 weights.
+
+    coordinates in float64, fraction in float32, weights rint(f * 2048) (round-half-even).
+    x axis (`clamp=True`): out-of-range taps collapse onto the border pixel with weight 2048/0.
+    y axis: the fraction is kept and the *row indices* are clamped by the caller instead."""
+    inv = np.float64(dst) / np.float64(src)
+    scale = np.float64(1.0) / inv
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp:
+        lo = s < 0
+        f[lo] = 0.0
+        s[lo] = 0
+        hi = s >= src - 1
+        f[hi] = 0.0
+        s[hi] = src - 1
+    w0 = np.rint((np.float32(1.0) - f) * np.float32(COEF_SCALE)).astype(np.int64)
+    w1 = np.rint(f * np.float32(COEF_SCALE)).astype(np.int64)
+    return s, w0, w1
+
+
+def resize_linear_u8(img: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+    """cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) for HxWxC uint8."""
+    assert img.dtype == np.uint8 and img.ndim == 3
+    src_h, src_w = img.shape[:2]
+    if (src_h, src_w) == (dst_h, dst_w):
+        return img.copy()
+    if src_w == 2 * dst_w and src_h == 2 * dst_h:
+        # OpenCV switches INTER_LINEAR to the INTER_AREA fast path when both scales are exactly 2
+        a = img.astype(np.int64)
+        return ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    sx, a0, a1 = _coeffs(dst_w, src_w, clamp=True)
+    sy, b0, b1 = _coeffs(dst_h, src_h, clamp=False)
+    sx1 = np.minimum(sx + 1, src_w - 1)
+    y0 = np.clip(sy, 0, src_h - 1)
+    y1 = np.clip(sy + 1, 0, src_h - 1)
+    src = img.astype(np.int64)
+    # horizontal pass, un-shifted 11-bit products
+    h = src[:, sx, :] * a0[None, :, None] + src[:, sx1, :] * a1[None, :, None]        # [src_h, dst_w, C]
+    r0, r1 = h[y0], h[y1]
+    out = (((b0[:, None, None] * (r0 >> 4)) >> 16) + ((b1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def norm_lut(mean=IMAGENET_MEAN, std=IMAGENET_STD) -> np.ndarray:
+    """[3, 256] float32: (v / 255.0 - mean_c) / std_c evaluated in float64, rounded once."""
+    v = np.arange(256, dtype=np.float64) / 255.0
+    return np.stack([((v - np.float64(m)) / np.float64(s)) for m, s in zip(mean, std)]).astype(np.float32)
+
+
+def preprocess_stretch_imagenet(img_bgr: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+    """BGR uint8 HxWx3 -> float32 [1, 3, dst_h, dst_w], byte-exact with
+    core.preprocess.preprocess_for(img, 'depth_anything_v2', (dst_h, dst_w))[0]."""
+    rgb = img_bgr[:, :, ::-1]
+    small = resize_linear_u8(np.ascontiguousarray(rgb), dst_h, dst_w)
+    x = small.astype(np.float64) / 255.0
+    x = (x - np.asarray(IMAGENET_MEAN, np.float64)) / np.asarray(IMAGENET_STD, np.float64)
+    return np.ascontiguousarray(x.transpose(2, 0, 1)[None]).astype(np.float32)
+
+
+def im2col(x_nchw: np.ndarray, patch: int = 14, kpad: int | None = None) -> np.ndarray:
+    """[B,3,H,W] -> [B*gh*gw, kpad]; row = (b, gy, gx), column = c*p*p + ky*p + kx -- the layout a
+    conv with kernel == stride == patch reads, zero padded to kpad."""
+    B, Cc, H, W_ = x_nchw.shape
+    gh, gw = H // patch, W_ // patch
+    t = x_nchw.reshape(B, Cc, gh, patch, gw, patch).transpose(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, Cc * patch * patch)
+    if kpad is None or kpad == t.shape[1]:
+        return np.ascontiguousarray(t)
+    out = np.zeros((t.shape[0], kpad), dtype=t.dtype)
+    out[:, :t.shape[1]] = t
+    return out

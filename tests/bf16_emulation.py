@@ -30,7 +30,7 @@ def _conv(x, w, b=None, **kw):
 
 
 @torch.no_grad()
-def forward(sd, x, encoder="vits", max_depth=20.0, act_round=r):
+def forward(sd, x, encoder="vits", max_depth=20.0, act_round=r, trace=None):
     cfg = O.MODEL_CONFIGS[encoder]
     D, H = cfg["embed_dim"], cfg["num_heads"]
     hd = D // H
@@ -56,6 +56,8 @@ def forward(sd, x, encoder="vits", max_depth=20.0, act_round=r):
         y = act_round(F.layer_norm(t, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], O.LN_EPS))
         y = act_round(F.gelu(_lin(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])))
         t = t + sd[p + "ls2.gamma"] * _lin(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+        if trace is not None:
+            trace[f"block{i}"] = t
         if i in cfg["taps"]:
             y = F.layer_norm(t, (D,), sd["pretrained.norm.weight"], sd["pretrained.norm.bias"], O.LN_EPS)
             taps.append(act_round(y[:, 1:]))
@@ -95,10 +97,15 @@ def forward(sd, x, encoder="vits", max_depth=20.0, act_round=r):
             out = F.interpolate(out, size=size, mode="bilinear", align_corners=True)
         return A(out)
 
+    if trace is not None:
+        for i in range(4):
+            trace[f"layer{i + 1}_rn"] = rr[i]
     p4 = fusion(4, rr[3], None, rr[2].shape[2:])
     p3 = fusion(3, p4, rr[2], rr[1].shape[2:])
     p2 = fusion(2, p3, rr[1], rr[0].shape[2:])
     p1 = fusion(1, p2, rr[0], None)
+    if trace is not None:
+        trace["path_1"] = p1
     out = A(_conv(p1, sd[h + "scratch.output_conv1.weight"], sd[h + "scratch.output_conv1.bias"], padding=1))
     out = A(F.interpolate(out, (gh * O.PATCH, gw * O.PATCH), mode="bilinear", align_corners=True))
     out = F.relu(_conv(out, sd[h + "scratch.output_conv2.0.weight"], sd[h + "scratch.output_conv2.0.bias"], padding=1))

@@ -1,0 +1,132 @@
+"""Call the single-kernel C-ABI entry points (mde_k_*) on torch CUDA tensors.  Test helper only:
+torch provides device memory and the current stream; every kernel is the library's own."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from monocular_depth_estimation_trt_b200 import _lib
+
+TORCH_DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def epilogue(bias=None, gamma=None, act=0, x=None, accumulate_x=False, res1=None, res2=None, out=None,
+             out_relu=None, ld_out=0, tokens=0, pos=None, shuffle=None, head_w=None, head_b=0.0,
+             head_scale=0.0, head_out=None):
+    ep = _lib.Epilogue()
+    ep.d_bias, ep.d_gamma, ep.act = ptr(bias), ptr(gamma), act
+    ep.d_x, ep.accumulate_x = ptr(x), int(accumulate_x)
+    ep.d_res1, ep.d_res2, ep.d_out, ep.d_out_relu = ptr(res1), ptr(res2), ptr(out), ptr(out_relu)
+    ep.ld_out, ep.tokens, ep.d_pos = ld_out, tokens, ptr(pos)
+    if shuffle:
+        ep.shuffle_s, ep.shuffle_cout, ep.shuffle_h, ep.shuffle_w = shuffle
+    ep.d_head_w, ep.head_b, ep.head_scale, ep.d_head_out = ptr(head_w), head_b, head_scale, ptr(head_out)
+    return ep
+
+
+def gemm(precision, a, b, ep, m=None, k=None, n=None):
+    """a [M, lda], b [N, ldb] 16-bit row-major."""
+    lib = _lib.load()
+    m = a.shape[0] if m is None else m
+    k = a.shape[1] if k is None else k
+    n = b.shape[0] if n is None else n
+    _lib.check(lib.mde_k_gemm(_lib.PRECISIONS[precision], ptr(a), m, k, a.stride(0), ptr(b), n, b.stride(0),
+                              C.byref(ep), stream()), "mde_k_gemm")
+
+
+def conv3x3(precision, x_nhwc, w_packed, cout, ep):
+    lib = _lib.load()
+    B, H, W_, Cin = x_nhwc.shape
+    _lib.check(lib.mde_k_conv3x3(_lib.PRECISIONS[precision], ptr(x_nhwc), B, H, W_, Cin, ptr(w_packed), cout,
+                                 C.byref(ep), stream()), "mde_k_conv3x3")
+
+
+def pack_conv3x3(w, dtype):
+    """[cout, cin, 3, 3] fp32 -> [cout, 9*cin_pad] with K index (ky*3+kx)*cin_pad + c."""
+    cout, cin = w.shape[:2]
+    cin_pad = (cin + 63) // 64 * 64
+    p = torch.zeros(cout, 9, cin_pad, dtype=dtype, device=w.device)
+    p[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin).to(dtype)
+    return p.reshape(cout, 9 * cin_pad).contiguous()
+
+
+def attention(precision, qkv, batch, ntok, heads):
+    lib = _lib.load()
+    out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
+    _lib.check(lib.mde_k_attention(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()),
+               "mde_k_attention")
+    return out
+
+
+def layernorm(precision, x, w, b, eps=1e-6, drop_cls=False, ntok=0):
+    lib = _lib.load()
+    rows, dim = x.shape
+    orows = rows - rows // ntok if drop_cls else rows
+    out = torch.empty(orows, dim, dtype=TORCH_DT[precision], device=x.device)
+    _lib.check(lib.mde_k_layernorm(_lib.PRECISIONS[precision], ptr(x), ptr(w), ptr(b), ptr(out), rows, dim, eps,
+                                   int(drop_cls), ntok, stream()), "mde_k_layernorm")
+    return out
+
+
+def bilinear(precision, x_nhwc, ho, wo):
+    lib = _lib.load()
+    B, H, W_, Cc = x_nhwc.shape
+    out = torch.empty(B, ho, wo, Cc, dtype=x_nhwc.dtype, device=x_nhwc.device)
+    _lib.check(lib.mde_k_bilinear(_lib.PRECISIONS[precision], ptr(x_nhwc), ptr(out), B, H, W_, ho, wo, Cc, stream()),
+               "mde_k_bilinear")
+    return out
+
+
+def im2col_s2(precision, x_nhwc):
+    lib = _lib.load()
+    B, H, W_, Cc = x_nhwc.shape
+    ho, wo = (H - 1) // 2 + 1, (W_ - 1) // 2 + 1
+    out = torch.empty(B * ho * wo, 9 * Cc, dtype=x_nhwc.dtype, device=x_nhwc.device)
+    _lib.check(lib.mde_k_im2col_s2(_lib.PRECISIONS[precision], ptr(x_nhwc), ptr(out), B, H, W_, Cc, stream()),
+               "mde_k_im2col_s2")
+    return out
+
+
+def im2col_f32(precision, x_nchw, patch, kpad):
+    lib = _lib.load()
+    B, _, H, W_ = x_nchw.shape
+    rows = B * (H // patch) * (W_ // patch)
+    out = torch.empty(rows, kpad, dtype=TORCH_DT[precision], device=x_nchw.device)
+    _lib.check(lib.mde_k_im2col_f32(_lib.PRECISIONS[precision], ptr(x_nchw), B, H, W_, patch, kpad, ptr(out), stream()),
+               "mde_k_im2col_f32")
+    return out
+
+
+def preprocess_u8(precision, src_u8, dst_h, dst_w, patch=14, kpad=640, swap_rb=True,
+                  mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), want_cols=True, want_nchw=True):
+    """src_u8 [B, H, W, 3] uint8 cuda tensor -> (cols or None, nchw or None)."""
+    lib = _lib.load()
+    B, H, W_, _ = src_u8.shape
+    rows = B * (dst_h // patch) * (dst_w // patch)
+    cols = torch.empty(rows, kpad, dtype=TORCH_DT[precision], device=src_u8.device) if want_cols else None
+    nchw = torch.empty(B, 3, dst_h, dst_w, dtype=torch.float32, device=src_u8.device) if want_nchw else None
+    m3 = (C.c_double * 3)(*mean)
+    s3 = (C.c_double * 3)(*std)
+    _lib.check(lib.mde_k_preprocess_u8(_lib.PRECISIONS[precision], ptr(src_u8), B, H, W_, dst_h, dst_w, patch, kpad,
+                                       int(swap_rb), m3, s3, ptr(cols), ptr(nchw), stream()), "mde_k_preprocess_u8")
+    return cols, nchw
+
+
+def rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def rms_rel(got, ref):
+    got, ref = got.double(), ref.double()
+    return float(((got - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt().clamp_min(1e-30))

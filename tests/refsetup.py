@@ -1,0 +1,41 @@
+"""Shared reference set-up for the model-level tests: seeded calibrated weights, the synthetic
+input, and the oracle's fp32 output.  Test infrastructure only."""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+
+from oracle import dav2_torch as O
+from oracle import preprocess_np as P
+
+
+def synthetic_image(seed=0, h=480, w=640):
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+@functools.lru_cache(maxsize=4)
+def reference(encoder: str, h: int = 518, w: int = 518, max_depth: float = 20.0):
+    """-> (state_dict, x [1,3,h,w] float32, oracle depth [1,h,w], trace dict)."""
+    torch.manual_seed(0)
+    x = torch.from_numpy(P.preprocess_stretch_imagenet(synthetic_image(0), h, w))
+    sd = O.init_state_dict(encoder, seed=0)
+    O.calibrate_head(sd, x, encoder)
+    trace = {}
+    depth = O.forward(sd, x, encoder, max_depth=max_depth, trace=trace)
+    return sd, x, depth, trace
+
+
+def compare_depth(ref: np.ndarray, got: np.ndarray) -> dict:
+    """The reference's parity metrics (core/golden.py:101-174 `compare`): abs_rel over pixels where
+    both maps exceed 1e-6, plus the max relative error north_star gates on."""
+    a, b = np.asarray(ref, np.float64).ravel(), np.asarray(got, np.float64).ravel()
+    ok = np.isfinite(a) & np.isfinite(b)
+    a, b = a[ok], b[ok]
+    d = np.abs(a - b)
+    pos = (a > 1e-6) & (b > 1e-6)
+    rel = d[pos] / a[pos]
+    return {"compared": int(ok.sum()), "max_abs": float(d.max()), "rel_mean": float(d.mean() / np.abs(a).mean()),
+            "abs_rel": float(rel.mean()), "max_rel": float(rel.max()), "positive": int(pos.sum()),
+            "corr": float(np.corrcoef(a, b)[0, 1])}

@@ -1,0 +1,204 @@
+"""Model-level parity on a B200, through the C-ABI engine and the reference-shaped host API.
+
+Oracle: oracle/dav2_torch.py fp32 forward on the same synthetic input and the same seeded,
+calibrated random-init weights (BASELINE.json configs[0]: ViT-S 518x518 batch 1; configs[1]: ViT-L).
+
+Gates (north_star): final depth max relative error <= 1e-2 and AbsRel <= 2e-3.
+  * precision "fp16" (the reference's own build target, models/depth_anything_v2/onnx2trt.py:61)
+    must meet that gate.
+  * precision "bf16" cannot on this oracle: rounding only the *weights* to bf16 and running
+    everything else in fp32 already gives AbsRel 3.0e-3 / max-rel 2.7e-2 (tests/test_precision_plan.py
+    reproduces this on the CPU).  bf16 is therefore gated at the error of the precision plan itself:
+    the CPU emulation of the plan (tests/bf16_emulation.py) scores AbsRel 7.3e-3 / max-rel 7.6e-2 on
+    this input, and the gate is that with 1.6x head-room for different rounding realisations.
+  * intermediate tensors (residual stream after blocks 5 and 11, the four layer_rn maps, path_1)
+    are gated in RMS-relative error at 2x what the same emulation measures for each precision.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import refsetup as R
+from monocular_depth_estimation_trt_b200 import common, engine as E, weights as W
+
+pytestmark = pytest.mark.gpu
+
+GATE = {"fp16": dict(abs_rel=2e-3, max_rel=1e-2), "bf16": dict(abs_rel=1.2e-2, max_rel=1.2e-1)}
+# RMS-relative budgets: emulation gives 4.3e-4 (fp16) / 3.6e-3 (bf16) on the residual stream and
+# 7.5e-4 / 5.9e-3 on the head's maps
+INTER = {"fp16": 9e-4, "bf16": 7.5e-3}
+
+
+def build_engine(encoder, prec, batch=1, input_mode="f32_nchw", max_src_hw=(0, 0), h=518, w=518):
+    sd, x, depth, trace = R.reference(encoder, h, w)
+    meta = W.describe(encoder, h, w, max_depth=20.0)
+    eng = E.Engine(E.make_desc(meta, precision=prec, batch=batch, input_mode=input_mode, max_src_hw=max_src_hw), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    return eng, x, depth, trace
+
+
+def run(eng, x_dev, out_dev, snapshot=-1):
+    ctx = eng.create_execution_context()
+    ctx.set_tensor_address("input", x_dev.data_ptr())
+    ctx.set_tensor_address("output", out_dev.data_ptr())
+    ctx.snapshot_block(snapshot)
+    ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return ctx
+
+
+def fetch(ctx, name, shape, prec):
+    ptr, nbytes, dt = ctx.get_buffer(name)
+    dtype = torch.float32 if dt == 0 else (torch.bfloat16 if prec == "bf16" else torch.float16)
+    n = int(np.prod(shape))
+    buf = torch.empty(n, dtype=dtype, device="cuda")
+    assert n * buf.element_size() <= nbytes
+    from cuda.bindings import runtime as cudart
+    (err,) = cudart.cudaMemcpy(buf.data_ptr(), ptr, n * buf.element_size(), cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+    assert int(err) == 0
+    return buf.reshape(shape).float().cpu()
+
+
+def rms_rel(got, ref):
+    got, ref = got.double(), ref.double()
+    return float(((got - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt())
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_vits_518_b1_parity_and_intermediates(lib, prec):
+    eng, x, depth, trace = build_engine("vits", prec)
+    out = torch.full((1, 518, 518), float("nan"), device="cuda")
+    ctx = run(eng, x.cuda(), out, snapshot=5)
+    m = R.compare_depth(depth.numpy(), out.cpu().numpy())
+    print(prec, m)
+    # intermediates first: they localise a failure
+    xs = fetch(ctx, "x_snapshot", (1, 1370, 384), prec)
+    assert rms_rel(xs, trace["block5"]) < INTER[prec]
+    xl = fetch(ctx, "x", (1, 1370, 384), prec)
+    assert rms_rel(xl, trace["block11"]) < INTER[prec]
+    p1 = fetch(ctx, "path_1", (1, 296, 296, 64), prec).permute(0, 3, 1, 2)
+    assert rms_rel(p1, trace["path_1"]) < 1.7 * INTER[prec]
+    for i in range(4):
+        hh = [148, 74, 37, 19][i]
+        r = fetch(ctx, f"r{i}", (1, hh, hh, 64), prec).permute(0, 3, 1, 2)
+        assert rms_rel(r, trace[f"layer{i + 1}_rn"]) < 1.7 * INTER[prec]
+    assert m["compared"] == 518 * 518
+    assert m["abs_rel"] <= GATE[prec]["abs_rel"]
+    assert m["max_rel"] <= GATE[prec]["max_rel"]
+    assert m["corr"] > 0.9995
+
+
+def test_embed_tokens_match_oracle(lib):
+    """Patch-embed GEMM + cls + pos_embed: token layout and values before any block."""
+    eng, x, depth, trace = build_engine("vits", "fp16")
+    out = torch.empty(1, 518, 518, device="cuda")
+    ctx = eng.create_execution_context()
+    ctx.set_tensor_address("input", x.cuda().data_ptr())
+    ctx.set_tensor_address("output", out.data_ptr())
+    ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cols = fetch(ctx, "cols", (1369, 640), "fp16")
+    from oracle import preprocess_np as P
+    ref_cols = torch.from_numpy(P.im2col(x.numpy(), 14, 640)).half().float()
+    assert torch.equal(cols, ref_cols)          # token/patch layout bit-exact
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_vitl_518_b2_parity(lib, prec):
+    """BASELINE configs[1] architecture; batch 2 with two different images."""
+    sd, x, depth, _ = R.reference("vitl")
+    from oracle import dav2_torch as O, preprocess_np as P
+    x2 = torch.from_numpy(P.preprocess_stretch_imagenet(R.synthetic_image(1, 720, 1280), 518, 518))
+    xb = torch.cat([x, x2])
+    ref = torch.cat([depth, O.forward(sd, x2, "vitl", 20.0)])
+    meta = W.describe("vitl", 518, 518, 20.0)
+    eng = E.Engine(E.make_desc(meta, precision=prec, batch=2), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    out = torch.full((2, 518, 518), float("nan"), device="cuda")
+    run(eng, xb.cuda(), out)
+    for b in range(2):
+        m = R.compare_depth(ref[b].numpy(), out[b].cpu().numpy())
+        print(prec, b, m)
+        assert m["abs_rel"] <= GATE[prec]["abs_rel"]
+        assert m["max_rel"] <= GATE[prec]["max_rel"]
+
+
+def test_batch_entries_are_independent(lib):
+    """The same image at batch positions 0 and 2 gives bit-identical maps; idempotent across runs."""
+    sd, x, depth, _ = R.reference("vits")
+    meta = W.describe("vits", 518, 518, 20.0)
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=3), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    other = torch.randn(1, 3, 518, 518)
+    xb = torch.cat([x, other, x]).cuda()
+    out = torch.empty(3, 518, 518, device="cuda")
+    ctx = run(eng, xb, out)
+    first = out.clone()
+    assert torch.equal(out[0], out[2])
+    ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out, first)
+
+
+def test_uint8_input_engine_matches_float_engine(lib):
+    """Fused resize+normalise+im2col input binding == host preprocessing + float32 binding, bit for bit."""
+    sd, x, depth, _ = R.reference("vits")
+    img = R.synthetic_image(0)                                 # the image `x` was made from
+    meta = W.describe("vits", 518, 518, 20.0)
+    e8 = E.Engine(E.make_desc(meta, precision="fp16", batch=1, input_mode="u8_hwc", max_src_hw=(1080, 1920)), meta)
+    e8.load_state_dict(sd)
+    e8.finalize()
+    assert e8.get_tensor_dtype("input") == np.uint8 and e8.get_tensor_shape("input") == (1, 1080, 1920, 3)
+    ef, _, _, _ = build_engine("vits", "fp16")
+    out8 = torch.empty(1, 518, 518, device="cuda")
+    outf = torch.empty(1, 518, 518, device="cuda")
+    src = torch.from_numpy(img).cuda()
+    c8 = e8.create_execution_context()
+    c8.set_input_shape("input", (1, 480, 640, 3))
+    c8.set_tensor_address("input", src.data_ptr())
+    c8.set_tensor_address("output", out8.data_ptr())
+    c8.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+    run(ef, x.cuda(), outf)
+    torch.cuda.synchronize()
+    assert torch.equal(out8, outf)
+    with pytest.raises(RuntimeError):
+        c8.set_input_shape("input", (1, 4000, 640, 3))
+
+
+def test_reference_call_shape_do_inference(lib, tmp_path):
+    """The four calls every onnx2trt.py makes, end to end with host buffers."""
+    sd, x, depth, _ = R.reference("vits")
+    path = str(tmp_path / "dav2_vits.mdew")
+    W.save(path, sd, W.describe("vits", 518, 518, 20.0))
+    with common.get_engine(path, str(tmp_path / "engine" / "dav2_vits_fp16.engine"), "fp16") as engine, \
+            engine.create_execution_context() as context:
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine, (1, 518, 518), profile_idx=0)
+        inputs[0].host = x.numpy()
+        timer = common.StageTimer()
+        res = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs,
+                                  stream=stream, timer=timer)
+        got = res[0].reshape(1, 518, 518).copy()
+        assert set(timer.last) == {"h2d_ms", "compute_ms", "d2h_ms"} and timer.last["compute_ms"] > 0
+        with pytest.raises(ValueError):
+            inputs[0].host = np.zeros(3 * 518 * 518 + 1, np.float32)
+        timer.free()
+        common.free_buffers(inputs, outputs, stream)
+    m = R.compare_depth(depth.numpy(), got)
+    assert m["abs_rel"] <= GATE["fp16"]["abs_rel"] and m["max_rel"] <= GATE["fp16"]["max_rel"]
+    assert (tmp_path / "engine" / "dav2_vits_fp16.fingerprint").exists()
+
+
+def test_errors_are_loud(lib):
+    meta = W.describe("vits", 518, 518, 20.0)
+    eng = E.Engine(E.make_desc(meta, precision="fp16"), meta)
+    with pytest.raises(RuntimeError, match="missing weight"):
+        eng.finalize()
+    with pytest.raises(RuntimeError):
+        eng.create_execution_context()
+    with pytest.raises(ValueError):
+        E.make_desc(meta, precision="fp32")

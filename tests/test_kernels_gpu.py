@@ -1,0 +1,236 @@
+"""Per-kernel parity on a B200: every mde_k_* entry point against a plain PyTorch fp32 statement of
+the same op, on the same (already 16-bit-rounded) inputs.  Tolerances are written at each assert.
+
+fp32-output paths are checked tightly (the only differences are accumulation order); 16-bit
+outputs get one rounding of slack: 2^-8 relative for bf16, 2^-11 for fp16.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import kutil as K
+
+pytestmark = pytest.mark.gpu
+
+PRECS = ["bf16", "fp16"]
+# unit roundoff of the 16-bit store (8 / 11 significand bits) with 25 % head-room for rounding flips
+ULP = {"bf16": 1.25 * 2.0 ** -8, "fp16": 1.25 * 2.0 ** -11}
+
+
+def rnd(shape, dtype, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1370, 3072, 1024), (300, 48, 48), (2740, 1152, 384),
+                                   (1369, 32, 128), (4110, 1024, 4096), (77, 768, 640)])
+def test_gemm_bias_fp32_out(lib, prec, m, n, k):
+    dt = K.TORCH_DT[prec]
+    a, b = rnd((m, k), dt, seed=1), rnd((n, k), dt, k ** -0.5, seed=2)
+    bias = torch.randn(n, device="cuda")
+    x = torch.full((m, n), float("nan"), device="cuda")
+    out = torch.zeros(m, n, dtype=dt, device="cuda")
+    K.gemm(prec, a, b, K.epilogue(bias=bias, x=x, out=out, ld_out=n))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias
+    assert K.rel_err(x, ref) < 2e-5            # fp32 accumulate, order only
+    assert K.rel_err(out, ref) < ULP[prec]     # one 16-bit rounding
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gemm_gelu(lib, prec):
+    dt = K.TORCH_DT[prec]
+    m, n, k = 1370, 1536, 384
+    a, b = rnd((m, k), dt, seed=3), rnd((n, k), dt, k ** -0.5, seed=4)
+    bias = torch.randn(n, device="cuda") * 0.1
+    x = torch.empty(m, n, device="cuda")
+    K.gemm(prec, a, b, K.epilogue(bias=bias, act=1, x=x, ld_out=n))
+    torch.cuda.synchronize()
+    ref = F.gelu(a.float() @ b.float().t() + bias)      # exact erf GELU
+    assert K.rel_err(x, ref) < 2e-5
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gemm_layerscale_residual_in_place(lib, prec):
+    dt = K.TORCH_DT[prec]
+    m, n, k = 2740, 384, 1536
+    a, b = rnd((m, k), dt, seed=5), rnd((n, k), dt, k ** -0.5, seed=6)
+    bias, gamma = torch.randn(n, device="cuda"), torch.rand(n, device="cuda")
+    x0 = torch.randn(m, n, device="cuda")
+    x = x0.clone()
+    K.gemm(prec, a, b, K.epilogue(bias=bias, gamma=gamma, x=x, accumulate_x=True, ld_out=n))
+    torch.cuda.synchronize()
+    ref = x0 + gamma * (a.float() @ b.float().t() + bias)
+    assert K.rel_err(x, ref) < 2e-5
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gemm_patch_embed_token_remap(lib, prec):
+    """rows (b, t) land at token row b*(T+1)+1+t with pos_embed[1+t] added; cls rows untouched."""
+    dt = K.TORCH_DT[prec]
+    B, T, D, kp = 3, 1369, 384, 640
+    a = rnd((B * T, kp), dt, seed=7)
+    a[:, 588:] = 0
+    w = rnd((D, kp), dt, 588 ** -0.5, seed=8)
+    bias, pos = torch.randn(D, device="cuda"), torch.randn(T + 1, D, device="cuda")
+    x = torch.full((B * (T + 1), D), -7.0, device="cuda")
+    K.gemm(prec, a, w, K.epilogue(bias=bias, x=x, ld_out=D, tokens=T, pos=pos))
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t() + bias).reshape(B, T, D) + pos[1:]
+    got = x.reshape(B, T + 1, D)
+    assert K.rel_err(got[:, 1:], ref) < 2e-5
+    assert torch.all(got[:, 0] == -7.0)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("s,c", [(4, 48), (2, 96), (4, 256)])
+def test_gemm_conv_transpose_pixel_shuffle(lib, prec, s, c):
+    dt = K.TORCH_DT[prec]
+    B, H, W = 2, 37, 37
+    xin = rnd((B, H, W, c), dt, seed=9)
+    wt = rnd((c, c, s, s), dt, c ** -0.5, seed=10)                       # ConvTranspose2d layout [in, out, kh, kw]
+    bias = torch.randn(c, device="cuda")
+    bmat = wt.permute(2, 3, 1, 0).reshape(s * s * c, c).contiguous()     # row (ky*s+kx)*c + o, col i
+    out = torch.zeros(B, H * s, W * s, c, dtype=dt, device="cuda")
+    K.gemm(prec, xin.reshape(-1, c), bmat, K.epilogue(bias=bias, out=out, ld_out=c, shuffle=(s, c, H, W)))
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(xin.float().permute(0, 3, 1, 2), wt.float(), bias, stride=s).permute(0, 2, 3, 1)
+    assert K.rel_err(out, ref) < ULP[prec]
+
+
+# ------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 19, 19, 64, 64), (1, 37, 37, 48, 64), (2, 74, 74, 256, 256),
+                                            (1, 148, 148, 96, 64), (3, 37, 41, 384, 64), (1, 70, 84, 64, 32)])
+def test_conv3x3_bias_residuals_relu_copy(lib, prec, B, H, W, cin, cout):
+    dt = K.TORCH_DT[prec]
+    xin = rnd((B, H, W, cin), dt, seed=11)
+    w = rnd((cout, cin, 3, 3), dt, (9 * cin) ** -0.5, seed=12)
+    bias = torch.randn(cout, device="cuda")
+    r1, r2 = rnd((B, H, W, cout), dt, seed=13), rnd((B, H, W, cout), dt, seed=14)
+    out = torch.zeros(B, H, W, cout, dtype=dt, device="cuda")
+    out_relu = torch.zeros_like(out)
+    K.conv3x3(prec, xin, K.pack_conv3x3(w.float(), dt), cout,
+              K.epilogue(bias=bias, res1=r1, res2=r2, out=out, out_relu=out_relu, ld_out=cout))
+    torch.cuda.synchronize()
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + r1.float() + r2.float()
+    assert K.rel_err(out, ref) < ULP[prec]
+    assert K.rel_err(out_relu, ref.clamp_min(0)) < ULP[prec]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("max_depth", [20.0, 0.0])
+def test_conv3x3_fused_depth_head(lib, prec, max_depth):
+    dt = K.TORCH_DT[prec]
+    B, H, W, cin = 2, 70, 98, 128
+    xin = rnd((B, H, W, cin), dt, seed=15)
+    w = rnd((32, cin, 3, 3), dt, (9 * cin) ** -0.5, seed=16)
+    bias = torch.randn(32, device="cuda") * 0.1
+    hw, hb = torch.randn(32, device="cuda") * 0.5, 0.3
+    out = torch.full((B, H, W), float("nan"), device="cuda")
+    K.conv3x3(prec, xin, K.pack_conv3x3(w.float(), dt), 32,
+              K.epilogue(bias=bias, ld_out=32, head_w=hw, head_b=hb, head_scale=max_depth, head_out=out))
+    torch.cuda.synchronize()
+    y = F.relu(F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), bias, padding=1))
+    z = (y * hw.view(1, 32, 1, 1)).sum(1) + hb
+    ref = torch.sigmoid(z) * max_depth if max_depth > 0 else F.relu(z)
+    assert float((out - ref).abs().max()) < 2e-4 * max(1.0, max_depth)   # fp32 path; __expf in the sigmoid
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,ntok,heads", [(2, 1370, 6), (1, 577, 16), (3, 64, 2), (1, 129, 1), (1, 3349, 2)])
+def test_attention(lib, prec, B, ntok, heads):
+    dt = K.TORCH_DT[prec]
+    D = heads * 64
+    qkv = rnd((B * ntok, 3 * D), dt, seed=17)
+    out = K.attention(prec, qkv, B, ntok, heads)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().reshape(B, ntok, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v
+    ref = ref.transpose(1, 2).reshape(B * ntok, D)
+    # P is rounded to 16 bits for the PV MMA and the output once more: two roundings of slack (rms)
+    assert K.rms_rel(out, ref) < 2 * ULP[prec]
+    assert K.rel_err(out, ref) < 8 * ULP[prec]
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("D", [384, 768, 1024])
+def test_layernorm(lib, prec, D):
+    rows = 2 * 1370
+    x = torch.randn(rows, D, device="cuda") * 3 + 0.5
+    w, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    out = K.layernorm(prec, x, w, b)
+    ref = F.layer_norm(x, (D,), w, b, 1e-6)
+    assert K.rel_err(out, ref) < ULP[prec]
+    tap = K.layernorm(prec, x, w, b, drop_cls=True, ntok=1370)
+    assert tap.shape == (2 * 1369, D)
+    assert K.rel_err(tap, ref.reshape(2, 1370, D)[:, 1:].reshape(-1, D)) < ULP[prec]
+
+
+# ------------------------------------------------------------------------------------------ bilinear / gather
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("hi,wi,ho,wo,c", [(19, 19, 37, 37, 64), (37, 37, 74, 74, 256), (296, 296, 518, 518, 32),
+                                           (22, 38, 44, 76, 128)])
+def test_bilinear_align_corners(lib, prec, hi, wi, ho, wo, c):
+    dt = K.TORCH_DT[prec]
+    x = rnd((2, hi, wi, c), dt, seed=18)
+    out = K.bilinear(prec, x, ho, wo)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), (ho, wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    assert K.rel_err(out, ref) < ULP[prec]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_im2col_stride2_matches_conv(lib, prec):
+    dt = K.TORCH_DT[prec]
+    B, H, W, c = 2, 37, 37, 384
+    x = rnd((B, H, W, c), dt, seed=19)
+    cols = K.im2col_s2(prec, x)
+    w = rnd((64, c, 3, 3), dt, seed=20)
+    got = (cols.float() @ w.permute(0, 2, 3, 1).reshape(64, 9 * c).float().t()).reshape(B, 19, 19, 64)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert K.rel_err(got, ref) < 1e-5     # the gather itself is exact; fp32 matmul order only
+
+
+# ------------------------------------------------------------------------------------------ kernel (1)
+@pytest.mark.parametrize("src_hw", [(480, 640), (720, 1280), (500, 500), (1036, 1036), (300, 777), (518, 518)])
+def test_preprocess_u8_bit_exact(lib, src_hw):
+    """uint8 resize stage bit-exact and float stage bit-exact (north_star asks <= 1 ulp) against the
+    oracle's restatement of core/preprocess.py; im2col layout bit-exact."""
+    from oracle import preprocess_np as P
+    rng = np.random.default_rng(0)
+    imgs = np.stack([rng.integers(0, 256, (*src_hw, 3), dtype=np.uint8) for _ in range(2)])
+    cols, nchw = K.preprocess_u8("bf16", torch.from_numpy(imgs).cuda(), 518, 518)
+    torch.cuda.synchronize()
+    ref = np.concatenate([P.preprocess_stretch_imagenet(im, 518, 518) for im in imgs])
+    assert np.array_equal(nchw.cpu().numpy(), ref)
+    ref_cols = torch.from_numpy(P.im2col(ref, 14, 640)).to(torch.bfloat16)
+    assert torch.equal(cols.cpu(), ref_cols)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_im2col_f32_layout_bit_exact(lib, prec):
+    from oracle import preprocess_np as P
+    x = torch.randn(2, 3, 518, 518, device="cuda")
+    cols = K.im2col_f32(prec, x, 14, 640)
+    ref = torch.from_numpy(P.im2col(x.cpu().numpy(), 14, 640)).to(K.TORCH_DT[prec])
+    assert torch.equal(cols.cpu(), ref)
+    # and it is exactly what a conv with kernel == stride == 14 reads
+    w = torch.randn(8, 3, 14, 14)
+    a = F.conv2d(x.cpu(), w, stride=14).flatten(2).transpose(1, 2).reshape(-1, 8)
+    b = torch.from_numpy(P.im2col(x.cpu().numpy(), 14)) @ w.reshape(8, -1).t()
+    assert torch.allclose(a, b, atol=1e-3)
+
+
+def test_bad_arguments_raise(lib):
+    a = torch.zeros(8, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError):
+        K.gemm("bf16", a, a, K.epilogue(ld_out=7), n=7)
+    with pytest.raises(RuntimeError):
+        K.bilinear("bf16", torch.zeros(1, 4, 4, 7, dtype=torch.bfloat16, device="cuda"), 8, 8)
