@@ -111,6 +111,12 @@ int mde_context_set_input_shape(mde_context* c, const char* name, int32_t ndim, 
 int mde_context_enqueue(mde_context* c, void* stream);
 /* Number of kernels one enqueue launches (bench.py's gpu_launches). */
 int mde_context_launches_per_enqueue(const mde_context* c);
+/* Profiling variant of enqueue: CUDA events between the launches, then a stream synchronise.
+ * ms[i] = device time of launch i (capacity >= mde_context_launches_per_enqueue). */
+int mde_context_enqueue_timed(mde_context* c, void* stream, float* ms, int32_t capacity);
+/* Label ("gemm256 fc1+gelu 87680x4096x1024", ...), algorithmic FLOPs (2*MACs, logical sizes) and
+ * algorithmic bytes (operands read once, results written once) of launch i. */
+int mde_context_op_info(const mde_context* c, int32_t i, char* label, int32_t label_capacity, double* flops, double* bytes);
 /* Intermediate tensors for the per-stage parity gates: "cols", "x" (residual stream after the
  * last block), "tap0".."tap3", "path_1", "r0".."r3".  Valid after enqueue + stream sync.
  * dtype: 0 = fp32, 1 = 16-bit in the engine's precision. */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "mde_engine_io_dtype", "mde_engine_io_is_input", "mde_engine_workspace_bytes",
     "mde_context_create", "mde_context_destroy", "mde_context_set_tensor_address",
     "mde_context_set_input_shape", "mde_context_enqueue", "mde_context_launches_per_enqueue",
-    "mde_context_get_buffer", "mde_context_snapshot_block",
+    "mde_context_get_buffer", "mde_context_snapshot_block", "mde_context_enqueue_timed", "mde_context_op_info",
     "mde_k_preprocess_u8", "mde_k_im2col_f32", "mde_k_gemm", "mde_k_conv3x3", "mde_k_attention",
     "mde_k_layernorm", "mde_k_bilinear", "mde_k_im2col_s2",
 ]
@@ -87,6 +87,8 @@ def load() -> C.CDLL:
         "mde_context_launches_per_enqueue": (C.c_int, [vp]),
         "mde_context_get_buffer": (C.c_int, [vp, C.c_char_p, P(vp), P(i64), P(i32)]),
         "mde_context_snapshot_block": (C.c_int, [vp, i32]),
+        "mde_context_enqueue_timed": (C.c_int, [vp, vp, P(f32), i32]),
+        "mde_context_op_info": (C.c_int, [vp, i32, C.c_char_p, i32, P(C.c_double), P(C.c_double)]),
         "mde_k_preprocess_u8": (C.c_int, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32,
                                           P(C.c_double), P(C.c_double), vp, vp, vp]),
         "mde_k_im2col_f32": (C.c_int, [i32, vp, i32, i32, i32, i32, i32, vp, vp]),

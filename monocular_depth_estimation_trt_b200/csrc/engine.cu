@@ -91,6 +91,9 @@ struct Op {
   long long rows = 0;
   int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
   int block = -1;   // encoder block this op belongs to (SNAPSHOT ops)
+  std::string label;   // what the launch is, for per-op timing reports
+  double flops = 0.0;  // algorithmic FLOPs (2*MACs, logical sizes, no padding)
+  double bytes = 0.0;  // algorithmic bytes (operands read once + result written once)
 };
 
 }  // namespace
@@ -109,6 +112,7 @@ struct mde_context {
   float* x = nullptr;
   int64_t x_bytes = 0;
   int64_t workspace_bytes = 0;
+  std::vector<cudaEvent_t> events;
 };
 
 // =============================================================================================== engine
@@ -417,21 +421,46 @@ struct Planner {
   }
   void* alloc16(int64_t elems, const char* name = nullptr) { return alloc(elems * 2, name, 1); }
 
-  void gemm(const void* a, long long m, int k, int lda, const void* b, int n, int ldb, const mde_epilogue& ep) {
+  void gemm(const char* what, const void* a, long long m, int k, int lda, const void* b, int n, int ldb,
+            const mde_epilogue& ep, int k_real = 0) {
     if (dry || rc != MDE_OK) return;
     Op op; op.kind = Op::GEMM;
     rc = make_gemm_op(&op.g, prec, a, m, k, lda, b, n, ldb, &ep);
+    if (k_real <= 0) k_real = k;
+    char buf[160];
+    snprintf(buf, sizeof(buf), "gemm%d %s %lldx%dx%d", op.g.block_n, what, m, n, k_real);
+    op.label = buf;
+    op.flops = 2.0 * static_cast<double>(m) * n * k_real;
+    op.bytes = 2.0 * (static_cast<double>(m) * k_real + static_cast<double>(n) * k_real) + epilogue_bytes(ep, static_cast<double>(m) * n);
     if (rc == MDE_OK) c->plan.push_back(op);
   }
-  void conv(const void* in, int B, int H, int W, int cin, const void* w, int cout, const mde_epilogue& ep) {
+  void conv(const char* what, const void* in, int B, int H, int W, int cin, const void* w, int cout, const mde_epilogue& ep) {
     if (dry || rc != MDE_OK) return;
     Op op; op.kind = Op::GEMM;
     rc = make_conv_op(&op.g, prec, in, B, H, W, cin, w, cout, &ep);
+    char buf[160];
+    snprintf(buf, sizeof(buf), "conv%d %s %dx%dx%d %d->%d", op.g.block_n, what, B, H, W, cin, cout);
+    op.label = buf;
+    const double px = static_cast<double>(B) * H * W;
+    op.flops = 2.0 * px * cout * 9.0 * cin + (ep.d_head_w ? 2.0 * px * 32 : 0.0);
+    op.bytes = 2.0 * (px * cin + 9.0 * cin * cout) + (ep.d_head_w ? 4.0 * px : epilogue_bytes(ep, px * cout));
     if (rc == MDE_OK) c->plan.push_back(op);
   }
-  void push(const Op& op) {
+  static double epilogue_bytes(const mde_epilogue& ep, double elems) {
+    double b = 0.0;
+    if (ep.d_x) b += (ep.accumulate_x ? 8.0 : 4.0) * elems;
+    if (ep.d_out) b += 2.0 * elems;
+    if (ep.d_out_relu) b += 2.0 * elems;
+    if (ep.d_res1) b += 2.0 * elems;
+    if (ep.d_res2) b += 2.0 * elems;
+    return b;
+  }
+  void push(const Op& op, const char* label = "", double bytes = 0.0, double flops = 0.0) {
     if (dry || rc != MDE_OK) return;
     c->plan.push_back(op);
+    c->plan.back().label = label;
+    c->plan.back().bytes = bytes;
+    c->plan.back().flops = flops;
   }
 };
 
@@ -469,34 +498,39 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     Op op;
     if (d.input_mode == MDE_INPUT_U8_HWC) { op.kind = Op::PREPROC_U8; op.out = cols; }
     else { op.kind = Op::IM2COL_F32; op.out = cols; }
-    pl.push(op);
+    const int kreal = 3 * d.patch_size * d.patch_size;
+    if (d.input_mode == MDE_INPUT_U8_HWC)   // bytes depend on the source size bound at enqueue; counted for the maximum
+      pl.push(op, "preprocess_u8 resize+normalise+im2col", static_cast<double>(B) * d.max_src_h * d.max_src_w * 3 + 2.0 * prow * e->kpad);
+    else
+      pl.push(op, "im2col_f32", 4.0 * B * 3 * d.input_h * d.input_w + 2.0 * prow * e->kpad);
     mde_epilogue ep = ep_zero();
     ep.d_bias = e->pe_b; ep.d_x = x; ep.ld_out = D; ep.tokens = T; ep.d_pos = e->pos;
-    pl.gemm(cols, prow, e->kpad, e->kpad, e->pe_w, D, e->kpad, ep);
+    pl.gemm("patch_embed", cols, prow, e->kpad, e->kpad, e->pe_w, D, e->kpad, ep, kreal);
     Op cr; cr.kind = Op::CLS_ROW; cr.out = x;
-    pl.push(cr);
+    pl.push(cr, "cls_row", 12.0 * D * B);
   }
   // ---- encoder
   int next_tap = 0;
   for (int i = 0; i < d.depth; ++i) {
     const Block& b = e->blocks.empty() ? Block{} : e->blocks[i];
     Op l1; l1.kind = Op::LAYERNORM; l1.in = x; l1.out = ln; l1.w = b.ln1_w; l1.b = b.ln1_b; l1.rows = rows; l1.i0 = 0;
-    pl.push(l1);
+    pl.push(l1, "layernorm", 6.0 * rows * D);
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.qkv_b; ep.d_out = qkv; ep.ld_out = 3 * D;
-      pl.gemm(ln, rows, D, D, b.qkv_w, 3 * D, D, ep); }
-    { Op a; a.kind = Op::ATTENTION; a.in = qkv; a.out = att; pl.push(a); }
+      pl.gemm("qkv", ln, rows, D, D, b.qkv_w, 3 * D, D, ep); }
+    { Op a; a.kind = Op::ATTENTION; a.in = qkv; a.out = att;
+      pl.push(a, "attention", 8.0 * rows * D, 4.0 * static_cast<double>(B) * NT * NT * D); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.proj_b; ep.d_gamma = b.ls1; ep.d_x = x; ep.accumulate_x = 1; ep.ld_out = D;
-      pl.gemm(att, rows, D, D, b.proj_w, D, D, ep); }
+      pl.gemm("proj+ls+res", att, rows, D, D, b.proj_w, D, D, ep); }
     Op l2 = l1; l2.w = b.ln2_w; l2.b = b.ln2_b;
-    pl.push(l2);
+    pl.push(l2, "layernorm", 6.0 * rows * D);
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.fc1_b; ep.act = 1; ep.d_out = hid; ep.ld_out = 4 * D;
-      pl.gemm(ln, rows, D, D, b.fc1_w, 4 * D, D, ep); }
+      pl.gemm("fc1+gelu", ln, rows, D, D, b.fc1_w, 4 * D, D, ep); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.fc2_b; ep.d_gamma = b.ls2; ep.d_x = x; ep.accumulate_x = 1; ep.ld_out = D;
-      pl.gemm(hid, rows, 4 * D, 4 * D, b.fc2_w, D, 4 * D, ep); }
-    { Op s; s.kind = Op::SNAPSHOT; s.block = i; pl.push(s); }
+      pl.gemm("fc2+ls+res", hid, rows, 4 * D, 4 * D, b.fc2_w, D, 4 * D, ep); }
+    { Op s; s.kind = Op::SNAPSHOT; s.block = i; pl.push(s, "snapshot"); }
     if (next_tap < 4 && d.taps[next_tap] == i) {
       Op t; t.kind = Op::LAYERNORM; t.in = x; t.out = tap[next_tap]; t.w = e->norm_w; t.b = e->norm_b; t.rows = rows; t.i0 = 1;
-      pl.push(t);
+      pl.push(t, "layernorm tap", 4.0 * rows * D + 2.0 * prow * D);
       ++next_tap;
     }
   }
@@ -506,23 +540,23 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   for (int i = 0; i < 4; ++i) {
     void* pr = pl.alloc16(prow * oc[i]);
     mde_epilogue ep = ep_zero(); ep.d_bias = e->proj_b[i]; ep.d_out = pr; ep.ld_out = oc[i];
-    pl.gemm(tap[i], prow, D, D, e->proj_w[i], oc[i], D, ep);
+    pl.gemm("projects", tap[i], prow, D, D, e->proj_w[i], oc[i], D, ep);
     if (i == 0 || i == 1) {
       const int s = i == 0 ? 4 : 2;
       l[i] = pl.alloc16(prow * s * s * oc[i]);
       mde_epilogue e2 = ep_zero(); e2.d_bias = i == 0 ? e->ct0_b : e->ct1_b; e2.d_out = l[i]; e2.ld_out = oc[i];
       e2.shuffle_s = s; e2.shuffle_cout = oc[i]; e2.shuffle_h = gh; e2.shuffle_w = gw;
-      pl.gemm(pr, prow, oc[i], oc[i], i == 0 ? e->ct0_w : e->ct1_w, s * s * oc[i], oc[i], e2);
+      pl.gemm("convT+shuffle", pr, prow, oc[i], oc[i], i == 0 ? e->ct0_w : e->ct1_w, s * s * oc[i], oc[i], e2);
     } else if (i == 2) {
       l[i] = pr;
     } else {
       const long long r4 = static_cast<long long>(B) * e->lvl_h[3] * e->lvl_w[3];
       void* g = pl.alloc16(r4 * 9 * oc[3]);
       Op s2; s2.kind = Op::IM2COL_S2; s2.in = pr; s2.out = g; s2.i0 = gh; s2.i1 = gw; s2.i2 = oc[3];
-      pl.push(s2);
+      pl.push(s2, "im2col_s2", 2.0 * prow * oc[3] + 2.0 * r4 * 9 * oc[3]);
       l[i] = pl.alloc16(r4 * oc[3]);
       mde_epilogue e2 = ep_zero(); e2.d_bias = e->rs3_b; e2.d_out = l[i]; e2.ld_out = oc[3];
-      pl.gemm(g, r4, 9 * oc[3], 9 * oc[3], e->rs3_w, oc[3], 9 * oc[3], e2);
+      pl.gemm("conv3x3s2", g, r4, 9 * oc[3], 9 * oc[3], e->rs3_w, oc[3], 9 * oc[3], e2);
     }
   }
   // ---- layer_rn: raw r_i (residual of the first RCU) and relu(r_i) (input of its first conv)
@@ -533,7 +567,7 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     r[i] = pl.alloc16(px * F, r_names[i]);
     r_relu[i] = pl.alloc16(px * F);
     mde_epilogue ep = ep_zero(); ep.d_out = r[i]; ep.d_out_relu = r_relu[i]; ep.ld_out = F;
-    pl.conv(l[i], B, e->lvl_h[i], e->lvl_w[i], oc[i], e->rn_w[i], F, ep);
+    pl.conv("layer_rn", l[i], B, e->lvl_h[i], e->lvl_w[i], oc[i], e->rn_w[i], F, ep);
   }
   // ---- RefineNets 4 -> 1
   void* path = nullptr;   // output of the previous fusion block, already at this level's resolution
@@ -549,41 +583,41 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
       void* s = pl.alloc16(px * F);
       void* sr = pl.alloc16(px * F);
       { mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu1.b1; ep.act = 2; ep.d_out = a; ep.ld_out = F;
-        pl.conv(r_relu[i], B, H, W, F, rf.rcu1.w1, F, ep); }
+        pl.conv("rcu1.conv1", r_relu[i], B, H, W, F, rf.rcu1.w1, F, ep); }
       { mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu1.b2; ep.d_res1 = r[i]; ep.d_res2 = path; ep.d_out = s; ep.d_out_relu = sr; ep.ld_out = F;
-        pl.conv(a, B, H, W, F, rf.rcu1.w2, F, ep); }
+        pl.conv("rcu1.conv2+res", a, B, H, W, F, rf.rcu1.w2, F, ep); }
       s_relu = sr; s_raw = s;
     }
     // u = RCU2(s)
     void* a2 = pl.alloc16(px * F);
     void* u = pl.alloc16(px * F);
     { mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu2.b1; ep.act = 2; ep.d_out = a2; ep.ld_out = F;
-      pl.conv(s_relu, B, H, W, F, rf.rcu2.w1, F, ep); }
+      pl.conv("rcu2.conv1", s_relu, B, H, W, F, rf.rcu2.w1, F, ep); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu2.b2; ep.d_res1 = s_raw; ep.d_out = u; ep.ld_out = F;
-      pl.conv(a2, B, H, W, F, rf.rcu2.w2, F, ep); }
+      pl.conv("rcu2.conv2+res", a2, B, H, W, F, rf.rcu2.w2, F, ep); }
     // 1x1 out_conv at this resolution, then bilinear (align_corners=True) to the next level's size:
     // both are linear and the interpolation weights sum to 1, so they commute exactly in real arithmetic.
     void* q = pl.alloc16(px * F);
     { mde_epilogue ep = ep_zero(); ep.d_bias = rf.out_b; ep.d_out = q; ep.ld_out = F;
-      pl.gemm(u, px, F, F, rf.out_w, F, F, ep); }
+      pl.gemm("out_conv1x1", u, px, F, F, rf.out_w, F, F, ep); }
     const int Ho = i > 0 ? e->lvl_h[i - 1] : 2 * H, Wo = i > 0 ? e->lvl_w[i - 1] : 2 * W;
     path = pl.alloc16(static_cast<long long>(B) * Ho * Wo * F, i == 0 ? "path_1" : nullptr);
     Op bl; bl.kind = Op::BILINEAR; bl.in = q; bl.out = path; bl.i0 = H; bl.i1 = W; bl.i2 = Ho; bl.i3 = Wo; bl.i4 = F;
-    pl.push(bl);
+    pl.push(bl, "bilinear", 2.0 * F * (px + static_cast<double>(B) * Ho * Wo));
   }
   // ---- output convs + fused depth head
   {
     const int H1 = 2 * e->lvl_h[0], W1 = 2 * e->lvl_w[0];
     void* o1 = pl.alloc16(static_cast<long long>(B) * H1 * W1 * (F / 2));
     { mde_epilogue ep = ep_zero(); ep.d_bias = e->oc1_b; ep.d_out = o1; ep.ld_out = F / 2;
-      pl.conv(path, B, H1, W1, F, e->oc1_w, F / 2, ep); }
+      pl.conv("output_conv1", path, B, H1, W1, F, e->oc1_w, F / 2, ep); }
     void* up = pl.alloc16(static_cast<long long>(B) * d.input_h * d.input_w * (F / 2));
     Op bl; bl.kind = Op::BILINEAR; bl.in = o1; bl.out = up; bl.i0 = H1; bl.i1 = W1; bl.i2 = d.input_h; bl.i3 = d.input_w; bl.i4 = F / 2;
-    pl.push(bl);
+    pl.push(bl, "bilinear", 1.0 * F * (static_cast<double>(B) * H1 * W1 + static_cast<double>(B) * d.input_h * d.input_w));
     mde_epilogue ep = ep_zero(); ep.d_bias = e->oc2_b; ep.ld_out = 32;
     ep.d_head_w = e->head_w; ep.head_b = e->head_b; ep.head_scale = d.max_depth > 0.f ? d.max_depth : 0.f;
     ep.d_head_out = reinterpret_cast<float*>(0x10);   // patched with the bound output address at enqueue
-    pl.conv(up, B, d.input_h, d.input_w, F / 2, e->oc2_w, 32, ep);
+    pl.conv("output_conv2+head", up, B, d.input_h, d.input_w, F / 2, e->oc2_w, 32, ep);
   }
   if (bytes_out) *bytes_out = pl.bytes;
   return pl.rc;
@@ -623,6 +657,7 @@ extern "C" int mde_context_create(mde_engine* e, mde_context** out) {
 extern "C" void mde_context_destroy(mde_context* c) {
   if (!c) return;
   for (void* p : c->allocs) cudaFree(p);
+  for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -681,15 +716,14 @@ extern "C" int mde_context_get_buffer(mde_context* c, const char* name, void** d
   return MDE_OK;
 }
 
-extern "C" int mde_context_enqueue(mde_context* c, void* stream) {
-  clear_error();
-  if (!c) return fail(MDE_ERR_INVALID, "null context");
+static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
   if (!c->d_input || !c->d_output) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'input' and 'output' before enqueue");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   mde_engine* e = c->e;
   const mde_engine_desc& d = e->d;
   const int prec = d.precision;
+  size_t ev = 0;
   for (Op& op : c->plan) {
+    if (timed && op.kind != Op::SNAPSHOT) MDE_CUDA_TRY(cudaEventRecord(c->events[ev++], s));
     switch (op.kind) {
       case Op::PREPROC_U8:
         MDE_TRY(launch_preprocess_u8(prec, static_cast<const uint8_t*>(c->d_input), static_cast<long long>(c->src_h) * c->src_w * 3,
@@ -724,5 +758,48 @@ extern "C" int mde_context_enqueue(mde_context* c, void* stream) {
         break;
     }
   }
+  if (timed) MDE_CUDA_TRY(cudaEventRecord(c->events[ev], s));
   return MDE_OK;
+}
+
+extern "C" int mde_context_enqueue(mde_context* c, void* stream) {
+  clear_error();
+  if (!c) return fail(MDE_ERR_INVALID, "null context");
+  return enqueue_impl(c, static_cast<cudaStream_t>(stream), false);
+}
+
+// Profiling variant: CUDA events between the launches, then a stream synchronise; ms[i] is the device time
+// of launch i of the plan (mde_context_launches_per_enqueue entries).
+extern "C" int mde_context_enqueue_timed(mde_context* c, void* stream, float* ms, int32_t capacity) {
+  clear_error();
+  if (!c || !ms) return fail(MDE_ERR_INVALID, "bad argument to mde_context_enqueue_timed");
+  const int n = mde_context_launches_per_enqueue(c);
+  if (capacity < n) return fail(MDE_ERR_INVALID, "ms[] holds %d entries, %d needed", capacity, n);
+  while (static_cast<int>(c->events.size()) < n + 1) {
+    cudaEvent_t ev;
+    MDE_CUDA_TRY(cudaEventCreate(&ev));
+    c->events.push_back(ev);
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MDE_TRY(enqueue_impl(c, s, true));
+  MDE_CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) MDE_CUDA_TRY(cudaEventElapsedTime(&ms[i], c->events[i], c->events[i + 1]));
+  return MDE_OK;
+}
+
+// Label, algorithmic FLOPs and algorithmic bytes of launch i of the plan.
+extern "C" int mde_context_op_info(const mde_context* c, int32_t i, char* label, int32_t label_capacity, double* flops, double* bytes) {
+  clear_error();
+  if (!c || !label || label_capacity < 1 || !flops || !bytes) return fail(MDE_ERR_INVALID, "bad argument to mde_context_op_info");
+  int k = 0;
+  for (const Op& op : c->plan) {
+    if (op.kind == Op::SNAPSHOT) continue;
+    if (k++ == i) {
+      snprintf(label, static_cast<size_t>(label_capacity), "%s", op.label.c_str());
+      *flops = op.flops;
+      *bytes = op.bytes;
+      return MDE_OK;
+    }
+  }
+  return fail(MDE_ERR_INVALID, "launch index %d out of range", i);
 }

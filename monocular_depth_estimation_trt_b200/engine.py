@@ -99,6 +99,19 @@ class ExecutionContext:
                    "get_buffer")
         return int(p.value), int(n.value), int(dt.value)
 
+    def execute_timed(self, stream_handle):
+        """Profiling: one forward with CUDA events between launches -> [(label, ms, flops, bytes)]."""
+        n = self.launches_per_enqueue
+        ms = (C.c_float * n)()
+        _lib.check(self._lib.mde_context_enqueue_timed(self._h, C.c_void_p(int(stream_handle)), ms, n), "enqueue_timed")
+        out = []
+        buf = C.create_string_buffer(192)
+        for i in range(n):
+            fl, by = C.c_double(), C.c_double()
+            _lib.check(self._lib.mde_context_op_info(self._h, i, buf, 192, C.byref(fl), C.byref(by)), "op_info")
+            out.append((buf.value.decode(), float(ms[i]), fl.value, by.value))
+        return out
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.mde_context_destroy(self._h)
