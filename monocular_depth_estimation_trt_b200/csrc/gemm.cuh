@@ -58,14 +58,31 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kMaxStages = (226 * 1024 - 2048) / kStageBytes;
+  static constexpr int kEpiBytes = 4 * 32 * 32 * 4 + 4 * 32 * 8;   // staging chunks + row offsets
+  static constexpr int kMaxStages = (226 * 1024 - 2048 - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
   static constexpr int kThreads = 256;
 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// GELU(v) = v * Phi(v) with the exact-erf Phi, evaluated through Abramowitz & Stegun 7.1.26
+// (|erf error| <= 1.5e-7): q = poly(t) * exp(-v^2/2), t = 1 / (1 + p |v| / sqrt(2)); Phi = v >= 0 ? 1 - q/2 : q/2.
+// The negative branch has no cancellation; two MUFU ops (rcp, ex2) and about twelve FMA-class ops per element.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float a = fabsf(v);
+  float t;   // rcp.approx (1 ulp) -- __frcp_rn expands to a ~60-instruction IEEE sequence
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(a, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * a * (-0.5f * 1.44269504088896340736f)));
+  const float hq = 0.5f * poly * e;
+  return v * (v >= 0.f ? 1.0f - hq : hq);
+}
 
 template <int BLOCK_N, typename T>
 __global__ void __launch_bounds__(256, 1)
@@ -85,6 +102,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes + 256;   // 4 x (32x32 fp32) staging + 4 x 32 row offsets
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,8 +196,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue
+    // Phase 1 (thread = row, as tcgen05.ld 32x32b delivers it): a raw 32 x 32 fp32 chunk goes to this
+    // warp's swizzled staging buffer; the TMEM load of the next chunk is already in flight.
+    // Phase 2 (lanes = columns): bias / activation / LayerScale / residuals and all global traffic run
+    // over whole row segments, so every 32-byte sector that is touched is touched completely, per-column
+    // parameters live in one register per lane, and all loads of a chunk are issued before its stores.
     const int ew = warp - 4;                 // == warp % 4: TMEM lane quarter this warp may read
     const int r = ew * 32 + lane;            // row inside the 128-row tile
+    float* stage_f = reinterpret_cast<float*>(epi_smem) + ew * (32 * 32);
+    long long* row_off = reinterpret_cast<long long*>(epi_smem + 4 * 32 * 32 * 4) + ew * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     T* out = static_cast<T*>(p.out);
@@ -192,7 +217,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // ---- where does this thread's row go?
       bool valid;
       long long orow;            // output row (ROW_SHUFFLE: row of sub-pixel (0,0))
-      long long prow = 0;        // ROW_TOKENS: row of the pos_embed table
       if (p.conv) {
         const int per_img = p.tiles_x * p.tiles_y;
         const int img = m_blk / per_img;
@@ -206,10 +230,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         valid = m < p.M;
         orow = m;
         if (p.row_map == ROW_TOKENS) {
-          const long long b = m / p.tokens;
-          const long long t = m % p.tokens;
-          orow = b * (p.tokens + 1) + 1 + t;
-          prow = 1 + t;
+          orow = (m / p.tokens) * (p.tokens + 1) + 1 + (m % p.tokens);
         } else if (p.row_map == ROW_SHUFFLE) {
           const int hw = p.H * p.W;
           const long long b = m / hw;
@@ -219,17 +240,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                  static_cast<long long>(x) * p.shuffle_s;
         }
       }
+      __syncwarp();                          // previous tile's phase 2 is done with row_off
+      row_off[lane] = valid ? orow : -1;
+      // The residual stream tile this epilogue will read-modify-write: pull it into L2 while the MMAs of
+      // the tile are still running (the row is contiguous: BLOCK_N fp32 = BLOCK_N / 32 lines).
+      if (p.x && p.accumulate_x && valid) {
+        const char* xrow = reinterpret_cast<const char*>(p.x + orow * p.ld_out + n_blk * BLOCK_N);
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / 32; ++i)
+          if (n_blk * BLOCK_N + i * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + i * 128));
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+      const int n_tile = n_blk * BLOCK_N;
+      const int chunks = min(BLOCK_N, p.N - n_tile + 31) / 32;   // warp-uniform; N is a multiple of 8
 
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(t_base, raw);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(t_base + c0, raw);
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int n_base = n_tile + ch * 32;
         tmem_ld_wait();
-        const int n_base = n_blk * BLOCK_N + c0;
         if (p.head_w != nullptr) {
           // fused depth head: 3x3 conv (+bias, ReLU) -> 1x1 conv 32->1 -> activation
           float z = p.head_b;
@@ -241,78 +274,122 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (valid) p.head_out[orow] = p.head_scale < 0.f ? fmaxf(z, 0.f) : p.head_scale / (1.0f + __expf(-z));
           continue;
         }
-        if (!valid) continue;
+        // ---- phase 1
+        __syncwarp();                        // previous chunk's phase 2 has drained the staging buffer
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n_base + g * 8;
-          if (n >= p.N) break;
-          float v[8];
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(stage_f + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+              make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
+        if (ch + 1 < chunks) tmem_ld_32x32b_x32(t_base + (ch + 1) * 32, raw);   // in flight during phase 2
+        __syncwarp();
+        // ---- phase 2a: fp32 residual stream, 8 lanes x float4 per row, 4 rows per pass
+        if (p.x) {
+          const int c4 = lane & 7;
+          const int n = n_base + 4 * c4;
+          if (n < p.N) {
+            float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), gam = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            if (p.gamma) gam = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
+            long long ro[8];
+            float4 xin[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[g * 8 + j]);
-          long long row = orow;
-          int col = n;
-          if (p.row_map == ROW_SHUFFLE) {
-            const int q = n / p.shuffle_cout;
-            col = n % p.shuffle_cout;
-            row = orow + static_cast<long long>(q / p.shuffle_s) * (p.W * p.shuffle_s) + (q % p.shuffle_s);
-          }
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.act == ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.gamma) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4));
-            v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-            v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-          }
-          const long long off = row * p.ld_out + col;
-          if (p.pos) {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.pos + prow * p.ld_out + col));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.pos + prow * p.ld_out + col + 4));
-            v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w;
-            v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
-          }
-          if (res1) {
-            const uint4 u = *reinterpret_cast<const uint4*>(res1 + off);
-            const float2 a = Tr::unpack2(u.x), b = Tr::unpack2(u.y), c = Tr::unpack2(u.z), d = Tr::unpack2(u.w);
-            v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
-          }
-          if (res2) {
-            const uint4 u = *reinterpret_cast<const uint4*>(res2 + off);
-            const float2 a = Tr::unpack2(u.x), b = Tr::unpack2(u.y), c = Tr::unpack2(u.z), d = Tr::unpack2(u.w);
-            v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
-          }
-          if (p.x) {
-            float4* xp = reinterpret_cast<float4*>(p.x + off);
-            if (p.accumulate_x) {
-              const float4 x0 = xp[0], x1 = xp[1];
-              v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
-              v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+            for (int pass = 0; pass < 8; ++pass) {
+              ro[pass] = row_off[pass * 4 + (lane >> 3)];
+              xin[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ro[pass] >= 0) {
+                if (p.accumulate_x) xin[pass] = *reinterpret_cast<const float4*>(p.x + ro[pass] * p.ld_out + n);
+                else if (p.pos) xin[pass] = __ldg(reinterpret_cast<const float4*>(p.pos + (ro[pass] % (p.tokens + 1)) * p.ld_out + n));
+              }
             }
-            xp[0] = make_float4(v[0], v[1], v[2], v[3]);
-            xp[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int pass = 0; pass < 8; ++pass) {
+              if (ro[pass] < 0) continue;
+              const int rr = pass * 4 + (lane >> 3);
+              float4 v = *reinterpret_cast<const float4*>(stage_f + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+              v.x += bia.x; v.y += bia.y; v.z += bia.z; v.w += bia.w;
+              if (p.act == ACT_GELU) {
+                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+              } else if (p.act == ACT_RELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              v.x = fmaf(v.x, gam.x, xin[pass].x); v.y = fmaf(v.y, gam.y, xin[pass].y);
+              v.z = fmaf(v.z, gam.z, xin[pass].z); v.w = fmaf(v.w, gam.w, xin[pass].w);
+              *reinterpret_cast<float4*>(p.x + ro[pass] * p.ld_out + n) = v;
+            }
           }
-          if (out) {
-            uint4 u;
-            u.x = Tr::pack2(v[0], v[1]); u.y = Tr::pack2(v[2], v[3]);
-            u.z = Tr::pack2(v[4], v[5]); u.w = Tr::pack2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(out + off) = u;
-          }
-          if (out_relu) {
-            uint4 u;
-            u.x = Tr::pack2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f)); u.y = Tr::pack2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-            u.z = Tr::pack2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f)); u.w = Tr::pack2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
-            *reinterpret_cast<uint4*>(out_relu + off) = u;
+        }
+        // ---- phase 2b: 16-bit outputs (+ 16-bit residuals), 4 lanes x 8 columns per row, 8 rows per pass
+        if (out || out_relu) {
+          const int c8 = lane & 3;
+          const int n = n_base + 8 * c8;
+          if (n < p.N) {
+            int col = n;
+            long long sub = 0;
+            if (p.row_map == ROW_SHUFFLE) {
+              const int q = n / p.shuffle_cout;
+              col = n % p.shuffle_cout;
+              sub = static_cast<long long>(q / p.shuffle_s) * (p.W * p.shuffle_s) + (q % p.shuffle_s);
+            }
+            float bia[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float gam[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              bia[0] = b0.x; bia[1] = b0.y; bia[2] = b0.z; bia[3] = b0.w; bia[4] = b1.x; bia[5] = b1.y; bia[6] = b1.z; bia[7] = b1.w;
+            }
+            if (p.gamma) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4));
+              gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+            }
+            long long off[4];
+            uint4 ra[4], rb[4];
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              const long long ro = row_off[pass * 8 + (lane >> 2)];
+              off[pass] = ro < 0 ? -1 : (ro + sub) * p.ld_out + col;
+              ra[pass] = make_uint4(0u, 0u, 0u, 0u);
+              rb[pass] = make_uint4(0u, 0u, 0u, 0u);
+              if (off[pass] >= 0) {
+                if (res1) ra[pass] = *reinterpret_cast<const uint4*>(res1 + off[pass]);
+                if (res2) rb[pass] = *reinterpret_cast<const uint4*>(res2 + off[pass]);
+              }
+            }
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              if (off[pass] < 0) continue;
+              const int rr = pass * 8 + (lane >> 2);
+              const float4 v0 = *reinterpret_cast<const float4*>(stage_f + rr * 32 + (((2 * c8) ^ (rr & 7)) << 2));
+              const float4 v1 = *reinterpret_cast<const float4*>(stage_f + rr * 32 + (((2 * c8 + 1) ^ (rr & 7)) << 2));
+              float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              const uint32_t* pa = &ra[pass].x;
+              const uint32_t* pb = &rb[pass].x;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j] += bia[j];
+                if (p.act == ACT_GELU) v[j] = gelu_erf(v[j]);
+                else if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+                v[j] *= gam[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 a = Tr::unpack2(pa[j]), b = Tr::unpack2(pb[j]);   // bit pattern 0 == +0.0 in both formats
+                v[2 * j] += a.x + b.x;
+                v[2 * j + 1] += a.y + b.y;
+              }
+              if (out) {
+                uint4 u;
+                u.x = Tr::pack2(v[0], v[1]); u.y = Tr::pack2(v[2], v[3]);
+                u.z = Tr::pack2(v[4], v[5]); u.w = Tr::pack2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(out + off[pass]) = u;
+              }
+              if (out_relu) {
+                uint4 u;
+                u.x = Tr::pack2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f)); u.y = Tr::pack2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+                u.z = Tr::pack2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f)); u.w = Tr::pack2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
+                *reinterpret_cast<uint4*>(out_relu + off[pass]) = u;
+              }
+            }
           }
         }
       }
