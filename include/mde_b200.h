@@ -173,6 +173,10 @@ int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h,
 /* softmax(Q K^T / 8) V over [B*ntok][3*D] packed q|k|v rows, head dim 64 -> [B*ntok][D]. */
 int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                     void* stream);
+/* The same op on warp-level mma.sync tensor-core instructions: an independent cross-check of the
+ * tcgen05 kernel for the tests; the engine never launches it. */
+int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                        void* stream);
 /* LayerNorm of fp32 rows -> 16-bit.  drop_cls != 0: rows are [B][ntok]; token 0 of each image is
  * skipped and the output is dense [B][ntok-1]. */
 int mde_k_layernorm(int32_t precision, const float* d_x, const float* d_w, const float* d_b, void* d_out,

@@ -1,0 +1,268 @@
+// Fused softmax(Q K^T * scale) V on tcgen05 tensor cores with TMEM accumulators, head dim 64.
+//
+// One CTA = 256 query rows (two 128-row tiles) of one (image, head); it walks the keys in tiles of 128.
+//   warp 8      TMA producer: Q tiles once, then K and V tiles through a 2-stage ring
+//   warp 9      MMA issuer (one thread):  S_t = Q_t K_j^T  (M128 N128 K64, both operands K-major in smem)
+//                                         O_t = P_t V_j    (M128 N64 K128, P K-major in smem, V MN-major)
+//   warps 0-3   softmax group for tile 0 (thread = query row = TMEM lane); warps 4-7 the same for tile 1
+// The two softmax groups alternate on the SFUs while the other's MMAs run.  Each P V product lands in
+// TMEM un-accumulated; the softmax thread folds it into its fp32 register accumulator with the online-
+// softmax correction, so there is no TMEM read-modify-write and no separate correction role.
+// At head dim 64 the kernel is bound by the 16 ex2/clk/SM special-function rate, not by the tensor pipe.
+#pragma once
+#include "attention_mma.cuh"   // AttnParams, fast_exp2
+#include "ptx.cuh"
+
+namespace mde {
+
+constexpr int kAtcThreads = 320;
+constexpr int kAtcQBytes = 128 * 64 * 2;          // one 128 x 64 16-bit tile
+constexpr int kAtcPBytes = 128 * 128 * 2;         // P tile: two K-major 128 x 64 sub-tiles
+constexpr int kAtcStages = 2;
+// smem: Q[2] | K[stages] | V[stages] | P[2] | barriers
+constexpr int kAtcSmemBytes = 1024 + 2 * kAtcQBytes + 2 * kAtcStages * kAtcQBytes + 2 * kAtcPBytes + 256;
+
+// Operand tile with the N (or M) index contiguous: rows of 128 bytes are K indices, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(16384 >> 4) << 16;   // LBO: next 64-wide MN block (unused for N = 64)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO: next group of 8 K rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+  using Tr = F16Traits<T>;
+  extern __shared__ uint8_t atc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * kAtcQBytes;
+  uint8_t* sV = sK + kAtcStages * kAtcQBytes;
+  uint8_t* sP = sV + kAtcStages * kAtcQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAtcPBytes);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [stages]
+  uint64_t* k_empty = k_full + kAtcStages;
+  uint64_t* v_full = k_empty + kAtcStages;
+  uint64_t* v_empty = v_full + kAtcStages;
+  uint64_t* s_full = v_empty + kAtcStages; // [2]  S_t ready in TMEM
+  uint64_t* sp_ready = s_full + 2;         // [2]  S_t consumed and P_t written (128 arrivals)
+  uint64_t* o_full = sp_ready + 2;         // [2]  P_t V_j ready in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, img = blockIdx.z;
+  const int q0 = blockIdx.x * 256;
+  const int ntq = (q0 + 128 < p.ntok) ? 2 : 1;                    // query tiles with at least one valid row
+  const int nkv = (p.ntok + 127) / 128;
+  const int row_base = img * p.ntok;
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&map_qkv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kAtcStages; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1); mbar_init(&sp_ready[t], 128); mbar_init(&o_full[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)
+
+  if (warp == 8) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, ntq * kAtcQBytes);
+      for (int t = 0; t < ntq; ++t) tma_load_2d(sQ + t * kAtcQBytes, &map_qkv, q_full, head * 64, row_base + q0 + t * 128);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % kAtcStages;
+        const uint32_t ph = (j / kAtcStages) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kAtcQBytes);
+        tma_load_2d(sK + st * kAtcQBytes, &map_qkv, &k_full[st], p.D + head * 64, row_base + j * 128);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kAtcQBytes);
+        tma_load_2d(sV + st * kAtcQBytes, &map_qkv, &v_full[st], 2 * p.D + head * 64, row_base + j * 128);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(Tr::kFmt, 128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_f16(Tr::kFmt, 128, 64) | (1u << 16);   // B (= V) is MN-major
+      auto issue_s = [&](int t, int st) {
+        const uint64_t a = umma_desc_k_sw128(smem_u32(sQ + t * kAtcQBytes));
+        const uint64_t b = umma_desc_k_sw128(smem_u32(sK + st * kAtcQBytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + t * 128, a + 2 * k, b + 2 * k, idesc_s, k != 0);
+        tc_commit(&s_full[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < ntq; ++t) issue_s(t, 0);
+      tc_commit(&k_empty[0]);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % kAtcStages;
+        const uint32_t ph = (j / kAtcStages) & 1;
+        const int st1 = (j + 1) % kAtcStages;
+        const uint32_t ph1 = ((j + 1) / kAtcStages) & 1;
+        for (int t = 0; t < ntq; ++t) {
+          mbar_wait(&sp_ready[t], j & 1);        // S_t(j) consumed, P_t(j) in smem, O_t(j-1) folded
+          tc_fence_after();
+          if (j + 1 < nkv) {
+            if (t == 0) { mbar_wait(&k_full[st1], ph1); tc_fence_after(); }
+            issue_s(t, st1);
+            if (t == ntq - 1) tc_commit(&k_empty[st1]);
+          }
+          if (t == 0) { mbar_wait(&v_full[st], ph); tc_fence_after(); }
+          const uint32_t pa = smem_u32(sP + t * kAtcPBytes);
+          const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // 16 keys per step: P sub-tile k/4 (+32 bytes inside it), V advances two 8-row groups (2048 bytes)
+            const uint64_t a = umma_desc_k_sw128(pa + (k >> 2) * kAtcQBytes) + 2 * (k & 3);
+            tc_mma_f16(tmem_base + 256 + t * 64, a, vb + 128 * k, idesc_o, k != 0);
+          }
+          tc_commit(&o_full[t]);
+          if (t == ntq - 1) tc_commit(&v_empty[st]);
+        }
+      }
+    }
+  } else {
+    // ===================================================== softmax groups (thread = query row)
+    const int t = warp >> 2;
+    if (t < ntq) {
+      const int r = (warp & 3) * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t s_addr = tmem_base + lane_base + t * 128;
+      const uint32_t o_addr = tmem_base + lane_base + 256 + t * 64;
+      uint8_t* prow = sP + t * kAtcPBytes + r * 128;
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, c_pending = 1.f;
+      const float sl = p.scale_log2;
+
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        const int kv0 = j * 128;
+        const int nvalid = min(128, p.ntok - kv0);          // keys of this tile that exist
+        // ---- pass 1: row maximum
+        float mx = m_run;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch * 32 >= nvalid) break;
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(s_addr + ch * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        }
+        const float c_now = fast_exp2((m_run - mx) * sl);     // exp2(-inf) = 0 on the first tile
+        m_run = mx;
+        const float msl = mx * sl;
+        // ---- fold the previous tile's P V product (its MMAs ran while pass 1 did)
+        if (j > 0) {
+          mbar_wait(&o_full[t], (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[h * 32 + i] = fmaf(acc[h * 32 + i], c_pending, __uint_as_float(raw[i]));
+          }
+        }
+        c_pending = c_now;
+        // ---- pass 2: P = exp2(S * sl - m * sl) -> 16-bit -> smem (K-major, 128-byte swizzle)
+        float rs = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t pk[16];
+          if (ch * 32 < nvalid) {
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(s_addr + ch * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), sl, -msl));
+              float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), sl, -msl));
+              if (ch * 32 + i >= nvalid) p0 = 0.f;
+              if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
+              rs += p0 + p1;
+              pk[i >> 1] = Tr::pack2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
+          uint8_t* sub = prow + (ch >> 1) * kAtcQBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = (ch & 1) * 4 + c;
+            *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+        }
+        l_run = l_run * c_now + rs;
+        tc_fence_before();            // this thread's TMEM reads of S_t are complete
+        fence_proxy_async_smem();     // P_t visible to the tensor core's async proxy
+        mbar_arrive(&sp_ready[t]);
+      }
+      // ---- last P V product, normalise, store this row (128 contiguous bytes)
+      mbar_wait(&o_full[t], (nkv - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      const int n = q0 + t * 128 + r;
+      T* gout = static_cast<T*>(p.out) + (static_cast<long long>(row_base) + n) * p.D + head * 64;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+        tmem_ld_wait();
+        if (n < p.ntok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            uint32_t* uw = &u.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = c * 8 + e * 2;
+              const float a0 = fmaf(acc[h * 32 + i], c_pending, __uint_as_float(raw[i])) * inv;
+              const float a1 = fmaf(acc[h * 32 + i + 1], c_pending, __uint_as_float(raw[i + 1])) * inv;
+              uw[e] = Tr::pack2(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(gout + h * 32 + c * 8) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace mde

@@ -84,6 +84,7 @@ namespace {
 struct Op {
   enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, SNAPSHOT } kind;
   GemmOp g;
+  AttnOp attn;
   // generic scalar/pointer slots for the small kernels
   const void* in = nullptr;
   void* out = nullptr;
@@ -518,6 +519,7 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.qkv_b; ep.d_out = qkv; ep.ld_out = 3 * D;
       pl.gemm("qkv", ln, rows, D, D, b.qkv_w, 3 * D, D, ep); }
     { Op a; a.kind = Op::ATTENTION; a.in = qkv; a.out = att;
+      if (!dry && pl.rc == MDE_OK) pl.rc = make_attention_op(&a.attn, d.precision, qkv, att, B, NT, d.num_heads);
       pl.push(a, "attention", 8.0 * rows * D, 4.0 * static_cast<double>(B) * NT * NT * D); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.proj_b; ep.d_gamma = b.ls1; ep.d_x = x; ep.accumulate_x = 1; ep.ld_out = D;
       pl.gemm("proj+ls+res", att, rows, D, D, b.proj_w, D, D, ep); }
@@ -744,7 +746,7 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         MDE_TRY(launch_layernorm(prec, static_cast<const float*>(op.in), op.w, op.b, op.out, op.rows, d.embed_dim, 1e-6f, op.i0, e->ntok, s));
         break;
       case Op::ATTENTION:
-        MDE_TRY(launch_attention(prec, op.in, op.out, d.batch, e->ntok, d.num_heads, s));
+        MDE_TRY(launch_attention_op(op.attn, s));
         break;
       case Op::BILINEAR:
         MDE_TRY(launch_bilinear(prec, op.in, op.out, d.batch, op.i0, op.i1, op.i2, op.i3, op.i4, s));

@@ -46,7 +46,17 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
                  int cout, const mde_epilogue* ep);
 int launch_gemm(const GemmOp& op, cudaStream_t stream);
 
-int launch_attention(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);
+// tcgen05 attention launch, described at plan-build time (tensor map over the packed q|k|v rows)
+struct AttnOp {
+  alignas(64) CUtensorMap map_qkv;
+  const void* qkv;
+  void* out;
+  int batch, ntok, heads, precision;
+};
+int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads);
+int launch_attention_op(const AttnOp& op, cudaStream_t s);
+// warp-level mma.sync variant (kept as an independent cross-check of the tcgen05 kernel in the tests)
+int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);
 int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,
                      int dim, float eps, int drop_cls, int ntok, cudaStream_t s);
 int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int hi, int wi, int ho, int wo, int c,

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "attention_mma.cuh"
+#include "attention_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -246,11 +247,45 @@ static int launch_attention_t(const void* d_qkv, void* d_out, int batch, int nto
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
-int launch_attention(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s) {
+int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s) {
   if (batch <= 0 || ntok <= 0 || heads <= 0) return fail(MDE_ERR_INVALID, "attention: empty problem");
   if (batch > 65535 || heads > 65535) return fail(MDE_ERR_INVALID, "attention: batch/heads exceed grid limits");
   return precision == MDE_BF16 ? launch_attention_t<__nv_bfloat16>(d_qkv, d_out, batch, ntok, heads, s)
                                : launch_attention_t<__half>(d_qkv, d_out, batch, ntok, heads, s);
+}
+
+int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads) {
+  if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
+  if (batch <= 0 || ntok <= 0 || heads <= 0) return fail(MDE_ERR_INVALID, "attention: empty problem");
+  if (batch > 65535 || heads > 65535) return fail(MDE_ERR_INVALID, "attention: batch/heads exceed grid limits");
+  if ((reinterpret_cast<uintptr_t>(d_qkv) | reinterpret_cast<uintptr_t>(d_out)) & 15) return fail(MDE_ERR_INVALID, "attention: buffers must be 16-byte aligned");
+  const long long rows = static_cast<long long>(batch) * ntok;
+  if (rows > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "attention: too many rows");
+  op->qkv = d_qkv; op->out = d_out; op->batch = batch; op->ntok = ntok; op->heads = heads; op->precision = precision;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(3 * heads * 64), static_cast<cuuint64_t>(rows)};
+  cuuint64_t str[1] = {static_cast<cuuint64_t>(3 * heads * 64) * 2};
+  cuuint32_t box[2] = {64, 128};
+  return encode_map(&op->map_qkv, precision, d_qkv, 2, dims, str, box);
+}
+
+template <typename T>
+static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = attention_tc_kernel<T>;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  dim3 grid((op.ntok + 255) / 256, op.heads, op.batch);
+  kern<<<grid, kAtcThreads, kAtcSmemBytes, s>>>(op.map_qkv, p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+int launch_attention_op(const AttnOp& op, cudaStream_t s) {
+  return op.precision == MDE_BF16 ? launch_attention_tc_t<__nv_bfloat16>(op, s) : launch_attention_tc_t<__half>(op, s);
 }
 
 template <typename T>
@@ -403,7 +438,15 @@ int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h,
 int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                     void* stream) {
   clear_error();
-  return launch_attention(precision, d_qkv, d_out, batch, ntok, heads, static_cast<cudaStream_t>(stream));
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                        void* stream) {
+  clear_error();
+  return launch_attention_mma(precision, d_qkv, d_out, batch, ntok, heads, static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_layernorm(int32_t precision, const float* d_x, const float* d_w, const float* d_b, void* d_out,

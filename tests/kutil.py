@@ -60,11 +60,11 @@ def pack_conv3x3(w, dtype):
     return p.reshape(cout, 9 * cin_pad).contiguous()
 
 
-def attention(precision, qkv, batch, ntok, heads):
+def attention(precision, qkv, batch, ntok, heads, variant="tc"):
     lib = _lib.load()
     out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
-    _lib.check(lib.mde_k_attention(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()),
-               "mde_k_attention")
+    fn = lib.mde_k_attention if variant == "tc" else lib.mde_k_attention_mma
+    _lib.check(fn(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()), "mde_k_attention")
     return out
 
 

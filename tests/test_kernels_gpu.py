@@ -143,13 +143,15 @@ def test_conv3x3_fused_depth_head(lib, prec, max_depth):
 
 
 # ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("variant", ["tc", "mma"])
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("B,ntok,heads", [(2, 1370, 6), (1, 577, 16), (3, 64, 2), (1, 129, 1), (1, 3349, 2)])
-def test_attention(lib, prec, B, ntok, heads):
+@pytest.mark.parametrize("B,ntok,heads", [(2, 1370, 6), (1, 577, 16), (3, 64, 2), (1, 129, 1), (1, 3349, 2),
+                                          (2, 256, 3), (1, 257, 2), (2, 128, 1)])
+def test_attention(lib, prec, B, ntok, heads, variant):
     dt = K.TORCH_DT[prec]
     D = heads * 64
     qkv = rnd((B * ntok, 3 * D), dt, seed=17)
-    out = K.attention(prec, qkv, B, ntok, heads)
+    out = K.attention(prec, qkv, B, ntok, heads, variant)
     torch.cuda.synchronize()
     q, k, v = qkv.float().reshape(B, ntok, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v
