@@ -10,6 +10,8 @@
 // softmax correction, so there is no TMEM read-modify-write and no separate correction role.
 // At head dim 64 the kernel is bound by the 16 ex2/clk/SM special-function rate, not by the tensor pipe.
 #pragma once
+#include <cuda/std/type_traits>
+
 #include "attention_mma.cuh"   // AttnParams, fast_exp2
 #include "ptx.cuh"
 
@@ -158,74 +160,78 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       float m_run = -INFINITY, l_run = 0.f, c_pending = 1.f;
       const float sl = p.scale_log2;
 
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&s_full[t], j & 1);
-        tc_fence_after();
-        const int kv0 = j * 128;
-        const int nvalid = min(128, p.ntok - kv0);          // keys of this tile that exist
+      // One KV tile.  kFull: all 128 keys exist (no per-element masking in the hot loops).
+      // TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is processed.
+      auto tile = [&](auto full_tag, int j) {
+        constexpr bool kFull = decltype(full_tag)::value;
+        const int nvalid = kFull ? 128 : p.ntok - j * 128;
+        uint32_t raw[2][32];
         // ---- pass 1: row maximum
         float mx = m_run;
-#pragma unroll 1
+        tmem_ld_32x32b_x32(s_addr, raw[0]);
+#pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          if (ch * 32 >= nvalid) break;
-          uint32_t raw[32];
-          tmem_ld_32x32b_x32(s_addr + ch * 32, raw);
           tmem_ld_wait();
+          if (ch < 3) tmem_ld_32x32b_x32(s_addr + (ch + 1) * 32, raw[(ch + 1) & 1]);
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+            if (kFull || ch * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(raw[ch & 1][i]));
         }
         const float c_now = fast_exp2((m_run - mx) * sl);     // exp2(-inf) = 0 on the first tile
         m_run = mx;
         const float msl = mx * sl;
+        tmem_ld_32x32b_x32(s_addr, raw[0]);                   // pass 2's first chunk, in flight during the fold
         // ---- fold the previous tile's P V product (its MMAs ran while pass 1 did)
         if (j > 0) {
           mbar_wait(&o_full[t], (j - 1) & 1);
           tc_fence_after();
+          tmem_ld_32x32b_x32(o_addr, raw[1]);
+          tmem_ld_wait();                                     // covers raw[0] (S chunk 0) and raw[1] (O columns 0-31)
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t raw[32];
-            tmem_ld_32x32b_x32(o_addr + h * 32, raw);
-            tmem_ld_wait();
+          for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], c_pending, __uint_as_float(raw[1][i]));
+          tmem_ld_32x32b_x32(o_addr + 32, raw[1]);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[h * 32 + i] = fmaf(acc[h * 32 + i], c_pending, __uint_as_float(raw[i]));
-          }
+          for (int i = 0; i < 32; ++i) acc[32 + i] = fmaf(acc[32 + i], c_pending, __uint_as_float(raw[1][i]));
         }
         c_pending = c_now;
         // ---- pass 2: P = exp2(S * sl - m * sl) -> 16-bit -> smem (K-major, 128-byte swizzle)
         float rs = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint32_t pk[16];
-          if (ch * 32 < nvalid) {
-            uint32_t raw[32];
-            tmem_ld_32x32b_x32(s_addr + ch * 32, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), sl, -msl));
-              float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), sl, -msl));
-              if (ch * 32 + i >= nvalid) p0 = 0.f;
-              if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
-              rs += p0 + p1;
-              pk[i >> 1] = Tr::pack2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-          }
+          tmem_ld_wait();
+          if (ch < 3) tmem_ld_32x32b_x32(s_addr + (ch + 1) * 32, raw[(ch + 1) & 1]);
           uint8_t* sub = prow + (ch >> 1) * kAtcQBytes;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c) {          // 8 keys -> one 16-byte chunk of the P row
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = c * 8 + e * 2;
+              float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch & 1][i]), sl, -msl));
+              float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch & 1][i + 1]), sl, -msl));
+              if (!kFull) {
+                if (ch * 32 + i >= nvalid) p0 = 0.f;
+                if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
+              }
+              rs += p0 + p1;
+              pk[e] = Tr::pack2(p0, p1);
+            }
             const int chunk = (ch & 1) * 4 + c;
-            *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
-                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
         l_run = l_run * c_now + rs;
         tc_fence_before();            // this thread's TMEM reads of S_t are complete
         fence_proxy_async_smem();     // P_t visible to the tensor core's async proxy
         mbar_arrive(&sp_ready[t]);
+      };
+
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        if (j * 128 + 128 <= p.ntok) tile(cuda::std::true_type{}, j);
+        else tile(cuda::std::false_type{}, j);
       }
       // ---- last P V product, normalise, store this row (128 contiguous bytes)
       mbar_wait(&o_full[t], (nkv - 1) & 1);
