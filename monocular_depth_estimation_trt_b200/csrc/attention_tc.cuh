@@ -3,11 +3,15 @@
 // One CTA = 256 query rows (two 128-row tiles) of one (image, head); it walks the keys in tiles of 128.
 //   warp 8      TMA producer: Q tiles once, then K and V tiles through a 2-stage ring
 //   warp 9      MMA issuer (one thread):  S_t = Q_t K_j^T  (M128 N128 K64, both operands K-major in smem)
-//                                         O_t = P_t V_j    (M128 N64 K128, P K-major in smem, V MN-major)
+//                                         O_t += P_t V_j   (M128 N64 K128, P K-major in smem, V MN-major)
 //   warps 0-3   softmax group for tile 0 (thread = query row = TMEM lane); warps 4-7 the same for tile 1
-// The two softmax groups alternate on the SFUs while the other's MMAs run.  Each P V product lands in
-// TMEM un-accumulated; the softmax thread folds it into its fp32 register accumulator with the online-
-// softmax correction, so there is no TMEM read-modify-write and no separate correction role.
+//
+// A softmax thread pulls its whole score row (128 fp32) out of TMEM in one go and hands the S buffer
+// straight back, so the tensor core computes S of the next key tile while this one is exponentiated.
+// O accumulates in TMEM across key tiles.  The running maximum is applied lazily: the row keeps a stale
+// reference maximum and only when the true maximum has grown by more than 2^8 is O (and the running sum)
+// rescaled -- a TMEM load / multiply / store by the same thread, before it releases P for the next MMA.
+// Probabilities therefore stay <= 256, exactly representable ranges for bf16 and fp16.
 // At head dim 64 the kernel is bound by the 16 ex2/clk/SM special-function rate, not by the tensor pipe.
 #pragma once
 #include <cuda/std/type_traits>
@@ -17,12 +21,13 @@
 
 namespace mde {
 
-constexpr int kAtcThreads = 320;
+constexpr int kAtcThreads = 384;   // 2 softmax warpgroups + 1 warpgroup holding the TMA and MMA warps
 constexpr int kAtcQBytes = 128 * 64 * 2;          // one 128 x 64 16-bit tile
 constexpr int kAtcPBytes = 128 * 128 * 2;         // P tile: two K-major 128 x 64 sub-tiles
 constexpr int kAtcStages = 2;
 // smem: Q[2] | K[stages] | V[stages] | P[2] | barriers
 constexpr int kAtcSmemBytes = 1024 + 2 * kAtcQBytes + 2 * kAtcStages * kAtcQBytes + 2 * kAtcPBytes + 256;
+constexpr float kAtcRescaleThreshold = 8.0f;      // log2 units
 
 // Operand tile with the N (or M) index contiguous: rows of 128 bytes are K indices, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -51,9 +56,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   uint64_t* k_empty = k_full + kAtcStages;
   uint64_t* v_full = k_empty + kAtcStages;
   uint64_t* v_empty = v_full + kAtcStages;
-  uint64_t* s_full = v_empty + kAtcStages; // [2]  S_t ready in TMEM
-  uint64_t* sp_ready = s_full + 2;         // [2]  S_t consumed and P_t written (128 arrivals)
-  uint64_t* o_full = sp_ready + 2;         // [2]  P_t V_j ready in TMEM
+  uint64_t* s_full = v_empty + kAtcStages; // [2]  S_t ready in TMEM (tcgen05.commit)
+  uint64_t* s_free = s_full + 2;           // [2]  S_t copied to registers (128 arrivals)
+  uint64_t* p_ready = s_free + 2;          // [2]  P_t in smem, O_t rescaled if needed (128 arrivals)
+  uint64_t* o_full = p_ready + 2;          // [2]  O_t += P_t V_j complete (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,7 +77,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&sp_ready[t], 128); mbar_init(&o_full[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128); mbar_init(&p_ready[t], 128); mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
   }
@@ -85,8 +91,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)
 
+  // Register re-partition (per warpgroup): the two single-thread roles need almost nothing, a softmax
+  // thread holds a 128-wide score row.  384 threads start at 168 registers each.
   if (warp == 8) {
     // ===================================================== TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, ntq * kAtcQBytes);
       for (int t = 0; t < ntq; ++t) tma_load_2d(sQ + t * kAtcQBytes, &map_qkv, q_full, head * 64, row_base + q0 + t * 128);
@@ -103,6 +112,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
     }
   } else if (warp == 9) {
     // ===================================================== MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(Tr::kFmt, 128, 128);
       constexpr uint32_t idesc_o = umma_idesc_f16(Tr::kFmt, 128, 64) | (1u << 16);   // B (= V) is MN-major
@@ -121,32 +131,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kAtcStages;
         const uint32_t ph = (j / kAtcStages) & 1;
-        const int st1 = (j + 1) % kAtcStages;
-        const uint32_t ph1 = ((j + 1) / kAtcStages) & 1;
-        for (int t = 0; t < ntq; ++t) {
-          mbar_wait(&sp_ready[t], j & 1);        // S_t(j) consumed, P_t(j) in smem, O_t(j-1) folded
-          tc_fence_after();
-          if (j + 1 < nkv) {
-            if (t == 0) { mbar_wait(&k_full[st1], ph1); tc_fence_after(); }
+        if (j + 1 < nkv) {
+          // S of the next key tile as soon as the softmax threads hold the current scores in registers
+          const int st1 = (j + 1) % kAtcStages;
+          mbar_wait(&k_full[st1], ((j + 1) / kAtcStages) & 1);
+          for (int t = 0; t < ntq; ++t) {
+            mbar_wait(&s_free[t], j & 1);
+            tc_fence_after();
             issue_s(t, st1);
-            if (t == ntq - 1) tc_commit(&k_empty[st1]);
           }
-          if (t == 0) { mbar_wait(&v_full[st], ph); tc_fence_after(); }
+          tc_commit(&k_empty[st1]);
+        }
+        mbar_wait(&v_full[st], ph);
+        for (int t = 0; t < ntq; ++t) {
+          mbar_wait(&p_ready[t], j & 1);           // P_t(j) in smem, O_t rescaled
+          tc_fence_after();
           const uint32_t pa = smem_u32(sP + t * kAtcPBytes);
           const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             // 16 keys per step: P sub-tile k/4 (+32 bytes inside it), V advances two 8-row groups (2048 bytes)
             const uint64_t a = umma_desc_k_sw128(pa + (k >> 2) * kAtcQBytes) + 2 * (k & 3);
-            tc_mma_f16(tmem_base + 256 + t * 64, a, vb + 128 * k, idesc_o, k != 0);
+            tc_mma_f16(tmem_base + 256 + t * 64, a, vb + 128 * k, idesc_o, (j | k) != 0);
           }
           tc_commit(&o_full[t]);
-          if (t == ntq - 1) tc_commit(&v_empty[st]);
         }
+        tc_commit(&v_empty[st]);
       }
     }
+  } else if (warp >= 10) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // idle half of the producer warpgroup
   } else {
     // ===================================================== softmax groups (thread = query row)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int t = warp >> 2;
     if (t < ntq) {
       const int r = (warp & 3) * 32 + lane;
@@ -154,77 +171,80 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       const uint32_t s_addr = tmem_base + lane_base + t * 128;
       const uint32_t o_addr = tmem_base + lane_base + 256 + t * 64;
       uint8_t* prow = sP + t * kAtcPBytes + r * 128;
-      float acc[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, c_pending = 1.f;
+      float m_ref = -INFINITY;      // (possibly stale) maximum the probabilities are taken against
+      float l_run = 0.f;
       const float sl = p.scale_log2;
 
-      // One KV tile.  kFull: all 128 keys exist (no per-element masking in the hot loops).
-      // TMEM loads are software-pipelined: the load of chunk c+1 is in flight while chunk c is processed.
       auto tile = [&](auto full_tag, int j) {
         constexpr bool kFull = decltype(full_tag)::value;
         const int nvalid = kFull ? 128 : p.ntok - j * 128;
-        uint32_t raw[2][32];
-        // ---- pass 1: row maximum
-        float mx = m_run;
-        tmem_ld_32x32b_x32(s_addr, raw[0]);
+        uint32_t raw[4][32];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          tmem_ld_wait();
-          if (ch < 3) tmem_ld_32x32b_x32(s_addr + (ch + 1) * 32, raw[(ch + 1) & 1]);
+        for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32b_x32(s_addr + ch * 32, raw[ch]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);                   // the tensor core may overwrite S_t now
+        // ---- row maximum, four independent chains
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (kFull || ch * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(raw[ch & 1][i]));
-        }
-        const float c_now = fast_exp2((m_run - mx) * sl);     // exp2(-inf) = 0 on the first tile
-        m_run = mx;
-        const float msl = mx * sl;
-        tmem_ld_32x32b_x32(s_addr, raw[0]);                   // pass 2's first chunk, in flight during the fold
-        // ---- fold the previous tile's P V product (its MMAs ran while pass 1 did)
+            if (kFull || ch * 32 + i < nvalid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        // ---- lazy rescale: only when the maximum grew by more than 2^8 (always on the first tile)
+        const bool grow = (mx - m_ref) * sl > kAtcRescaleThreshold;
+        // The previous P V product must have landed before P_t is overwritten (and before O_t is touched).
+        // Waiting here every tile also keeps this thread in step with the barrier's phase parity.
         if (j > 0) {
           mbar_wait(&o_full[t], (j - 1) & 1);
           tc_fence_after();
-          tmem_ld_32x32b_x32(o_addr, raw[1]);
-          tmem_ld_wait();                                     // covers raw[0] (S chunk 0) and raw[1] (O columns 0-31)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], c_pending, __uint_as_float(raw[1][i]));
-          tmem_ld_32x32b_x32(o_addr + 32, raw[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[32 + i] = fmaf(acc[32 + i], c_pending, __uint_as_float(raw[1][i]));
         }
-        c_pending = c_now;
-        // ---- pass 2: P = exp2(S * sl - m * sl) -> 16-bit -> smem (K-major, 128-byte swizzle)
-        float rs = 0.f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float factor = grow ? fast_exp2((m_ref - mx) * sl) : 1.0f;
+          if (grow) { m_ref = mx; l_run *= factor; }
+          if (j > 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(o_addr + h * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st_32x32b_x32(o_addr + h * 32, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        // ---- P = exp2(S * sl - m_ref * sl) -> 16-bit -> smem (K-major, 128-byte swizzle)
+        const float msl = m_ref * sl;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          tmem_ld_wait();
-          if (ch < 3) tmem_ld_32x32b_x32(s_addr + (ch + 1) * 32, raw[(ch + 1) & 1]);
           uint8_t* sub = prow + (ch >> 1) * kAtcQBytes;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {          // 8 keys -> one 16-byte chunk of the P row
+          for (int c = 0; c < 4; ++c) {            // 8 keys -> one 16-byte chunk of the P row
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = c * 8 + e * 2;
-              float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch & 1][i]), sl, -msl));
-              float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch & 1][i + 1]), sl, -msl));
+              float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch][i]), sl, -msl));
+              float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch][i + 1]), sl, -msl));
               if (!kFull) {
                 if (ch * 32 + i >= nvalid) p0 = 0.f;
                 if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
               }
-              rs += p0 + p1;
+              rs4[e] += p0 + p1;
               pk[e] = Tr::pack2(p0, p1);
             }
             const int chunk = (ch & 1) * 4 + c;
             *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
-        l_run = l_run * c_now + rs;
-        tc_fence_before();            // this thread's TMEM reads of S_t are complete
+        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        tc_fence_before();            // TMEM stores of the rescale are ordered before the next MMA
         fence_proxy_async_smem();     // P_t visible to the tensor core's async proxy
-        mbar_arrive(&sp_ready[t]);
+        mbar_arrive(&p_ready[t]);
       };
 
       for (int j = 0; j < nkv; ++j) {
@@ -233,7 +253,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         if (j * 128 + 128 <= p.ntok) tile(cuda::std::true_type{}, j);
         else tile(cuda::std::false_type{}, j);
       }
-      // ---- last P V product, normalise, store this row (128 contiguous bytes)
+      // ---- normalise and store this row (128 contiguous bytes)
       mbar_wait(&o_full[t], (nkv - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
@@ -241,21 +261,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       T* gout = static_cast<T*>(p.out) + (static_cast<long long>(row_base) + n) * p.D + head * 64;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(o_addr + h * 32, raw);
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(o_addr + h * 32, o);
         tmem_ld_wait();
         if (n < p.ntok) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 u;
-            uint32_t* uw = &u.x;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = c * 8 + e * 2;
-              const float a0 = fmaf(acc[h * 32 + i], c_pending, __uint_as_float(raw[i])) * inv;
-              const float a1 = fmaf(acc[h * 32 + i + 1], c_pending, __uint_as_float(raw[i + 1])) * inv;
-              uw[e] = Tr::pack2(a0, a1);
-            }
+            u.x = Tr::pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+            u.y = Tr::pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+            u.z = Tr::pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+            u.w = Tr::pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
             *reinterpret_cast<uint4*>(gout + h * 32 + c * 8) = u;
           }
         }
