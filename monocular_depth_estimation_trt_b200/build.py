@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libmde_b200.so")
 SOURCES = ["kernels.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17",
+    "-lineinfo", "-O3", "-std=c++17", *os.environ.get("MDE_NVCC_EXTRA", "").split(),
     "-Xcompiler", "-fPIC",
     "--cudart", "static",
 ]

@@ -3,7 +3,7 @@
 // One CTA = 256 query rows (two 128-row tiles) of one (image, head); it walks the keys in tiles of 128.
 //   warp 8      TMA producer: Q tiles once, then K and V tiles through a 2-stage ring
 //   warp 9      MMA issuer (one thread):  S_t = Q_t K_j^T  (M128 N128 K64, both operands K-major in smem)
-//                                         O_t += P_t V_j   (M128 N64 K128, P K-major in smem, V MN-major)
+//                                         O_t += P_t V_j   (M128 N64 K128, P read from TMEM, V MN-major in smem)
 //   warps 0-3   softmax group for tile 0 (thread = query row = TMEM lane); warps 4-7 the same for tile 1
 //
 // A softmax thread pulls its whole score row (128 fp32) out of TMEM in one go and hands the S buffer
@@ -11,7 +11,10 @@
 // O accumulates in TMEM across key tiles.  The running maximum is applied lazily: the row keeps a stale
 // reference maximum and only when the true maximum has grown by more than 2^8 is O (and the running sum)
 // rescaled -- a TMEM load / multiply / store by the same thread, before it releases P for the next MMA.
-// Probabilities therefore stay <= 256, exactly representable ranges for bf16 and fp16.
+// Probabilities therefore stay <= 256, well inside the range of bf16 and fp16.  P never touches shared
+// memory: the softmax thread writes its packed 16-bit row back to TMEM (tcgen05.st) and the P V MMA takes
+// its A operand from there, which halves the shared-memory traffic of the kernel (the other resource that
+// would saturate next to the SFUs).
 // At head dim 64 the kernel is bound by the 16 ex2/clk/SM special-function rate, not by the tensor pipe.
 #pragma once
 #include <cuda/std/type_traits>
@@ -23,10 +26,9 @@ namespace mde {
 
 constexpr int kAtcThreads = 384;   // 2 softmax warpgroups + 1 warpgroup holding the TMA and MMA warps
 constexpr int kAtcQBytes = 128 * 64 * 2;          // one 128 x 64 16-bit tile
-constexpr int kAtcPBytes = 128 * 128 * 2;         // P tile: two K-major 128 x 64 sub-tiles
-constexpr int kAtcStages = 2;
-// smem: Q[2] | K[stages] | V[stages] | P[2] | barriers
-constexpr int kAtcSmemBytes = 1024 + 2 * kAtcQBytes + 2 * kAtcStages * kAtcQBytes + 2 * kAtcPBytes + 256;
+constexpr int kAtcStages = 3;
+// smem: Q[2] | K[stages] | V[stages] | barriers
+constexpr int kAtcSmemBytes = 1024 + 2 * kAtcQBytes + 2 * kAtcStages * kAtcQBytes + 256;
 constexpr float kAtcRescaleThreshold = 8.0f;      // log2 units
 
 // Operand tile with the N (or M) index contiguous: rows of 128 bytes are K indices, 8-row groups 1024 bytes apart.
@@ -49,8 +51,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * kAtcQBytes;
   uint8_t* sV = sK + kAtcStages * kAtcQBytes;
-  uint8_t* sP = sV + kAtcStages * kAtcQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAtcPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAtcStages * kAtcQBytes);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* k_full = bars + 1;             // [stages]
   uint64_t* k_empty = k_full + kAtcStages;
@@ -58,7 +59,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   uint64_t* v_empty = v_full + kAtcStages;
   uint64_t* s_full = v_empty + kAtcStages; // [2]  S_t ready in TMEM (tcgen05.commit)
   uint64_t* s_free = s_full + 2;           // [2]  S_t copied to registers (128 arrivals)
-  uint64_t* p_ready = s_free + 2;          // [2]  P_t in smem, O_t rescaled if needed (128 arrivals)
+  uint64_t* p_ready = s_free + 2;          // [2]  P_t in TMEM, O_t rescaled if needed (128 arrivals)
   uint64_t* o_full = p_ready + 2;          // [2]  O_t += P_t V_j complete (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
@@ -77,7 +78,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128); mbar_init(&p_ready[t], 128); mbar_init(&o_full[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128); mbar_init(&p_ready[t], 128);
+      mbar_init(&o_full[t], 1);
     }
     fence_mbar_init();
   }
@@ -89,7 +91,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)
+  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)  P0 [384,448)  P1 [448,512)
 
   // Register re-partition (per warpgroup): the two single-thread roles need almost nothing, a softmax
   // thread holds a 128-wide score row.  384 threads start at 168 registers each.
@@ -146,14 +148,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         for (int t = 0; t < ntq; ++t) {
           mbar_wait(&p_ready[t], j & 1);           // P_t(j) in smem, O_t rescaled
           tc_fence_after();
-          const uint32_t pa = smem_u32(sP + t * kAtcPBytes);
           const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            // 16 keys per step: P sub-tile k/4 (+32 bytes inside it), V advances two 8-row groups (2048 bytes)
-            const uint64_t a = umma_desc_k_sw128(pa + (k >> 2) * kAtcQBytes) + 2 * (k & 3);
-            tc_mma_f16(tmem_base + 256 + t * 64, a, vb + 128 * k, idesc_o, (j | k) != 0);
-          }
+          for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed P columns, two 8-row groups of V (2048 bytes)
+            tc_mma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
           tc_commit(&o_full[t]);
         }
         tc_commit(&v_empty[st]);
@@ -170,11 +168,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
       const uint32_t s_addr = tmem_base + lane_base + t * 128;
       const uint32_t o_addr = tmem_base + lane_base + 256 + t * 64;
-      uint8_t* prow = sP + t * kAtcPBytes + r * 128;
+      const uint32_t p_addr = tmem_base + lane_base + 384 + t * 64;
       float m_ref = -INFINITY;      // (possibly stale) maximum the probabilities are taken against
       float l_run = 0.f;
       const float sl = p.scale_log2;
 
+      const bool pingpong = ntq == 2;
+      if (pingpong && t == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");     // group 0 goes first
       auto tile = [&](auto full_tag, int j) {
         constexpr bool kFull = decltype(full_tag)::value;
         const int nvalid = kFull ? 128 : p.ntok - j * 128;
@@ -194,8 +194,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         // ---- lazy rescale: only when the maximum grew by more than 2^8 (always on the first tile)
         const bool grow = (mx - m_ref) * sl > kAtcRescaleThreshold;
-        // The previous P V product must have landed before P_t is overwritten (and before O_t is touched).
-        // Waiting here every tile also keeps this thread in step with the barrier's phase parity.
+        // ---- P = exp2(S * sl - m_ref * sl), packed to 16 bits in registers (the score registers die as we go)
+        // The two groups take turns on this SFU-bound section (named barriers 1 and 2: 128 arrivals from
+        // the group that just finished + the 128 waiters whose turn it is).
+        if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        const float msl_new = (grow ? mx : m_ref) * sl;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[2][32];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch][i]), sl, -msl_new));
+            float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch][i + 1]), sl, -msl_new));
+            if (!kFull) {
+              if (ch * 32 + i >= nvalid) p0 = 0.f;
+              if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
+            }
+            rs4[(i >> 1) & 3] += p0 + p1;
+            pk[ch >> 1][(ch & 1) * 16 + (i >> 1)] = Tr::pack2(p0, p1);
+          }
+        }
+        if (pingpong && !(t == 1 && j == nkv - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");
+        // ---- the previous product has read P_t (and, for a rescale, written O_t): only now may either change
         if (j > 0) {
           mbar_wait(&o_full[t], (j - 1) & 1);
           tc_fence_after();
@@ -213,37 +234,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
               tmem_st_32x32b_x32(o_addr + h * 32, o);
             }
-            tmem_st_wait();
           }
         }
-        // ---- P = exp2(S * sl - m_ref * sl) -> 16-bit -> smem (K-major, 128-byte swizzle)
-        const float msl = m_ref * sl;
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint8_t* sub = prow + (ch >> 1) * kAtcQBytes;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {            // 8 keys -> one 16-byte chunk of the P row
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = c * 8 + e * 2;
-              float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch][i]), sl, -msl));
-              float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch][i + 1]), sl, -msl));
-              if (!kFull) {
-                if (ch * 32 + i >= nvalid) p0 = 0.f;
-                if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
-              }
-              rs4[e] += p0 + p1;
-              pk[e] = Tr::pack2(p0, p1);
-            }
-            const int chunk = (ch & 1) * 4 + c;
-            *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
+        tmem_st_32x32b_x32(p_addr, pk[0]);
+        tmem_st_32x32b_x32(p_addr + 32, pk[1]);
+        tmem_st_wait();
         l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
-        tc_fence_before();            // TMEM stores of the rescale are ordered before the next MMA
-        fence_proxy_async_smem();     // P_t visible to the tensor core's async proxy
+        tc_fence_before();            // TMEM stores (P, rescaled O) are ordered before the MMA that reads them
         mbar_arrive(&p_ready[t]);
       };
 
