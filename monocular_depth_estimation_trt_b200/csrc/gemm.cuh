@@ -3,9 +3,10 @@
 //   D[M,N] = A[M,K] * B[N,K]^T      A, B 16-bit (fp16 or bf16) K-major, fp32 accumulation in TMEM.
 //
 // One CTA per SM loops over 128 x BLOCK_N output tiles.  Roles: warp 0 = TMA producer, warp 1 = MMA
-// issuer (one thread), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> fused
-// epilogue -> global).  Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of
-// tile i+1.  Operand tiles are 128-byte-swizzled K-major boxes of 64 elements written by TMA.
+// issuer (one thread), warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM -> registers -> fused
+// epilogue -> global; two warps per TMEM lane quarter, each taking half of the tile's columns).  Two
+// accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1; setmaxnreg moves
+// the registers of the three single-thread roles to the epilogue warps.  Operand tiles are 128-byte-swizzled K-major boxes of 64 elements written by TMA.
 //
 // Conv mode: A is an NHWC activation addressed through a 4-D tensor map {C, W, H, B}; k-block kb maps
 // to filter tap (kb / cin_blocks) and channel block (kb % cin_blocks); the box {64, tile_w, tile_h, 1}
@@ -58,12 +59,13 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = 4 * 32 * 32 * 4 + 4 * 32 * 8;   // staging chunks + row offsets
-  static constexpr int kMaxStages = (226 * 1024 - 2048 - kEpiBytes) / kStageBytes;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiBytes = kEpiWarps * (32 * 32 * 4 + 32 * 4);   // per warp: 32x32 fp32 staging chunk + 32 row indices
+  static constexpr int kMaxStages = (227 * 1024 - 1024 - 256 - kEpiBytes) / kStageBytes;   // 227 KB per CTA
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
-  static constexpr int kThreads = 256;
+  static constexpr int kThreads = 384;
 };
 
 // GELU(v) = v * Phi(v) with the exact-erf Phi, evaluated through Abramowitz & Stegun 7.1.26
@@ -85,7 +87,7 @@ __device__ __forceinline__ float gelu_erf(float v) {
 }
 
 template <int BLOCK_N, typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -102,7 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes + 256;   // 4 x (32x32 fp32) staging + 4 x 32 row offsets
+  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes + 256;   // per epilogue warp: staging chunk, then row indices
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,7 +121,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], Cfg::kEpiWarps);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -134,6 +136,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     // ===================================================== TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       const uint32_t a_bytes = p.conv ? static_cast<uint32_t>(p.tile_w * p.tile_h * 128) : Cfg::kABytes;
       int stage = 0;
@@ -167,6 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(Tr::kFmt, 128, BLOCK_N);
       int stage = 0;
@@ -194,17 +198,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // TMEM allocator warp and the spare one
+  } else {
     // ===================================================== epilogue
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // Phase 1 (thread = row, as tcgen05.ld 32x32b delivers it): a raw 32 x 32 fp32 chunk goes to this
     // warp's swizzled staging buffer; the TMEM load of the next chunk is already in flight.
     // Phase 2 (lanes = columns): bias / activation / LayerScale / residuals and all global traffic run
     // over whole row segments, so every 32-byte sector that is touched is touched completely, per-column
     // parameters live in one register per lane, and all loads of a chunk are issued before its stores.
-    const int ew = warp - 4;                 // == warp % 4: TMEM lane quarter this warp may read
-    const int r = ew * 32 + lane;            // row inside the 128-row tile
+    const int ew = warp - 4;                 // 0..7
+    const int quarter = ew & 3;              // == warp % 4: the TMEM lane quarter this warp may read
+    const int half = ew >> 2;                // which half of the tile's column chunks this warp takes
+    const int r = quarter * 32 + lane;       // row inside the 128-row tile
     float* stage_f = reinterpret_cast<float*>(epi_smem) + ew * (32 * 32);
-    long long* row_off = reinterpret_cast<long long*>(epi_smem + 4 * 32 * 32 * 4) + ew * 32;
+    int* row_off = reinterpret_cast<int*>(epi_smem + Cfg::kEpiWarps * 32 * 32 * 4) + ew * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     T* out = static_cast<T*>(p.out);
@@ -241,7 +250,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
       __syncwarp();                          // previous tile's phase 2 is done with row_off
-      row_off[lane] = valid ? orow : -1;
+      row_off[lane] = valid ? static_cast<int>(orow) : -1;   // output rows fit 31 bits (checked on the host)
       // The residual stream tile this epilogue will read-modify-write: pull it into L2 while the MMAs of
       // the tile are still running (the row is contiguous: BLOCK_N fp32 = BLOCK_N / 32 lines).
       if (p.x && p.accumulate_x && valid) {
@@ -253,14 +262,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       const int n_tile = n_blk * BLOCK_N;
       const int chunks = min(BLOCK_N, p.N - n_tile + 31) / 32;   // warp-uniform; N is a multiple of 8
+      const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2;
+      const int ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
 
       uint32_t raw[32];
-      tmem_ld_32x32b_x32(t_base, raw);
+      if (ch_begin < ch_end) tmem_ld_32x32b_x32(t_base + ch_begin * 32, raw);
 #pragma unroll 1
-      for (int ch = 0; ch < chunks; ++ch) {
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int n_base = n_tile + ch * 32;
         tmem_ld_wait();
         if (p.head_w != nullptr) {
@@ -280,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<uint4*>(stage_f + lane * 32 + ((g ^ (lane & 7)) << 2)) =
               make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
-        if (ch + 1 < chunks) tmem_ld_32x32b_x32(t_base + (ch + 1) * 32, raw);   // in flight during phase 2
+        if (ch + 1 < ch_end) tmem_ld_32x32b_x32(t_base + (ch + 1) * 32, raw);   // in flight during phase 2
         __syncwarp();
         // ---- phase 2a: fp32 residual stream, 8 lanes x float4 per row, 4 rows per pass
         if (p.x) {
@@ -294,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float4 xin[8];
 #pragma unroll
             for (int pass = 0; pass < 8; ++pass) {
-              ro[pass] = row_off[pass * 4 + (lane >> 3)];
+              ro[pass] = static_cast<long long>(row_off[pass * 4 + (lane >> 3)]);
               xin[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (ro[pass] >= 0) {
                 if (p.accumulate_x) xin[pass] = *reinterpret_cast<const float4*>(p.x + ro[pass] * p.ld_out + n);
@@ -346,7 +357,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint4 ra[4], rb[4];
 #pragma unroll
             for (int pass = 0; pass < 4; ++pass) {
-              const long long ro = row_off[pass * 8 + (lane >> 2)];
+              const long long ro = static_cast<long long>(row_off[pass * 8 + (lane >> 2)]);
               off[pass] = ro < 0 ? -1 : (ro + sub) * p.ld_out + col;
               ra[pass] = make_uint4(0u, 0u, 0u, 0u);
               rb[pass] = make_uint4(0u, 0u, 0u, 0u);

@@ -86,8 +86,7 @@ static int pick_block_n(int n) {
   return best;
 }
 
-static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_out_unused) {
-  (void)rows_out_unused;
+static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_out) {
   p.row_map = ROW_IDENTITY;
   p.tokens = 0; p.shuffle_s = 0; p.shuffle_cout = 0;
   p.act = ep->act;
@@ -99,6 +98,7 @@ static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_o
   p.head_scale = ep->head_scale > 0.f ? ep->head_scale : -1.f;
   p.head_out = ep->d_head_out;
   if (ep->ld_out % 8 != 0 && !ep->d_head_w) return fail(MDE_ERR_INVALID, "ld_out must be a multiple of 8");
+  if (rows_out > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "more than 2^31 output rows");
   if (ep->act < 0 || ep->act > 2) return fail(MDE_ERR_INVALID, "unknown activation %d", ep->act);
   return MDE_OK;
 }
@@ -112,7 +112,7 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
     return fail(MDE_ERR_INVALID, "gemm: operands must be 16-byte aligned");
   memset(&op->p, 0, sizeof(op->p));
   GemmParams& p = op->p;
-  MDE_TRY(fill_epilogue(p, ep, m));
+  MDE_TRY(fill_epilogue(p, ep, ep->shuffle_s > 0 ? m * ep->shuffle_s * ep->shuffle_s : (ep->tokens > 0 ? m + m / ep->tokens : m)));
   p.M = static_cast<int>(m); p.N = n; p.K = k;
   if (m > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "gemm: m too large");
   p.num_k_blocks = (k + 63) / 64;
@@ -158,7 +158,7 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
   if (ep->tokens > 0 || ep->shuffle_s > 0) return fail(MDE_ERR_INVALID, "conv: row remaps are GEMM-only");
   memset(&op->p, 0, sizeof(op->p));
   GemmParams& p = op->p;
-  MDE_TRY(fill_epilogue(p, ep, 0));
+  MDE_TRY(fill_epilogue(p, ep, static_cast<long long>(batch) * h * w));
   const int cin_pad = (cin + 63) / 64 * 64;
   p.M = batch * h * w; p.N = cout; p.K = 9 * cin_pad;
   p.num_k_blocks = 9 * (cin_pad / 64);
@@ -210,7 +210,7 @@ static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  kern<<<op.grid, 256, GemmCfg<BN>::kSmemBytes, s>>>(op.map_a, op.map_b, op.p);
+  kern<<<op.grid, GemmCfg<BN>::kThreads, GemmCfg<BN>::kSmemBytes, s>>>(op.map_a, op.map_b, op.p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
