@@ -102,6 +102,22 @@ def synthetic_batch(batch: int, rank: int):
                      for i in range(batch)])
 
 
+def max_over_ranks(value: float, world: int, device="cuda") -> float:
+    """Max of a per-rank scalar (the timing rule: a multi-GPU number is the slowest rank's)."""
+    if world == 1:
+        return value
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_rate(world: int, batch: int, steps: int, ms_total: float) -> float:
+    """Whole-job images/s: every rank processed `batch` images per step (weak scaling), in the slowest rank's time."""
+    return world * batch * steps / (ms_total / 1000.0)
+
+
 def oracle_setup(encoder: str):
     import torch
     from oracle import dav2_torch as O, preprocess_np as P
@@ -183,13 +199,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(v: float) -> float:
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---------------- device-resident arm
     d_in = torch.from_numpy(frames).cuda()
     d_out = torch.empty(B, 518, 518, dtype=torch.float32, device="cuda")
@@ -208,9 +217,9 @@ def run_ours(args):
         ctx.execute_async_v3(stream)
     ev1.record()
     barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1), world)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms_total / 1000.0)
+    value = aggregate_rate(world, B, args.steps, ms_total)
 
     # ---------------- per-launch timing of one step (events between launches) -> roofline of the dominant kernel
     ops = ctx.execute_timed(stream)
@@ -248,9 +257,9 @@ def run_ours(args):
         res = common.do_inference(ctx, engine=eng, bindings=bindings, inputs=inputs, outputs=outputs, stream=cstream)
     common.cuda_call(cudart.cudaEventRecord(e1, cstream))
     common.cuda_call(cudart.cudaEventSynchronize(e1))
-    e2e_ms = max_over_ranks(float(common.cuda_call(cudart.cudaEventElapsedTime(e0, e1))))
+    e2e_ms = max_over_ranks(float(common.cuda_call(cudart.cudaEventElapsedTime(e0, e1))), world)
     checksum = float(np.asarray(res[0][:518 * 518], dtype=np.float64).mean())      # the step's result was read on the host
-    e2e = {"value": world * B * args.steps / (e2e_ms / 1000.0), "unit": UNIT,
+    e2e = {"value": aggregate_rate(world, B, args.steps, e2e_ms), "unit": UNIT,
            "h2d_bytes_per_step": int(inputs[0].nbytes), "d2h_bytes_per_step": int(outputs[0].nbytes),
            "ms_per_step": e2e_ms / args.steps, "mean_depth_image0": checksum}
     h2d, d2h = inputs[0].nbytes, outputs[0].nbytes

@@ -1,0 +1,94 @@
+"""Pins oracle/preprocess_np.py (the CPU restatement of core/preprocess.py's stretch + ImageNet
+pipeline) against: the committed golden vectors made by the REFERENCE module itself
+(oracle/make_golden.py), the cv2 build in this image, and -- where /root/reference exists -- the
+reference module imported live."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import preprocess_np as P
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "preprocess_golden.npz")
+SOURCES = [(480, 640), (720, 1280), (500, 500), (1036, 1036), (300, 777)]
+
+
+def synthetic(seed, h, w):
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def test_against_reference_golden_vectors():
+    g = np.load(GOLDEN)
+    n_full = n_sha = 0
+    for i, (h, w) in enumerate(SOURCES):
+        img = synthetic(i, h, w)
+        for th, tw in [(70, 84), (56, 56)]:
+            ref = g[f"full_seed{i}_{h}x{w}_to_{th}x{tw}"]
+            got = P.preprocess_stretch_imagenet(img, th, tw)
+            assert got.dtype == np.float32 and got.shape == ref.shape
+            assert np.array_equal(got, ref)                      # byte-exact, not close
+            n_full += 1
+        got = P.preprocess_stretch_imagenet(img, 518, 518)
+        sha = hashlib.sha256(np.ascontiguousarray(got).tobytes()).digest()
+        assert sha == g[f"sha_seed{i}_{h}x{w}_to_518x518"].tobytes()
+        n_sha += 1
+    assert n_full == 10 and n_sha == 5
+
+
+@pytest.mark.parametrize("src", [(480, 640), (2268, 3024), (1036, 1036), (259, 259), (37, 41), (1, 1), (2, 3),
+                                 (1000, 333), (519, 517), (1035, 1037), (518, 518)])
+@pytest.mark.parametrize("dst", [(518, 518), (616, 1064), (384, 384), (14, 14)])
+def test_resize_restatement_bit_exact_vs_cv2(src, dst):
+    cv2 = pytest.importorskip("cv2")
+    img = synthetic(7, *src)
+    assert np.array_equal(cv2.resize(img, (dst[1], dst[0]), interpolation=cv2.INTER_LINEAR),
+                          P.resize_linear_u8(img, *dst))
+
+
+def test_exact_2x_downscale_uses_area_rule():
+    """cv2 silently switches INTER_LINEAR to the INTER_AREA fast path at exactly 2x (edge case of a-1)."""
+    cv2 = pytest.importorskip("cv2")
+    img = synthetic(3, 1036, 1036)
+    out = P.resize_linear_u8(img, 518, 518)
+    assert np.array_equal(out, cv2.resize(img, (518, 518), interpolation=cv2.INTER_LINEAR))
+    a = img.astype(np.int64)
+    assert np.array_equal(out, ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8))
+
+
+def test_lut_is_the_whole_float_stage():
+    lut = P.norm_lut()
+    assert lut.shape == (3, 256) and lut.dtype == np.float32
+    img = synthetic(0, 480, 640)
+    small = P.resize_linear_u8(np.ascontiguousarray(img[:, :, ::-1]), 518, 518)
+    via_lut = np.stack([lut[c][small[:, :, c]] for c in range(3)])[None]
+    assert np.array_equal(via_lut, P.preprocess_stretch_imagenet(img, 518, 518))
+
+
+def test_im2col_layout_is_conv_layout():
+    torch = pytest.importorskip("torch")
+    x = np.random.default_rng(0).standard_normal((2, 3, 28, 42)).astype(np.float32)
+    w = np.random.default_rng(1).standard_normal((5, 3, 14, 14)).astype(np.float32)
+    cols = P.im2col(x, 14, 640)
+    assert cols.shape == (2 * 2 * 3, 640) and np.all(cols[:, 588:] == 0)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), stride=14).flatten(2).transpose(1, 2).reshape(-1, 5)
+    got = cols[:, :588] @ w.reshape(5, -1).T
+    assert np.allclose(got, ref.numpy(), atol=1e-3)
+    # row = (b, gy, gx), column = c*196 + ky*14 + kx
+    assert cols[1 * 6 + 1 * 3 + 2, 2 * 196 + 5 * 14 + 7] == x[1, 2, 14 + 5, 28 + 7]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/core"), reason="reference checkout not present on this box")
+@pytest.mark.parametrize("model", ["depth_anything_v2", "depth_anything_v3", "distill_any_depth"])
+def test_against_live_reference_module(model):
+    sys.path.insert(0, "/root/reference")
+    try:
+        from core import preprocess as ref
+    finally:
+        sys.path.remove("/root/reference")
+    for i, (h, w) in enumerate(SOURCES[:3]):
+        img = synthetic(i, h, w)
+        r, geom = ref.preprocess_for(img, model, (518, 518))
+        assert np.array_equal(r, P.preprocess_stretch_imagenet(img, 518, 518))
+        assert (geom.src_h, geom.src_w, geom.dst_h, geom.dst_w) == (h, w, 518, 518)

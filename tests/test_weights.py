@@ -1,0 +1,54 @@
+"""The export artefact (.mdew) and the pos-embed rule (host side of `run.py export` / `build`)."""
+import numpy as np
+import pytest
+import torch
+
+from monocular_depth_estimation_trt_b200 import engine as E, weights as W
+from oracle import dav2_torch as O
+
+
+def test_mdew_roundtrip_and_native_loader(tmp_path, lib):
+    sd = O.init_state_dict("vits", seed=3)
+    meta = W.describe("vits", 518, 518, 20.0)
+    path = str(tmp_path / "m.mdew")
+    sha = W.save(path, sd, meta)
+    assert sha == W.file_sha256(path)
+    back, meta2 = W.load(path)
+    assert meta2 == meta and set(back) == set(sd)
+    for k in sd:
+        assert np.array_equal(back[k], sd[k].numpy())
+    assert W.read_meta(path)["encoder"] == "vits"
+    eng = E.Engine(E.make_desc(meta), meta)
+    eng.load_weights_file(path)               # the C loader parses the same file (host only; no GPU needed)
+    eng.close()
+    bad = tmp_path / "bad.mdew"
+    bad.write_bytes(b"NOTMDEW0" + b"\0" * 64)
+    eng = E.Engine(E.make_desc(meta), meta)
+    with pytest.raises(RuntimeError, match="MDEW0001"):
+        eng.load_weights_file(str(bad))
+    with pytest.raises(RuntimeError):
+        eng.load_weights_file(str(tmp_path / "missing.mdew"))
+    trunc = tmp_path / "trunc.mdew"
+    trunc.write_bytes(open(path, "rb").read()[:4000])
+    with pytest.raises(RuntimeError):
+        eng.load_weights_file(str(trunc))
+    eng.close()
+
+
+def test_describe_validates():
+    with pytest.raises(KeyError):
+        W.describe("vitg")
+    with pytest.raises(ValueError):
+        W.describe("vits", 520, 518)
+    m = W.describe("vitl", 616, 1064, None)
+    assert m["embed_dim"] == 1024 and m["taps"] == [4, 11, 17, 23] and m["max_depth"] is None
+
+
+def test_pos_embed_rule_matches_oracle():
+    pe = torch.randn(1, 1370, 64)
+    assert np.array_equal(W.resize_pos_embed(pe.numpy(), 37, 37), pe.numpy())          # trained grid: identity
+    for gh, gw in [(44, 76), (20, 30), (37, 50)]:
+        got = W.resize_pos_embed(pe.numpy(), gh, gw)
+        ref = O.interpolate_pos_embed(pe, gh, gw).numpy()
+        assert got.shape == (1, 1 + gh * gw, 64) and np.allclose(got, ref, atol=1e-6)
+        assert np.array_equal(got[:, 0], pe[:, 0].numpy())                              # cls part untouched
