@@ -1,10 +1,12 @@
 // Fused softmax(Q K^T * scale) V on tcgen05 tensor cores with TMEM accumulators, head dim 64.
 //
-// One CTA = 256 query rows (two 128-row tiles) of one (image, head); it walks the keys in tiles of 128.
-//   warp 8      TMA producer: Q tiles once, then K and V tiles through a 2-stage ring
-//   warp 9      MMA issuer (one thread):  S_t = Q_t K_j^T  (M128 N128 K64, both operands K-major in smem)
-//                                         O_t += P_t V_j   (M128 N64 K128, P read from TMEM, V MN-major in smem)
-//   warps 0-3   softmax group for tile 0 (thread = query row = TMEM lane); warps 4-7 the same for tile 1
+// One CTA = 128 query rows of one (image, head); it walks the keys in tiles of 128.  Two CTAs are resident per
+// SM (256 TMEM columns, ~113 KB of shared memory and 256 threads each), so one CTA's exponentials overlap the
+// other's TMEM traffic, MMAs and prologue without any explicit hand-shake between them.
+//   warps 0-3   softmax group (thread = query row = TMEM lane)
+//   warp 4      TMA producer: the Q tile once, then K and V tiles through a 3-stage ring
+//   warp 5      MMA issuer (one thread):  S = Q K_j^T   (M128 N128 K64, both operands K-major in smem)
+//                                         O += P V_j    (M128 N64 K128, P read from TMEM, V MN-major in smem)
 //
 // A softmax thread pulls its whole score row (128 fp32) out of TMEM in one go and hands the S buffer
 // straight back, so the tensor core computes S of the next key tile while this one is exponentiated.
@@ -24,11 +26,12 @@
 
 namespace mde {
 
-constexpr int kAtcThreads = 384;   // 2 softmax warpgroups + 1 warpgroup holding the TMA and MMA warps
+constexpr int kAtcThreads = 256;   // softmax warpgroup + a warpgroup holding the TMA and MMA warps
 constexpr int kAtcQBytes = 128 * 64 * 2;          // one 128 x 64 16-bit tile
 constexpr int kAtcStages = 3;
-// smem: Q[2] | K[stages] | V[stages] | barriers
-constexpr int kAtcSmemBytes = 1024 + 2 * kAtcQBytes + 2 * kAtcStages * kAtcQBytes + 256;
+constexpr int kAtcTmemCols = 256;  // S [0,128)  O [128,192)  P [192,256)
+// smem: Q | K[stages] | V[stages] | barriers     (two CTAs per SM)
+constexpr int kAtcSmemBytes = kAtcQBytes + 2 * kAtcStages * kAtcQBytes + 256;   // 114 944 B: two fit in 228 KB
 constexpr float kAtcRescaleThreshold = 8.0f;      // log2 units
 
 // Operand tile with the N (or M) index contiguous: rows of 128 bytes are K indices, 8-row groups 1024 bytes apart.
@@ -43,13 +46,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kAtcThreads, 1)
+__global__ void __launch_bounds__(kAtcThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
   using Tr = F16Traits<T>;
-  extern __shared__ uint8_t atc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 2 * kAtcQBytes;
+  extern __shared__ __align__(1024) uint8_t atc_smem[];   // 128-byte-swizzled operand tiles need 1024-byte alignment
+  if ((smem_u32(atc_smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = atc_smem;
+  uint8_t* sK = sQ + kAtcQBytes;
   uint8_t* sV = sK + kAtcStages * kAtcQBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAtcStages * kAtcQBytes);
   uint64_t* q_full = bars;                 // [1]
@@ -57,50 +60,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   uint64_t* k_empty = k_full + kAtcStages;
   uint64_t* v_full = k_empty + kAtcStages;
   uint64_t* v_empty = v_full + kAtcStages;
-  uint64_t* s_full = v_empty + kAtcStages; // [2]  S_t ready in TMEM (tcgen05.commit)
-  uint64_t* s_free = s_full + 2;           // [2]  S_t copied to registers (128 arrivals)
-  uint64_t* p_ready = s_free + 2;          // [2]  P_t in TMEM, O_t rescaled if needed (128 arrivals)
-  uint64_t* o_full = p_ready + 2;          // [2]  O_t += P_t V_j complete (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = v_empty + kAtcStages; // S ready in TMEM (tcgen05.commit)
+  uint64_t* s_free = s_full + 1;           // S copied to registers (128 arrivals)
+  uint64_t* p_ready = s_free + 1;          // P in TMEM, O rescaled if needed (128 arrivals)
+  uint64_t* o_full = p_ready + 1;          // O += P V_j complete (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, img = blockIdx.z;
-  const int q0 = blockIdx.x * 256;
-  const int ntq = (q0 + 128 < p.ntok) ? 2 : 1;                    // query tiles with at least one valid row
+  const int q0 = blockIdx.x * 128;
   const int nkv = (p.ntok + 127) / 128;
   const int row_base = img * p.ntok;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     prefetch_tmap(&map_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < kAtcStages; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 128); mbar_init(&p_ready[t], 128);
-      mbar_init(&o_full[t], 1);
-    }
+    mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_ready, 128); mbar_init(o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, 512);
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, kAtcTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)  P0 [384,448)  P1 [448,512)
 
-  // Register re-partition (per warpgroup): the two single-thread roles need almost nothing, a softmax
-  // thread holds a 128-wide score row.  384 threads start at 168 registers each.
-  if (warp == 8) {
+  // Register re-partition per warpgroup: the single-thread roles need almost nothing, a softmax thread
+  // holds a 128-wide score row.  2 CTAs x 256 threads start at 128 registers each.
+  if (warp == 4) {
     // ===================================================== TMA producer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, ntq * kAtcQBytes);
-      for (int t = 0; t < ntq; ++t) tma_load_2d(sQ + t * kAtcQBytes, &map_qkv, q_full, head * 64, row_base + q0 + t * 128);
+      mbar_arrive_expect_tx(q_full, kAtcQBytes);
+      tma_load_2d(sQ, &map_qkv, q_full, head * 64, row_base + q0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kAtcStages;
         const uint32_t ph = (j / kAtcStages) & 1;
@@ -112,165 +110,150 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         tma_load_2d(sV + st * kAtcQBytes, &map_qkv, &v_full[st], 2 * p.D + head * 64, row_base + j * 128);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 5) {
     // ===================================================== MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(Tr::kFmt, 128, 128);
       constexpr uint32_t idesc_o = umma_idesc_f16(Tr::kFmt, 128, 64) | (1u << 16);   // B (= V) is MN-major
-      auto issue_s = [&](int t, int st) {
-        const uint64_t a = umma_desc_k_sw128(smem_u32(sQ + t * kAtcQBytes));
+      auto issue_s = [&](int st) {
+        const uint64_t a = umma_desc_k_sw128(smem_u32(sQ));
         const uint64_t b = umma_desc_k_sw128(smem_u32(sK + st * kAtcQBytes));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + t * 128, a + 2 * k, b + 2 * k, idesc_s, k != 0);
-        tc_commit(&s_full[t]);
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base, a + 2 * k, b + 2 * k, idesc_s, k != 0);
+        tc_commit(s_full);
+        tc_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      for (int t = 0; t < ntq; ++t) issue_s(t, 0);
-      tc_commit(&k_empty[0]);
+      issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kAtcStages;
-        const uint32_t ph = (j / kAtcStages) & 1;
         if (j + 1 < nkv) {
           // S of the next key tile as soon as the softmax threads hold the current scores in registers
           const int st1 = (j + 1) % kAtcStages;
           mbar_wait(&k_full[st1], ((j + 1) / kAtcStages) & 1);
-          for (int t = 0; t < ntq; ++t) {
-            mbar_wait(&s_free[t], j & 1);
-            tc_fence_after();
-            issue_s(t, st1);
-          }
-          tc_commit(&k_empty[st1]);
-        }
-        mbar_wait(&v_full[st], ph);
-        for (int t = 0; t < ntq; ++t) {
-          mbar_wait(&p_ready[t], j & 1);           // P_t(j) in smem, O_t rescaled
+          mbar_wait(s_free, j & 1);
           tc_fence_after();
-          const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed P columns, two 8-row groups of V (2048 bytes)
-            tc_mma_f16_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
-          tc_commit(&o_full[t]);
+          issue_s(st1);
         }
+        mbar_wait(&v_full[st], (j / kAtcStages) & 1);
+        mbar_wait(p_ready, j & 1);                 // P(j) in TMEM, O rescaled
+        tc_fence_after();
+        const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed P columns, two 8-row groups of V (2048 bytes)
+          tc_mma_f16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
+        tc_commit(o_full);
         tc_commit(&v_empty[st]);
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp >= 6) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // idle half of the producer warpgroup
   } else {
-    // ===================================================== softmax groups (thread = query row)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int t = warp >> 2;
-    if (t < ntq) {
-      const int r = (warp & 3) * 32 + lane;
-      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t s_addr = tmem_base + lane_base + t * 128;
-      const uint32_t o_addr = tmem_base + lane_base + 256 + t * 64;
-      const uint32_t p_addr = tmem_base + lane_base + 384 + t * 64;
-      float m_ref = -INFINITY;      // (possibly stale) maximum the probabilities are taken against
-      float l_run = 0.f;
-      const float sl = p.scale_log2;
+    // ===================================================== softmax group (thread = query row)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int r = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base;
+    const uint32_t o_addr = tmem_base + lane_base + 128;
+    const uint32_t p_addr = tmem_base + lane_base + 192;
+    float m_ref = -INFINITY;      // (possibly stale) maximum the probabilities are taken against
+    float l_run = 0.f;
+    const float sl = p.scale_log2;
 
-      const bool pingpong = ntq == 2;
-      if (pingpong && t == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");     // group 0 goes first
-      auto tile = [&](auto full_tag, int j) {
-        constexpr bool kFull = decltype(full_tag)::value;
-        const int nvalid = kFull ? 128 : p.ntok - j * 128;
-        uint32_t raw[4][32];
+    auto tile = [&](auto full_tag, int j) {
+      constexpr bool kFull = decltype(full_tag)::value;
+      const int nvalid = kFull ? 128 : p.ntok - j * 128;
+      uint32_t raw[4][32];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32b_x32(s_addr + ch * 32, raw[ch]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_free[t]);                   // the tensor core may overwrite S_t now
-        // ---- row maximum, four independent chains
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32b_x32(s_addr + ch * 32, raw[ch]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                       // the tensor core may overwrite S now
+      // ---- row maximum, four independent chains
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
+      for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kFull || ch * 32 + i < nvalid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));
-        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        // ---- lazy rescale: only when the maximum grew by more than 2^8 (always on the first tile)
-        const bool grow = (mx - m_ref) * sl > kAtcRescaleThreshold;
-        // ---- P = exp2(S * sl - m_ref * sl), packed to 16 bits in registers (the score registers die as we go)
-        // The two groups take turns on this SFU-bound section (named barriers 1 and 2: 128 arrivals from
-        // the group that just finished + the 128 waiters whose turn it is).
-        if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-        const float msl_new = (grow ? mx : m_ref) * sl;
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[2][32];
+        for (int i = 0; i < 32; ++i)
+          if (kFull || ch * 32 + i < nvalid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      // ---- lazy rescale: only when the maximum grew by more than 2^8 (always on the first tile)
+      const bool grow = (mx - m_ref) * sl > kAtcRescaleThreshold;
+      // ---- P = exp2(S * sl - m * sl), packed to 16 bits in registers (the score registers die as we go)
+      const float msl_new = (grow ? mx : m_ref) * sl;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[2][32];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch][i]), sl, -msl_new));
-            float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch][i + 1]), sl, -msl_new));
-            if (!kFull) {
-              if (ch * 32 + i >= nvalid) p0 = 0.f;
-              if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
-            }
-            rs4[(i >> 1) & 3] += p0 + p1;
-            pk[ch >> 1][(ch & 1) * 16 + (i >> 1)] = Tr::pack2(p0, p1);
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch][i]), sl, -msl_new));
+          float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch][i + 1]), sl, -msl_new));
+          if (!kFull) {
+            if (ch * 32 + i >= nvalid) p0 = 0.f;
+            if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
           }
+          rs4[(i >> 1) & 3] += p0 + p1;
+          pk[ch >> 1][(ch & 1) * 16 + (i >> 1)] = Tr::pack2(p0, p1);
         }
-        if (pingpong && !(t == 1 && j == nkv - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");
-        // ---- the previous product has read P_t (and, for a rescale, written O_t): only now may either change
-        if (j > 0) {
-          mbar_wait(&o_full[t], (j - 1) & 1);
-          tc_fence_after();
-        }
-        if (__any_sync(0xffffffffu, grow)) {
-          const float factor = grow ? fast_exp2((m_ref - mx) * sl) : 1.0f;
-          if (grow) { m_ref = mx; l_run *= factor; }
-          if (j > 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t o[32];
-              tmem_ld_32x32b_x32(o_addr + h * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-              tmem_st_32x32b_x32(o_addr + h * 32, o);
-            }
-          }
-        }
-        tmem_st_32x32b_x32(p_addr, pk[0]);
-        tmem_st_32x32b_x32(p_addr + 32, pk[1]);
-        tmem_st_wait();
-        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
-        tc_fence_before();            // TMEM stores (P, rescaled O) are ordered before the MMA that reads them
-        mbar_arrive(&p_ready[t]);
-      };
-
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&s_full[t], j & 1);
-        tc_fence_after();
-        if (j * 128 + 128 <= p.ntok) tile(cuda::std::true_type{}, j);
-        else tile(cuda::std::false_type{}, j);
       }
-      // ---- normalise and store this row (128 contiguous bytes)
-      mbar_wait(&o_full[t], (nkv - 1) & 1);
-      tc_fence_after();
-      const float inv = 1.0f / l_run;
-      const int n = q0 + t * 128 + r;
-      T* gout = static_cast<T*>(p.out) + (static_cast<long long>(row_base) + n) * p.D + head * 64;
+      // ---- the previous product has read P (and, for a rescale, written O): only now may either change
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, grow)) {
+        const float factor = grow ? fast_exp2((m_ref - mx) * sl) : 1.0f;
+        if (grow) { m_ref = mx; l_run *= factor; }
+        if (j > 0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(o_addr + h * 32, o);
-        tmem_ld_wait();
-        if (n < p.ntok) {
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(o_addr + h * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 u;
-            u.x = Tr::pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-            u.y = Tr::pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-            u.z = Tr::pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-            u.w = Tr::pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(gout + h * 32 + c * 8) = u;
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st_32x32b_x32(o_addr + h * 32, o);
           }
+        }
+      }
+      tmem_st_32x32b_x32(p_addr, pk[0]);
+      tmem_st_32x32b_x32(p_addr + 32, pk[1]);
+      tmem_st_wait();
+      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      tc_fence_before();            // TMEM stores (P, rescaled O) are ordered before the MMA that reads them
+      mbar_arrive(p_ready);
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j * 128 + 128 <= p.ntok) tile(cuda::std::true_type{}, j);
+      else tile(cuda::std::false_type{}, j);
+    }
+    // ---- normalise and store this row (128 contiguous bytes)
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const int n = q0 + r;
+    T* gout = static_cast<T*>(p.out) + (static_cast<long long>(row_base) + n) * p.D + head * 64;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(o_addr + h * 32, o);
+      tmem_ld_wait();
+      if (n < p.ntok) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = Tr::pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+          u.y = Tr::pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+          u.z = Tr::pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+          u.w = Tr::pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(gout + h * 32 + c * 8) = u;
         }
       }
     }
@@ -278,9 +261,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, kAtcTmemCols);
   }
 }
 

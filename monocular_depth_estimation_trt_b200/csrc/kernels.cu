@@ -1,6 +1,7 @@
 // Kernel instantiations, launchers and the single-kernel C-ABI entry points (mde_k_*).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -274,12 +275,18 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   auto kern = attention_tc_kernel<T>;
   if (!attr_set) {
     MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("MDE_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAtcThreads, kAtcSmemBytes);
+      fprintf(stderr, "[MDET] attention_tc: %d CTAs/SM (smem %d B, %d threads)\n", nb, kAtcSmemBytes, kAtcThreads);
+    }
     attr_set = true;
   }
   AttnParams p;
   p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok + 255) / 256, op.heads, op.batch);
+  dim3 grid((op.ntok + 127) / 128, op.heads, op.batch);
   kern<<<grid, kAtcThreads, kAtcSmemBytes, s>>>(op.map_qkv, p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
