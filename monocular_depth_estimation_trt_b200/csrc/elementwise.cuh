@@ -224,27 +224,31 @@ struct BilinearParams {
   int B, Hi, Wi, Ho, Wo, C;
   float sy, sx;     // (Hi-1)/(Ho-1), (Wi-1)/(Wo-1)
 };
+// grid = (Ho, B): one output row per CTA, so the vertical taps and weight are CTA-uniform and the two source
+// rows (Wi*C*2 bytes each) stay in L1 while the row is produced; no 64-bit index arithmetic per element.
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const BilinearParams p) {
   using Tr = F16Traits<T>;
+  const int y = blockIdx.x, b = blockIdx.y;
   const int cv = p.C / 8;
-  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * cv;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv);
-    long long pix = i / cv;
-    const int x = static_cast<int>(pix % p.Wo); pix /= p.Wo;
-    const int y = static_cast<int>(pix % p.Ho);
-    const int b = static_cast<int>(pix / p.Ho);
-    const float fy = y * p.sy, fx = x * p.sx;
-    const int y0 = min(static_cast<int>(fy), p.Hi - 1), x0 = min(static_cast<int>(fx), p.Wi - 1);
-    const int y1 = min(y0 + 1, p.Hi - 1), x1 = min(x0 + 1, p.Wi - 1);
-    const float wy = fy - y0, wx = fx - x0;
-    const T* base = static_cast<const T*>(p.in) + static_cast<long long>(b) * p.Hi * p.Wi * p.C + c * 8;
-    const uint4 q00 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * p.Wi + x0) * p.C);
-    const uint4 q01 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * p.Wi + x1) * p.C);
-    const uint4 q10 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * p.Wi + x0) * p.C);
-    const uint4 q11 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * p.Wi + x1) * p.C);
+  const float fy = y * p.sy;
+  const int y0 = min(static_cast<int>(fy), p.Hi - 1);
+  const int y1 = min(y0 + 1, p.Hi - 1);
+  const float wy = fy - y0;
+  const T* row0 = static_cast<const T*>(p.in) + (static_cast<long long>(b) * p.Hi + y0) * p.Wi * p.C;
+  const T* row1 = static_cast<const T*>(p.in) + (static_cast<long long>(b) * p.Hi + y1) * p.Wi * p.C;
+  T* orow = static_cast<T*>(p.out) + (static_cast<long long>(b) * p.Ho + y) * p.Wo * p.C;
+  const int total = p.Wo * cv;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int x = i / cv, c = (i - x * cv) * 8;
+    const float fx = x * p.sx;
+    const int x0 = min(static_cast<int>(fx), p.Wi - 1);
+    const int x1 = min(x0 + 1, p.Wi - 1);
+    const float wx = fx - x0;
+    const uint4 q00 = *reinterpret_cast<const uint4*>(row0 + x0 * p.C + c);
+    const uint4 q01 = *reinterpret_cast<const uint4*>(row0 + x1 * p.C + c);
+    const uint4 q10 = *reinterpret_cast<const uint4*>(row1 + x0 * p.C + c);
+    const uint4 q11 = *reinterpret_cast<const uint4*>(row1 + x1 * p.C + c);
     const uint32_t* a = &q00.x; const uint32_t* bb = &q01.x; const uint32_t* cc = &q10.x; const uint32_t* d = &q11.x;
     uint4 r; uint32_t* ro = &r.x;
 #pragma unroll
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const BilinearParams
       const float bx0 = v10.x + wx * (v11.x - v10.x), bx1 = v10.y + wx * (v11.y - v10.y);
       ro[k] = Tr::pack2(tx0 + wy * (bx0 - tx0), tx1 + wy * (bx1 - tx1));
     }
-    *reinterpret_cast<uint4*>(static_cast<T*>(p.out) + ((static_cast<long long>(b) * p.Ho + y) * p.Wo + x) * p.C + c * 8) = r;
+    *reinterpret_cast<uint4*>(orow + static_cast<long long>(i) * 8) = r;
   }
 }
 

@@ -332,9 +332,10 @@ int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int
   p.in = d_in; p.out = d_out; p.B = batch; p.Hi = hi; p.Wi = wi; p.Ho = ho; p.Wo = wo; p.C = c;
   p.sy = ho > 1 ? static_cast<float>(hi - 1) / static_cast<float>(ho - 1) : 0.f;
   p.sx = wo > 1 ? static_cast<float>(wi - 1) / static_cast<float>(wo - 1) : 0.f;
-  const long long total = static_cast<long long>(batch) * ho * wo * (c / 8);
-  if (precision == MDE_BF16) bilinear_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(p);
-  else bilinear_nhwc_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(p);
+  if (batch > 65535) return fail(MDE_ERR_INVALID, "bilinear: batch exceeds grid limits");
+  dim3 grid(ho, batch);
+  if (precision == MDE_BF16) bilinear_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  else bilinear_nhwc_kernel<__half><<<grid, 256, 0, s>>>(p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
