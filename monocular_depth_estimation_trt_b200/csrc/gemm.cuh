@@ -273,6 +273,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll 1
       for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int n_base = n_tile + ch * 32;
+        // Per-lane column parameters of this chunk, requested before the TMEM wait so their latency hides
+        // behind it: lanes own 4 columns in the fp32 pass (2a) and 8 columns in the 16-bit pass (2b).
+        float4 bia_a = make_float4(0.f, 0.f, 0.f, 0.f), gam_a = make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 bia_b0 = bia_a, bia_b1 = bia_a, gam_b0 = gam_a, gam_b1 = gam_a;
+        if (p.head_w == nullptr) {
+          const int na = n_base + 4 * (lane & 7);
+          if (p.x && na < p.N) {
+            if (p.bias) bia_a = __ldg(reinterpret_cast<const float4*>(p.bias + na));
+            if (p.gamma) gam_a = __ldg(reinterpret_cast<const float4*>(p.gamma + na));
+          }
+          const int nb = n_base + 8 * (lane & 3);
+          if ((out || out_relu) && nb < p.N) {
+            const int pc = p.row_map == ROW_SHUFFLE ? nb % p.shuffle_cout : nb;
+            if (p.bias) {
+              bia_b0 = __ldg(reinterpret_cast<const float4*>(p.bias + pc));
+              bia_b1 = __ldg(reinterpret_cast<const float4*>(p.bias + pc + 4));
+            }
+            if (p.gamma) {
+              gam_b0 = __ldg(reinterpret_cast<const float4*>(p.gamma + pc));
+              gam_b1 = __ldg(reinterpret_cast<const float4*>(p.gamma + pc + 4));
+            }
+          }
+        }
         tmem_ld_wait();
         if (p.head_w != nullptr) {
           // fused depth head: 3x3 conv (+bias, ReLU) -> 1x1 conv 32->1 -> activation
@@ -298,9 +321,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int c4 = lane & 7;
           const int n = n_base + 4 * c4;
           if (n < p.N) {
-            float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), gam = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            if (p.gamma) gam = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
+            const float4 bia = bia_a, gam = gam_a;
             long long ro[8];
             float4 xin[8];
 #pragma unroll
@@ -341,18 +362,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               col = n % p.shuffle_cout;
               sub = static_cast<long long>(q / p.shuffle_s) * (p.W * p.shuffle_s) + (q % p.shuffle_s);
             }
-            float bia[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float gam[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              bia[0] = b0.x; bia[1] = b0.y; bia[2] = b0.z; bia[3] = b0.w; bia[4] = b1.x; bia[5] = b1.y; bia[6] = b1.z; bia[7] = b1.w;
-            }
-            if (p.gamma) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4));
-              gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
-            }
+            const float bia[8] = {bia_b0.x, bia_b0.y, bia_b0.z, bia_b0.w, bia_b1.x, bia_b1.y, bia_b1.z, bia_b1.w};
+            const float gam[8] = {gam_b0.x, gam_b0.y, gam_b0.z, gam_b0.w, gam_b1.x, gam_b1.y, gam_b1.z, gam_b1.w};
             long long off[4];
             uint4 ra[4], rb[4];
 #pragma unroll
@@ -375,18 +386,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
               const uint32_t* pa = &ra[pass].x;
               const uint32_t* pb = &rb[pass].x;
+              // every branch below is uniform over the launch: untaken ones cost nothing per element
+              if (p.bias) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[j] += bia[j];
-                if (p.act == ACT_GELU) v[j] = gelu_erf(v[j]);
-                else if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-                v[j] *= gam[j];
+                for (int j = 0; j < 8; ++j) v[j] += bia[j];
               }
+              if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a = Tr::unpack2(pa[j]), b = Tr::unpack2(pb[j]);   // bit pattern 0 == +0.0 in both formats
-                v[2 * j] += a.x + b.x;
-                v[2 * j + 1] += a.y + b.y;
+                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+              } else if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (p.gamma) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= gam[j];
+              }
+              if (res1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 a = Tr::unpack2(pa[j]);
+                  v[2 * j] += a.x; v[2 * j + 1] += a.y;
+                }
+              }
+              if (res2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 b = Tr::unpack2(pb[j]);
+                  v[2 * j] += b.x; v[2 * j + 1] += b.y;
+                }
               }
               if (out) {
                 uint4 u;
