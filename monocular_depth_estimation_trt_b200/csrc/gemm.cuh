@@ -45,6 +45,7 @@ struct GemmParams {
   const void* res2;
   void* out;            // 16-bit output
   void* out_relu;       // 16-bit relu(output) copy (input of the next pre-activation conv)
+  int tma_out;          // plain row-major 16-bit output (bias / activation only): registers -> smem -> TMA store
   // ---- fused depth head (BLOCK_N == 32 == N): z = sum_n relu(v_n) * head_w[n] + head_b
   const float* head_w;
   float head_b;
@@ -60,7 +61,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = 8;
-  static constexpr int kEpiBytes = kEpiWarps * (32 * 32 * 4 + 32 * 4);   // per warp: 32x32 fp32 staging chunk + 32 row indices
+  static constexpr int kEpiBytes = kEpiWarps * (32 * 32 * 4 + 32 * 4);   // per warp: 4 KB staging chunk + 32 row indices (a multiple of 1024)
   static constexpr int kMaxStages = (227 * 1024 - 1024 - 256 - kEpiBytes) / kStageBytes;   // 227 KB per CTA
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -86,10 +87,40 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return v * (v >= 0.f ? 1.0f - hq : hq);
 }
 
+// The same evaluation for two values at once on packed fp32 pairs: the FMA-class work (about two thirds of
+// the scalar version's issue slots) halves; the four MUFU operations stay.  0.5 is folded into the polynomial
+// and Phi = 0.5 + sign(v) * (0.5 - q/2), so there is no select.
+__device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
+  const f32x2 v = f2_pack(v0, v1);
+  const f32x2 a = f2_pack(fabsf(v0), fabsf(v1));
+  const f32x2 den = f2_fma(a, f2_splat(0.3275911f * 0.70710678118654752440f), f2_splat(1.0f));
+  float d0, d1, t0, t1;
+  f2_unpack(den, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const f32x2 t = f2_pack(t0, t1);
+  f32x2 poly = f2_fma(t, f2_splat(0.5f * 1.061405429f), f2_splat(0.5f * -1.453152027f));
+  poly = f2_fma(poly, t, f2_splat(0.5f * 1.421413741f));
+  poly = f2_fma(poly, t, f2_splat(0.5f * -0.284496736f));
+  poly = f2_fma(poly, t, f2_splat(0.5f * 0.254829592f));
+  poly = f2_mul(poly, t);
+  const f32x2 arg = f2_mul(f2_mul(a, f2_splat(-0.5f * 1.44269504088896340736f)), a);
+  float g0, g1, e0, e1;
+  f2_unpack(arg, g0, g1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const f32x2 r = f2_fma(f2_mul(poly, f2_pack(e0, e1)), f2_splat(-1.0f), f2_splat(0.5f));   // 0.5 - q/2 in [0, 0.5]
+  float r0, r1;
+  f2_unpack(r, r0, r1);
+  r0 = __uint_as_float(__float_as_uint(r0) ^ (__float_as_uint(v0) & 0x80000000u));
+  r1 = __uint_as_float(__float_as_uint(r1) ^ (__float_as_uint(v1) & 0x80000000u));
+  f2_unpack(f2_mul(v, f2_add(f2_pack(r0, r1), f2_splat(0.5f))), v0, v1);
+}
+
 template <int BLOCK_N, typename T>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   using Tr = F16Traits<T>;
   constexpr int kStages = Cfg::kStages;
@@ -98,13 +129,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;   // per epilogue warp: 4 KB staging chunk (1024-byte aligned); then 8 x 32 row indices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes + 256;   // per epilogue warp: staging chunk, then row indices
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
+    if (p.tma_out) prefetch_tmap(&map_out);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -220,6 +252,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     T* out_relu = static_cast<T*>(p.out_relu);
     const T* res1 = static_cast<const T*>(p.res1);
     const T* res2 = static_cast<const T*>(p.res2);
+    if (p.tma_out) {
+      // ---- plain row-major 16-bit output (QKV, FC1, DPT projections): thread = row, all arithmetic on the
+      // registers tcgen05.ld delivered, two 32-column chunks packed into one 128-byte-swizzled 32 x 64 box
+      // and written by one bulk tensor store per warp (the tensor map clips rows >= M).  About a third of
+      // the instructions of the staged path below: nothing is re-read from shared memory, no addresses,
+      // no predicates.
+      uint8_t* buf = epi_smem + ew * 4096;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_tile = (tile % p.n_tiles) * BLOCK_N;
+        constexpr int kPerWarp = BLOCK_N / 64;             // chunks per warp; the host guarantees N % BLOCK_N == 0, BLOCK_N >= 128
+        const int ch_begin = half * kPerWarp;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(t_base + ch_begin * 32, raw);
+#pragma unroll 1
+        for (int c = 0; c < kPerWarp; ++c) {
+          const int n_base = n_tile + (ch_begin + c) * 32;
+          float4 bia[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            bia[g] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n_base) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (c + 1 < kPerWarp) {
+            tmem_ld_32x32b_x32(t_base + (ch_begin + c + 1) * 32, raw);   // in flight during the arithmetic
+          } else {
+            tc_fence_before();                 // every TMEM read of this stage is complete: hand it back now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            f32x2 lo = f2_add(f2_pack(v[4 * g], v[4 * g + 1]), f2_pack(bia[g].x, bia[g].y));
+            f32x2 hi = f2_add(f2_pack(v[4 * g + 2], v[4 * g + 3]), f2_pack(bia[g].z, bia[g].w));
+            f2_unpack(lo, v[4 * g], v[4 * g + 1]);
+            f2_unpack(hi, v[4 * g + 2], v[4 * g + 3]);
+          }
+          if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
+          } else if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if ((c & 1) == 0) {
+            if (lane == 0) bulk_wait_read0();  // the previous store has finished reading the staging box
+            __syncwarp();
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = Tr::pack2(v[8 * g], v[8 * g + 1]); u.y = Tr::pack2(v[8 * g + 2], v[8 * g + 3]);
+            u.z = Tr::pack2(v[8 * g + 4], v[8 * g + 5]); u.w = Tr::pack2(v[8 * g + 6], v[8 * g + 7]);
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((((c & 1) * 4 + g) ^ (lane & 7)) << 4)) = u;
+          }
+          if (c & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_out, buf, n_base - 32, m_blk * 128 + quarter * 32);
+              bulk_commit();
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) bulk_wait0();
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile % p.n_tiles;
@@ -251,22 +356,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       __syncwarp();                          // previous tile's phase 2 is done with row_off
       row_off[lane] = valid ? static_cast<int>(orow) : -1;   // output rows fit 31 bits (checked on the host)
-      // The residual stream tile this epilogue will read-modify-write: pull it into L2 while the MMAs of
-      // the tile are still running (the row is contiguous: BLOCK_N fp32 = BLOCK_N / 32 lines).
+      const int n_tile = n_blk * BLOCK_N;
+      const int chunks = min(BLOCK_N, p.N - n_tile + 31) / 32;   // warp-uniform; N is a multiple of 8
+      const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2;
+      const int ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
+      // The residual stream values this warp will read-modify-write after its first chunk: pull them into L2
+      // while the MMAs of the tile are still running (one 128-byte line per row and chunk).
       if (p.x && p.accumulate_x && valid) {
-        const char* xrow = reinterpret_cast<const char*>(p.x + orow * p.ld_out + n_blk * BLOCK_N);
+        const char* xrow = reinterpret_cast<const char*>(p.x + orow * p.ld_out + n_tile);
+        for (int i = ch_begin + 1; i < ch_end; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + i * 128));
+      }
+      // fp32 pass (2a): this lane's 8 rows and the residual-stream values (or pos-embed rows) it will add.
+      // Nobody else touches these elements, so chunk c+1 is requested as soon as chunk c has been consumed
+      // and the first chunk before the accumulator is even complete: the loads overlap the MMAs / phase 1.
+      __syncwarp();
+      int rx[8];
+      float4 xin[8];
+      auto fetch_x = [&](int ch) {
+        const int n = n_tile + ch * 32 + 4 * (lane & 7);
 #pragma unroll
-        for (int i = 0; i < BLOCK_N / 32; ++i)
-          if (n_blk * BLOCK_N + i * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + i * 128));
+        for (int pass = 0; pass < 8; ++pass) {
+          xin[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rx[pass] >= 0 && n < p.N) {
+            if (p.accumulate_x) xin[pass] = *reinterpret_cast<const float4*>(p.x + static_cast<long long>(rx[pass]) * p.ld_out + n);
+            else if (p.pos) xin[pass] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(rx[pass] % (p.tokens + 1)) * p.ld_out + n));
+          }
+        }
+      };
+      if (p.x) {
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) rx[pass] = row_off[pass * 4 + (lane >> 3)];
+        if (ch_begin < ch_end) fetch_x(ch_begin);
       }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      const int n_tile = n_blk * BLOCK_N;
-      const int chunks = min(BLOCK_N, p.N - n_tile + 31) / 32;   // warp-uniform; N is a multiple of 8
-      const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2;
-      const int ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
 
       uint32_t raw[32];
       if (ch_begin < ch_end) tmem_ld_32x32b_x32(t_base + ch_begin * 32, raw);
@@ -322,20 +447,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int n = n_base + 4 * c4;
           if (n < p.N) {
             const float4 bia = bia_a, gam = gam_a;
-            long long ro[8];
-            float4 xin[8];
 #pragma unroll
             for (int pass = 0; pass < 8; ++pass) {
-              ro[pass] = static_cast<long long>(row_off[pass * 4 + (lane >> 3)]);
-              xin[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ro[pass] >= 0) {
-                if (p.accumulate_x) xin[pass] = *reinterpret_cast<const float4*>(p.x + ro[pass] * p.ld_out + n);
-                else if (p.pos) xin[pass] = __ldg(reinterpret_cast<const float4*>(p.pos + (ro[pass] % (p.tokens + 1)) * p.ld_out + n));
-              }
-            }
-#pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-              if (ro[pass] < 0) continue;
+              if (rx[pass] < 0) continue;
               const int rr = pass * 4 + (lane >> 3);
               float4 v = *reinterpret_cast<const float4*>(stage_f + rr * 32 + ((c4 ^ (rr & 7)) << 2));
               v.x += bia.x; v.y += bia.y; v.z += bia.z; v.w += bia.w;
@@ -346,9 +460,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               }
               v.x = fmaf(v.x, gam.x, xin[pass].x); v.y = fmaf(v.y, gam.y, xin[pass].y);
               v.z = fmaf(v.z, gam.z, xin[pass].z); v.w = fmaf(v.w, gam.w, xin[pass].w);
-              *reinterpret_cast<float4*>(p.x + ro[pass] * p.ld_out + n) = v;
+              *reinterpret_cast<float4*>(p.x + static_cast<long long>(rx[pass]) * p.ld_out + n) = v;
             }
           }
+          if (ch + 1 < ch_end) fetch_x(ch + 1);
         }
         // ---- phase 2b: 16-bit outputs (+ 16-bit residuals), 4 lanes x 8 columns per row, 8 rows per pass
         if (out || out_relu) {
@@ -393,7 +508,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               }
               if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+                for (int j = 0; j < 8; j += 2) gelu_erf2(v[j], v[j + 1]);
               } else if (p.act == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);

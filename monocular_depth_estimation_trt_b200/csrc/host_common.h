@@ -32,6 +32,7 @@ int num_sms();   // SM count of the current device (cached), 0 on failure
 struct GemmOp {
   alignas(64) CUtensorMap map_a;
   alignas(64) CUtensorMap map_b;
+  alignas(64) CUtensorMap map_out;   // 16-bit output as {N, M} with 64 x 32 boxes; only encoded when p.tma_out
   GemmParams p;
   int block_n;
   int precision;

@@ -61,6 +61,26 @@ static int get_encode(EncodeTiledFn* fn) {
 }
 
 static int encode_map(CUtensorMap* map, int precision, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
+// The bulk-store epilogue serves plain row-major 16-bit outputs: bias and activation only, whole tiles in N.
+static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long long m, int n) {
+  memset(&op->map_out, 0, sizeof(op->map_out));
+  GemmParams& p = op->p;
+  p.tma_out = 0;
+  if (getenv("MDE_NO_TMA_OUT")) return MDE_OK;
+  if (!ep->d_out || ep->d_x || ep->d_res1 || ep->d_res2 || ep->d_out_relu || ep->d_gamma || ep->d_head_w || p.conv ||
+      p.row_map != ROW_IDENTITY || op->block_n < 128 || n % op->block_n || (reinterpret_cast<uintptr_t>(ep->d_out) & 15))
+    return MDE_OK;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
+  cuuint64_t str[1] = {static_cast<cuuint64_t>(ep->ld_out) * 2};
+  cuuint32_t box[2] = {64, 32};
+  MDE_TRY(encode_map(&op->map_out, precision, ep->d_out, 2, dims, str, box));
+  p.tma_out = 1;
+  return MDE_OK;
+}
+
+static int encode_map(CUtensorMap* map, int precision, const void* base, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn enc;
   MDE_TRY(get_encode(&enc));
@@ -145,6 +165,7 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n)};
     MDE_TRY(encode_map(&op->map_b, precision, d_b, 2, dims, str, box));
   }
+  MDE_TRY(maybe_tma_out(op, precision, ep, m, n));
   const int sms = num_sms();
   if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
   op->grid = std::min(sms, p.m_tiles * p.n_tiles);
@@ -197,6 +218,7 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n)};
     MDE_TRY(encode_map(&op->map_b, precision, d_w, 2, dims, str, box));
   }
+  memset(&op->map_out, 0, sizeof(op->map_out));
   const int sms = num_sms();
   if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
   op->grid = std::min(sms, p.m_tiles * p.n_tiles);
@@ -211,7 +233,7 @@ static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  kern<<<op.grid, GemmCfg<BN>::kThreads, GemmCfg<BN>::kSmemBytes, s>>>(op.map_a, op.map_b, op.p);
+  kern<<<op.grid, GemmCfg<BN>::kThreads, GemmCfg<BN>::kSmemBytes, s>>>(op.map_a, op.map_b, op.map_out, op.p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }

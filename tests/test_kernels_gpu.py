@@ -56,6 +56,25 @@ def test_gemm_gelu(lib, prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("m,n,k,act,pad", [(1370, 3072, 1024, 0, 0), (2745, 1536, 384, 1, 0), (77, 256, 64, 2, 64),
+                                           (4110, 1152, 384, 1, 0), (129, 512, 128, 1, 8), (31, 128, 64, 0, 0)])
+def test_gemm_bulk_store_epilogue(lib, prec, m, n, k, act, pad):
+    """16-bit output only (QKV / FC1 shape class): registers -> swizzled smem box -> TMA store.  Row tails are
+    clipped by the tensor map; the pitch may exceed N; nothing outside [0,m) x [0,n) is written."""
+    dt = K.TORCH_DT[prec]
+    a, b = rnd((m, k), dt, seed=21), rnd((n, k), dt, k ** -0.5, seed=22)
+    bias = torch.randn(n, device="cuda") * 0.5
+    ld = n + pad
+    out = torch.full((m + 3, ld), 7.0, dtype=dt, device="cuda")
+    K.gemm(prec, a, b, K.epilogue(bias=bias, act=act, out=out, ld_out=ld))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias
+    ref = F.gelu(ref) if act == 1 else (F.relu(ref) if act == 2 else ref)
+    assert K.rel_err(out[:m, :n], ref) < ULP[prec]
+    assert torch.all(out[m:] == 7.0) and torch.all(out[:, n:] == 7.0)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 def test_gemm_layerscale_residual_in_place(lib, prec):
     dt = K.TORCH_DT[prec]
     m, n, k = 2740, 384, 1536
