@@ -9,8 +9,9 @@ A step is one forward of the hot path over one batch of synthetic images.  One J
                 with CUDA events on the launching stream, max over ranks
   e2e           the same metric through the reference-facing call (`do_inference`: pinned host
                 buffers, H2D of the uint8 frames and D2H of the float32 depth maps inside the region)
-  roofline      the dominant kernel (tcgen05 GEMM, BLOCK_N 256): algorithmic FLOPs of its launches in
-                one step / their summed CUDA-event durations, against MEASURED_PEAKS.json
+  roofline      the dominant kernel (the launch label with the largest share of the step): algorithmic
+                FLOPs (or bytes) of its launches in one step / their summed CUDA-event durations, against
+                MEASURED_PEAKS.json; `top_kernels` lists the same for the eight largest kernels
   cpu_baseline  the oracle (CPU fp32 PyTorch port of the reference's forward) on the host cores, bounded
                 sample, rank 0 / N=1 only
   --impl reference   times that CPU forward alone (the reference's own CPU path) and prints the same line
@@ -225,21 +226,36 @@ def run_ours(args):
     ops = ctx.execute_timed(stream)
     ops = ctx.execute_timed(stream)
     pk = peaks()
-    groups = {}
+    groups, kernels = {}, {}
     for label, ms, fl, by in ops:
-        key = label.split(" ")[0]
-        g = groups.setdefault(key, [0.0, 0.0, 0.0, 0])
-        g[0] += ms; g[1] += fl; g[2] += by; g[3] += 1
+        for table, key in ((groups, label.split(" ")[0]), (kernels, label)):
+            g = table.setdefault(key, [0.0, 0.0, 0.0, 0])
+            g[0] += ms; g[1] += fl; g[2] += by; g[3] += 1
     step_ms_timed = sum(o[1] for o in ops)
-    dom_key = max((k for k in groups if groups[k][1] > 0), key=lambda k: groups[k][0])
-    dg = groups[dom_key]
-    achieved = dg[1] / (dg[0] / 1000.0) / 1e12
-    roofline = {"bound": "tensor", "kernel": f"{dom_key} ({dg[3]} launches per step)", "achieved": achieved,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
-                "peak_source": pk["source"], "share_of_step": dg[0] / step_ms_timed,
-                "whole_step": {"achieved": value / world * FLOPS_PER_IMAGE[enc] / 1e12,
-                               "frac": value / world * FLOPS_PER_IMAGE[enc] / 1e12 / pk["tflops"],
-                               "frac_of_burst": value / world * FLOPS_PER_IMAGE[enc] / 1e12 / pk["tflops_burst"]}}
+    # dominant kernel = the (kernel, shape) whose launches take the largest share of the step
+    dom_key = max(kernels, key=lambda k: kernels[k][0])
+    dg = kernels[dom_key]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from `ncu --set full` captures
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom_key, {}).get("dram_bytes_per_launch")
+
+    def kernel_roofline(key, g):
+        tensor = g[1] > 0
+        ach = (g[1] / (g[0] / 1000.0) / 1e12) if tensor else (g[2] / (g[0] / 1000.0) / 1e9)
+        peak = pk["tflops"] if tensor else pk["hbm"]
+        return {"kernel": key, "launches_per_step": g[3], "ms_per_launch": g[0] / g[3], "bound": "tensor" if tensor else "hbm",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
+                "share_of_step": g[0] / step_ms_timed}
+
+    roofline = kernel_roofline(dom_key, dg)
+    roofline.update({"traffic": traffic, "peak_source": pk["source"],
+                     "algorithmic_per_launch": {"flops": dg[1] / dg[3], "bytes": dg[2] / dg[3]},
+                     "whole_step": {"achieved": value / world * FLOPS_PER_IMAGE[enc] / 1e12,
+                                    "frac": value / world * FLOPS_PER_IMAGE[enc] / 1e12 / pk["tflops"],
+                                    "frac_of_burst": value / world * FLOPS_PER_IMAGE[enc] / 1e12 / pk["tflops_burst"]},
+                     "top_kernels": [kernel_roofline(k, g) for k, g in sorted(kernels.items(), key=lambda kv: -kv[1][0])[:8]]})
     breakdown = {k: {"ms": round(v[0], 3), "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 1) if v[1] else None,
                      "gbs": round(v[2] / max(v[0], 1e-9) / 1e6, 1), "launches": v[3]} for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])}
 

@@ -184,6 +184,13 @@ int mde_k_layernorm(int32_t precision, const float* d_x, const float* d_w, const
 /* bilinear, align_corners=True, NHWC 16-bit, c multiple of 8 */
 int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t hi, int32_t wi, int32_t ho,
                    int32_t wo, int32_t c, void* stream);
+/* Tail of the DPT head (models/depth_anything_v2: output_conv1 -> interpolate(align_corners=True) -> output_conv2)
+ * with the 3x3 conv's channel contraction done before the interpolation.  d_z: [B][hs][ws][ldz] 16-bit with
+ * z[.., (ky*3+kx)*32 + o] = sum_c W2[o][c][ky][kx] * o1[.., c] (no bias); d_bias: [32] conv bias; d_head_w: [32]
+ * weights of the 1x1 conv, head_b its bias; head_scale > 0: head_scale*sigmoid, else ReLU.  d_out: [B][ho][wo] fp32. */
+int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t batch, int32_t hs, int32_t ws, int32_t ho,
+                      int32_t wo, const float* d_bias, const float* d_head_w, float head_b, float head_scale,
+                      float* d_out, void* stream);
 /* 3x3 / stride 2 / pad 1 gather: NHWC -> [(b,oy,ox)][tap*c + ch] */
 int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t h, int32_t w, int32_t c,
                     void* stream);

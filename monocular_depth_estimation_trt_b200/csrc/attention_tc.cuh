@@ -45,7 +45,37 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <typename T>
+// 2^x for two values on the FMA pipe (Cody-Waite: x = n + f, |f| <= 0.5, 2^f by a minimax polynomial, 2^n added
+// into the exponent field).  Relative error 1.0e-4 (degree 3, bf16 probabilities round at 2^-9) or 3.7e-6
+// (degree 4, fp16).  The special-function unit delivers 16 ex2 per clock and SM and is what bounds this kernel
+// at head dim 64; kPoly of every 8 element pairs take this path instead and run beside it.
+template <int kDegree>
+__device__ __forceinline__ void exp2_fma2(f32x2 x, float& p0, float& p1) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const f32x2 r = f2_add(x, f2_splat(12582912.0f));            // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const f32x2 n = f2_add(r, f2_splat(-12582912.0f));
+  const f32x2 f = f2_fma(n, f2_splat(-1.0f), x);
+  f32x2 q;
+  if (kDegree == 3) {
+    q = f2_fma(f, f2_splat(0.05592203512787819f), f2_splat(0.24264007806777954f));
+    q = f2_fma(q, f, f2_splat(0.6931210160255432f));
+    q = f2_fma(q, f, f2_splat(0.9999244809150696f));
+  } else {
+    q = f2_fma(f, f2_splat(0.009676037356257439f), f2_splat(0.05592203512787819f));
+    q = f2_fma(q, f, f2_splat(0.2402210682630539f));
+    q = f2_fma(q, f, f2_splat(0.6931210160255432f));
+    q = f2_fma(q, f, f2_splat(1.0000001192092896f));
+  }
+  float q0, q1, r0, r1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(r, r0, r1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
+
+template <typename T, int kPoly>
 __global__ void __launch_bounds__(kAtcThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
   using Tr = F16Traits<T>;
@@ -190,8 +220,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch][i]), sl, -msl_new));
-          float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch][i + 1]), sl, -msl_new));
+          const f32x2 xs = f2_fma(f2_pack(__uint_as_float(raw[ch][i]), __uint_as_float(raw[ch][i + 1])), f2_splat(sl), f2_splat(-msl_new));
+          float p0, p1;
+          if (((i >> 1) & 7) < kPoly) {
+            exp2_fma2<Tr::kFmt == 1 ? 3 : 4>(xs, p0, p1);
+          } else {
+            float x0, x1;
+            f2_unpack(xs, x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+          }
           if (!kFull) {
             if (ch * 32 + i >= nvalid) p0 = 0.f;
             if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;

@@ -82,7 +82,7 @@ struct mde_engine {
 namespace {
 
 struct Op {
-  enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, SNAPSHOT } kind;
+  enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, UPCONV_HEAD, SNAPSHOT } kind;
   GemmOp g;
   AttnOp attn;
   // generic scalar/pointer slots for the small kernels
@@ -344,7 +344,18 @@ extern "C" int mde_engine_finalize(mde_engine* e) {
   MDE_TRY(upload_f32(e, h + "resize_layers.3.bias", {oc[3]}, &e->rs3_b));
   MDE_TRY(upload_conv3x3(e, h + "scratch.output_conv1.weight", F / 2, F, Fp, &e->oc1_w));
   MDE_TRY(upload_f32(e, h + "scratch.output_conv1.bias", {F / 2}, &e->oc1_b));
-  MDE_TRY(upload_conv3x3(e, h + "scratch.output_conv2.0.weight", 32, F / 2, round_up(F / 2, 64), &e->oc2_w));
+  // output_conv2[0] as nine 1x1 contractions applied BEFORE the bilinear upsampling (csrc/upconv_head.cuh):
+  // GEMM B operand [384][F/2], row (ky*3+kx)*32 + o; rows 288..383 are zero padding up to a whole number of 128-wide tiles
+  MDE_TRY(require(e, h + "scratch.output_conv2.0.weight", {32, F / 2, 3, 3}, &t));
+  {
+    const int cin = F / 2;
+    std::vector<uint16_t> wz(static_cast<size_t>(384) * cin, 0);
+    for (int o = 0; o < 32; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int tap = 0; tap < 9; ++tap)
+          wz[(static_cast<size_t>(tap) * 32 + o) * cin + c] = to16(t->data[(static_cast<size_t>(o) * cin + c) * 9 + tap], d.precision);
+    MDE_TRY(upload(e, wz.data(), wz.size() * 2, &e->oc2_w));
+  }
   MDE_TRY(upload_f32(e, h + "scratch.output_conv2.0.bias", {32}, &e->oc2_b));
   MDE_TRY(upload_f32(e, h + "scratch.output_conv2.2.weight", {1, 32, 1, 1}, &e->head_w));
   MDE_TRY(require(e, h + "scratch.output_conv2.2.bias", {1}, &t));
@@ -423,16 +434,17 @@ struct Planner {
   void* alloc16(int64_t elems, const char* name = nullptr) { return alloc(elems * 2, name, 1); }
 
   void gemm(const char* what, const void* a, long long m, int k, int lda, const void* b, int n, int ldb,
-            const mde_epilogue& ep, int k_real = 0) {
+            const mde_epilogue& ep, int k_real = 0, int n_real = 0) {
     if (dry || rc != MDE_OK) return;
     Op op; op.kind = Op::GEMM;
     rc = make_gemm_op(&op.g, prec, a, m, k, lda, b, n, ldb, &ep);
     if (k_real <= 0) k_real = k;
+    if (n_real <= 0) n_real = n;      // algorithmic sizes: zero padding of K or N is not counted
     char buf[160];
-    snprintf(buf, sizeof(buf), "gemm%d %s %lldx%dx%d", op.g.block_n, what, m, n, k_real);
+    snprintf(buf, sizeof(buf), "gemm%d %s %lldx%dx%d", op.g.block_n, what, m, n_real, k_real);
     op.label = buf;
-    op.flops = 2.0 * static_cast<double>(m) * n * k_real;
-    op.bytes = 2.0 * (static_cast<double>(m) * k_real + static_cast<double>(n) * k_real) + epilogue_bytes(ep, static_cast<double>(m) * n);
+    op.flops = 2.0 * static_cast<double>(m) * n_real * k_real;
+    op.bytes = 2.0 * (static_cast<double>(m) * k_real + static_cast<double>(n_real) * k_real) + epilogue_bytes(ep, static_cast<double>(m) * n_real);
     if (rc == MDE_OK) c->plan.push_back(op);
   }
   void conv(const char* what, const void* in, int B, int H, int W, int cin, const void* w, int cout, const mde_epilogue& ep) {
@@ -613,13 +625,15 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     void* o1 = pl.alloc16(static_cast<long long>(B) * H1 * W1 * (F / 2));
     { mde_epilogue ep = ep_zero(); ep.d_bias = e->oc1_b; ep.d_out = o1; ep.ld_out = F / 2;
       pl.conv("output_conv1", path, B, H1, W1, F, e->oc1_w, F / 2, ep); }
-    void* up = pl.alloc16(static_cast<long long>(B) * d.input_h * d.input_w * (F / 2));
-    Op bl; bl.kind = Op::BILINEAR; bl.in = o1; bl.out = up; bl.i0 = H1; bl.i1 = W1; bl.i2 = d.input_h; bl.i3 = d.input_w; bl.i4 = F / 2;
-    pl.push(bl, "bilinear", 1.0 * F * (static_cast<double>(B) * H1 * W1 + static_cast<double>(B) * d.input_h * d.input_w));
-    mde_epilogue ep = ep_zero(); ep.d_bias = e->oc2_b; ep.ld_out = 32;
-    ep.d_head_w = e->head_w; ep.head_b = e->head_b; ep.head_scale = d.max_depth > 0.f ? d.max_depth : 0.f;
-    ep.d_head_out = reinterpret_cast<float*>(0x10);   // patched with the bound output address at enqueue
-    pl.conv("output_conv2+head", up, B, d.input_h, d.input_w, F / 2, e->oc2_w, 32, ep);
+    // output_conv2[0]'s channel contraction at THIS resolution (nine taps x 32 channels = 288 columns, padded to 384),
+    // then one kernel interpolates z to the input size, sums the taps, applies bias/ReLU and the 1x1 head.
+    const long long px1 = static_cast<long long>(B) * H1 * W1;
+    void* z = pl.alloc16(px1 * 384, "z_taps");
+    { mde_epilogue ep = ep_zero(); ep.d_out = z; ep.ld_out = 384;
+      pl.gemm("output_conv2 taps", o1, px1, F / 2, F / 2, e->oc2_w, 384, F / 2, ep, 0, 288); }
+    Op uh; uh.kind = Op::UPCONV_HEAD; uh.in = z; uh.i0 = H1; uh.i1 = W1; uh.i2 = d.input_h; uh.i3 = d.input_w;
+    const double opx = static_cast<double>(B) * d.input_h * d.input_w;
+    pl.push(uh, "upconv_head interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
   }
   if (bytes_out) *bytes_out = pl.bytes;
   return pl.rc;
@@ -750,6 +764,10 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         break;
       case Op::BILINEAR:
         MDE_TRY(launch_bilinear(prec, op.in, op.out, d.batch, op.i0, op.i1, op.i2, op.i3, op.i4, s));
+        break;
+      case Op::UPCONV_HEAD:
+        MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->oc2_b, e->head_w, e->head_b,
+                                   d.max_depth > 0.f ? d.max_depth : 0.f, static_cast<float*>(c->d_output), s));
         break;
       case Op::IM2COL_S2:
         MDE_TRY(launch_im2col_s2(prec, op.in, op.out, d.batch, op.i0, op.i1, op.i2, s));

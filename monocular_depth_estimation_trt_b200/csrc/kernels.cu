@@ -12,6 +12,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
+#include "upconv_head.cuh"
 
 namespace mde {
 
@@ -291,17 +292,17 @@ int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out,
   return encode_map(&op->map_qkv, precision, d_qkv, 2, dims, str, box);
 }
 
-template <typename T>
+template <typename T, int kPoly>
 static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   static bool attr_set = false;
-  auto kern = attention_tc_kernel<T>;
+  auto kern = attention_tc_kernel<T, kPoly>;
   if (!attr_set) {
     MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
     MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (getenv("MDE_DEBUG")) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAtcThreads, kAtcSmemBytes);
-      fprintf(stderr, "[MDET] attention_tc: %d CTAs/SM (smem %d B, %d threads)\n", nb, kAtcSmemBytes, kAtcThreads);
+      fprintf(stderr, "[MDET] attention_tc: %d CTAs/SM (smem %d B, %d threads), %d/8 of the exponentials on the FMA pipe\n", nb, kAtcSmemBytes, kAtcThreads, kPoly);
     }
     attr_set = true;
   }
@@ -313,8 +314,27 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
+// Share of the exponentials evaluated on the FMA pipe instead of the SFU, in eighths (tuning knob: MDE_ATTN_POLY).
+static int attn_poly() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDE_ATTN_POLY");
+    v = e ? atoi(e) : 3;
+    if (v != 0 && v != 2 && v != 3 && v != 4) v = 3;
+  }
+  return v;
+}
+template <typename T>
+static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s) {
+  switch (attn_poly()) {
+    case 0: return launch_attention_tc_t<T, 0>(op, s);
+    case 2: return launch_attention_tc_t<T, 2>(op, s);
+    case 4: return launch_attention_tc_t<T, 4>(op, s);
+    default: return launch_attention_tc_t<T, 3>(op, s);
+  }
+}
 int launch_attention_op(const AttnOp& op, cudaStream_t s) {
-  return op.precision == MDE_BF16 ? launch_attention_tc_t<__nv_bfloat16>(op, s) : launch_attention_tc_t<__half>(op, s);
+  return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s) : launch_attention_tc_p<__half>(op, s);
 }
 
 template <typename T>
@@ -431,6 +451,45 @@ int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batc
   return MDE_OK;
 }
 
+int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int hs, int ws, int ho, int wo,
+                       const float* d_bias, const float* d_head_w, float head_b, float head_scale, float* d_out,
+                       cudaStream_t s) {
+  if (batch <= 0 || hs <= 0 || ws <= 0 || ho <= 0 || wo <= 0) return fail(MDE_ERR_INVALID, "upconv_head: empty problem");
+  if (ldz < kUpZc || ldz % 8 || (reinterpret_cast<uintptr_t>(d_z) & 15)) return fail(MDE_ERR_INVALID, "upconv_head: z needs >= 288 channels, a pitch that is a multiple of 8 and 16-byte alignment");
+  if (batch > 65535) return fail(MDE_ERR_INVALID, "upconv_head: batch exceeds grid limits");
+  UpconvHeadParams p;
+  p.z = d_z; p.out = d_out; p.bias = d_bias; p.head_w = d_head_w; p.head_b = head_b;
+  p.head_scale = head_scale > 0.f ? head_scale : -1.f;
+  p.B = batch; p.Hs = hs; p.Ws = ws; p.Ho = ho; p.Wo = wo; p.ldz = ldz;
+  p.sy = ho > 1 ? static_cast<float>(hs - 1) / static_cast<float>(ho - 1) : 0.f;
+  p.sx = wo > 1 ? static_cast<float>(ws - 1) / static_cast<float>(wo - 1) : 0.f;
+  // staged window: the largest footprint over all tile origins, with exactly the kernel's arithmetic
+  auto extent = [](int out_n, int src_n, float sc) {
+    int best = 1;
+    for (int o0 = 0; o0 < out_n; o0 += kUpTile) {
+      const int lo = std::max(o0 - 1, 0), hi = std::min(o0 + kUpTile, out_n - 1);
+      const int s_lo = std::min(static_cast<int>(lo * sc), src_n - 1);
+      const int s_hi = std::min(std::min(static_cast<int>(hi * sc), src_n - 1) + 1, src_n - 1);
+      best = std::max(best, s_hi - s_lo + 1);
+    }
+    return best;
+  };
+  p.fh = extent(ho, hs, p.sy);
+  p.fw = extent(wo, ws, p.sx);
+  const int smem = p.fh * p.fw * kUpPixBytes;
+  if (smem > 113 * 1024) return fail(MDE_ERR_INVALID, "upconv_head: scale %dx%d -> %dx%d needs %d bytes of shared memory per tile", hs, ws, ho, wo, smem);
+  dim3 grid((wo + kUpTile - 1) / kUpTile, (ho + kUpTile - 1) / kUpTile, batch);
+  if (precision == MDE_BF16) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(upconv_head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    upconv_head_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
+  } else {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(upconv_head_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    upconv_head_kernel<__half><<<grid, 256, smem, s>>>(p);
+  }
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, int batch, int ntok, int dim, cudaStream_t s) {
   cls_row_kernel<<<batch, 256, 0, s>>>(d_x, d_cls, d_pos, ntok, dim);
   MDE_CUDA_TRY(cudaGetLastError());
@@ -496,6 +555,15 @@ int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t ba
                     void* stream) {
   clear_error();
   return launch_im2col_s2(precision, d_in, d_out, batch, h, w, c, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t batch, int32_t hs, int32_t ws, int32_t ho,
+                      int32_t wo, const float* d_bias, const float* d_head_w, float head_b, float head_scale,
+                      float* d_out, void* stream) {
+  clear_error();
+  if (!d_z || !d_bias || !d_head_w || !d_out) return fail(MDE_ERR_INVALID, "upconv_head: null pointer");
+  return launch_upconv_head(precision, d_z, ldz, batch, hs, ws, ho, wo, d_bias, d_head_w, head_b, head_scale, d_out,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int32_t h, int32_t w, int32_t patch,

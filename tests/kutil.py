@@ -97,6 +97,16 @@ def im2col_s2(precision, x_nhwc):
     return out
 
 
+def upconv_head(precision, z_nhwc, ho, wo, bias, head_w, head_b, head_scale):
+    """z [B, hs, ws, ldz] 16-bit (first 288 channels live) -> depth [B, ho, wo] fp32."""
+    lib = _lib.load()
+    B, hs, ws, ldz = z_nhwc.shape
+    out = torch.full((B, ho, wo), float("nan"), dtype=torch.float32, device=z_nhwc.device)
+    _lib.check(lib.mde_k_upconv_head(_lib.PRECISIONS[precision], ptr(z_nhwc), ldz, B, hs, ws, ho, wo, ptr(bias), ptr(head_w),
+                                     float(head_b), float(head_scale), ptr(out), stream()), "mde_k_upconv_head")
+    return out
+
+
 def im2col_f32(precision, x_nchw, patch, kpad):
     lib = _lib.load()
     B, _, H, W_ = x_nchw.shape

@@ -255,3 +255,32 @@ def test_bad_arguments_raise(lib):
         K.gemm("bf16", a, a, K.epilogue(ld_out=7), n=7)
     with pytest.raises(RuntimeError):
         K.bilinear("bf16", torch.zeros(1, 4, 4, 7, dtype=torch.bfloat16, device="cuda"), 8, 8)
+
+
+# ------------------------------------------------------------------------------------------ upsample + conv + head tail
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,hs,ws,ho,wo,scale", [(2, 296, 296, 518, 518, 20.0), (1, 40, 56, 70, 98, 0.0), (3, 19, 23, 33, 40, 80.0),
+                                                 (1, 8, 8, 16, 16, 0.0), (1, 352, 608, 616, 1064, 0.0)])
+def test_upconv_head_matches_upsample_conv_head(lib, prec, B, hs, ws, ho, wo, scale):
+    """interpolate(align_corners=True) -> conv3x3 128->32 + bias -> ReLU -> conv1x1 32->1 -> activation, computed as
+    tap-contracted z at the low resolution + interpolation of z (csrc/upconv_head.cuh); the fp32 torch chain on the
+    same 16-bit input is the reference."""
+    dt = K.TORCH_DT[prec]
+    o1 = rnd((B, hs, ws, 128), dt, seed=31)
+    w2 = rnd((32, 128, 3, 3), torch.float32, (9 * 128) ** -0.5, seed=32)
+    b2 = torch.randn(32, device="cuda") * 0.2
+    w3 = torch.randn(32, device="cuda") * 0.3
+    b3 = 0.1
+    # z[.., t*32+o] = sum_c w2[o, c, ky, kx] * o1[.., c], rounded once to 16 bits (what the GEMM epilogue stores)
+    wz = w2.permute(2, 3, 0, 1).reshape(288, 128)
+    z = torch.zeros(B, hs, ws, 384, dtype=dt, device="cuda")
+    z[..., :288] = (o1.float() @ wz.t()).to(dt)
+    z[..., 288:] = 1e4          # the pad channels must never be read
+    got = K.upconv_head(prec, z, ho, wo, b2, w3, b3, scale)
+    torch.cuda.synchronize()
+    up = F.interpolate(o1.float().permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", align_corners=True)
+    h = F.relu(F.conv2d(up, w2, b2, padding=1))
+    v = (h * w3.view(1, 32, 1, 1)).sum(1) + b3
+    ref = scale * torch.sigmoid(v) if scale > 0 else F.relu(v)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) < (4.0 if prec == "bf16" else 1.0) * 2.0 ** -8 * max(1.0, float(ref.abs().max()))
