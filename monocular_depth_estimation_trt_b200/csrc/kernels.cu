@@ -63,13 +63,31 @@ static int get_encode(EncodeTiledFn* fn) {
 
 static int encode_map(CUtensorMap* map, int precision, const void* base, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box);
+static int get_encode(EncodeTiledFn* fn);
 
 // The bulk-store epilogue serves plain row-major 16-bit outputs: bias and activation only, whole tiles in N.
 static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long long m, int n) {
   memset(&op->map_out, 0, sizeof(op->map_out));
   GemmParams& p = op->p;
   p.tma_out = 0;
+  p.tma_x = 0;
   if (getenv("MDE_NO_TMA_OUT")) return MDE_OK;
+  // residual-stream update on plain rows: the fp32 x boxes travel by TMA in both directions
+  if (ep->d_x && ep->accumulate_x && !ep->d_out && !ep->d_out_relu && !ep->d_res1 && !ep->d_res2 && !ep->d_pos && !ep->d_head_w &&
+      ep->act == 0 && !p.conv && p.row_map == ROW_IDENTITY && op->block_n >= 128 && n % op->block_n == 0 && ep->ld_out % 4 == 0 &&
+      !(reinterpret_cast<uintptr_t>(ep->d_x) & 15)) {
+    EncodeTiledFn enc;
+    MDE_TRY(get_encode(&enc));
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(ep->ld_out) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op->map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ep->d_x, dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MDE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the fp32 residual stream", static_cast<int>(r));
+    p.tma_x = 1;
+    return MDE_OK;
+  }
   if (!ep->d_out || ep->d_x || ep->d_res1 || ep->d_res2 || ep->d_out_relu || ep->d_gamma || ep->d_head_w || p.conv ||
       p.row_map != ROW_IDENTITY || op->block_n < 128 || n % op->block_n || (reinterpret_cast<uintptr_t>(ep->d_out) & 15))
     return MDE_OK;

@@ -75,17 +75,23 @@ def test_gemm_bulk_store_epilogue(lib, prec, m, n, k, act, pad):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-def test_gemm_layerscale_residual_in_place(lib, prec):
+@pytest.mark.parametrize("m,n,k,pad", [(2740, 384, 1536, 0), (4110, 1024, 1024, 0), (87, 768, 64, 32), (1370, 1024, 4096, 0),
+                                       (129, 256, 128, 8), (300, 48, 64, 0)])
+def test_gemm_layerscale_residual_in_place(lib, prec, m, n, k, pad):
+    """x += gamma * (A B^T + bias) in fp32 (attention projection / FC2 epilogue).  Whole-tile shapes take the TMA
+    load / in-place / TMA store path, the last one the staged generic path; rows beyond m and columns beyond n
+    are never touched."""
     dt = K.TORCH_DT[prec]
-    m, n, k = 2740, 384, 1536
     a, b = rnd((m, k), dt, seed=5), rnd((n, k), dt, k ** -0.5, seed=6)
     bias, gamma = torch.randn(n, device="cuda"), torch.rand(n, device="cuda")
-    x0 = torch.randn(m, n, device="cuda")
+    ld = n + pad
+    x0 = torch.randn(m + 2, ld, device="cuda")
     x = x0.clone()
-    K.gemm(prec, a, b, K.epilogue(bias=bias, gamma=gamma, x=x, accumulate_x=True, ld_out=n))
+    K.gemm(prec, a, b, K.epilogue(bias=bias, gamma=gamma, x=x, accumulate_x=True, ld_out=ld))
     torch.cuda.synchronize()
-    ref = x0 + gamma * (a.float() @ b.float().t() + bias)
-    assert K.rel_err(x, ref) < 2e-5
+    ref = x0[:m, :n] + gamma * (a.float() @ b.float().t() + bias)
+    assert K.rel_err(x[:m, :n], ref) < 2e-5
+    assert torch.equal(x[m:], x0[m:]) and torch.equal(x[:, n:], x0[:, n:])
 
 
 @pytest.mark.parametrize("prec", PRECS)
