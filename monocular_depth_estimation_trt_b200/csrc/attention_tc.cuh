@@ -100,6 +100,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   const int head = blockIdx.y, img = blockIdx.z;
   const int q0 = blockIdx.x * 128;
   const int nkv = (p.ntok + 127) / 128;
+  const int last_chunks = (p.ntok - (nkv - 1) * 128 + 31) / 32;   // 32-key chunks of the last key tile that hold real keys (1..4)
   const int row_base = img * p.ntok;
 
   if (warp == 4 && lane == 0) {
@@ -144,9 +145,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
     // ===================================================== MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(Tr::kFmt, 128, 128);
       constexpr uint32_t idesc_o = umma_idesc_f16(Tr::kFmt, 128, 64) | (1u << 16);   // B (= V) is MN-major
-      auto issue_s = [&](int st) {
+      // the last key tile only spans the 32-key chunks that hold real keys: fewer S columns, fewer P V steps
+      auto issue_s = [&](int st, int j) {
+        const uint32_t idesc_s = umma_idesc_f16(Tr::kFmt, 128, j == nkv - 1 ? last_chunks * 32 : 128);
         const uint64_t a = umma_desc_k_sw128(smem_u32(sQ));
         const uint64_t b = umma_desc_k_sw128(smem_u32(sK + st * kAtcQBytes));
 #pragma unroll
@@ -157,7 +159,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0);
+      issue_s(0, 0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kAtcStages;
         if (j + 1 < nkv) {
@@ -166,15 +168,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
           mbar_wait(&k_full[st1], ((j + 1) / kAtcStages) & 1);
           mbar_wait(s_free, j & 1);
           tc_fence_after();
-          issue_s(st1);
+          issue_s(st1, j + 1);
         }
         mbar_wait(&v_full[st], (j / kAtcStages) & 1);
         mbar_wait(p_ready, j & 1);                 // P(j) in TMEM, O rescaled
         tc_fence_after();
         const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
+        const int ksteps = j == nkv - 1 ? 2 * last_chunks : 8;
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed P columns, two 8-row groups of V (2048 bytes)
-          tc_mma_f16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
+          if (k < ksteps) tc_mma_f16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
         tc_commit(o_full);
         tc_commit(&v_empty[st]);
       }
@@ -193,12 +196,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
     float l_run = 0.f;
     const float sl = p.scale_log2;
 
-    auto tile = [&](auto full_tag, int j) {
+    // nch_tag: 32-key chunks of this tile that hold real keys (4 with every key valid = the fast path; the last key
+    // tile of a row may have fewer and a ragged end).  A compile-time count keeps every register array statically indexed.
+    auto tile = [&](auto nch_tag, auto full_tag, int j) {
       constexpr bool kFull = decltype(full_tag)::value;
+      constexpr int nch = decltype(nch_tag)::value;
       const int nvalid = kFull ? 128 : p.ntok - j * 128;
       uint32_t raw[4][32];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32b_x32(s_addr + ch * 32, raw[ch]);
+      for (int ch = 0; ch < 4; ++ch)
+        if (ch < nch) tmem_ld_32x32b_x32(s_addr + ch * 32, raw[ch]);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_free);                       // the tensor core may overwrite S now
@@ -208,16 +215,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (kFull || ch * 32 + i < nvalid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));
+          if (ch < nch && (kFull || ch * 32 + i < nvalid)) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));
       const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       // ---- lazy rescale: only when the maximum grew by more than 2^8 (always on the first tile)
       const bool grow = (mx - m_ref) * sl > kAtcRescaleThreshold;
       // ---- P = exp2(S * sl - m * sl), packed to 16 bits in registers (the score registers die as we go)
       const float msl_new = (grow ? mx : m_ref) * sl;
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      f32x2 rs2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[2][32];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nch) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const f32x2 xs = f2_fma(f2_pack(__uint_as_float(raw[ch][i]), __uint_as_float(raw[ch][i + 1])), f2_splat(sl), f2_splat(-msl_new));
@@ -234,8 +242,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             if (ch * 32 + i >= nvalid) p0 = 0.f;
             if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
           }
-          rs4[(i >> 1) & 3] += p0 + p1;
+          rs2[(i >> 1) & 3] = f2_add(rs2[(i >> 1) & 3], f2_pack(p0, p1));
           pk[ch >> 1][(ch & 1) * 16 + (i >> 1)] = Tr::pack2(p0, p1);
+        }
         }
       }
       // ---- the previous product has read P (and, for a rescale, written O): only now may either change
@@ -259,9 +268,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         }
       }
       tmem_st_32x32b_x32(p_addr, pk[0]);
-      tmem_st_32x32b_x32(p_addr + 32, pk[1]);
+      if (nch > 2) tmem_st_32x32b_x32(p_addr + 32, pk[1]);
       tmem_st_wait();
-      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      {
+        float a0, a1, b0, b1;
+        f2_unpack(f2_add(rs2[0], rs2[1]), a0, a1);
+        f2_unpack(f2_add(rs2[2], rs2[3]), b0, b1);
+        l_run += (a0 + a1) + (b0 + b1);
+      }
       tc_fence_before();            // TMEM stores (P, rescaled O) are ordered before the MMA that reads them
       mbar_arrive(p_ready);
     };
@@ -269,8 +283,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      if (j * 128 + 128 <= p.ntok) tile(cuda::std::true_type{}, j);
-      else tile(cuda::std::false_type{}, j);
+      using cuda::std::integral_constant;
+      if (j * 128 + 128 <= p.ntok) tile(integral_constant<int, 4>{}, cuda::std::true_type{}, j);
+      else if (last_chunks == 1) tile(integral_constant<int, 1>{}, cuda::std::false_type{}, j);
+      else if (last_chunks == 2) tile(integral_constant<int, 2>{}, cuda::std::false_type{}, j);
+      else if (last_chunks == 3) tile(integral_constant<int, 3>{}, cuda::std::false_type{}, j);
+      else tile(integral_constant<int, 4>{}, cuda::std::false_type{}, j);
     }
     // ---- normalise and store this row (128 contiguous bytes)
     mbar_wait(o_full, (nkv - 1) & 1);
