@@ -54,12 +54,15 @@ struct GemmParams {
   float* head_out;      // [M] fp32
 };
 
-template <int BLOCK_N>
+// kCtas == 2: a pair of CTAs on the two SMs of a TPC works on a 256 x BLOCK_N tile with tcgen05 cta_group::2: each CTA
+// stages its own 128 rows of A but only HALF of the B tile, so the L2 -> shared-memory traffic per FLOP drops by a
+// third (the single-CTA kernel sits at the ~64 B/clk/SM an SM can pull from L2) and two more stages fit.
+template <int BLOCK_N, int kCtas = 1>
 struct GemmCfg {
   static constexpr int kBlockM = 128;
   static constexpr int kBlockK = 64;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N / kCtas * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiBytes = kEpiWarps * (32 * 32 * 4 + 32 * 4);   // per warp: 4 KB staging chunk + 32 row indices (a multiple of 1024)
@@ -118,11 +121,11 @@ __device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
   f2_unpack(f2_mul(v, f2_add(f2_pack(r0, r1), f2_splat(0.5f))), v0, v1);
 }
 
-template <int BLOCK_N, typename T>
+template <int BLOCK_N, typename T, int kCtas>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, kCtas>;
   using Tr = F16Traits<T>;
   constexpr int kStages = Cfg::kStages;
 
@@ -141,7 +144,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // A work item is one (128 * kCtas) x BLOCK_N tile; CTA `rank` of a pair owns rows [rank * 128, rank * 128 + 128) of it.
+  const int rank = kCtas == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int num_tiles = ((p.m_tiles + kCtas - 1) / kCtas) * p.n_tiles;
+  const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
+  auto m_block = [&](int tile) { return (tile / p.n_tiles) * kCtas + rank; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
@@ -156,16 +163,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int i = 0; i < Cfg::kEpiWarps; ++i) mbar_init(&x_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], Cfg::kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], Cfg::kEpiWarps * kCtas);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (kCtas == 2) { tmem_alloc_pair(tmem_slot, Cfg::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -176,8 +184,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t a_bytes = p.conv ? static_cast<uint32_t>(p.tile_w * p.tile_h * 128) : Cfg::kABytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = m_block(tile);
         const int n_blk = tile % p.n_tiles;
         int img = 0, y0 = 0, x0 = 0;
         if (p.conv) {
@@ -189,6 +197,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kCtas == 2) {
+            // both CTAs' bytes are counted on the leader's barrier; the leader alone arrives on it
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + Cfg::kBBytes));
+            if (p.conv) {
+              const int tap = kb / p.cin_blocks;
+              const int c0 = (kb % p.cin_blocks) * 64;
+              tma_load_4d_pair(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], c0, x0 + tap % 3 - 1,
+                               y0 + tap / 3 - 1, img);
+            } else {
+              tma_load_2d_pair(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], kb * 64, m_blk * 128);
+            }
+            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &map_b, &full_bar[stage], kb * 64,
+                             n_blk * BLOCK_N + rank * (BLOCK_N / 2));
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::kBBytes);
           if (p.conv) {
             const int tap = kb / p.cin_blocks;
@@ -199,6 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tma_load_2d(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], kb * 64, m_blk * 128);
           }
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &map_b, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -206,13 +229,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(Tr::kFmt, 128, BLOCK_N);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(Tr::kFmt, 128 * kCtas, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -224,12 +247,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);
+          if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);
+        if (kCtas == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -251,6 +275,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int* row_off = reinterpret_cast<int*>(epi_smem + Cfg::kEpiWarps * 32 * 32 * 4) + ew * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // hand an accumulator stage back to the MMA issuer (which lives in the pair's leader CTA)
+    auto release_acc = [&](int a) {
+      if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&tmem_empty[a], 0);
+      else mbar_arrive(&tmem_empty[a]);
+    };
     T* out = static_cast<T*>(p.out);
     T* out_relu = static_cast<T*>(p.out_relu);
     const T* res1 = static_cast<const T*>(p.res1);
@@ -262,8 +291,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // the instructions of the staged path below: nothing is re-read from shared memory, no addresses,
       // no predicates.
       uint8_t* buf = epi_smem + ew * 4096;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = m_block(tile);
         const int n_tile = (tile % p.n_tiles) * BLOCK_N;
         constexpr int kPerWarp = BLOCK_N / 64;             // chunks per warp; the host guarantees N % BLOCK_N == 0, BLOCK_N >= 128
         const int ch_begin = half * kPerWarp;
@@ -288,7 +317,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           } else {
             tc_fence_before();                 // every TMEM read of this stage is complete: hand it back now
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) release_acc(acc);
           }
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -339,13 +368,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       constexpr int kPerWarp = BLOCK_N / 64;
       const int ch_begin = half * kPerWarp;
       uint32_t x_phase = 0;
-      if (lane == 0 && blockIdx.x < num_tiles) {
+      if (lane == 0 && tile0 < num_tiles) {
         mbar_arrive_expect_tx(&x_bar[ew], 4096);
-        tma_load_2d(buf, &map_out, &x_bar[ew], (blockIdx.x % p.n_tiles) * BLOCK_N + ch_begin * 32,
-                    (blockIdx.x / p.n_tiles) * 128 + quarter * 32);
+        tma_load_2d(buf, &map_out, &x_bar[ew], (tile0 % p.n_tiles) * BLOCK_N + ch_begin * 32, m_block(tile0) * 128 + quarter * 32);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = (tile / p.n_tiles) * 128 + quarter * 32;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int row0 = m_block(tile) * 128 + quarter * 32;
         const int n_tile = (tile % p.n_tiles) * BLOCK_N;
         if (lane == 0) {
           for (int c = 1; c < kPerWarp; ++c) tma_prefetch_l2_2d(&map_out, n_tile + (ch_begin + c) * 32, row0);
@@ -367,7 +395,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           } else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) release_acc(acc);
           }
           mbar_wait(&x_bar[ew], x_phase);
           x_phase ^= 1;
@@ -391,12 +419,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             bulk_commit();
             // next box of this warp: the next chunk of this tile, or the first chunk of the CTA's next tile
             int nt = tile, nc = c + 1;
-            if (nc == kPerWarp) { nt = tile + gridDim.x; nc = 0; }
+            if (nc == kPerWarp) { nt = tile + tile_step; nc = 0; }
             if (nt < num_tiles) {
               bulk_wait_read0();               // the store has drained the buffer
               mbar_arrive_expect_tx(&x_bar[ew], 4096);
               tma_load_2d(buf, &map_out, &x_bar[ew], (nt % p.n_tiles) * BLOCK_N + (ch_begin + nc) * 32,
-                          (nt / p.n_tiles) * 128 + quarter * 32);
+                          m_block(nt) * 128 + quarter * 32);
             }
           }
         }
@@ -404,8 +432,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       if (lane == 0) bulk_wait0();
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = m_block(tile);
       const int n_blk = tile % p.n_tiles;
       // ---- where does this thread's row go?
       bool valid;
@@ -416,7 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int t = m_blk % per_img;
         const int y = (t / p.tiles_x) * p.tile_h + r / p.tile_w;
         const int x = (t % p.tiles_x) * p.tile_w + r % p.tile_w;
-        valid = (r < p.tile_w * p.tile_h) && y < p.H && x < p.W;
+        valid = (r < p.tile_w * p.tile_h) && y < p.H && x < p.W && m_blk < p.m_tiles;
         orow = (static_cast<long long>(img) * p.H + y) * p.W + x;
       } else {
         const long long m = static_cast<long long>(m_blk) * 128 + r;
@@ -629,16 +657,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // all of this warp's TMEM reads of the stage are complete (wait::ld above): hand it back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) release_acc(acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all();      // nothing of the pair is still addressed to this CTA
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kCtas == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -37,6 +37,7 @@ struct GemmOp {
   int block_n;
   int precision;
   int grid;
+  int ctas;       // 2: launched as clusters of two CTAs working on 256-row tiles (tcgen05 cta_group::2)
 };
 
 // D[M,N] = A[M,K] B[N,K]^T

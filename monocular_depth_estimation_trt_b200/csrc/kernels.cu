@@ -126,6 +126,19 @@ static int pick_block_n(int n) {
   return best;
 }
 
+// One persistent CTA per SM -- or, for wide tiles with enough rows, one CTA pair per TPC (MDE_NO_PAIR=1 turns pairs off).
+static void pick_ctas(GemmOp* op) {
+  op->ctas = (op->block_n >= 128 && op->p.m_tiles >= 2 && !getenv("MDE_NO_PAIR")) ? 2 : 1;
+}
+static int pick_grid(GemmOp* op) {
+  const int sms = num_sms();
+  if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
+  const GemmParams& p = op->p;
+  if (op->ctas == 2) op->grid = 2 * std::min(sms / 2, ((p.m_tiles + 1) / 2) * p.n_tiles);
+  else op->grid = std::min(sms, p.m_tiles * p.n_tiles);
+  return MDE_OK;
+}
+
 static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_out) {
   p.row_map = ROW_IDENTITY;
   p.tokens = 0; p.shuffle_s = 0; p.shuffle_cout = 0;
@@ -172,6 +185,7 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
       return fail(MDE_ERR_INVALID, "gemm: inconsistent pixel-shuffle description");
   }
   op->precision = precision;
+  pick_ctas(op);
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(m)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(lda) * 2};
@@ -181,14 +195,11 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(n)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(ldb) * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n / op->ctas)};   // each CTA of a pair stages half of the B tile
     MDE_TRY(encode_map(&op->map_b, precision, d_b, 2, dims, str, box));
   }
   MDE_TRY(maybe_tma_out(op, precision, ep, m, n));
-  const int sms = num_sms();
-  if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
-  op->grid = std::min(sms, p.m_tiles * p.n_tiles);
-  return MDE_OK;
+  return pick_grid(op);
 }
 
 int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, int w, int cin, const void* d_w,
@@ -223,6 +234,7 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
   p.m_tiles = batch * p.tiles_x * p.tiles_y;
   p.n_tiles = (cout + op->block_n - 1) / op->block_n;
   op->precision = precision;
+  pick_ctas(op);
   {
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
                           static_cast<cuuint64_t>(batch)};
@@ -234,36 +246,56 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(9 * cin_pad), static_cast<cuuint64_t>(cout)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(9 * cin_pad) * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(op->block_n / op->ctas)};
     MDE_TRY(encode_map(&op->map_b, precision, d_w, 2, dims, str, box));
   }
   memset(&op->map_out, 0, sizeof(op->map_out));
-  const int sms = num_sms();
-  if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
-  op->grid = std::min(sms, p.m_tiles * p.n_tiles);
-  return MDE_OK;
+  return pick_grid(op);
 }
 
-template <int BN, typename T>
+template <int BN, typename T, int kCtas>
 static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<BN, T>;
+  auto kern = gemm_tcgen05_kernel<BN, T, kCtas>;
+  using Cfg = GemmCfg<BN, kCtas>;
   if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<op.grid, GemmCfg<BN>::kThreads, GemmCfg<BN>::kSmemBytes, s>>>(op.map_a, op.map_b, op.map_out, op.p);
+  if (kCtas == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(op.grid);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    MDE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, op.map_a, op.map_b, op.map_out, op.p));
+  } else {
+    kern<<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(op.map_a, op.map_b, op.map_out, op.p);
+  }
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
 
 template <typename T>
 static int launch_gemm_bn(const GemmOp& op, cudaStream_t s) {
+  if (op.ctas == 2) {
+    switch (op.block_n) {
+      case 256: return launch_gemm_t<256, T, 2>(op, s);
+      case 128: return launch_gemm_t<128, T, 2>(op, s);
+    }
+    return fail(MDE_ERR_INVALID, "CTA pairs need BLOCK_N 128 or 256, not %d", op.block_n);
+  }
   switch (op.block_n) {
-    case 256: return launch_gemm_t<256, T>(op, s);
-    case 128: return launch_gemm_t<128, T>(op, s);
-    case 64: return launch_gemm_t<64, T>(op, s);
-    case 32: return launch_gemm_t<32, T>(op, s);
+    case 256: return launch_gemm_t<256, T, 1>(op, s);
+    case 128: return launch_gemm_t<128, T, 1>(op, s);
+    case 64: return launch_gemm_t<64, T, 1>(op, s);
+    case 32: return launch_gemm_t<32, T, 1>(op, s);
   }
   return fail(MDE_ERR_INVALID, "unsupported BLOCK_N %d", op.block_n);
 }
