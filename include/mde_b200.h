@@ -173,6 +173,10 @@ int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h,
 /* softmax(Q K^T / 8) V over [B*ntok][3*D] packed q|k|v rows, head dim 64 -> [B*ntok][D]. */
 int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                     void* stream);
+/* The same op with 64-key tiles and four CTAs per SM (csrc/attention_tc64.cuh): the measured alternative to the
+ * default kernel, kept for comparison; the engine launches it only when MDE_ATTN_KV=64 is set. */
+int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                         void* stream);
 /* The same op on warp-level mma.sync tensor-core instructions: an independent cross-check of the
  * tcgen05 kernel for the tests; the engine never launches it. */
 int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

@@ -50,13 +50,14 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream);
 
 // tcgen05 attention launch, described at plan-build time (tensor map over the packed q|k|v rows)
 struct AttnOp {
-  alignas(64) CUtensorMap map_qkv;
+  alignas(64) CUtensorMap map_qkv;   // 128-row boxes (query tiles; key/value tiles of the two-CTA-per-SM kernel)
+  alignas(64) CUtensorMap map_kv;    // 64-row boxes (key/value tiles of the four-CTA-per-SM kernel)
   const void* qkv;
   void* out;
   int batch, ntok, heads, precision;
 };
 int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads);
-int launch_attention_op(const AttnOp& op, cudaStream_t s);
+int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv = 0);   // kv: 0 = default kernel, 64 / 128 = key-tile variant
 // warp-level mma.sync variant (kept as an independent cross-check of the tcgen05 kernel in the tests)
 int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);
 int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,

@@ -9,6 +9,7 @@
 
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc64.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -128,7 +129,8 @@ static int pick_block_n(int n) {
 
 // One persistent CTA per SM -- or, for wide tiles with enough rows, one CTA pair per TPC (MDE_NO_PAIR=1 turns pairs off).
 static void pick_ctas(GemmOp* op) {
-  op->ctas = (op->block_n >= 128 && op->p.m_tiles >= 2 && !getenv("MDE_NO_PAIR")) ? 2 : 1;
+  // pairs pay off for 256-wide tiles with a real K loop; short K (a few k-blocks per tile) is epilogue-bound either way
+  op->ctas = (op->block_n == 256 && op->p.m_tiles >= 2 && op->p.num_k_blocks >= 4 && !getenv("MDE_NO_PAIR")) ? 2 : 1;
 }
 static int pick_grid(GemmOp* op) {
   const int sms = num_sms();
@@ -339,7 +341,35 @@ int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out,
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(3 * heads * 64), static_cast<cuuint64_t>(rows)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(3 * heads * 64) * 2};
   cuuint32_t box[2] = {64, 128};
-  return encode_map(&op->map_qkv, precision, d_qkv, 2, dims, str, box);
+  MDE_TRY(encode_map(&op->map_qkv, precision, d_qkv, 2, dims, str, box));
+  cuuint32_t box_kv[2] = {64, 64};
+  return encode_map(&op->map_kv, precision, d_qkv, 2, dims, str, box_kv);
+}
+
+template <typename T, int kPoly>
+static int launch_attention_tc64_t(const AttnOp& op, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = attention_tc64_kernel<T, kPoly>;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kA64SmemBytes));
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("MDE_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAtcThreads, kA64SmemBytes);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, kern);
+      fprintf(stderr, "[MDET] attention_tc64: %d CTAs/SM (smem %d B, %d threads, %d regs, %zu B local, %zu B static smem), %d/8 of the exponentials on the FMA pipe\n",
+              nb, kA64SmemBytes, kAtcThreads, fa.numRegs, fa.localSizeBytes, fa.sharedSizeBytes, kPoly);
+    }
+    attr_set = true;
+  }
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  dim3 grid((op.ntok + 127) / 128, op.heads, op.batch);
+  kern<<<grid, kAtcThreads, kA64SmemBytes, s>>>(op.map_qkv, op.map_kv, p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
 }
 
 template <typename T, int kPoly>
@@ -374,8 +404,27 @@ static int attn_poly() {
   }
   return v;
 }
+// Default: 128-key tiles, two CTAs per SM (attention_tc.cuh).  MDE_ATTN_KV=64 (or kv == 64 from mde_k_attention_kv64)
+// selects the four-CTAs-per-SM kernel with 64-key tiles (attention_tc64.cuh): measured slower on B200 (0.84 vs 0.70 ms
+// at B=64, N=1370: both sit at ~60 % of the SFU bound, see profiles/), kept as the measured alternative.
+static int attn_kv() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDE_ATTN_KV");
+    v = (e && atoi(e) == 64) ? 64 : 128;
+  }
+  return v;
+}
 template <typename T>
-static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s) {
+static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s, int kv = 0) {
+  if ((kv ? kv : attn_kv()) == 64) {
+    switch (attn_poly()) {
+      case 0: return launch_attention_tc64_t<T, 0>(op, s);
+      case 2: return launch_attention_tc64_t<T, 2>(op, s);
+      case 4: return launch_attention_tc64_t<T, 4>(op, s);
+      default: return launch_attention_tc64_t<T, 3>(op, s);
+    }
+  }
   switch (attn_poly()) {
     case 0: return launch_attention_tc_t<T, 0>(op, s);
     case 2: return launch_attention_tc_t<T, 2>(op, s);
@@ -383,8 +432,8 @@ static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s) {
     default: return launch_attention_tc_t<T, 3>(op, s);
   }
 }
-int launch_attention_op(const AttnOp& op, cudaStream_t s) {
-  return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s) : launch_attention_tc_p<__half>(op, s);
+int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv) {
+  return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s, kv) : launch_attention_tc_p<__half>(op, s, kv);
 }
 
 template <typename T>
@@ -580,6 +629,14 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                         void* stream) {
+  clear_error();
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 64);
 }
 
 int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
