@@ -127,6 +127,24 @@ def test_vitl_518_b2_parity(lib, prec):
         assert m["max_rel"] <= GATE[prec]["max_rel"]
 
 
+@pytest.mark.parametrize("h,w", [(616, 1064), (518, 700), (266, 518)])
+def test_vits_non_square_token_grids(lib, h, w):
+    """Non-square patch grids: 44 x 76 (the Metric3D V2 input size, BASELINE configs[2]; pos_embed resized
+    bicubically from 37 x 37 as `interpolate_pos_encoding` does), 37 x 50 (Depth-Anything-AC's keep-ratio sizes)
+    and 19 x 37.  Odd grids exercise the ceil'd level-4 map and the `size=` upsampling of refinenet4."""
+    eng, x, depth, trace = build_engine("vits", "fp16", h=h, w=w)
+    out = torch.full((1, h, w), float("nan"), device="cuda")
+    ctx = run(eng, x.cuda(), out)
+    gh, gw = h // 14, w // 14
+    xl = fetch(ctx, "x", (1, gh * gw + 1, 384), "fp16")
+    assert rms_rel(xl, trace["block11"]) < INTER["fp16"]
+    m = R.compare_depth(depth.numpy(), out.cpu().numpy())
+    print(h, w, m)
+    assert m["compared"] == h * w
+    assert m["abs_rel"] <= GATE["fp16"]["abs_rel"]
+    assert m["max_rel"] <= GATE["fp16"]["max_rel"]
+
+
 def test_batch_entries_are_independent(lib):
     """The same image at batch positions 0 and 2 gives bit-identical maps; idempotent across runs."""
     sd, x, depth, _ = R.reference("vits")
