@@ -43,6 +43,13 @@ extern "C" {
 /* tensor dtypes reported by mde_engine_io_dtype */
 #define MDE_DT_F32 0
 #define MDE_DT_U8 1
+#define MDE_DT_F16 2
+#define MDE_DT_BF16 3
+
+/* what the engine computes behind the shared DINOv2 trunk */
+#define MDE_HEAD_DPT 0          /* Depth Anything V2: DPT head, output float32 depth [B,H,W] */
+#define MDE_HEAD_ENCODER_TAPS 1 /* trunk only (the patch-encoder stage of Depth Pro, models/depth_pro/onnx_export.py:15-22):
+                                 * output = the four tapped block outputs, cls dropped, 16-bit [4][B][T][D] */
 
 /* error codes */
 #define MDE_OK 0
@@ -76,6 +83,9 @@ typedef struct mde_engine_desc {
   double norm_std[3];      /*   core/preprocess.py:294-328 with float64 dtypes */
   float max_depth;         /* > 0: metric head, sigmoid * max_depth;  <= 0: relative head, ReLU */
   int32_t device;          /* CUDA device ordinal */
+  int32_t head_mode;       /* MDE_HEAD_* */
+  int32_t tap_norm_mask;   /* bit i: tap i goes through the trunk's final LayerNorm (0xF for Depth Anything; 0x8 for
+                            * Depth Pro's hooks, which take raw block outputs and normalise only the last one) */
 } mde_engine_desc;
 
 const char* mde_last_error(void);
@@ -109,6 +119,12 @@ int mde_context_set_tensor_address(mde_context* c, const char* name, void* d_ptr
 int mde_context_set_input_shape(mde_context* c, const char* name, int32_t ndim, const int64_t* dims);
 /* Launch one forward of the whole batch on `stream`.  Asynchronous. */
 int mde_context_enqueue(mde_context* c, void* stream);
+/* MDE_HEAD_ENCODER_TAPS engines, one process per GPU: fuse the all-gather of the taps into the kernel that produces
+ * them.  d_peer_outputs[r] is rank r's gather buffer, 16-bit [4][n_ranks * B][T][D], mapped into this process (own
+ * buffer for r == rank, cudaIpcOpenMemHandle'd peers otherwise); this rank's B images are written at image offset
+ * rank * B of every buffer with plain stores over NVLink.  The "output" binding is then unused.  n_ranks == 0 turns
+ * it off.  The caller orders the ranks (a barrier after the stream has drained) before anyone reads a buffer. */
+int mde_context_set_gather(mde_context* c, int32_t n_ranks, int32_t rank, void* const* d_peer_outputs);
 /* Number of kernels one enqueue launches (bench.py's gpu_launches). */
 int mde_context_launches_per_enqueue(const mde_context* c);
 /* Profiling variant of enqueue: CUDA events between the launches, then a stream synchronise.

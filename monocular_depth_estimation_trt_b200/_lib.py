@@ -9,7 +9,8 @@ LIB_PATH = os.path.join(HERE, "libmde_b200.so")
 
 MDE_FP16, MDE_BF16 = 0, 1
 MDE_INPUT_F32_NCHW, MDE_INPUT_U8_HWC = 0, 1
-MDE_DT_F32, MDE_DT_U8 = 0, 1
+MDE_DT_F32, MDE_DT_U8, MDE_DT_F16, MDE_DT_BF16 = 0, 1, 2, 3
+MDE_HEAD_DPT, MDE_HEAD_ENCODER_TAPS = 0, 1
 PRECISIONS = {"fp16": MDE_FP16, "bf16": MDE_BF16}
 
 # every symbol include/mde_b200.h declares (tests/test_abi.py checks the header against this list)
@@ -19,7 +20,7 @@ SYMBOLS = [
     "mde_engine_destroy", "mde_engine_num_io", "mde_engine_io_name", "mde_engine_io_shape",
     "mde_engine_io_dtype", "mde_engine_io_is_input", "mde_engine_workspace_bytes",
     "mde_context_create", "mde_context_destroy", "mde_context_set_tensor_address",
-    "mde_context_set_input_shape", "mde_context_enqueue", "mde_context_launches_per_enqueue",
+    "mde_context_set_input_shape", "mde_context_enqueue", "mde_context_set_gather", "mde_context_launches_per_enqueue",
     "mde_context_get_buffer", "mde_context_snapshot_block", "mde_context_enqueue_timed", "mde_context_op_info",
     "mde_k_preprocess_u8", "mde_k_im2col_f32", "mde_k_gemm", "mde_k_conv3x3", "mde_k_attention", "mde_k_attention_kv64", "mde_k_attention_mma",
     "mde_k_layernorm", "mde_k_bilinear", "mde_k_im2col_s2", "mde_k_upconv_head",
@@ -36,6 +37,7 @@ class EngineDesc(C.Structure):
         ("max_src_h", C.c_int32), ("max_src_w", C.c_int32), ("swap_rb", C.c_int32),
         ("norm_mean", C.c_double * 3), ("norm_std", C.c_double * 3),
         ("max_depth", C.c_float), ("device", C.c_int32),
+        ("head_mode", C.c_int32), ("tap_norm_mask", C.c_int32),
     ]
 
 
@@ -84,6 +86,7 @@ def load() -> C.CDLL:
         "mde_context_set_tensor_address": (C.c_int, [vp, C.c_char_p, vp]),
         "mde_context_set_input_shape": (C.c_int, [vp, C.c_char_p, i32, P(i64)]),
         "mde_context_enqueue": (C.c_int, [vp, vp]),
+        "mde_context_set_gather": (C.c_int, [vp, i32, i32, P(vp)]),
         "mde_context_launches_per_enqueue": (C.c_int, [vp]),
         "mde_context_get_buffer": (C.c_int, [vp, C.c_char_p, P(vp), P(i64), P(i32)]),
         "mde_context_snapshot_block": (C.c_int, [vp, i32]),

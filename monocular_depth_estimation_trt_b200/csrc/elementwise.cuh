@@ -161,6 +161,10 @@ struct LayerNormParams {
   float eps;
   int drop_cls;
   int ntok;
+  int identity;        // 1: no normalisation, the row is only converted (raw block output taps)
+  int n_dst;           // > 0: the row is written to dst[0..n_dst) instead of out (gather buffers of the ranks, peer memory)
+  long long dst_row0;  // row offset of this rank's rows inside every dst
+  void* dst[8];
 };
 template <typename T, int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p) {
@@ -195,16 +199,31 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq * (1.0f / D) + p.eps);
-  T* out = static_cast<T*>(p.out) + orow * D;
+  uint2 u[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = (lane + i * 32) * 4;
-    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.b + c));
-    uint2 u;
-    u.x = F16Traits<T>::pack2((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y);
-    u.y = F16Traits<T>::pack2((v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
-    *reinterpret_cast<uint2*>(out + c) = u;
+    if (p.identity) {
+      u[i].x = F16Traits<T>::pack2(v[i].x, v[i].y);
+      u[i].y = F16Traits<T>::pack2(v[i].z, v[i].w);
+    } else {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.b + c));
+      u[i].x = F16Traits<T>::pack2((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y);
+      u[i].y = F16Traits<T>::pack2((v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+    }
+  }
+  if (p.n_dst == 0) {
+    T* out = static_cast<T*>(p.out) + orow * D;
+#pragma unroll
+    for (int i = 0; i < V; ++i) *reinterpret_cast<uint2*>(out + (lane + i * 32) * 4) = u[i];
+  } else {
+    // fused all-gather: the same row goes to every rank's buffer (local HBM for our own, NVLink stores for the peers)
+    for (int d = 0; d < p.n_dst; ++d) {
+      T* out = static_cast<T*>(p.dst[d]) + (p.dst_row0 + orow) * D;
+#pragma unroll
+      for (int i = 0; i < V; ++i) *reinterpret_cast<uint2*>(out + (lane + i * 32) * 4) = u[i];
+    }
   }
 }
 

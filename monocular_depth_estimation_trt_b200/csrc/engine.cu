@@ -109,6 +109,8 @@ struct mde_context {
   void* d_output = nullptr;
   int src_h = 0, src_w = 0;
   int snapshot_block = -1;
+  int gather_ranks = 0, gather_rank = 0;       // mde_context_set_gather
+  void* gather_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float* x_snapshot = nullptr;
   float* x = nullptr;
   int64_t x_bytes = 0;
@@ -203,9 +205,12 @@ static int validate_desc(const mde_engine_desc* d) {
   if (d->patch_size <= 0 || d->input_h <= 0 || d->input_w <= 0 || d->input_h % d->patch_size || d->input_w % d->patch_size)
     return fail(MDE_ERR_INVALID, "input %dx%d must be a positive multiple of patch %d", d->input_h, d->input_w, d->patch_size);
   if (d->batch <= 0 || d->batch > 4096) return fail(MDE_ERR_INVALID, "bad batch %d", d->batch);
-  if (d->features <= 0 || d->features % 16) return fail(MDE_ERR_INVALID, "features must be a positive multiple of 16");
+  if (d->head_mode != MDE_HEAD_DPT && d->head_mode != MDE_HEAD_ENCODER_TAPS) return fail(MDE_ERR_INVALID, "unknown head_mode %d", d->head_mode);
+  if (d->tap_norm_mask < 0 || d->tap_norm_mask > 0xF) return fail(MDE_ERR_INVALID, "tap_norm_mask must be a 4-bit mask");
+  if (d->head_mode == MDE_HEAD_DPT && d->tap_norm_mask != 0xF) return fail(MDE_ERR_INVALID, "the DPT head takes all four taps through the final LayerNorm (tap_norm_mask 0xF)");
+  if (d->head_mode == MDE_HEAD_DPT && (d->features <= 0 || d->features % 16)) return fail(MDE_ERR_INVALID, "features must be a positive multiple of 16");
   for (int i = 0; i < 4; ++i) {
-    if (d->out_channels[i] <= 0 || d->out_channels[i] % 8) return fail(MDE_ERR_INVALID, "out_channels must be positive multiples of 8");
+    if (d->head_mode == MDE_HEAD_DPT && (d->out_channels[i] <= 0 || d->out_channels[i] % 8)) return fail(MDE_ERR_INVALID, "out_channels must be positive multiples of 8");
     if (d->taps[i] < 0 || d->taps[i] >= d->depth || (i > 0 && d->taps[i] <= d->taps[i - 1]))
       return fail(MDE_ERR_INVALID, "taps must be increasing block indices below depth");
   }
@@ -321,6 +326,16 @@ extern "C" int mde_engine_finalize(mde_engine* e) {
     MDE_TRY(upload_f32(e, p + "mlp.fc2.bias", {D}, &b.fc2_b));
     MDE_TRY(upload_f32(e, p + "ls2.gamma", {D}, &b.ls2));
   }
+  if (d.head_mode == MDE_HEAD_ENCODER_TAPS) {
+    if (d.input_mode == MDE_INPUT_U8_HWC) {
+      float lut[768];
+      build_norm_lut(d.norm_mean, d.norm_std, lut);
+      MDE_TRY(upload(e, lut, sizeof(lut), reinterpret_cast<void**>(&e->lut)));
+    }
+    e->raw.clear();
+    e->finalized = true;
+    return MDE_OK;
+  }
   // ---- DPT head
   const std::string h = "depth_head.";
   const int* oc = d.out_channels;
@@ -391,6 +406,9 @@ extern "C" int mde_engine_io_shape(const mde_engine* e, int32_t i, int32_t* ndim
     } else {
       dims[0] = e->d.batch; dims[1] = e->d.max_src_h; dims[2] = e->d.max_src_w; dims[3] = 3;
     }
+  } else if (e->d.head_mode == MDE_HEAD_ENCODER_TAPS) {
+    *ndim = 4;
+    dims[0] = 4; dims[1] = e->d.batch; dims[2] = e->T; dims[3] = e->d.embed_dim;
   } else {
     *ndim = 3;
     dims[0] = e->d.batch; dims[1] = e->d.input_h; dims[2] = e->d.input_w;
@@ -399,6 +417,7 @@ extern "C" int mde_engine_io_shape(const mde_engine* e, int32_t i, int32_t* ndim
 }
 extern "C" int mde_engine_io_dtype(const mde_engine* e, int32_t i) {
   if (!e || i < 0 || i > 1) return -1;
+  if (i == 1 && e->d.head_mode == MDE_HEAD_ENCODER_TAPS) return e->d.precision == MDE_BF16 ? MDE_DT_BF16 : MDE_DT_F16;
   return (i == 0 && e->d.input_mode == MDE_INPUT_U8_HWC) ? MDE_DT_U8 : MDE_DT_F32;
 }
 extern "C" int mde_engine_io_is_input(const mde_engine* e, int32_t i) {
@@ -501,9 +520,11 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   void* qkv = pl.alloc16(rows * 3 * D);
   void* att = pl.alloc16(rows * D);
   void* hid = pl.alloc16(rows * 4 * D);
-  void* tap[4];
+  const bool taps_only = d.head_mode == MDE_HEAD_ENCODER_TAPS;   // the taps go straight to the output binding / the gather buffers
+  void* tap[4] = {nullptr, nullptr, nullptr, nullptr};
   const char* tap_names[4] = {"tap0", "tap1", "tap2", "tap3"};
-  for (int i = 0; i < 4; ++i) tap[i] = pl.alloc16(prow * D, tap_names[i]);
+  if (!taps_only)
+    for (int i = 0; i < 4; ++i) tap[i] = pl.alloc16(prow * D, tap_names[i]);
   if (!dry) { c->x = x; c->x_snapshot = xs; c->x_bytes = rows * D * 4; }
 
   // ---- embed
@@ -526,7 +547,7 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   int next_tap = 0;
   for (int i = 0; i < d.depth; ++i) {
     const Block& b = e->blocks.empty() ? Block{} : e->blocks[i];
-    Op l1; l1.kind = Op::LAYERNORM; l1.in = x; l1.out = ln; l1.w = b.ln1_w; l1.b = b.ln1_b; l1.rows = rows; l1.i0 = 0;
+    Op l1; l1.kind = Op::LAYERNORM; l1.in = x; l1.out = ln; l1.w = b.ln1_w; l1.b = b.ln1_b; l1.rows = rows; l1.i0 = 0; l1.i1 = 0; l1.i2 = -1;
     pl.push(l1, "layernorm", 6.0 * rows * D);
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.qkv_b; ep.d_out = qkv; ep.ld_out = 3 * D;
       pl.gemm("qkv", ln, rows, D, D, b.qkv_w, 3 * D, D, ep); }
@@ -544,9 +565,15 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     { Op s; s.kind = Op::SNAPSHOT; s.block = i; pl.push(s, "snapshot"); }
     if (next_tap < 4 && d.taps[next_tap] == i) {
       Op t; t.kind = Op::LAYERNORM; t.in = x; t.out = tap[next_tap]; t.w = e->norm_w; t.b = e->norm_b; t.rows = rows; t.i0 = 1;
+      t.i1 = ((d.tap_norm_mask >> next_tap) & 1) ? 0 : 1;     // identity: raw block output
+      t.i2 = taps_only ? next_tap : -1;                        // which slice of the output binding
       pl.push(t, "layernorm tap", 4.0 * rows * D + 2.0 * prow * D);
       ++next_tap;
     }
+  }
+  if (taps_only) {
+    if (bytes_out) *bytes_out = pl.bytes;
+    return pl.rc;
   }
   // ---- DPT reassemble
   const int gh = e->gh, gw = e->gw;
@@ -732,8 +759,23 @@ extern "C" int mde_context_get_buffer(mde_context* c, const char* name, void** d
   return MDE_OK;
 }
 
+extern "C" int mde_context_set_gather(mde_context* c, int32_t n_ranks, int32_t rank, void* const* d_peer_outputs) {
+  clear_error();
+  if (!c) return fail(MDE_ERR_INVALID, "null context");
+  if (n_ranks == 0) { c->gather_ranks = 0; return MDE_OK; }
+  if (c->e->d.head_mode != MDE_HEAD_ENCODER_TAPS) return fail(MDE_ERR_STATE, "the fused gather belongs to MDE_HEAD_ENCODER_TAPS engines");
+  if (n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks || !d_peer_outputs) return fail(MDE_ERR_INVALID, "gather: 1..8 ranks, 0 <= rank < n_ranks");
+  for (int r = 0; r < n_ranks; ++r) {
+    if (!d_peer_outputs[r] || (reinterpret_cast<uintptr_t>(d_peer_outputs[r]) & 15)) return fail(MDE_ERR_INVALID, "gather: buffer of rank %d is null or not 16-byte aligned", r);
+    c->gather_dst[r] = d_peer_outputs[r];
+  }
+  c->gather_ranks = n_ranks;
+  c->gather_rank = rank;
+  return MDE_OK;
+}
+
 static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
-  if (!c->d_input || !c->d_output) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'input' and 'output' before enqueue");
+  if (!c->d_input || (!c->d_output && c->gather_ranks == 0)) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'input' and 'output' before enqueue");
   mde_engine* e = c->e;
   const mde_engine_desc& d = e->d;
   const int prec = d.precision;
@@ -757,7 +799,22 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         MDE_TRY(launch_gemm(op.g, s));
         break;
       case Op::LAYERNORM:
-        MDE_TRY(launch_layernorm(prec, static_cast<const float*>(op.in), op.w, op.b, op.out, op.rows, d.embed_dim, 1e-6f, op.i0, e->ntok, s));
+        if (op.i2 >= 0) {
+          // trunk-only engine: tap op.i2 lands in slice op.i2 of the output binding, or of every rank's gather buffer
+          const long long slice = static_cast<long long>(d.batch) * e->T * d.embed_dim;     // elements of one tap of one rank
+          if (c->gather_ranks > 0) {
+            void* dst[8];
+            for (int r = 0; r < c->gather_ranks; ++r)
+              dst[r] = static_cast<uint16_t*>(c->gather_dst[r]) + static_cast<long long>(op.i2) * c->gather_ranks * slice;
+            MDE_TRY(launch_layernorm(prec, static_cast<const float*>(op.in), op.w, op.b, nullptr, op.rows, d.embed_dim, 1e-6f, op.i0,
+                                     e->ntok, s, op.i1, c->gather_ranks, dst, static_cast<long long>(c->gather_rank) * d.batch * e->T));
+          } else {
+            MDE_TRY(launch_layernorm(prec, static_cast<const float*>(op.in), op.w, op.b,
+                                     static_cast<uint16_t*>(c->d_output) + op.i2 * slice, op.rows, d.embed_dim, 1e-6f, op.i0, e->ntok, s, op.i1));
+          }
+          break;
+        }
+        MDE_TRY(launch_layernorm(prec, static_cast<const float*>(op.in), op.w, op.b, op.out, op.rows, d.embed_dim, 1e-6f, op.i0, e->ntok, s, op.i1));
         break;
       case Op::ATTENTION:
         MDE_TRY(launch_attention_op(op.attn, s));

@@ -61,7 +61,8 @@ int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv = 0);   // kv: 
 // warp-level mma.sync variant (kept as an independent cross-check of the tcgen05 kernel in the tests)
 int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);
 int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,
-                     int dim, float eps, int drop_cls, int ntok, cudaStream_t s);
+                     int dim, float eps, int drop_cls, int ntok, cudaStream_t s, int identity = 0, int n_dst = 0,
+                     void* const* dst = nullptr, long long dst_row0 = 0);
 int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int hi, int wi, int ho, int wo, int c,
                     cudaStream_t s);
 int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s);

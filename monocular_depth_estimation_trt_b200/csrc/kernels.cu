@@ -451,11 +451,15 @@ static int launch_layernorm_t(const LayerNormParams& p, cudaStream_t s) {
   return MDE_OK;
 }
 int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,
-                     int dim, float eps, int drop_cls, int ntok, cudaStream_t s) {
+                     int dim, float eps, int drop_cls, int ntok, cudaStream_t s, int identity, int n_dst, void* const* dst,
+                     long long dst_row0) {
   if (rows <= 0) return fail(MDE_ERR_INVALID, "layernorm: no rows");
   if (drop_cls && (ntok < 2 || rows % ntok)) return fail(MDE_ERR_INVALID, "layernorm: rows not a multiple of ntok");
+  if (n_dst < 0 || n_dst > 8 || (n_dst > 0 && !dst)) return fail(MDE_ERR_INVALID, "layernorm: at most 8 gather destinations");
   LayerNormParams p;
   p.x = d_x; p.w = d_w; p.b = d_b; p.out = d_out; p.rows = rows; p.D = dim; p.eps = eps; p.drop_cls = drop_cls; p.ntok = ntok;
+  p.identity = identity; p.n_dst = n_dst; p.dst_row0 = dst_row0;
+  for (int i = 0; i < 8; ++i) p.dst[i] = i < n_dst ? dst[i] : nullptr;
   return precision == MDE_BF16 ? launch_layernorm_t<__nv_bfloat16>(p, s) : launch_layernorm_t<__half>(p, s);
 }
 

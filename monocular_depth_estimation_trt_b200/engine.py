@@ -29,13 +29,15 @@ class TensorIOMode(enum.Enum):
     OUTPUT = 2
 
 
-_NP_DTYPES = {_lib.MDE_DT_F32: np.dtype(np.float32), _lib.MDE_DT_U8: np.dtype(np.uint8)}
+# bf16 has no numpy dtype: such a binding is described as uint16 (the bit pattern), as TensorRT's numpy helpers do
+_NP_DTYPES = {_lib.MDE_DT_F32: np.dtype(np.float32), _lib.MDE_DT_U8: np.dtype(np.uint8),
+              _lib.MDE_DT_F16: np.dtype(np.float16), _lib.MDE_DT_BF16: np.dtype(np.uint16)}
 
 
 def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode: str = "f32_nchw",
               max_src_hw: Tuple[int, int] = (0, 0), swap_rb: bool = True,
               mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
-              device: int = 0) -> _lib.EngineDesc:
+              device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF) -> _lib.EngineDesc:
     if precision not in _lib.PRECISIONS:
         # The reference also builds "fp32" engines (core/common.py:141-150).  The B200 path is a
         # 16-bit tensor-core path with fp32 accumulation; refuse instead of silently downgrading.
@@ -58,6 +60,10 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
         d.norm_mean[i], d.norm_std[i] = float(mean[i]), float(std[i])
     d.max_depth = float(meta["max_depth"]) if meta.get("max_depth") else 0.0
     d.device = int(device)
+    if head not in ("dpt", "encoder_taps"):
+        raise ValueError(f"[MDET] unknown head {head!r}")
+    d.head_mode = _lib.MDE_HEAD_ENCODER_TAPS if head == "encoder_taps" else _lib.MDE_HEAD_DPT
+    d.tap_norm_mask = int(tap_norm_mask)
     return d
 
 
@@ -79,6 +85,12 @@ class ExecutionContext:
         dims = (C.c_int64 * len(shape))(*[int(s) for s in shape])
         _lib.check(self._lib.mde_context_set_input_shape(self._h, name.encode(), len(shape), dims), "set_input_shape")
         return True
+
+    def set_gather(self, n_ranks: int, rank: int, peer_outputs: Sequence[int]) -> None:
+        """Trunk-only engines: write the taps into every rank's gather buffer (device pointers mapped into this
+        process) instead of the "output" binding -- the all-gather fused into the kernel that produces the taps."""
+        arr = (C.c_void_p * max(1, len(peer_outputs)))(*[C.c_void_p(int(p)) for p in peer_outputs])
+        _lib.check(self._lib.mde_context_set_gather(self._h, int(n_ranks), int(rank), arr), "set_gather")
 
     def execute_async_v3(self, stream_handle) -> bool:
         _lib.check(self._lib.mde_context_enqueue(self._h, C.c_void_p(int(stream_handle))), "enqueue")

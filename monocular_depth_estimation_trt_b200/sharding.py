@@ -1,0 +1,187 @@
+"""Patch sharding of Depth Pro's patch-encoder stage over the GPUs of one box (SURVEY section 8 e, row 2).
+
+Depth Pro (models/depth_pro/onnx_export.py:15-22: `dinov2l16_384` trunks, 1536 x 1536 input) cuts its input pyramid
+into 35 overlapping 384 x 384 crops -- 25 at full resolution (stride 288), 9 at half (stride 192), 1 at quarter --
+and pushes all of them through ONE shared ViT-L/16 trunk, keeping the final tokens and two hooked block outputs.
+The crops are independent, so they shard over ranks (one process per GPU, weights replicated); the only exchange is
+an all-gather of the trunk's outputs, after which every rank holds all 35 and can run the decoder.
+
+Two ways to do that exchange are provided:
+
+* ``mode="fused"``   the kernel that produces a tap (final LayerNorm / conversion of the residual stream) writes each
+                     row straight into every rank's gather buffer -- local HBM for its own, plain stores over
+                     NVLink into cudaIpc-mapped peer memory for the others.  No collective launch, no staging copy;
+                     the transfer overlaps the rest of the trunk (three of the four taps are produced long before
+                     the last block finishes).
+* ``mode="nccl"``    the trunk writes its own output binding and ``torch.distributed.all_gather_into_tensor`` (NCCL
+                     over NVLink / NVSwitch) assembles the result: the baseline the fused path is measured against.
+
+The host logic (crop geometry, shard bounds, buffer layout) is pure Python and is tested on the CPU with gloo.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+PATCH = 384
+LEVELS = ((1.0, 0.25), (0.5, 0.5), (0.25, 0.0))     # (image scale, overlap ratio) of the three pyramid levels
+
+
+def crop_origins(size: int, overlap: float, patch: int = PATCH) -> List[int]:
+    """Top-left coordinates of the sliding crops along one axis (upstream `split`: stride = int(patch * (1 - overlap)),
+    steps = ceil((size - patch) / stride) + 1)."""
+    if size < patch:
+        raise ValueError(f"image side {size} is smaller than the crop {patch}")
+    if size == patch:
+        return [0]
+    stride = int(patch * (1.0 - overlap))
+    steps = int(math.ceil((size - patch) / stride)) + 1
+    return [min(i * stride, size - patch) for i in range(steps)]
+
+
+def pyramid_plan(image_size: int = 1536) -> List[Tuple[int, int, int, int]]:
+    """[(level, level_size, y0, x0)] for every crop, in upstream's order (level by level, row-major): 25 + 9 + 1 = 35."""
+    plan = []
+    for lvl, (scale, overlap) in enumerate(LEVELS):
+        side = int(round(image_size * scale))
+        for y0 in crop_origins(side, overlap):
+            for x0 in crop_origins(side, overlap):
+                plan.append((lvl, side, y0, x0))
+    return plan
+
+
+def make_crops(image):
+    """image: torch float tensor [3, S, S] (already normalised) -> [35, 3, 384, 384].  The lower pyramid levels are
+    bilinear down-samplings (align_corners=False), as upstream builds them."""
+    import torch
+    import torch.nn.functional as F
+    S = image.shape[-1]
+    levels = {}
+    out = []
+    for lvl, side, y0, x0 in pyramid_plan(S):
+        if lvl not in levels:
+            levels[lvl] = image if side == S else F.interpolate(image[None], size=(side, side), mode="bilinear", align_corners=False)[0]
+        out.append(levels[lvl][:, y0:y0 + PATCH, x0:x0 + PATCH])
+    return torch.stack(out)
+
+
+def shard_bounds(n_items: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """Equal-size shards: every rank owns `per_rank = ceil(n / world)` slots so that one static engine serves all of
+    them; the trailing slots of the last rank(s) are padding.  -> (per_rank, [(first_item, n_real_items)] per rank)."""
+    if n_items < 1 or world < 1:
+        raise ValueError("need at least one item and one rank")
+    per = -(-n_items // world)
+    return per, [(r * per, max(0, min(per, n_items - r * per))) for r in range(world)]
+
+
+class _DevBuf:
+    """A cudaMalloc'd (IPC-shareable) buffer exposed through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr: int, shape: Sequence[int], typestr: str):
+        self.ptr = int(ptr)
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr,
+                                         "data": (self.ptr, False), "version": 2}
+
+
+class GatherBuffers:
+    """One gather buffer per rank, 16-bit [4][world * per_rank][T][D], each mapped into every process."""
+
+    def __init__(self, world: int, rank: int, per_rank: int, tokens: int, dim: int, precision: str):
+        import torch.distributed as dist
+        from cuda.bindings import runtime as cudart
+        from . import common
+        self._cudart, self._common = cudart, common
+        self.world, self.rank = world, rank
+        self.shape = (4, world * per_rank, tokens, dim)
+        self.precision = precision
+        self.nbytes = int(np.prod(self.shape)) * 2
+        self.own = int(common.cuda_call(cudart.cudaMalloc(self.nbytes)))
+        common.cuda_call(cudart.cudaMemset(self.own, 0, self.nbytes))
+        self.ptrs = [0] * world
+        self.ptrs[rank] = self.own
+        self._opened = []
+        if world > 1:
+            handle = common.cuda_call(cudart.cudaIpcGetMemHandle(self.own))
+            blobs = [None] * world
+            dist.all_gather_object(blobs, bytes(handle.reserved))
+            for r, blob in enumerate(blobs):
+                if r == rank:
+                    continue
+                h = cudart.cudaIpcMemHandle_t()
+                h.reserved = blob
+                p = int(common.cuda_call(cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess)))
+                self.ptrs[r] = p
+                self._opened.append(p)
+
+    def view(self):
+        """torch view of this rank's gather buffer, [4, world * per_rank, T, D] in the engine's 16-bit type."""
+        import torch
+        t = torch.as_tensor(_DevBuf(self.own, self.shape, "<i2"), device="cuda")
+        return t.view(torch.bfloat16 if self.precision == "bf16" else torch.float16)
+
+    def close(self):
+        for p in self._opened:
+            self._cudart.cudaIpcCloseMemHandle(p)
+        self._opened = []
+        if self.own:
+            self._cudart.cudaFree(self.own)
+            self.own = 0
+
+
+class ShardedPatchEncoder:
+    """Runs a trunk-only engine (head "encoder_taps", batch = per_rank) on this rank's crops and leaves ALL crops'
+    taps in ``gathered()``.  ``engine`` must have been built with batch == shard_bounds(n_items, world)[0]."""
+
+    def __init__(self, engine, n_items: int, world: int, rank: int, mode: str = "fused"):
+        import torch
+        if mode not in ("fused", "nccl"):
+            raise ValueError(f"[MDET] unknown gather mode {mode!r}")
+        self.engine, self.world, self.rank, self.mode, self.n_items = engine, world, rank, mode, n_items
+        self.per_rank, self.bounds = shard_bounds(n_items, world)
+        shape = engine.get_tensor_shape("output")              # [4, per_rank, T, D]
+        if shape[1] != self.per_rank:
+            raise ValueError(f"[MDET] engine batch {shape[1]} != shard size {self.per_rank}")
+        self.tokens, self.dim = shape[2], shape[3]
+        self.precision = "bf16" if engine.get_tensor_dtype("output") == np.dtype(np.uint16) else "fp16"
+        self.ctx = engine.create_execution_context()
+        self.buffers = GatherBuffers(world, rank, self.per_rank, self.tokens, self.dim, self.precision)
+        self.local = None
+        if mode == "fused":
+            self.ctx.set_gather(world, rank, self.buffers.ptrs)
+        else:
+            dt = torch.bfloat16 if self.precision == "bf16" else torch.float16
+            self.local = torch.empty(shape, dtype=dt, device="cuda")
+            self.ctx.set_tensor_address("output", self.local.data_ptr())
+
+    def enqueue(self, input_ptr: int, stream_handle: int) -> None:
+        """Launch the trunk on this rank's crops (float32 [per_rank,3,384,384] at `input_ptr`); in "nccl" mode also the
+        collective.  Asynchronous: call `finish()` before reading `gathered()`."""
+        import torch
+        import torch.distributed as dist
+        self.ctx.set_tensor_address("input", input_ptr)
+        self.ctx.execute_async_v3(stream_handle)
+        if self.mode == "nccl" and self.world > 1:
+            g = self.buffers.view()
+            # per tap: the ranks' [per_rank, T, D] slabs are contiguous in the gathered layout
+            for i in range(4):
+                dist.all_gather_into_tensor(g[i], self.local[i])
+        elif self.mode == "nccl":
+            self.buffers.view().copy_(self.local)
+
+    def finish(self) -> None:
+        """Every rank's stores have landed in every buffer: drain the stream, then a barrier across the ranks."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+    def gathered(self):
+        """[4, n_items, T, D]: the padded slots of the last rank(s) are cut off."""
+        return self.buffers.view()[:, :self.n_items]
+
+    def close(self):
+        self.ctx.close()
+        self.buffers.close()

@@ -220,3 +220,40 @@ def test_errors_are_loud(lib):
         eng.create_execution_context()
     with pytest.raises(ValueError):
         E.make_desc(meta, precision="fp32")
+
+
+# ------------------------------------------------------------------ trunk-only engine (Depth Pro's patch-encoder stage)
+def _trunk_reference(encoder, batch, seed=5):
+    from oracle import dav2_torch as O
+    torch.manual_seed(seed)
+    x = torch.randn(batch, 3, 384, 384)
+    sd = O.init_state_dict(encoder, seed=seed, patch=16, pos_grid=24)
+    with torch.no_grad():
+        taps = torch.stack(O.encoder_taps(sd, x, O.MODEL_CONFIGS[encoder], norm_mask=0x8))     # [4, B, 576, D]
+    return sd, x, taps
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_trunk_only_engine_patch16_taps(lib, prec):
+    """ViT/16 at 384 x 384 (24 x 24 tokens), raw hooked block outputs + normalised final tokens, 16-bit [4][B][T][D]:
+    through the output binding and through the fused-gather path with a single rank (both must agree bit for bit)."""
+    from monocular_depth_estimation_trt_b200 import sharding as S
+    B = 3
+    sd, x, taps = _trunk_reference("vits", B)
+    meta = W.describe("vits", 384, 384, max_depth=None, patch_size=16)
+    eng = E.Engine(E.make_desc(meta, precision=prec, batch=B, head="encoder_taps", tap_norm_mask=0x8), meta)
+    eng.load_state_dict({k: v for k, v in sd.items() if k.startswith("pretrained.")})
+    eng.finalize()
+    assert eng.get_tensor_shape("output") == (4, B, 576, 384)
+    dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    out = torch.full((4, B, 576, 384), float("nan"), dtype=dt, device="cuda")
+    xd = x.cuda()
+    run(eng, xd, out)
+    for i in range(4):
+        assert rms_rel(out[i].float().cpu(), taps[i]) < INTER[prec], i
+    enc = S.ShardedPatchEncoder(eng, n_items=B, world=1, rank=0, mode="fused")
+    enc.enqueue(xd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    enc.finish()
+    assert torch.equal(enc.gathered(), out)
+    enc.close()
+    eng.close()

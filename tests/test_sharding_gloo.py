@@ -54,3 +54,72 @@ def test_two_ranks_shard_images_and_report_the_slowest_rank():
 def test_single_rank_needs_no_process_group():
     assert bench.max_over_ranks(3.5, 1) == 3.5
     assert bench.aggregate_rate(1, 64, 10, 1000.0) == 640.0
+
+
+# ------------------------------------------------------------------ Depth Pro patch sharding (host logic)
+from monocular_depth_estimation_trt_b200 import sharding as S
+
+
+def test_depth_pro_pyramid_is_35_overlapping_crops():
+    plan = S.pyramid_plan(1536)
+    assert len(plan) == 35
+    assert [sum(1 for p in plan if p[0] == lvl) for lvl in range(3)] == [25, 9, 1]
+    assert S.crop_origins(1536, 0.25) == [0, 288, 576, 864, 1152]          # stride 288, last crop ends at 1536
+    assert S.crop_origins(768, 0.5) == [0, 192, 384]
+    assert S.crop_origins(384, 0.0) == [0]
+    img = torch.arange(3 * 1536 * 1536, dtype=torch.float32).reshape(3, 1536, 1536)
+    crops = S.make_crops(img)
+    assert crops.shape == (35, 3, 384, 384)
+    assert torch.equal(crops[7], img[:, 288:672, 576:960])                 # level 0 is cut from the image itself (crop 7 = row 1, col 2)
+    assert torch.equal(crops[34], torch.nn.functional.interpolate(img[None], size=(384, 384), mode="bilinear", align_corners=False)[0])
+
+
+def test_shard_bounds_pad_the_tail():
+    assert S.shard_bounds(35, 1) == (35, [(0, 35)])
+    assert S.shard_bounds(35, 2) == (18, [(0, 18), (18, 17)])
+    assert S.shard_bounds(35, 4) == (9, [(0, 9), (9, 9), (18, 9), (27, 8)])
+    assert S.shard_bounds(35, 8) == (5, [(0, 5), (5, 5), (10, 5), (15, 5), (20, 5), (25, 5), (30, 5), (35, 0)])
+    assert S.shard_bounds(3, 8)[0] == 1
+
+
+def _patch_worker(rank, world, port, out):
+    """Each rank runs the ORACLE trunk on its shard of crops and the ranks all-gather the taps in the layout the CUDA
+    path uses ([4][world * per_rank][T][D]); rank 0 checks the result against the unsharded run."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import dav2_torch as O
+    torch.manual_seed(0)
+    torch.set_num_threads(2)
+    n_items = 5
+    crops = torch.randn(n_items, 3, 64, 64)                      # tiny crops: 4 x 4 tokens of 16 x 16 pixels
+    sd = O.init_state_dict("vits", seed=3, patch=16, pos_grid=4)
+    cfg = O.MODEL_CONFIGS["vits"]
+    per, bounds = S.shard_bounds(n_items, world)
+    first, count = bounds[rank]
+    mine = torch.zeros(per, 3, 64, 64)
+    mine[:count] = crops[first:first + count]
+    with torch.no_grad():
+        taps = torch.stack(O.encoder_taps(sd, mine, cfg, norm_mask=0x8))        # [4, per, T, D]
+    gathered = torch.zeros(4, world * per, 16, 384)
+    for i in range(4):
+        dist.all_gather_into_tensor(gathered[i], taps[i].contiguous())
+    if rank == 0:
+        with torch.no_grad():
+            ref = torch.stack(O.encoder_taps(sd, crops, cfg, norm_mask=0x8))
+        out.put(float((gathered[:, :n_items] - ref).abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_crops_and_all_gather_the_taps():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_patch_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-5          # batch composition changes fp32 summation order at most
