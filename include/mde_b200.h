@@ -46,6 +46,9 @@ extern "C" {
 #define MDE_DT_F16 2
 #define MDE_DT_BF16 3
 
+#define MDE_OUTPUT_MODEL_GRID 0
+#define MDE_OUTPUT_SOURCE_GRID 1
+
 /* what the engine computes behind the shared DINOv2 trunk */
 #define MDE_HEAD_DPT 0          /* Depth Anything V2: DPT head, output float32 depth [B,H,W] */
 #define MDE_HEAD_ENCODER_TAPS 1 /* trunk only (the patch-encoder stage of Depth Pro, models/depth_pro/onnx_export.py:15-22):
@@ -83,6 +86,10 @@ typedef struct mde_engine_desc {
   double norm_std[3];      /*   core/preprocess.py:294-328 with float64 dtypes */
   float max_depth;         /* > 0: metric head, sigmoid * max_depth;  <= 0: relative head, ReLU */
   int32_t device;          /* CUDA device ordinal */
+  int32_t output_mode;     /* MDE_OUTPUT_MODEL_GRID: float32 [B][input_h][input_w] (spec.json's contract);
+                            * MDE_OUTPUT_SOURCE_GRID: the scripts' post-processing fused in -- float32 [B][src_h][src_w],
+                            * resized back to the source size (align_corners=True) and clamped to [1e-3, 1e3].  The source
+                            * size is the one bound with set_input_shape (uint8 input) or max_src_h x max_src_w */
   int32_t head_mode;       /* MDE_HEAD_* */
   int32_t tap_norm_mask;   /* bit i: tap i goes through the trunk's final LayerNorm (0xF for Depth Anything; 0x8 for
                             * Depth Pro's hooks, which take raw block outputs and normalise only the last one) */
@@ -211,6 +218,10 @@ int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t bat
 int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t batch, int32_t hs, int32_t ws, int32_t ho,
                       int32_t wo, const float* d_bias, const float* d_head_w, float head_b, float head_scale,
                       float* d_out, void* stream);
+/* The reference scripts' post-processing on the device (models/depth_anything_v2/onnx2trt.py:111-117):
+ * F.interpolate(depth, (ho, wo), mode="bilinear", align_corners=True) then clamp(clamp_lo, clamp_hi); fp32 [B][h][w]. */
+int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,
+                       float clamp_lo, float clamp_hi, void* stream);
 /* 3x3 / stride 2 / pad 1 gather: NHWC -> [(b,oy,ox)][tap*c + ch] */
 int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t h, int32_t w, int32_t c,
                     void* stream);

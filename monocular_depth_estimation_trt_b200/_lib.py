@@ -11,6 +11,7 @@ MDE_FP16, MDE_BF16 = 0, 1
 MDE_INPUT_F32_NCHW, MDE_INPUT_U8_HWC = 0, 1
 MDE_DT_F32, MDE_DT_U8, MDE_DT_F16, MDE_DT_BF16 = 0, 1, 2, 3
 MDE_HEAD_DPT, MDE_HEAD_ENCODER_TAPS = 0, 1
+MDE_OUTPUT_MODEL_GRID, MDE_OUTPUT_SOURCE_GRID = 0, 1
 PRECISIONS = {"fp16": MDE_FP16, "bf16": MDE_BF16}
 
 # every symbol include/mde_b200.h declares (tests/test_abi.py checks the header against this list)
@@ -23,7 +24,7 @@ SYMBOLS = [
     "mde_context_set_input_shape", "mde_context_enqueue", "mde_context_set_gather", "mde_context_launches_per_enqueue",
     "mde_context_get_buffer", "mde_context_snapshot_block", "mde_context_enqueue_timed", "mde_context_op_info",
     "mde_k_preprocess_u8", "mde_k_im2col_f32", "mde_k_gemm", "mde_k_conv3x3", "mde_k_attention", "mde_k_attention_kv64", "mde_k_attention_mma",
-    "mde_k_layernorm", "mde_k_bilinear", "mde_k_im2col_s2", "mde_k_upconv_head",
+    "mde_k_layernorm", "mde_k_bilinear", "mde_k_im2col_s2", "mde_k_upconv_head", "mde_k_resize_depth",
 ]
 
 
@@ -37,7 +38,7 @@ class EngineDesc(C.Structure):
         ("max_src_h", C.c_int32), ("max_src_w", C.c_int32), ("swap_rb", C.c_int32),
         ("norm_mean", C.c_double * 3), ("norm_std", C.c_double * 3),
         ("max_depth", C.c_float), ("device", C.c_int32),
-        ("head_mode", C.c_int32), ("tap_norm_mask", C.c_int32),
+        ("output_mode", C.c_int32), ("head_mode", C.c_int32), ("tap_norm_mask", C.c_int32),
     ]
 
 
@@ -103,6 +104,7 @@ def load() -> C.CDLL:
         "mde_k_layernorm": (C.c_int, [i32, vp, vp, vp, vp, i64, i32, f32, i32, i32, vp]),
         "mde_k_bilinear": (C.c_int, [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "mde_k_im2col_s2": (C.c_int, [i32, vp, vp, i32, i32, i32, i32, vp]),
+        "mde_k_resize_depth": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, f32, f32, vp]),
         "mde_k_upconv_head": (C.c_int, [i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, f32, vp, vp]),
     }
     assert sorted(protos) == sorted(SYMBOLS)

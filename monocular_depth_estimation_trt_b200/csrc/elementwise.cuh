@@ -282,6 +282,31 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const BilinearParams
 }
 
 // ---------------------------------------------------------------------------------------------
+// Post-processing of the reference's inference scripts on the device (models/depth_anything_v2/onnx2trt.py:111-117):
+// F.interpolate(depth, (src_h, src_w), mode="bilinear", align_corners=True) then clamp(min, max), fp32, one channel.
+// ---------------------------------------------------------------------------------------------
+struct ResizeDepthParams {
+  const float* in;   // [B][Hi][Wi]
+  float* out;        // [B][Ho][Wo]
+  int B, Hi, Wi, Ho, Wo;
+  float sy, sx, lo, hi;
+};
+__global__ void __launch_bounds__(256) resize_depth_kernel(const ResizeDepthParams p) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= p.Wo) return;
+  const float fy = y * p.sy, fx = x * p.sx;
+  const int y0 = min(static_cast<int>(fy), p.Hi - 1), x0 = min(static_cast<int>(fx), p.Wi - 1);
+  const int y1 = min(y0 + 1, p.Hi - 1), x1 = min(x0 + 1, p.Wi - 1);
+  const float wy = fy - y0, wx = fx - x0;
+  const float* r0 = p.in + (static_cast<long long>(b) * p.Hi + y0) * p.Wi;
+  const float* r1 = p.in + (static_cast<long long>(b) * p.Hi + y1) * p.Wi;
+  const float t = __ldg(r0 + x0) + wx * (__ldg(r0 + x1) - __ldg(r0 + x0));
+  const float u = __ldg(r1 + x0) + wx * (__ldg(r1 + x1) - __ldg(r1 + x0));
+  p.out[(static_cast<long long>(b) * p.Ho + y) * p.Wo + x] = fminf(fmaxf(t + wy * (u - t), p.lo), p.hi);
+}
+
+// ---------------------------------------------------------------------------------------------
 // 3x3 / stride 2 / pad 1 gather: NHWC [B][H][W][C] -> rows [(b, oy, ox)][tap*C + c] for a plain GEMM
 // (resize_layers[3]: 37x37 -> 19x19; 0.5 % of the FLOPs, not worth a strided tensor map).
 // ---------------------------------------------------------------------------------------------

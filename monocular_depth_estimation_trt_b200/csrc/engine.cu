@@ -82,7 +82,7 @@ struct mde_engine {
 namespace {
 
 struct Op {
-  enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, UPCONV_HEAD, SNAPSHOT } kind;
+  enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, UPCONV_HEAD, RESIZE_DEPTH, SNAPSHOT } kind;
   GemmOp g;
   AttnOp attn;
   // generic scalar/pointer slots for the small kernels
@@ -205,6 +205,9 @@ static int validate_desc(const mde_engine_desc* d) {
   if (d->patch_size <= 0 || d->input_h <= 0 || d->input_w <= 0 || d->input_h % d->patch_size || d->input_w % d->patch_size)
     return fail(MDE_ERR_INVALID, "input %dx%d must be a positive multiple of patch %d", d->input_h, d->input_w, d->patch_size);
   if (d->batch <= 0 || d->batch > 4096) return fail(MDE_ERR_INVALID, "bad batch %d", d->batch);
+  if (d->output_mode != MDE_OUTPUT_MODEL_GRID && d->output_mode != MDE_OUTPUT_SOURCE_GRID) return fail(MDE_ERR_INVALID, "unknown output_mode %d", d->output_mode);
+  if (d->output_mode == MDE_OUTPUT_SOURCE_GRID && (d->head_mode != MDE_HEAD_DPT || d->max_src_h <= 0 || d->max_src_w <= 0))
+    return fail(MDE_ERR_INVALID, "MDE_OUTPUT_SOURCE_GRID needs the DPT head and max_src_h / max_src_w");
   if (d->head_mode != MDE_HEAD_DPT && d->head_mode != MDE_HEAD_ENCODER_TAPS) return fail(MDE_ERR_INVALID, "unknown head_mode %d", d->head_mode);
   if (d->tap_norm_mask < 0 || d->tap_norm_mask > 0xF) return fail(MDE_ERR_INVALID, "tap_norm_mask must be a 4-bit mask");
   if (d->head_mode == MDE_HEAD_DPT && d->tap_norm_mask != 0xF) return fail(MDE_ERR_INVALID, "the DPT head takes all four taps through the final LayerNorm (tap_norm_mask 0xF)");
@@ -409,6 +412,9 @@ extern "C" int mde_engine_io_shape(const mde_engine* e, int32_t i, int32_t* ndim
   } else if (e->d.head_mode == MDE_HEAD_ENCODER_TAPS) {
     *ndim = 4;
     dims[0] = 4; dims[1] = e->d.batch; dims[2] = e->T; dims[3] = e->d.embed_dim;
+  } else if (e->d.output_mode == MDE_OUTPUT_SOURCE_GRID) {
+    *ndim = 3;
+    dims[0] = e->d.batch; dims[1] = e->d.max_src_h; dims[2] = e->d.max_src_w;
   } else {
     *ndim = 3;
     dims[0] = e->d.batch; dims[1] = e->d.input_h; dims[2] = e->d.input_w;
@@ -660,7 +666,14 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
       pl.gemm("output_conv2 taps", o1, px1, F / 2, F / 2, e->oc2_w, 384, F / 2, ep, 0, 288); }
     Op uh; uh.kind = Op::UPCONV_HEAD; uh.in = z; uh.i0 = H1; uh.i1 = W1; uh.i2 = d.input_h; uh.i3 = d.input_w;
     const double opx = static_cast<double>(B) * d.input_h * d.input_w;
-    pl.push(uh, "upconv_head interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
+    if (d.output_mode == MDE_OUTPUT_SOURCE_GRID) {
+      uh.out = pl.alloc(static_cast<long long>(B) * d.input_h * d.input_w * 4, "depth_model_grid", 0);   // head output; the binding gets the resized map
+      pl.push(uh, "upconv_head interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
+      Op rs; rs.kind = Op::RESIZE_DEPTH; rs.in = uh.out;
+      pl.push(rs, "resize_depth to source size + clamp", 4.0 * opx + 4.0 * B * d.max_src_h * d.max_src_w);
+    } else {
+      pl.push(uh, "upconv_head interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
+    }
   }
   if (bytes_out) *bytes_out = pl.bytes;
   return pl.rc;
@@ -692,7 +705,7 @@ extern "C" int mde_context_create(mde_engine* e, mde_context** out) {
     return fail(rc, "%s", msg.c_str());
   }
   c->workspace_bytes = bytes;
-  if (e->d.input_mode == MDE_INPUT_U8_HWC) { c->src_h = e->d.max_src_h; c->src_w = e->d.max_src_w; }
+  if (e->d.input_mode == MDE_INPUT_U8_HWC || e->d.output_mode == MDE_OUTPUT_SOURCE_GRID) { c->src_h = e->d.max_src_h; c->src_w = e->d.max_src_w; }
   *out = c;
   return MDE_OK;
 }
@@ -824,7 +837,11 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         break;
       case Op::UPCONV_HEAD:
         MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->oc2_b, e->head_w, e->head_b,
-                                   d.max_depth > 0.f ? d.max_depth : 0.f, static_cast<float*>(c->d_output), s));
+                                   d.max_depth > 0.f ? d.max_depth : 0.f, static_cast<float*>(op.out ? op.out : c->d_output), s));
+        break;
+      case Op::RESIZE_DEPTH:
+        MDE_TRY(launch_resize_depth(static_cast<const float*>(op.in), d.batch, d.input_h, d.input_w, static_cast<float*>(c->d_output),
+                                    c->src_h, c->src_w, 1e-3f, 1e3f, s));
         break;
       case Op::IM2COL_S2:
         MDE_TRY(launch_im2col_s2(prec, op.in, op.out, d.batch, op.i0, op.i1, op.i2, s));

@@ -485,6 +485,20 @@ int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int
   return MDE_OK;
 }
 
+int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_out, int ho, int wo, float lo, float hi_clamp,
+                        cudaStream_t s) {
+  if (batch <= 0 || hi <= 0 || wi <= 0 || ho <= 0 || wo <= 0) return fail(MDE_ERR_INVALID, "resize_depth: empty problem");
+  if (batch > 65535 || ho > 65535) return fail(MDE_ERR_INVALID, "resize_depth: batch / height exceed grid limits");
+  ResizeDepthParams p;
+  p.in = d_in; p.out = d_out; p.B = batch; p.Hi = hi; p.Wi = wi; p.Ho = ho; p.Wo = wo; p.lo = lo; p.hi = hi_clamp;
+  p.sy = ho > 1 ? static_cast<float>(hi - 1) / static_cast<float>(ho - 1) : 0.f;
+  p.sx = wo > 1 ? static_cast<float>(wi - 1) / static_cast<float>(wo - 1) : 0.f;
+  dim3 grid((wo + 255) / 256, ho, batch);
+  resize_depth_kernel<<<grid, 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s) {
   if (c % 8) return fail(MDE_ERR_INVALID, "im2col_s2: channels must be a multiple of 8");
   Im2colS2Params p;
@@ -666,6 +680,13 @@ int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t ba
                     void* stream) {
   clear_error();
   return launch_im2col_s2(precision, d_in, d_out, batch, h, w, c, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,
+                       float clamp_lo, float clamp_hi, void* stream) {
+  clear_error();
+  if (!d_in || !d_out) return fail(MDE_ERR_INVALID, "resize_depth: null pointer");
+  return launch_resize_depth(d_in, batch, hi, wi, d_out, ho, wo, clamp_lo, clamp_hi, static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t batch, int32_t hs, int32_t ws, int32_t ho,

@@ -37,7 +37,7 @@ _NP_DTYPES = {_lib.MDE_DT_F32: np.dtype(np.float32), _lib.MDE_DT_U8: np.dtype(np
 def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode: str = "f32_nchw",
               max_src_hw: Tuple[int, int] = (0, 0), swap_rb: bool = True,
               mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
-              device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF) -> _lib.EngineDesc:
+              device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF, output: str = "model_grid") -> _lib.EngineDesc:
     if precision not in _lib.PRECISIONS:
         # The reference also builds "fp32" engines (core/common.py:141-150).  The B200 path is a
         # 16-bit tensor-core path with fp32 accumulation; refuse instead of silently downgrading.
@@ -64,6 +64,9 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
         raise ValueError(f"[MDET] unknown head {head!r}")
     d.head_mode = _lib.MDE_HEAD_ENCODER_TAPS if head == "encoder_taps" else _lib.MDE_HEAD_DPT
     d.tap_norm_mask = int(tap_norm_mask)
+    if output not in ("model_grid", "source_grid"):
+        raise ValueError(f"[MDET] unknown output {output!r}")
+    d.output_mode = _lib.MDE_OUTPUT_SOURCE_GRID if output == "source_grid" else _lib.MDE_OUTPUT_MODEL_GRID
     return d
 
 

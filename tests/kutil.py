@@ -107,6 +107,14 @@ def upconv_head(precision, z_nhwc, ho, wo, bias, head_w, head_b, head_scale):
     return out
 
 
+def resize_depth(depth, ho, wo, lo=1e-3, hi=1e3):
+    lib = _lib.load()
+    B, h, w = depth.shape
+    out = torch.full((B, ho, wo), float("nan"), dtype=torch.float32, device=depth.device)
+    _lib.check(lib.mde_k_resize_depth(ptr(depth), B, h, w, ptr(out), ho, wo, float(lo), float(hi), stream()), "mde_k_resize_depth")
+    return out
+
+
 def im2col_f32(precision, x_nchw, patch, kpad):
     lib = _lib.load()
     B, _, H, W_ = x_nchw.shape

@@ -257,3 +257,25 @@ def test_trunk_only_engine_patch16_taps(lib, prec):
     assert torch.equal(enc.gathered(), out)
     enc.close()
     eng.close()
+
+
+def test_source_grid_output_fuses_the_scripts_postprocessing(lib):
+    """output="source_grid": the engine's binding is the depth map resized back to the source frame and clamped
+    (onnx2trt.py:111-117), equal to doing that on the host from the model-grid output of the same engine."""
+    import torch.nn.functional as F
+    sd, x, depth, _ = R.reference("vits")
+    meta = W.describe("vits", 518, 518, 20.0)
+    frames = np.stack([R.synthetic_image(i, 480, 640) for i in range(2)])
+    outs = {}
+    for mode in ("model_grid", "source_grid"):
+        eng = E.Engine(E.make_desc(meta, precision="fp16", batch=2, input_mode="u8_hwc", max_src_hw=(480, 640), output=mode), meta)
+        eng.load_state_dict(sd)
+        eng.finalize()
+        shape = eng.get_tensor_shape("output")
+        assert shape == ((2, 518, 518) if mode == "model_grid" else (2, 480, 640))
+        out = torch.full(shape, float("nan"), device="cuda")
+        run(eng, torch.from_numpy(frames).cuda(), out)
+        outs[mode] = out.cpu()
+        eng.close()
+    ref = torch.clamp(F.interpolate(outs["model_grid"][:, None], (480, 640), mode="bilinear", align_corners=True)[:, 0], 1e-3, 1e3)
+    assert float((outs["source_grid"] - ref).abs().max()) <= 2e-5 * float(ref.abs().max())

@@ -290,3 +290,16 @@ def test_upconv_head_matches_upsample_conv_head(lib, prec, B, hs, ws, ho, wo, sc
     ref = scale * torch.sigmoid(v) if scale > 0 else F.relu(v)
     assert torch.isfinite(got).all()
     assert float((got - ref).abs().max()) < (4.0 if prec == "bf16" else 1.0) * 2.0 ** -8 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,h,w,ho,wo", [(2, 518, 518, 480, 640), (1, 518, 518, 2268, 3024), (3, 37, 50, 37, 50), (1, 266, 518, 1, 7)])
+def test_resize_depth_matches_the_scripts_postprocessing(lib, B, h, w, ho, wo):
+    """models/depth_anything_v2/onnx2trt.py:111-117: interpolate(bilinear, align_corners=True) then clamp(1e-3, 1e3)."""
+    g = torch.Generator(device="cuda").manual_seed(41)
+    d = torch.rand(B, h, w, generator=g, device="cuda") * 30.0 - 1.0          # some values below the lower clamp
+    d[0, 0, 0] = 5000.0                                                        # and one above the upper
+    got = K.resize_depth(d, ho, wo)
+    torch.cuda.synchronize()
+    ref = torch.clamp(F.interpolate(d[:, None], (ho, wo), mode="bilinear", align_corners=True)[:, 0], 1e-3, 1e3)
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    assert float(got.min()) >= 1e-3 and float(got.max()) <= 1e3
