@@ -183,6 +183,12 @@ typedef struct mde_epilogue {
   const float* d_head_w;
   float head_b, head_scale;
   float* d_head_out;
+  /* GEMM -> all-gather fused (plain 16-bit outputs only): columns [gather_col0, N) are written to d_gather[0..gather_n)
+   * -- every rank's gathered buffer, ALREADY offset to this rank's first row, pitch gather_ld elements, column
+   * n - gather_col0 -- instead of d_out.  Peer buffers are cudaIpc-mapped device pointers.  gather_n == 0: off.
+   * gather_col0 must be a multiple of 64 and N a multiple of the tile width. */
+  int32_t gather_n, gather_col0, gather_ld;
+  void* d_gather[8];
 } mde_epilogue;
 
 /* D[M,N] = A[M,K] * B[N,K]^T.  A: 16-bit row-major, pitch lda elements; B: 16-bit row-major, pitch ldb.
@@ -196,6 +202,12 @@ int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h,
 /* softmax(Q K^T / 8) V over [B*ntok][3*D] packed q|k|v rows, head dim 64 -> [B*ntok][D]. */
 int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                     void* stream);
+/* Queries and keys/values from different row sets (sequence-sharded global attention, SURVEY section 8 e row 3: the
+ * queries are this rank's tokens, the keys/values all ranks' tokens gathered into one buffer).
+ * d_q: [batch*ntok_q][ldq] with the q columns first; d_kv: [batch*ntok_kv][ldkv] with K of head 0 at column k_col0 and
+ * V at v_col0; d_out: [batch*ntok_q][heads*64]. */
+int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
+                       int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream);
 /* The same op with 64-key tiles and four CTAs per SM (csrc/attention_tc64.cuh): the measured alternative to the
  * default kernel, kept for comparison; the engine launches it only when MDE_ATTN_KV=64 is set. */
 int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

@@ -14,10 +14,14 @@ namespace mde {
 struct AttnParams {
   const void* qkv;   // [B*ntok, 3*D], 16-bit
   void* out;         // [B*ntok, D], 16-bit
-  int ntok;          // tokens per image
+  int ntok;          // keys per image (== tokens per image for self-attention)
   int heads;
   int D;             // heads * 64
   float scale_log2;  // head_dim^-0.5 * log2(e)
+  // tcgen05 kernels only: queries and keys/values may come from different row sets (sequence-sharded global attention:
+  // the queries are this rank's tokens, the keys/values every rank's, gathered into one [ntok, 2D] k|v buffer)
+  int ntok_q;        // queries per image
+  int k_col0, v_col0;// first column of K / V of head 0 in the key/value tensor (D and 2D in a packed q|k|v tensor)
 };
 
 constexpr int kAttnBlockQ = 128;

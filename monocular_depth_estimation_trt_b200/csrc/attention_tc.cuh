@@ -77,7 +77,7 @@ __device__ __forceinline__ void exp2_fma2(f32x2 x, float& p0, float& p1) {
 
 template <typename T, int kPoly>
 __global__ void __launch_bounds__(kAtcThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {
   using Tr = F16Traits<T>;
   extern __shared__ __align__(1024) uint8_t atc_smem[];   // 128-byte-swizzled operand tiles need 1024-byte alignment
   if ((smem_u32(atc_smem) & 1023u) != 0) __trap();
@@ -101,10 +101,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
   const int q0 = blockIdx.x * 128;
   const int nkv = (p.ntok + 127) / 128;
   const int last_chunks = (p.ntok - (nkv - 1) * 128 + 31) / 32;   // 32-key chunks of the last key tile that hold real keys (1..4)
-  const int row_base = img * p.ntok;
+  const int row_base = img * p.ntok_q;     // first query row of this image
+  const int kv_base = img * p.ntok;        // first key/value row of this image
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&map_qkv);
+    prefetch_tmap(&map_kv);
     mbar_init(q_full, 1);
     for (int i = 0; i < kAtcStages; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
@@ -135,10 +137,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         const uint32_t ph = (j / kAtcStages) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], kAtcQBytes);
-        tma_load_2d(sK + st * kAtcQBytes, &map_qkv, &k_full[st], p.D + head * 64, row_base + j * 128);
+        tma_load_2d(sK + st * kAtcQBytes, &map_kv, &k_full[st], p.k_col0 + head * 64, kv_base + j * 128);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kAtcQBytes);
-        tma_load_2d(sV + st * kAtcQBytes, &map_qkv, &v_full[st], 2 * p.D + head * 64, row_base + j * 128);
+        tma_load_2d(sV + st * kAtcQBytes, &map_kv, &v_full[st], p.v_col0 + head * 64, kv_base + j * 128);
       }
     }
   } else if (warp == 5) {
@@ -301,7 +303,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
       uint32_t o[32];
       tmem_ld_32x32b_x32(o_addr + h * 32, o);
       tmem_ld_wait();
-      if (n < p.ntok) {
+      if (n < p.ntok_q) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;

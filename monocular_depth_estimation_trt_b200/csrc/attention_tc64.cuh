@@ -49,7 +49,8 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int q0 = blockIdx.x * 128;
   const int nkv = (p.ntok + 63) / 64;
   const int last_chunks = (p.ntok - (nkv - 1) * 64 + 31) / 32;   // 1 or 2 live 32-key chunks in the last key tile
-  const int row_base = img * p.ntok;
+  const int row_base = img * p.ntok_q;     // first query row of this image
+  const int kv_base = img * p.ntok;        // first key/value row of this image
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&map_q);
@@ -82,10 +83,10 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const uint32_t ph = (j / kA64Stages) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], kA64TileBytes);
-        tma_load_2d(sK + st * kA64TileBytes, &map_kv, &k_full[st], p.D + head * 64, row_base + j * 64);
+        tma_load_2d(sK + st * kA64TileBytes, &map_kv, &k_full[st], p.k_col0 + head * 64, kv_base + j * 64);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kA64TileBytes);
-        tma_load_2d(sV + st * kA64TileBytes, &map_kv, &v_full[st], 2 * p.D + head * 64, row_base + j * 64);
+        tma_load_2d(sV + st * kA64TileBytes, &map_kv, &v_full[st], p.v_col0 + head * 64, kv_base + j * 64);
       }
     }
   } else if (warp == 5) {
@@ -227,7 +228,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       uint32_t o[32];
       tmem_ld_32x32b_x32(o_addr + h * 32, o);
       tmem_ld_wait();
-      if (n < p.ntok) {
+      if (n < p.ntok_q) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;

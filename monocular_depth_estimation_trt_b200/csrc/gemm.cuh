@@ -46,6 +46,8 @@ struct GemmParams {
   void* out;            // 16-bit output
   void* out_relu;       // 16-bit relu(output) copy (input of the next pre-activation conv)
   int tma_out;          // plain row-major 16-bit output (bias / activation only): registers -> smem -> TMA store
+  int gather_n;         // tma_out only: column boxes at or beyond gather_col0 are stored to gather_n tensors (the ranks'
+  int gather_col0;      //   gathered K|V buffers, peer memory) instead of `out`; see GatherMaps
   int tma_x;            // x += gamma * (acc + bias) on plain rows: TMA load of the x box -> in-place update in smem -> TMA store
   // ---- fused depth head (BLOCK_N == 32 == N): z = sum_n relu(v_n) * head_w[n] + head_b
   const float* head_w;
@@ -121,10 +123,17 @@ __device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
   f2_unpack(f2_mul(v, f2_add(f2_pack(r0, r1), f2_splat(0.5f))), v0, v1);
 }
 
+// GEMM -> all-gather in one kernel (sequence-sharded global attention: the QKV projection of this rank's tokens):
+// m[r] describes THIS rank's row range inside rank r's gathered buffer ({columns, rows of this rank}, 64 x 32 boxes),
+// so a box that hangs over this rank's last row is clipped instead of spilling into the next rank's rows.
+struct GatherMaps {
+  CUtensorMap m[8];
+};
+
 template <int BLOCK_N, typename T, int kCtas>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ GatherMaps gather, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, kCtas>;
   using Tr = F16Traits<T>;
   constexpr int kStages = Cfg::kStages;
@@ -348,7 +357,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&map_out, buf, n_base - 32, m_blk * 128 + quarter * 32);
+              if (p.gather_n > 0 && n_base - 32 >= p.gather_col0) {
+                // K / V columns: one bulk store per rank, into local HBM for our own buffer and over NVLink for the peers'
+                for (int r = 0; r < p.gather_n; ++r)
+                  tma_store_2d(&gather.m[r], buf, n_base - 32 - p.gather_col0, m_blk * 128 + quarter * 32);
+              } else {
+                tma_store_2d(&map_out, buf, n_base - 32, m_blk * 128 + quarter * 32);
+              }
               bulk_commit();
             }
           }

@@ -33,6 +33,7 @@ struct GemmOp {
   alignas(64) CUtensorMap map_a;
   alignas(64) CUtensorMap map_b;
   alignas(64) CUtensorMap map_out;   // 16-bit output as {N, M} with 64 x 32 boxes; only encoded when p.tma_out
+  alignas(64) GatherMaps gather;     // p.gather_n destinations of the fused all-gather
   GemmParams p;
   int block_n;
   int precision;
@@ -52,11 +53,16 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream);
 struct AttnOp {
   alignas(64) CUtensorMap map_qkv;   // 128-row boxes (query tiles; key/value tiles of the two-CTA-per-SM kernel)
   alignas(64) CUtensorMap map_kv;    // 64-row boxes (key/value tiles of the four-CTA-per-SM kernel)
+  alignas(64) CUtensorMap map_kv128; // key/value source with 128-row boxes (== map_qkv for self-attention)
   const void* qkv;
   void* out;
   int batch, ntok, heads, precision;
+  int ntok_q, k_col0, v_col0;        // queries per image; first K / V column of head 0 in the key/value source
 };
 int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads);
+// queries from d_q ([batch*ntok_q][ldq], q columns first), keys/values from d_kv ([batch*ntok_kv][ldkv], K at k_col0, V at v_col0)
+int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, const void* d_kv, int ldkv, int k_col0, int v_col0,
+                         void* d_out, int batch, int ntok_q, int ntok_kv, int heads);
 int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv = 0);   // kv: 0 = default kernel, 64 / 128 = key-tile variant
 // warp-level mma.sync variant (kept as an independent cross-check of the tcgen05 kernel in the tests)
 int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);

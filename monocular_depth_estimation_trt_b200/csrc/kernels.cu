@@ -69,9 +69,13 @@ static int get_encode(EncodeTiledFn* fn);
 // The bulk-store epilogue serves plain row-major 16-bit outputs: bias and activation only, whole tiles in N.
 static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long long m, int n) {
   memset(&op->map_out, 0, sizeof(op->map_out));
+  memset(&op->gather, 0, sizeof(op->gather));
   GemmParams& p = op->p;
   p.tma_out = 0;
   p.tma_x = 0;
+  p.gather_n = 0;
+  p.gather_col0 = 0;
+  if (ep->gather_n < 0 || ep->gather_n > 8) return fail(MDE_ERR_INVALID, "gemm: at most 8 gather destinations");
   if (getenv("MDE_NO_TMA_OUT")) return MDE_OK;
   // residual-stream update on plain rows: the fp32 x boxes travel by TMA in both directions
   if (ep->d_x && ep->accumulate_x && !ep->d_out && !ep->d_out_relu && !ep->d_res1 && !ep->d_res2 && !ep->d_pos && !ep->d_head_w &&
@@ -97,6 +101,18 @@ static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long
   cuuint32_t box[2] = {64, 32};
   MDE_TRY(encode_map(&op->map_out, precision, ep->d_out, 2, dims, str, box));
   p.tma_out = 1;
+  if (ep->gather_n > 0) {
+    if (ep->gather_col0 % 64 || ep->gather_col0 < 0 || ep->gather_col0 >= n || ep->gather_ld % 8 || ep->gather_ld < n - ep->gather_col0)
+      return fail(MDE_ERR_INVALID, "gemm: gather_col0 must be a multiple of 64 inside [0, N) and gather_ld >= N - gather_col0, a multiple of 8");
+    for (int r = 0; r < ep->gather_n; ++r) {
+      if (!ep->d_gather[r] || (reinterpret_cast<uintptr_t>(ep->d_gather[r]) & 15)) return fail(MDE_ERR_INVALID, "gemm: gather destination %d is null or misaligned", r);
+      cuuint64_t gdims[2] = {static_cast<cuuint64_t>(n - ep->gather_col0), static_cast<cuuint64_t>(m)};
+      cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ep->gather_ld) * 2};
+      MDE_TRY(encode_map(&op->gather.m[r], precision, ep->d_gather[r], 2, gdims, gstr, box));
+    }
+    p.gather_n = ep->gather_n;
+    p.gather_col0 = ep->gather_col0;
+  }
   return MDE_OK;
 }
 
@@ -201,6 +217,7 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
     MDE_TRY(encode_map(&op->map_b, precision, d_b, 2, dims, str, box));
   }
   MDE_TRY(maybe_tma_out(op, precision, ep, m, n));
+  if (ep->gather_n > 0 && !p.gather_n) return fail(MDE_ERR_INVALID, "gemm: the fused gather needs a plain 16-bit output (bias / activation only) with N a multiple of the tile width");
   return pick_grid(op);
 }
 
@@ -276,9 +293,9 @@ static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    MDE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, op.map_a, op.map_b, op.map_out, op.p));
+    MDE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, op.map_a, op.map_b, op.map_out, op.gather, op.p));
   } else {
-    kern<<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(op.map_a, op.map_b, op.map_out, op.p);
+    kern<<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(op.map_a, op.map_b, op.map_out, op.gather, op.p);
   }
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -330,20 +347,36 @@ int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batc
                                : launch_attention_t<__half>(d_qkv, d_out, batch, ntok, heads, s);
 }
 
-int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads) {
+int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, const void* d_kv, int ldkv, int k_col0, int v_col0,
+                         void* d_out, int batch, int ntok_q, int ntok_kv, int heads) {
   if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
-  if (batch <= 0 || ntok <= 0 || heads <= 0) return fail(MDE_ERR_INVALID, "attention: empty problem");
+  if (batch <= 0 || ntok_q <= 0 || ntok_kv <= 0 || heads <= 0) return fail(MDE_ERR_INVALID, "attention: empty problem");
   if (batch > 65535 || heads > 65535) return fail(MDE_ERR_INVALID, "attention: batch/heads exceed grid limits");
-  if ((reinterpret_cast<uintptr_t>(d_qkv) | reinterpret_cast<uintptr_t>(d_out)) & 15) return fail(MDE_ERR_INVALID, "attention: buffers must be 16-byte aligned");
-  const long long rows = static_cast<long long>(batch) * ntok;
-  if (rows > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "attention: too many rows");
-  op->qkv = d_qkv; op->out = d_out; op->batch = batch; op->ntok = ntok; op->heads = heads; op->precision = precision;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(3 * heads * 64), static_cast<cuuint64_t>(rows)};
-  cuuint64_t str[1] = {static_cast<cuuint64_t>(3 * heads * 64) * 2};
-  cuuint32_t box[2] = {64, 128};
-  MDE_TRY(encode_map(&op->map_qkv, precision, d_qkv, 2, dims, str, box));
-  cuuint32_t box_kv[2] = {64, 64};
-  return encode_map(&op->map_kv, precision, d_qkv, 2, dims, str, box_kv);
+  if ((reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_kv) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+    return fail(MDE_ERR_INVALID, "attention: buffers must be 16-byte aligned");
+  const int D = heads * 64;
+  if (ldq < D || ldq % 8 || ldkv % 8 || k_col0 < 0 || v_col0 < 0 || k_col0 % 8 || v_col0 % 8 || k_col0 + D > ldkv || v_col0 + D > ldkv)
+    return fail(MDE_ERR_INVALID, "attention: inconsistent pitches / column offsets");
+  const long long rows_q = static_cast<long long>(batch) * ntok_q, rows_kv = static_cast<long long>(batch) * ntok_kv;
+  if (rows_q > 0x7fffffffLL || rows_kv > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "attention: too many rows");
+  op->qkv = d_q; op->out = d_out; op->batch = batch; op->ntok = ntok_kv; op->heads = heads; op->precision = precision;
+  op->ntok_q = ntok_q; op->k_col0 = k_col0; op->v_col0 = v_col0;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ldq), static_cast<cuuint64_t>(rows_q)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(ldq) * 2};
+    cuuint32_t box[2] = {64, 128};
+    MDE_TRY(encode_map(&op->map_qkv, precision, d_q, 2, dims, str, box));
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(ldkv), static_cast<cuuint64_t>(rows_kv)};
+  cuuint64_t str[1] = {static_cast<cuuint64_t>(ldkv) * 2};
+  cuuint32_t box128[2] = {64, 128}, box64[2] = {64, 64};
+  MDE_TRY(encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128));
+  return encode_map(&op->map_kv, precision, d_kv, 2, dims, str, box64);
+}
+
+int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads) {
+  const int D = heads * 64;
+  return make_attention_op_kv(op, precision, d_qkv, 3 * D, d_qkv, 3 * D, D, 2 * D, d_out, batch, ntok, ntok, heads);
 }
 
 template <typename T, int kPoly>
@@ -365,8 +398,9 @@ static int launch_attention_tc64_t(const AttnOp& op, cudaStream_t s) {
   }
   AttnParams p;
   p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok + 127) / 128, op.heads, op.batch);
+  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
   kern<<<grid, kAtcThreads, kA64SmemBytes, s>>>(op.map_qkv, op.map_kv, p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -388,9 +422,10 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   }
   AttnParams p;
   p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok + 127) / 128, op.heads, op.batch);
-  kern<<<grid, kAtcThreads, kAtcSmemBytes, s>>>(op.map_qkv, p);
+  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
+  kern<<<grid, kAtcThreads, kAtcSmemBytes, s>>>(op.map_qkv, op.map_kv128, p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
@@ -646,6 +681,14 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
   clear_error();
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
+                       int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream) {
+  clear_error();
+  AttnOp op;
+  MDE_TRY(make_attention_op_kv(&op, precision, d_q, ldq, d_kv, ldkv, k_col0, v_col0, d_out, batch, ntok_q, ntok_kv, heads));
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
 }
 

@@ -85,16 +85,17 @@ class _DevBuf:
                                          "data": (self.ptr, False), "version": 2}
 
 
-class GatherBuffers:
-    """One gather buffer per rank, 16-bit [4][world * per_rank][T][D], each mapped into every process."""
+class PeerBuffers:
+    """One 16-bit buffer of `shape` per rank, cudaMalloc'd and mapped into every process of the job with cudaIpc
+    (`ptrs[r]` is rank r's buffer as seen from this process; `ptrs[rank]` is our own)."""
 
-    def __init__(self, world: int, rank: int, per_rank: int, tokens: int, dim: int, precision: str):
+    def __init__(self, world: int, rank: int, shape: Sequence[int], precision: str):
         import torch.distributed as dist
         from cuda.bindings import runtime as cudart
         from . import common
         self._cudart, self._common = cudart, common
         self.world, self.rank = world, rank
-        self.shape = (4, world * per_rank, tokens, dim)
+        self.shape = tuple(int(v) for v in shape)
         self.precision = precision
         self.nbytes = int(np.prod(self.shape)) * 2
         self.own = int(common.cuda_call(cudart.cudaMalloc(self.nbytes)))
@@ -116,7 +117,7 @@ class GatherBuffers:
                 self._opened.append(p)
 
     def view(self):
-        """torch view of this rank's gather buffer, [4, world * per_rank, T, D] in the engine's 16-bit type."""
+        """torch view of this rank's own buffer in the 16-bit type."""
         import torch
         t = torch.as_tensor(_DevBuf(self.own, self.shape, "<i2"), device="cuda")
         return t.view(torch.bfloat16 if self.precision == "bf16" else torch.float16)
@@ -128,6 +129,13 @@ class GatherBuffers:
         if self.own:
             self._cudart.cudaFree(self.own)
             self.own = 0
+
+
+class GatherBuffers(PeerBuffers):
+    """The patch encoder's gather buffers: [4][world * per_rank][T][D] per rank."""
+
+    def __init__(self, world: int, rank: int, per_rank: int, tokens: int, dim: int, precision: str):
+        super().__init__(world, rank, (4, world * per_rank, tokens, dim), precision)
 
 
 class ShardedPatchEncoder:

@@ -22,7 +22,7 @@ def stream():
 
 def epilogue(bias=None, gamma=None, act=0, x=None, accumulate_x=False, res1=None, res2=None, out=None,
              out_relu=None, ld_out=0, tokens=0, pos=None, shuffle=None, head_w=None, head_b=0.0,
-             head_scale=0.0, head_out=None):
+             head_scale=0.0, head_out=None, gather=None):
     ep = _lib.Epilogue()
     ep.d_bias, ep.d_gamma, ep.act = ptr(bias), ptr(gamma), act
     ep.d_x, ep.accumulate_x = ptr(x), int(accumulate_x)
@@ -31,6 +31,11 @@ def epilogue(bias=None, gamma=None, act=0, x=None, accumulate_x=False, res1=None
     if shuffle:
         ep.shuffle_s, ep.shuffle_cout, ep.shuffle_h, ep.shuffle_w = shuffle
     ep.d_head_w, ep.head_b, ep.head_scale, ep.d_head_out = ptr(head_w), head_b, head_scale, ptr(head_out)
+    if gather:       # (col0, ld, [device pointers, already offset to this rank's first row])
+        ep.gather_col0, ep.gather_ld, ptrs = gather
+        ep.gather_n = len(ptrs)
+        for i, p_ in enumerate(ptrs):
+            ep.d_gather[i] = int(p_)
     return ep
 
 
@@ -65,6 +70,18 @@ def attention(precision, qkv, batch, ntok, heads, variant="tc"):
     out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
     fn = {"tc": lib.mde_k_attention, "kv64": lib.mde_k_attention_kv64, "mma": lib.mde_k_attention_mma}[variant]
     _lib.check(fn(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()), "mde_k_attention")
+    return out
+
+
+def attention_kv(precision, q, ldq, kv, ldkv, k_col0, v_col0, batch, ntok_q, ntok_kv, heads):
+    """q: tensor or device pointer of [batch*ntok_q, ldq]; kv: tensor or device pointer of [batch*ntok_kv, ldkv]."""
+    lib = _lib.load()
+    dt = q.dtype if hasattr(q, "dtype") else TORCH_DT[precision]
+    out = torch.empty(batch * ntok_q, heads * 64, dtype=dt, device="cuda")
+    qp = ptr(q) if hasattr(q, "data_ptr") else int(q)
+    kp = ptr(kv) if hasattr(kv, "data_ptr") else int(kv)
+    _lib.check(lib.mde_k_attention_kv(_lib.PRECISIONS[precision], qp, ldq, kp, ldkv, k_col0, v_col0, ptr(out), batch, ntok_q,
+                                      ntok_kv, heads, stream()), "mde_k_attention_kv")
     return out
 
 

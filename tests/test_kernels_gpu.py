@@ -303,3 +303,43 @@ def test_resize_depth_matches_the_scripts_postprocessing(lib, B, h, w, ho, wo):
     ref = torch.clamp(F.interpolate(d[:, None], (ho, wo), mode="bilinear", align_corners=True)[:, 0], 1e-3, 1e3)
     assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
     assert float(got.min()) >= 1e-3 and float(got.max()) <= 1e3
+
+
+# ------------------------------------------------------------------------------------------ sharded global attention pieces (one GPU)
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,nq,nkv,heads", [(1, 700, 2748, 6), (2, 130, 517, 2), (1, 1374, 1374, 16)])
+def test_attention_queries_and_keys_from_different_row_sets(lib, prec, B, nq, nkv, heads):
+    """Queries = a rank's tokens, keys/values = everybody's tokens in a gathered [nkv, 2D] k|v buffer."""
+    dt = K.TORCH_DT[prec]
+    D = heads * 64
+    qkv = rnd((B * nq, 3 * D), dt, seed=51)
+    kv = rnd((B * nkv, 2 * D), dt, seed=52)
+    out = K.attention_kv(prec, qkv, 3 * D, kv, 2 * D, 0, D, B, nq, nkv, heads)
+    torch.cuda.synchronize()
+    q = qkv[:, :D].float().reshape(B, nq, heads, 64).transpose(1, 2)
+    k = kv[:, :D].float().reshape(B, nkv, heads, 64).transpose(1, 2)
+    v = kv[:, D:].float().reshape(B, nkv, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * nq, D)
+    assert K.rel_err(out, ref) < 4 * ULP[prec]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gemm_fused_gather_single_rank(lib, prec):
+    """QKV projection whose K|V column boxes go to `gather` destinations (here: two local buffers standing in for two
+    ranks) instead of the local output; rows beyond m are clipped in every destination."""
+    dt = K.TORCH_DT[prec]
+    m, D = 1374 + 13, 384
+    a, w = rnd((m, D), dt, seed=53), rnd((3 * D, D), dt, D ** -0.5, seed=54)
+    bias = torch.randn(3 * D, device="cuda") * 0.3
+    out = torch.full((m, 3 * D), 7.0, dtype=dt, device="cuda")
+    g = [torch.full((2 * m + 5, 2 * D), 7.0, dtype=dt, device="cuda") for _ in range(2)]
+    row0 = m                                                   # we are "rank 1" of 2: our rows start at row m
+    ptrs = [t.data_ptr() + row0 * 2 * D * 2 for t in g]
+    K.gemm(prec, a, w, K.epilogue(bias=bias, out=out, ld_out=3 * D, gather=(D, 2 * D, ptrs)))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    assert K.rel_err(out[:, :D], ref[:, :D]) < ULP[prec]
+    assert torch.all(out[:, D:] == 7.0)                        # K|V did not go to the local output
+    for t in g:
+        assert K.rel_err(t[row0:row0 + m], ref[:, D:]) < ULP[prec]
+        assert torch.all(t[:row0] == 7.0) and torch.all(t[row0 + m:] == 7.0)
