@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""VGGT-style global attention on N GPUs (one process per GPU, launch with torchrun): the F frames of a scene are
+sharded by frame, every rank projects ITS tokens to q|k|v and attends with its queries over ALL ranks' keys/values.
+
+  fused   the QKV GEMM's epilogue bulk-stores its K|V column boxes straight into every rank's gathered [S, 2D] buffer
+          (cudaIpc-mapped peer memory, TMA stores over NVLink); q stays local.  GEMM -> all-gather is ONE kernel.
+  nccl    plain QKV GEMM, then torch.distributed.all_gather_into_tensor of the K|V slice: the baseline.
+
+Both feed the same tcgen05 attention kernel (queries: local rows; keys/values: the gathered buffer).  Rank 0 checks
+its output rows against an fp32 torch reference built from every rank's inputs and prints one JSON line
+(CUDA events, max over ranks).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 \
+        tests/mgpu/sharded_global_attention.py [--frames 16] [--tokens 1374] [--heads 16] [--precision bf16]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+import kutil as K
+from monocular_depth_estimation_trt_b200 import sharding as S
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=16); ap.add_argument("--tokens", type=int, default=1374)
+ap.add_argument("--heads", type=int, default=16); ap.add_argument("--precision", default="bf16"); ap.add_argument("--reps", type=int, default=5)
+a = ap.parse_args()
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+assert a.frames % world == 0, "frames must divide over the ranks"
+dt = K.TORCH_DT[a.precision]
+D = a.heads * 64
+s_local = a.frames // world * a.tokens
+s_total = a.frames * a.tokens
+
+
+def tokens_of(r):      # LayerNorm'd tokens of rank r's frames (seeded: every rank can rebuild every shard for the check)
+    g = torch.Generator(device="cuda").manual_seed(100 + r)
+    return torch.randn(s_local, D, generator=g, device="cuda").to(dt)
+
+
+g = torch.Generator(device="cuda").manual_seed(7)
+w_qkv = (torch.randn(3 * D, D, generator=g, device="cuda") * D ** -0.5).to(dt)
+b_qkv = torch.randn(3 * D, generator=g, device="cuda") * 0.1
+x = tokens_of(rank)
+qkv = torch.empty(s_local, 3 * D, dtype=dt, device="cuda")
+kvbuf = S.PeerBuffers(world, rank, (s_total, 2 * D), a.precision)         # every rank's gathered K|V
+mine = [p + rank * s_local * 2 * D * 2 for p in kvbuf.ptrs]              # our row range inside each of them
+
+
+def run_fused():
+    K.gemm(a.precision, x, w_qkv, K.epilogue(bias=b_qkv, out=qkv, ld_out=3 * D, gather=(D, 2 * D, mine)))
+
+
+def run_nccl():
+    K.gemm(a.precision, x, w_qkv, K.epilogue(bias=b_qkv, out=qkv, ld_out=3 * D))
+    dist.all_gather_into_tensor(kvbuf.view(), qkv[:, D:].contiguous())
+
+
+def attend():
+    return K.attention_kv(a.precision, qkv, 3 * D, kvbuf.own, 2 * D, 0, D, 1, s_local, s_total, a.heads)
+
+
+result = {"world": world, "frames": a.frames, "tokens_per_frame": a.tokens, "heads": a.heads, "precision": a.precision,
+          "kv_bytes_gathered_per_rank": s_total * 2 * D * 2}
+outs = {}
+for mode, proj in (("fused", run_fused), ("nccl", run_nccl)):
+    kvbuf.view().zero_(); torch.cuda.synchronize(); dist.barrier()
+    ts_proj, ts_all = [], []
+    for it in range(a.reps + 2):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(); proj(); e1.record()
+        torch.cuda.synchronize(); dist.barrier()              # every rank's K|V has landed everywhere
+        e2a = torch.cuda.Event(enable_timing=True); e2a.record()
+        out = attend(); e2.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), e2a.elapsed_time(e2)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= 2:
+            ts_proj.append(float(t[0])); ts_all.append(float(t[1]))
+    result[f"{mode}_qkv_plus_gather_ms"] = sorted(ts_proj)[len(ts_proj) // 2]
+    result[f"{mode}_attention_ms"] = sorted(ts_all)[len(ts_all) // 2]
+    outs[mode] = out.clone()
+same = torch.tensor([int(torch.equal(outs["fused"], outs["nccl"]))], device="cuda")
+dist.all_reduce(same, op=dist.ReduceOp.MIN)
+result["fused_equals_nccl_on_every_rank"] = bool(same.item())
+if rank == 0:
+    # fp32 reference for rank 0's queries over everybody's keys/values (same 16-bit q|k|v roundings as the kernels see)
+    full = torch.cat([(tokens_of(r).float() @ w_qkv.float().t() + b_qkv).to(dt) for r in range(world)])
+    q = full[:s_local, :D].float().reshape(1, s_local, a.heads, 64).transpose(1, 2)
+    k = full[:, D:2 * D].float().reshape(1, s_total, a.heads, 64).transpose(1, 2)
+    v = full[:, 2 * D:].float().reshape(1, s_total, a.heads, 64).transpose(1, 2)
+    ref = torch.cat([F.scaled_dot_product_attention(q[:, :, i:i + 2048], k, v) for i in range(0, s_local, 2048)], dim=2)
+    ref = ref.transpose(1, 2).reshape(s_local, D)
+    result["rel_err_vs_fp32_reference"] = K.rel_err(outs["fused"], ref)
+    print(json.dumps(result))
+dist.barrier()
+kvbuf.close()
+dist.destroy_process_group()
