@@ -279,3 +279,27 @@ def test_source_grid_output_fuses_the_scripts_postprocessing(lib):
         eng.close()
     ref = torch.clamp(F.interpolate(outs["model_grid"][:, None], (480, 640), mode="bilinear", align_corners=True)[:, 0], 1e-3, 1e3)
     assert float((outs["source_grid"] - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+def test_graph_replay_matches_plain_launches(lib):
+    """On a capturable stream the launch sequence is recorded into a CUDA graph at the first enqueue and replayed
+    afterwards; new bindings re-record.  Every variant must reproduce the plain-launch result bit for bit."""
+    eng, x, depth, _ = build_engine("vits", "fp16")
+    xd = x.cuda()
+    ref = torch.full((1, 518, 518), float("nan"), device="cuda")
+    run(eng, xd, ref)                                     # legacy default stream: plain launches
+    side = torch.cuda.Stream()
+    ctx = eng.create_execution_context()
+    out_a = torch.full_like(ref, float("nan"))
+    out_b = torch.full_like(ref, float("nan"))
+    ctx.set_tensor_address("input", xd.data_ptr())
+    side.wait_stream(torch.cuda.current_stream())
+    for out in (out_a, out_a, out_b, out_b):              # capture, replay, re-capture for the new binding, replay
+        ctx.set_tensor_address("output", out.data_ptr())
+        out.fill_(float("nan"))
+        side.wait_stream(torch.cuda.current_stream())
+        ctx.execute_async_v3(side.cuda_stream)
+        side.synchronize()
+        assert torch.equal(out, ref)
+    ctx.close()
+    eng.close()
