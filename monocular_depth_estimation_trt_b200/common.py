@@ -87,6 +87,7 @@ def get_engine(
     max_src_hw: Tuple[int, int] = (0, 0),
     swap_rb: bool = True,
     device: int = 0,
+    output: str = "model_grid",
 ) -> Engine:
     """Build the engine for the exported model at `onnx_file_path` (an .mdew file here).
 
@@ -98,7 +99,9 @@ def get_engine(
     `workspace_gib`, `opt_level` and `obey_precision_constraints` only enter the fingerprint.
     Keyword-only extras: `batch` (images per execute), `input_mode` ("f32_nchw" = the reference's
     float32 contract fed by core/preprocess.py; "u8_hwc" = raw source frames, preprocessing fused
-    on the GPU), `max_src_hw` for the latter.
+    on the GPU), `max_src_hw` for the latter; `output` ("model_grid" = spec.json's [B, H, W] map; "source_grid" =
+    the scripts' post-processing fused in: resized back to `max_src_hw` / the bound source size and clamped,
+    models/depth_anything_v2/onnx2trt.py:111-117).
     """
     model_path = os.fspath(onnx_file_path)
     if not os.path.exists(model_path):
@@ -109,7 +112,7 @@ def get_engine(
     begin = time.time()
     meta = W.read_meta(model_path)
     desc = make_desc(meta, precision=precision, batch=batch, input_mode=input_mode,
-                     max_src_hw=max_src_hw, swap_rb=swap_rb, device=device)
+                     max_src_hw=max_src_hw, swap_rb=swap_rb, device=device, output=output)
 
     fingerprint = None
     fingerprint_path = os.path.splitext(engine_file_path)[0] + ".fingerprint" if engine_file_path else ""

@@ -48,7 +48,7 @@ struct GemmParams {
   int tma_out;          // plain row-major 16-bit output (bias / activation only): registers -> smem -> TMA store
   int gather_n;         // tma_out only: column boxes at or beyond gather_col0 are stored to gather_n tensors (the ranks'
   int gather_col0;      //   gathered K|V buffers, peer memory) instead of `out`; see GatherMaps
-  int tma_x;            // x += gamma * (acc + bias) on plain rows: TMA load of the x box -> in-place update in smem -> TMA store
+  int tma_x;            // x += gamma * (acc + bias) on plain rows as a bulk tensor reduction (fp32 add in the L2)
   // ---- fused depth head (BLOCK_N == 32 == N): z = sum_n relu(v_n) * head_w[n] + head_b
   const float* head_w;
   float head_b;
@@ -148,8 +148,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
-  uint64_t* x_bar = bars + 2 * kStages + 4;       // [kEpiWarps]: residual-stream box of an epilogue warp has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + Cfg::kEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,7 +168,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < Cfg::kEpiWarps; ++i) mbar_init(&x_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], Cfg::kEpiWarps * kCtas);   // one arrive per epilogue warp (of both CTAs of a pair)
@@ -372,27 +370,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       if (lane == 0) bulk_wait0();
     } else if (p.tma_x) {
-      // ---- residual-stream update on plain rows (attention projection, FC2): x += gamma * (acc + bias), fp32.
-      // The 32 x 32 fp32 box of x this warp updates next is fetched by TMA into the warp's 128-byte-swizzled
-      // staging buffer (the first box of a tile while its MMAs still run, the others right after the previous
-      // store has drained the buffer, out of L2 where a prefetch issued at the start of the tile put them);
-      // thread = row reads its 128 bytes, updates them in place and one bulk tensor store writes the box back.
-      // No global load/store instructions, addresses or predicates in the loop; rows >= M are zero-filled on
-      // the way in and clipped on the way out.
+      // ---- residual-stream update on plain rows (attention projection, FC2) as a bulk tensor REDUCTION:
+      // x[box] += gamma * (acc + bias), the add done by the L2 (cp.reduce.async.bulk.tensor ... .add, fp32).  The SM never
+      // loads x: nothing to wait for, no global load/store instructions, addresses or predicates in the loop; rows >= M are
+      // clipped.  (A TMA-load / update-in-place / TMA-store variant measured 897 vs 990 TFLOP/s on the projection.)
       uint8_t* buf = epi_smem + ew * 4096;
       constexpr int kPerWarp = BLOCK_N / 64;
       const int ch_begin = half * kPerWarp;
-      uint32_t x_phase = 0;
-      if (lane == 0 && tile0 < num_tiles) {
-        mbar_arrive_expect_tx(&x_bar[ew], 4096);
-        tma_load_2d(buf, &map_out, &x_bar[ew], (tile0 % p.n_tiles) * BLOCK_N + ch_begin * 32, m_block(tile0) * 128 + quarter * 32);
-      }
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int row0 = m_block(tile) * 128 + quarter * 32;
         const int n_tile = (tile % p.n_tiles) * BLOCK_N;
-        if (lane == 0) {
-          for (int c = 1; c < kPerWarp; ++c) tma_prefetch_l2_2d(&map_out, n_tile + (ch_begin + c) * 32, row0);
-        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
@@ -412,35 +399,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             __syncwarp();
             if (lane == 0) release_acc(acc);
           }
-          mbar_wait(&x_bar[ew], x_phase);
-          x_phase ^= 1;
+          if (lane == 0) bulk_wait_read0();      // the previous reduction has drained the staging box
+          __syncwarp();
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            float4* px = reinterpret_cast<float4*>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));
-            float4 xv = *px;
             float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), gam = make_float4(1.f, 1.f, 1.f, 1.f);
             if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + n_base) + g);
             if (p.gamma) gam = __ldg(reinterpret_cast<const float4*>(p.gamma + n_base) + g);
-            xv.x = fmaf(v[4 * g] + bia.x, gam.x, xv.x);
-            xv.y = fmaf(v[4 * g + 1] + bia.y, gam.y, xv.y);
-            xv.z = fmaf(v[4 * g + 2] + bia.z, gam.z, xv.z);
-            xv.w = fmaf(v[4 * g + 3] + bia.w, gam.w, xv.w);
-            *px = xv;
+            float4 d;
+            d.x = (v[4 * g] + bia.x) * gam.x; d.y = (v[4 * g + 1] + bia.y) * gam.y;
+            d.z = (v[4 * g + 2] + bia.z) * gam.z; d.w = (v[4 * g + 3] + bia.w) * gam.w;
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((g ^ (lane & 7)) << 4)) = d;
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_out, buf, n_base, row0);
+            tma_reduce_add_2d(&map_out, buf, n_base, row0);
             bulk_commit();
-            // next box of this warp: the next chunk of this tile, or the first chunk of the CTA's next tile
-            int nt = tile, nc = c + 1;
-            if (nc == kPerWarp) { nt = tile + tile_step; nc = 0; }
-            if (nt < num_tiles) {
-              bulk_wait_read0();               // the store has drained the buffer
-              mbar_arrive_expect_tx(&x_bar[ew], 4096);
-              tma_load_2d(buf, &map_out, &x_bar[ew], (nt % p.n_tiles) * BLOCK_N + (ch_begin + nc) * 32,
-                          m_block(nt) * 128 + quarter * 32);
-            }
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -77,7 +77,7 @@ static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long
   p.gather_col0 = 0;
   if (ep->gather_n < 0 || ep->gather_n > 8) return fail(MDE_ERR_INVALID, "gemm: at most 8 gather destinations");
   if (getenv("MDE_NO_TMA_OUT")) return MDE_OK;
-  // residual-stream update on plain rows: the fp32 x boxes travel by TMA in both directions
+  // residual-stream update on plain rows: fp32 boxes of gamma * (acc + bias) are added to x by bulk tensor reductions
   if (ep->d_x && ep->accumulate_x && !ep->d_out && !ep->d_out_relu && !ep->d_res1 && !ep->d_res2 && !ep->d_pos && !ep->d_head_w &&
       ep->act == 0 && !p.conv && p.row_map == ROW_IDENTITY && op->block_n >= 128 && n % op->block_n == 0 && ep->ld_out % 4 == 0 &&
       !(reinterpret_cast<uintptr_t>(ep->d_x) & 15)) {
