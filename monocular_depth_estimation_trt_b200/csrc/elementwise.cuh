@@ -166,7 +166,9 @@ struct LayerNormParams {
   long long dst_row0;  // row offset of this rank's rows inside every dst
   void* dst[8];
 };
-template <typename T, int D>
+// kTap = false: the plain per-block LayerNorm (the hot one: 48 launches per forward); kTap = true adds the tap options
+// (no normalisation, several destinations) without costing the plain instantiation a register or a branch.
+template <typename T, int D, bool kTap>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p) {
   constexpr int V = D / 128;   // float4 per lane
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -199,6 +201,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq * (1.0f / D) + p.eps);
+  if (!kTap) {
+    T* out = static_cast<T*>(p.out) + orow * D;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = (lane + i * 32) * 4;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.b + c));
+      uint2 u;
+      u.x = F16Traits<T>::pack2((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y);
+      u.y = F16Traits<T>::pack2((v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+      *reinterpret_cast<uint2*>(out + c) = u;
+    }
+    return;
+  }
   uint2 u[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {

@@ -471,15 +471,15 @@ int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv) {
   return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s, kv) : launch_attention_tc_p<__half>(op, s, kv);
 }
 
-template <typename T>
+template <typename T, bool kTap>
 static int launch_layernorm_t(const LayerNormParams& p, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((p.rows + 7) / 8);
   switch (p.D) {
-    case 384: layernorm_kernel<T, 384><<<grid, 256, 0, s>>>(p); break;
-    case 768: layernorm_kernel<T, 768><<<grid, 256, 0, s>>>(p); break;
-    case 1024: layernorm_kernel<T, 1024><<<grid, 256, 0, s>>>(p); break;
-    case 128: layernorm_kernel<T, 128><<<grid, 256, 0, s>>>(p); break;
-    case 1536: layernorm_kernel<T, 1536><<<grid, 256, 0, s>>>(p); break;
+    case 384: layernorm_kernel<T, 384, kTap><<<grid, 256, 0, s>>>(p); break;
+    case 768: layernorm_kernel<T, 768, kTap><<<grid, 256, 0, s>>>(p); break;
+    case 1024: layernorm_kernel<T, 1024, kTap><<<grid, 256, 0, s>>>(p); break;
+    case 128: layernorm_kernel<T, 128, kTap><<<grid, 256, 0, s>>>(p); break;
+    case 1536: layernorm_kernel<T, 1536, kTap><<<grid, 256, 0, s>>>(p); break;
     default: return fail(MDE_ERR_INVALID, "layernorm: unsupported width %d", p.D);
   }
   MDE_CUDA_TRY(cudaGetLastError());
@@ -495,7 +495,9 @@ int launch_layernorm(int precision, const float* d_x, const float* d_w, const fl
   p.x = d_x; p.w = d_w; p.b = d_b; p.out = d_out; p.rows = rows; p.D = dim; p.eps = eps; p.drop_cls = drop_cls; p.ntok = ntok;
   p.identity = identity; p.n_dst = n_dst; p.dst_row0 = dst_row0;
   for (int i = 0; i < 8; ++i) p.dst[i] = i < n_dst ? dst[i] : nullptr;
-  return precision == MDE_BF16 ? launch_layernorm_t<__nv_bfloat16>(p, s) : launch_layernorm_t<__half>(p, s);
+  if (identity || n_dst > 0)
+    return precision == MDE_BF16 ? launch_layernorm_t<__nv_bfloat16, true>(p, s) : launch_layernorm_t<__half, true>(p, s);
+  return precision == MDE_BF16 ? launch_layernorm_t<__nv_bfloat16, false>(p, s) : launch_layernorm_t<__half, false>(p, s);
 }
 
 static unsigned grid_for(long long total, int per_block) {
