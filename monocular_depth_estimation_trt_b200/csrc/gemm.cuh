@@ -48,6 +48,8 @@ struct GemmParams {
   int tma_out;          // plain row-major 16-bit output (bias / activation only): registers -> smem -> TMA store
   int gather_n;         // tma_out only: column boxes at or beyond gather_col0 are stored to gather_n tensors (the ranks'
   int gather_col0;      //   gathered K|V buffers, peer memory) instead of `out`; see GatherMaps
+  int splits;           // split-K (tma_x only, >= 1): work item w = split * tiles + tile covers k-blocks [split * kb_per_split, ...);
+  int kb_per_split;     //   the partial products meet in the L2's fp32 adds.  Fills the SMs when a small batch has few tiles
   int tma_x;            // x += gamma * (acc + bias) on plain rows as a bulk tensor reduction (fp32 add in the L2)
   // ---- fused depth head (BLOCK_N == 32 == N): z = sum_n relu(v_n) * head_w[n] + head_b
   const float* head_w;
@@ -191,7 +193,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t a_bytes = p.conv ? static_cast<uint32_t>(p.tile_w * p.tile_h * 128) : Cfg::kABytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int work = tile0; work < num_tiles * p.splits; work += tile_step) {
+        const int tile = work % num_tiles;
+        const int kb_begin = (work / num_tiles) * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         const int m_blk = m_block(tile);
         const int n_blk = tile % p.n_tiles;
         int img = 0, y0 = 0, x0 = 0;
@@ -202,7 +206,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           y0 = (t / p.tiles_x) * p.tile_h;
           x0 = (t % p.tiles_x) * p.tile_w;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kCtas == 2) {
             // both CTAs' bytes are counted on the leader's barrier; the leader alone arrives on it
@@ -242,11 +246,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int work = tile0; work < num_tiles * p.splits; work += tile_step) {
+        const int kb_begin = (work / num_tiles) * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
@@ -254,8 +259,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+            else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
           }
           if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -377,7 +382,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint8_t* buf = epi_smem + ew * 4096;
       constexpr int kPerWarp = BLOCK_N / 64;
       const int ch_begin = half * kPerWarp;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int work = tile0; work < num_tiles * p.splits; work += tile_step) {
+        const int tile = work % num_tiles;
+        const bool first_split = work < num_tiles;       // the bias is added once per output element
         const int row0 = m_block(tile) * 128 + quarter * 32;
         const int n_tile = (tile % p.n_tiles) * BLOCK_N;
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -404,7 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), gam = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + n_base) + g);
+            if (p.bias && first_split) bia = __ldg(reinterpret_cast<const float4*>(p.bias + n_base) + g);
             if (p.gamma) gam = __ldg(reinterpret_cast<const float4*>(p.gamma + n_base) + g);
             float4 d;
             d.x = (v[4 * g] + bia.x) * gam.x; d.y = (v[4 * g + 1] + bia.y) * gam.y;

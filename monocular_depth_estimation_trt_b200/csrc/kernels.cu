@@ -152,8 +152,19 @@ static int pick_grid(GemmOp* op) {
   const int sms = num_sms();
   if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
   const GemmParams& p = op->p;
-  if (op->ctas == 2) op->grid = 2 * std::min(sms / 2, ((p.m_tiles + 1) / 2) * p.n_tiles);
-  else op->grid = std::min(sms, p.m_tiles * p.n_tiles);
+  GemmParams& pw = op->p;
+  pw.splits = 1;
+  pw.kb_per_split = p.num_k_blocks;
+  const int units = op->ctas == 2 ? sms / 2 : sms;                                        // CTAs or CTA pairs that can run at once
+  const int tiles = op->ctas == 2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
+  if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && !getenv("MDE_NO_SPLITK")) {
+    // small batch: a handful of tiles on 148 SMs.  Split K so that every SM gets a piece (at least 8 k-blocks each);
+    // the reduction epilogue adds the partial products in the L2.
+    int splits = std::min(std::min(units / tiles, p.num_k_blocks / 8), 8);
+    pw.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+    pw.splits = (p.num_k_blocks + pw.kb_per_split - 1) / pw.kb_per_split;
+  }
+  op->grid = op->ctas * std::min(units, tiles * pw.splits);
   return MDE_OK;
 }
 
