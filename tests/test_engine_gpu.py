@@ -145,7 +145,7 @@ def test_vits_non_square_token_grids(lib, h, w):
     assert m["max_rel"] <= GATE["fp16"]["max_rel"]
 
 
-def test_batch_entries_are_independent(lib):
+def test_batch_entries_are_independent(lib, bitwise):
     """The same image at batch positions 0 and 2 gives bit-identical maps; idempotent across runs."""
     sd, x, depth, _ = R.reference("vits")
     meta = W.describe("vits", 518, 518, 20.0)
@@ -163,7 +163,7 @@ def test_batch_entries_are_independent(lib):
     assert torch.equal(out, first)
 
 
-def test_uint8_input_engine_matches_float_engine(lib):
+def test_uint8_input_engine_matches_float_engine(lib, bitwise):
     """Fused resize+normalise+im2col input binding == host preprocessing + float32 binding, bit for bit."""
     sd, x, depth, _ = R.reference("vits")
     img = R.synthetic_image(0)                                 # the image `x` was made from
@@ -234,7 +234,7 @@ def _trunk_reference(encoder, batch, seed=5):
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-def test_trunk_only_engine_patch16_taps(lib, prec):
+def test_trunk_only_engine_patch16_taps(lib, prec, bitwise):
     """ViT/16 at 384 x 384 (24 x 24 tokens), raw hooked block outputs + normalised final tokens, 16-bit [4][B][T][D]:
     through the output binding and through the fused-gather path with a single rank (both must agree bit for bit)."""
     from monocular_depth_estimation_trt_b200 import sharding as S
@@ -259,7 +259,7 @@ def test_trunk_only_engine_patch16_taps(lib, prec):
     eng.close()
 
 
-def test_source_grid_output_fuses_the_scripts_postprocessing(lib):
+def test_source_grid_output_fuses_the_scripts_postprocessing(lib, bitwise):
     """output="source_grid": the engine's binding is the depth map resized back to the source frame and clamped
     (onnx2trt.py:111-117), equal to doing that on the host from the model-grid output of the same engine."""
     import torch.nn.functional as F
@@ -281,7 +281,7 @@ def test_source_grid_output_fuses_the_scripts_postprocessing(lib):
     assert float((outs["source_grid"] - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
 
 
-def test_graph_replay_matches_plain_launches(lib):
+def test_graph_replay_matches_plain_launches(lib, bitwise):
     """On a capturable stream the launch sequence is recorded into a CUDA graph at the first enqueue and replayed
     afterwards; new bindings re-record.  Every variant must reproduce the plain-launch result bit for bit."""
     eng, x, depth, _ = build_engine("vits", "fp16")
@@ -303,3 +303,33 @@ def test_graph_replay_matches_plain_launches(lib):
         assert torch.equal(out, ref)
     ctx.close()
     eng.close()
+
+
+def test_split_k_changes_only_the_last_bits(lib, monkeypatch):
+    """Batch 1: FC2 / projection split K over the SMs and meet in the L2's fp32 adds (arrival order).  Against the
+    unsplit engine the depth map moves the way any re-association of fp32 sums moves a 16-bit pipeline (some 16-bit
+    roundings flip downstream); both stay inside the parity gate on the oracle."""
+    sd, x, depth, _ = R.reference("vits")
+    outs = []
+    for no_split in ("", "1"):
+        if no_split:
+            monkeypatch.setenv("MDE_NO_SPLITK", "1")
+        else:
+            monkeypatch.delenv("MDE_NO_SPLITK", raising=False)
+        meta = W.describe("vits", 518, 518, 20.0)
+        eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1), meta)
+        eng.load_state_dict(sd)
+        eng.finalize()
+        out = torch.full((1, 518, 518), float("nan"), device="cuda")
+        run(eng, x.cuda(), out)
+        outs.append(out.cpu())
+        eng.close()
+    m = R.compare_depth(outs[1].numpy(), outs[0].numpy())
+    print("split-K vs unsplit:", m)
+    # fp32 re-association upstream flips 16-bit roundings downstream, and twelve blocks later the two runs carry two
+    # independent realisations of the pipeline's rounding noise: they differ from each other by about as much as each
+    # differs from the fp32 oracle (measured AbsRel 7.0e-4 / max-rel 9.5e-3), i.e. inside north_star's gate, not bitwise
+    assert m["abs_rel"] < GATE["fp16"]["abs_rel"] and m["max_rel"] < 1.5 * GATE["fp16"]["max_rel"]
+    for o in outs:
+        g = R.compare_depth(depth.numpy(), o.numpy())
+        assert g["abs_rel"] <= GATE["fp16"]["abs_rel"] and g["max_rel"] <= GATE["fp16"]["max_rel"]
