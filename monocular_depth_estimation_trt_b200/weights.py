@@ -131,3 +131,41 @@ def file_sha256(path: str) -> str:
         for chunk in iter(lambda: f.read(1 << 20), b""):
             h.update(chunk)
     return h.hexdigest()
+
+
+# ------------------------------------------------------------------------------------------ upstream checkpoints
+def encoder_of(state_dict: Mapping[str, object]) -> str:
+    """Which of the released encoder sizes a state dict is, from the width of the trunk and its depth
+    (models/depth_anything_v2/infer.py:55-60 picks the same configs by name)."""
+    try:
+        dim = int(_shape(state_dict["pretrained.cls_token"])[-1])
+    except KeyError:
+        raise ValueError("[MDET] not a Depth Anything V2 state dict: 'pretrained.cls_token' is missing")
+    depth = 1 + max(int(k.split(".")[2]) for k in state_dict if k.startswith("pretrained.blocks."))
+    for name, cfg in ENCODERS.items():
+        if cfg["embed_dim"] == dim and cfg["depth"] == depth:
+            return name
+    raise ValueError(f"[MDET] no released encoder has width {dim} and depth {depth}")
+
+
+def _shape(v):
+    return tuple(v.shape)
+
+
+def export_checkpoint(checkpoint_path: str, out_path: str, input_h: int = 518, input_w: int = 518,
+                      max_depth: float | None = None) -> dict:
+    """Stage `export` for an upstream checkpoint (models/depth_anything_v2/infer.py:62-63:
+    `model.load_state_dict(torch.load(f"checkpoints/depth_anything_v2_{encoder}.pth"))`): read the .pth, keep the
+    tensors the engine needs under their upstream key names, write the .mdew file.  `max_depth` None = the relative
+    model, 20 / 80 = the metric Hypersim / VKITTI heads (infer_metric.py:61-65).  Returns the stored description."""
+    import torch
+    sd = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+    if isinstance(sd, dict) and "state_dict" in sd and "pretrained.cls_token" not in sd:
+        sd = sd["state_dict"]
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    enc = encoder_of(sd)
+    keep = {k: v for k, v in sd.items() if k.startswith(("pretrained.", "depth_head."))}
+    meta = describe(enc, input_h, input_w, max_depth)
+    meta["source_checkpoint_sha256"] = file_sha256(checkpoint_path)
+    save(out_path, keep, meta)
+    return meta

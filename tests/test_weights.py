@@ -52,3 +52,23 @@ def test_pos_embed_rule_matches_oracle():
         ref = O.interpolate_pos_embed(pe, gh, gw).numpy()
         assert got.shape == (1, 1 + gh * gw, 64) and np.allclose(got, ref, atol=1e-6)
         assert np.array_equal(got[:, 0], pe[:, 0].numpy())                              # cls part untouched
+
+
+def test_export_from_an_upstream_style_checkpoint(tmp_path, lib):
+    """A .pth with upstream's key names (here: the oracle's seeded init saved with torch.save, plus the kind of
+    wrapper keys checkpoints carry) -> .mdew -> engine description, without naming the encoder."""
+    sd = O.init_state_dict("vits", seed=4)
+    ck = tmp_path / "depth_anything_v2_metric_hypersim_vits.pth"
+    torch.save({"module." + k: v for k, v in sd.items()}, ck)
+    out = str(tmp_path / "m.mdew")
+    meta = W.export_checkpoint(str(ck), out, 518, 700, max_depth=20.0)
+    assert meta["encoder"] == "vits" and meta["embed_dim"] == 384 and (meta["input_h"], meta["input_w"]) == (518, 700)
+    assert meta["source_checkpoint_sha256"] == W.file_sha256(str(ck))
+    back, meta2 = W.load(out)
+    assert set(back) == set(sd) and meta2["max_depth"] == 20.0
+    eng = E.Engine(E.make_desc(meta2), meta2)
+    eng.load_weights_file(out)
+    eng.close()
+    assert W.encoder_of(O.init_state_dict("vitb", seed=1)) == "vitb"
+    with pytest.raises(ValueError):
+        W.encoder_of({"foo": torch.zeros(1)})
