@@ -333,3 +333,26 @@ def test_split_k_changes_only_the_last_bits(lib, monkeypatch):
     for o in outs:
         g = R.compare_depth(depth.numpy(), o.numpy())
         assert g["abs_rel"] <= GATE["fp16"]["abs_rel"] and g["max_rel"] <= GATE["fp16"]["max_rel"]
+
+
+def test_vitb_relative_head_parity(lib):
+    """The middle encoder size (D=768, 12 heads: 2304 / 3072-wide GEMMs, 128-wide DPT maps) with the RELATIVE head
+    (models/depth_anything_v2/infer.py: no max_depth -> ReLU instead of sigmoid * max_depth)."""
+    from oracle import dav2_torch as O, preprocess_np as P
+    x = torch.from_numpy(P.preprocess_stretch_imagenet(R.synthetic_image(0), 518, 518))
+    sd = O.init_state_dict("vitb", seed=0)
+    O.calibrate_head(sd, x, "vitb")
+    sd["depth_head.scratch.output_conv2.2.bias"] = sd["depth_head.scratch.output_conv2.2.bias"] + 6.0     # logits ~ N(6, 1): the whole map sits above the ReLU, relative errors stay meaningful
+    depth = O.forward(sd, x, "vitb", max_depth=None)
+    meta = W.describe("vitb", 518, 518, max_depth=None)
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    out = torch.full((1, 518, 518), float("nan"), device="cuda")
+    run(eng, x.cuda(), out)
+    got = out.cpu().numpy()
+    assert float(got.min()) >= 0.0
+    m = R.compare_depth(depth.numpy(), got)
+    print("vitb relative", m)
+    assert m["abs_rel"] <= GATE["fp16"]["abs_rel"] and m["max_rel"] <= 2 * GATE["fp16"]["max_rel"]
+    assert m["corr"] > 0.9995
