@@ -208,6 +208,10 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
  * V at v_col0; d_out: [batch*ntok_q][heads*64]. */
 int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
                        int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream);
+/* The same op with two query tiles per CTA and explicit turn-taking of the two softmax groups on the SFU
+ * (csrc/attention_tc2q.cuh). */
+int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       void* stream);
 /* The same op with 64-key tiles and four CTAs per SM (csrc/attention_tc64.cuh): the measured alternative to the
  * default kernel, kept for comparison; the engine launches it only when MDE_ATTN_KV=64 is set. */
 int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

@@ -168,7 +168,7 @@ def test_conv3x3_fused_depth_head(lib, prec, max_depth):
 
 
 # ------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("variant", ["tc", "kv64", "mma"])
+@pytest.mark.parametrize("variant", ["tc", "2q", "kv64", "mma"])
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,ntok,heads", [(2, 1370, 6), (1, 577, 16), (3, 64, 2), (1, 129, 1), (1, 3349, 2),
                                           (2, 256, 3), (1, 257, 2), (2, 128, 1)])
