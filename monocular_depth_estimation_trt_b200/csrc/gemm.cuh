@@ -67,7 +67,11 @@ struct GemmCfg {
   static constexpr int kBlockK = 64;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N / kCtas * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  // k-blocks (of 64) per pipeline stage.  One thread issues every MMA: a barrier wait + four tcgen05.mma + a commit cost
+  // about as many cycles as four 128 x 128 x 16 MMAs execute (measured: the tensor pipe of a 128-wide tile was 41 % busy
+  // whatever the L2 traffic), so narrow tiles take two k-blocks per hand-shake.
+  static constexpr int kKSub = BLOCK_N <= 128 ? 2 : 1;
+  static constexpr int kStageBytes = (kABytes + kBBytes) * kKSub;
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiBytes = kEpiWarps * (32 * 32 * 4 + 32 * 4);   // per warp: 4 KB staging chunk + 32 row indices (a multiple of 1024)
   static constexpr int kMaxStages = (227 * 1024 - 1024 - 256 - kEpiBytes) / kStageBytes;   // 227 KB per CTA
@@ -150,7 +154,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  constexpr int kKSub = Cfg::kKSub;
+  uint8_t* smem_b = smem + kStages * kKSub * Cfg::kABytes;
   uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;   // per epilogue warp: 4 KB staging chunk (1024-byte aligned); then 8 x 32 row indices
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;
@@ -213,32 +218,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           y0 = (t / p.tiles_x) * p.tile_h;
           x0 = (t % p.tiles_x) * p.tile_w;
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += kKSub) {
+          const int nsub = min(kKSub, kb_end - kb0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (kCtas == 2) {
-            // both CTAs' bytes are counted on the leader's barrier; the leader alone arrives on it
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + Cfg::kBBytes));
-            if (p.conv) {
-              const int tap = kb / p.cin_blocks;
-              const int c0 = (kb % p.cin_blocks) * 64;
-              tma_load_4d_pair(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], c0, x0 + tap % 3 - 1,
-                               y0 + tap / 3 - 1, img);
+          // pairs: both CTAs' bytes are counted on the leader's barrier; the leader alone arrives on it
+          if (kCtas == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kCtas * nsub * (a_bytes + Cfg::kBBytes));
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kb = kb0 + sub;
+            uint8_t* sa = smem_a + (stage * kKSub + sub) * Cfg::kABytes;
+            uint8_t* sb = smem_b + (stage * kKSub + sub) * Cfg::kBBytes;
+            if (kCtas == 2) {
+              if (p.conv) {
+                const int tap = kb / p.cin_blocks;
+                const int c0 = (kb % p.cin_blocks) * 64;
+                tma_load_4d_pair(sa, &map_a, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+              } else {
+                tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * 64, m_blk * 128);
+              }
+              tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * 64, n_blk * BLOCK_N + rank * (BLOCK_N / 2));
             } else {
-              tma_load_2d_pair(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], kb * 64, m_blk * 128);
+              if (p.conv) {
+                const int tap = kb / p.cin_blocks;
+                const int c0 = (kb % p.cin_blocks) * 64;
+                tma_load_4d(sa, &map_a, &full_bar[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+              } else {
+                tma_load_2d(sa, &map_a, &full_bar[stage], kb * 64, m_blk * 128);
+              }
+              tma_load_2d(sb, &map_b, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
             }
-            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &map_b, &full_bar[stage], kb * 64,
-                             n_blk * BLOCK_N + rank * (BLOCK_N / 2));
-          } else {
-          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + Cfg::kBBytes);
-          if (p.conv) {
-            const int tap = kb / p.cin_blocks;
-            const int c0 = (kb % p.cin_blocks) * 64;
-            tma_load_4d(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], c0, x0 + tap % 3 - 1,
-                        y0 + tap / 3 - 1, img);
-          } else {
-            tma_load_2d(smem_a + stage * Cfg::kABytes, &map_a, &full_bar[stage], kb * 64, m_blk * 128);
-          }
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &map_b, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -258,16 +265,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (int kb0 = kb_begin; kb0 < kb_end; kb0 += kKSub) {
+          const int nsub = min(kKSub, kb_end - kb0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          for (int sub = 0; sub < nsub; ++sub) {
+            const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + (stage * kKSub + sub) * Cfg::kABytes));
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + (stage * kKSub + sub) * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
-            else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              const uint32_t accumulate = ((kb0 + sub - kb_begin) | k) != 0;
+              if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+              else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+            }
           }
           if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }

@@ -147,7 +147,8 @@ static int pick_block_n(int n) {
 // One persistent CTA per SM -- or, for wide tiles with enough rows, one CTA pair per TPC (MDE_NO_PAIR=1 turns pairs off).
 static void pick_ctas(GemmOp* op) {
   // pairs pay off for 256-wide tiles with a real K loop; short K (a few k-blocks per tile) is epilogue-bound either way
-  op->ctas = (op->block_n == 256 && op->p.m_tiles >= 2 && op->p.num_k_blocks >= 4 && !getenv("MDE_NO_PAIR")) ? 2 : 1;
+  const bool wide = op->block_n == 256 || (op->block_n == 128 && op->p.num_k_blocks >= 8);
+  op->ctas = (wide && op->p.m_tiles >= 2 && op->p.num_k_blocks >= 4 && !getenv("MDE_NO_PAIR")) ? 2 : 1;
 }
 static int pick_grid(GemmOp* op) {
   const int sms = num_sms();
