@@ -288,25 +288,38 @@ def run_ours(args):
     # wall clock of one do_inference incl. both copies, warm-up 20, 100 iterations, nearest-rank p50)
     latency = None
     if rank == 0 and world == 1 and not args.no_latency:
-        e1 = E.Engine(E.make_desc(meta, precision=args.precision, batch=1, input_mode="u8_hwc", max_src_hw=SRC_HW, device=local), meta)
-        e1.load_state_dict(sd)
-        e1.finalize()
-        c1 = e1.create_execution_context()
-        c1.set_input_shape("input", (1, SRC_HW[0], SRC_HW[1], 3))
-        i1, o1, b1, s1 = common.allocate_buffers(e1, (1, 518, 518), profile_idx=0)
-        i1[0].host = frames[0]
-        samples = []
-        for it in range(120):
-            t0 = time.perf_counter()
-            common.do_inference(c1, engine=e1, bindings=b1, inputs=i1, outputs=o1, stream=s1)
-            if it >= 20:
-                samples.append((time.perf_counter() - t0) * 1000.0)
-        samples.sort()
-        rank_p = lambda q: samples[max(0, min(len(samples) - 1, int(np.ceil(q / 100.0 * len(samples))) - 1))]
-        latency = {"p50_ms": rank_p(50), "p90_ms": rank_p(90), "p99_ms": rank_p(99), "mean_ms": float(np.mean(samples)),
-                   "what": "batch 1, wall clock of do_inference incl. H2D (uint8 frame) and D2H (float32 map), warm-up 20, 100 iterations"}
-        common.free_buffers(i1, o1, s1)
-        c1.close(); e1.close()
+        def b1_latency():
+            e1 = E.Engine(E.make_desc(meta, precision=args.precision, batch=1, input_mode="u8_hwc", max_src_hw=SRC_HW, device=local), meta)
+            e1.load_state_dict(sd)
+            e1.finalize()
+            c1 = e1.create_execution_context()
+            c1.set_input_shape("input", (1, SRC_HW[0], SRC_HW[1], 3))
+            i1, o1, b1, s1 = common.allocate_buffers(e1, (1, 518, 518), profile_idx=0)
+            i1[0].host = frames[0]
+            samples = []
+            for it in range(120):
+                t0 = time.perf_counter()
+                common.do_inference(c1, engine=e1, bindings=b1, inputs=i1, outputs=o1, stream=s1)
+                if it >= 20:
+                    samples.append((time.perf_counter() - t0) * 1000.0)
+            samples.sort()
+            rank_p = lambda q: samples[max(0, min(len(samples) - 1, int(np.ceil(q / 100.0 * len(samples))) - 1))]
+            common.free_buffers(i1, o1, s1)
+            c1.close(); e1.close()
+            return {"p50_ms": rank_p(50), "p90_ms": rank_p(90), "p99_ms": rank_p(99), "mean_ms": float(np.mean(samples))}
+
+        latency = b1_latency()          # default configuration: bitwise reproducible
+        latency["what"] = ("batch 1, wall clock of do_inference incl. H2D (uint8 frame) and D2H (float32 map), warm-up 20, "
+                           "100 iterations")
+        prev = os.environ.get("MDE_SPLITK")
+        os.environ["MDE_SPLITK"] = "1"  # opt-in: split-K for the residual GEMMs (fp32 adds in arrival order, not bitwise reproducible)
+        try:
+            latency["with_split_k"] = b1_latency()
+        finally:
+            if prev is None:
+                del os.environ["MDE_SPLITK"]
+            else:
+                os.environ["MDE_SPLITK"] = prev
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

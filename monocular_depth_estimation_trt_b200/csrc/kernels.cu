@@ -159,9 +159,10 @@ static int pick_grid(GemmOp* op) {
   pw.kb_per_split = p.num_k_blocks;
   const int units = op->ctas == 2 ? sms / 2 : sms;                                        // CTAs or CTA pairs that can run at once
   const int tiles = op->ctas == 2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
-  if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && !getenv("MDE_NO_SPLITK")) {
+  if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && getenv("MDE_SPLITK")) {
     // small batch: a handful of tiles on 148 SMs.  Split K so that every SM gets a piece (at least 8 k-blocks each);
-    // the reduction epilogue adds the partial products in the L2.
+    // the reduction epilogue adds the partial products in the L2.  Opt-in (MDE_SPLITK=1): the fp32 adds happen in arrival
+    // order, so results are no longer reproducible bit for bit from run to run.
     int splits = std::min(std::min(units / tiles, p.num_k_blocks / 8), 8);
     pw.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
     pw.splits = (p.num_k_blocks + pw.kb_per_split - 1) / pw.kb_per_split;

@@ -40,7 +40,6 @@ def lib():
 
 @pytest.fixture
 def bitwise(monkeypatch):
-    """Small batches split K over the SMs and let the L2 add the partial products (fp32 adds in arrival order), so two
-    runs agree to ~1e-7 relative, not bit for bit.  Tests that compare two runs with `torch.equal` (same function
-    reached through two paths) switch the split off, as a deployment that needs bitwise reproducibility would."""
-    monkeypatch.setenv("MDE_NO_SPLITK", "1")
+    """Tests that compare two runs with `torch.equal` need the default, bitwise-reproducible configuration: split-K for
+    small batches (MDE_SPLITK=1: partial products meet in the L2's fp32 adds, in arrival order) must be off."""
+    monkeypatch.delenv("MDE_SPLITK", raising=False)
