@@ -62,3 +62,27 @@ def test_calibration_makes_the_gate_meaningful():
     sd, x, depth, _ = R.reference("vits")
     d = depth.numpy()
     assert d.max() - d.min() > 15.0 and (d < 5).mean() > 0.05 and (d > 15).mean() > 0.05
+
+
+def test_trunk_taps_match_transformers_dinov2_patch16():
+    """The trunk-only oracle (ViT/16 at 384 x 384, raw hooked block outputs + normalised final tokens: the form Depth
+    Pro's patch encoder uses) against transformers' independent Dinov2Model with the same weights."""
+    pytest.importorskip("transformers")
+    from transformers import Dinov2Config, Dinov2Model
+    import hf_bridge as H
+    torch.manual_seed(2)
+    c = O.MODEL_CONFIGS["vits"]
+    sd = O.init_state_dict("vits", seed=6, patch=16, pos_grid=24)
+    x = torch.randn(2, 3, 384, 384)
+    cfg = Dinov2Config(hidden_size=c["embed_dim"], num_hidden_layers=c["depth"], num_attention_heads=c["num_heads"],
+                       image_size=384, patch_size=16)
+    m = Dinov2Model(cfg).eval()
+    hf = {k[len("backbone."):]: v for k, v in H.to_hf({**O.init_state_dict("vits", seed=6), **sd}, "vits").items() if k.startswith("backbone.")}
+    m.load_state_dict(hf, strict=True)
+    with torch.no_grad():
+        out = m(pixel_values=x, output_hidden_states=True)
+        taps = O.encoder_taps(sd, x, c, norm_mask=0x8)
+    hs = out.hidden_states                      # hs[i + 1] = output of block i (cls included)
+    for t, blk in zip(taps[:3], c["taps"][:3]):
+        assert float((t - hs[blk + 1][:, 1:]).abs().max()) < 2e-4 * float(t.abs().max())
+    assert float((taps[3] - out.last_hidden_state[:, 1:]).abs().max()) < 2e-4 * float(taps[3].abs().max())

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-launch device times of one forward (CUDA events between launches), grouped by op label.
-    python tools/profile_step.py [--encoder vitl] [--batch 64] [--precision bf16]"""
+    python tools/profile_step.py [--encoder vitl] [--batch 64] [--precision bf16] [--h 518 --w 518]"""
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,14 +10,14 @@ from monocular_depth_estimation_trt_b200 import engine as E, weights as W
 ap = argparse.ArgumentParser()
 ap.add_argument("--encoder", default="vitl"); ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--precision", default="bf16"); ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--out", default="")
+ap.add_argument("--out", default=""); ap.add_argument("--h", type=int, default=518); ap.add_argument("--w", type=int, default=518)
 a = ap.parse_args()
-meta = W.describe(a.encoder, 518, 518, 20.0)
+meta = W.describe(a.encoder, a.h, a.w, 20.0)
 eng = E.Engine(E.make_desc(meta, precision=a.precision, batch=a.batch), meta)
 from oracle import dav2_torch as O   # weights for a profiling run only (tooling, not a product path)
 eng.load_state_dict(O.init_state_dict(a.encoder, 0)); eng.finalize()
 ctx = eng.create_execution_context()
-x = torch.randn(a.batch, 3, 518, 518, device="cuda"); out = torch.empty(a.batch, 518, 518, device="cuda")
+x = torch.randn(a.batch, 3, a.h, a.w, device="cuda"); out = torch.empty(a.batch, a.h, a.w, device="cuda")
 ctx.set_tensor_address("input", x.data_ptr()); ctx.set_tensor_address("output", out.data_ptr())
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(2): ctx.execute_async_v3(s)
