@@ -156,6 +156,14 @@ int mde_context_snapshot_block(mde_context* c, int32_t block);
 int mde_k_preprocess_u8(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
                         int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
                         const double* mean3, const double* std3, void* d_cols, float* d_nchw, void* stream);
+/* The keep-ratio + pad form (core/preprocess.py:191-219 `resize_pad`, rounding='trunc', centred: MODELS['metric3d_v2'],
+ * :487-491): INTER_LINEAR resize to (int(src_h*scale), int(src_w*scale)), scale = min(dst_h/src_h, dst_w/src_w), centred on
+ * a dst_h x dst_w canvas of pad_rgb3 (saturate-cast to uint8 like cv2.copyMakeBorder).  mean3 == std3 == NULL: no
+ * normalisation, values stay in 0..255 (what metric3d_v2's input binding carries). */
+int mde_k_preprocess_u8_pad(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
+                            int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
+                            const double* pad_rgb3, const double* mean3, const double* std3, void* d_cols, float* d_nchw,
+                            void* stream);
 int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int32_t h, int32_t w, int32_t patch,
                      int32_t kpad, void* d_cols, void* stream);
 

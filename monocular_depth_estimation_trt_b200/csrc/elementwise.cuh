@@ -28,6 +28,11 @@ struct PreprocParams {
   void* cols;               // [B*gh*gw][kpad] 16-bit, or null
   float* nchw;              // [B][3][dst_h][dst_w] float32, or null
   int exact2x;              // cv2 switches INTER_LINEAR to INTER_AREA when both scales are exactly 2
+  // keep-ratio + pad (Metric3D V2, core/preprocess.py:191-219): the resize target is inner_h x inner_w, placed at
+  // (pad_top, pad_left) of the dst_h x dst_w canvas; everything else is pad_src (uint8, SOURCE channel order).
+  // Stretch (Depth Anything): inner == dst, no offset.
+  int inner_h, inner_w, pad_top, pad_left;
+  uint8_t pad_src[4];
 };
 
 __device__ __forceinline__ void cv_linear_coeff(int d, double scale, int src_size, int& s0, short& a0, short& a1,
@@ -54,10 +59,10 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const PreprocParams 
   int* xofs = reinterpret_cast<int*>(pp_smem);
   short* xa = reinterpret_cast<short*>(xofs + p.dst_w);
   T* tile = reinterpret_cast<T*>(pp_smem + ((p.dst_w * 8 + 15) & ~15));
-  const double inv_x = static_cast<double>(p.dst_w) / p.src_w, inv_y = static_cast<double>(p.dst_h) / p.src_h;
+  const double inv_x = static_cast<double>(p.inner_w) / p.src_w, inv_y = static_cast<double>(p.inner_h) / p.src_h;
   const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
 
-  for (int dx = threadIdx.x; dx < p.dst_w; dx += blockDim.x) {
+  for (int dx = threadIdx.x; dx < p.inner_w; dx += blockDim.x) {      // indexed by the column INSIDE the resized image
     int s0; short a0, a1;
     cv_linear_coeff(dx, scale_x, p.src_w, s0, a0, a1, true);
     xofs[dx] = s0; xa[2 * dx] = a0; xa[2 * dx + 1] = a1;
@@ -76,19 +81,23 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const PreprocParams 
   for (int i = threadIdx.x; i < p.patch * p.dst_w; i += blockDim.x) {
     const int ky = i / p.dst_w, dx = i % p.dst_w;
     const int dy = gy * p.patch + ky;
+    const int iy = dy - p.pad_top, ix = dx - p.pad_left;       // position inside the resized image
     int out[3];
-    if (p.exact2x) {
-      const uint8_t* r0 = src + static_cast<long long>(2 * dy) * row_bytes + 6 * dx;
+    if (iy < 0 || iy >= p.inner_h || ix < 0 || ix >= p.inner_w) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[c] = p.pad_src[c];
+    } else if (p.exact2x) {
+      const uint8_t* r0 = src + static_cast<long long>(2 * iy) * row_bytes + 6 * ix;
       const uint8_t* r1 = r0 + row_bytes;
 #pragma unroll
       for (int c = 0; c < 3; ++c) out[c] = (r0[c] + r0[c + 3] + r1[c] + r1[c + 3] + 2) >> 2;
     } else {
       int sy; short b0, b1;
-      cv_linear_coeff(dy, scale_y, p.src_h, sy, b0, b1, false);
+      cv_linear_coeff(iy, scale_y, p.src_h, sy, b0, b1, false);
       const int y0 = min(max(sy, 0), p.src_h - 1), y1 = min(max(sy + 1, 0), p.src_h - 1);
-      const int sx = xofs[dx];
+      const int sx = xofs[ix];
       const int sx1 = min(sx + 1, p.src_w - 1);    // coefficient is 0 whenever this clamp acts
-      const int a0 = xa[2 * dx], a1 = xa[2 * dx + 1];
+      const int a0 = xa[2 * ix], a1 = xa[2 * ix + 1];
       const uint8_t* r0 = src + y0 * row_bytes;
       const uint8_t* r1 = src + y1 * row_bytes;
 #pragma unroll

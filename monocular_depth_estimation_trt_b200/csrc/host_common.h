@@ -76,7 +76,7 @@ int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int 
                       cudaStream_t s);
 int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batch_stride, int batch, int src_h,
                          int src_w, int dst_h, int dst_w, int patch, int kpad, int swap_rb, const float* d_lut,
-                         void* d_cols, float* d_nchw, cudaStream_t s);
+                         void* d_cols, float* d_nchw, cudaStream_t s, int keep_ratio_pad = 0, const double* pad_rgb = nullptr);
 // bilinear upsample -> 3x3 conv (tap-contracted z, see upconv_head.cuh) -> ReLU -> 1x1 -> activation
 int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int hs, int ws, int ho, int wo,
                        const float* d_bias, const float* d_head_w, float head_b, float head_scale, float* d_out,

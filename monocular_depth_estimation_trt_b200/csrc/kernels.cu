@@ -1,4 +1,5 @@
 // Kernel instantiations, launchers and the single-kernel C-ABI entry points (mde_k_*).
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -622,16 +623,40 @@ void build_norm_lut(const double* mean3, const double* std3, float* lut768) {
     }
 }
 
+void build_raw_lut(float* lut768) {
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) lut768[c * 256 + v] = static_cast<float>(v);
+}
+
 int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batch_stride, int batch, int src_h,
                          int src_w, int dst_h, int dst_w, int patch, int kpad, int swap_rb, const float* d_lut,
-                         void* d_cols, float* d_nchw, cudaStream_t s) {
+                         void* d_cols, float* d_nchw, cudaStream_t s, int keep_ratio_pad, const double* pad_rgb) {
   MDE_TRY(check_patch_geometry(dst_h, dst_w, patch, kpad));
   if (src_h < 1 || src_w < 1) return fail(MDE_ERR_INVALID, "preprocess: empty source image");
   PreprocParams p;
   p.src = d_src; p.src_batch_stride = src_batch_stride; p.src_h = src_h; p.src_w = src_w;
   p.dst_h = dst_h; p.dst_w = dst_w; p.patch = patch; p.kpad = kpad; p.swap_rb = swap_rb; p.lut = d_lut;
   p.cols = d_cols; p.nchw = d_nchw;
-  p.exact2x = (src_w == 2 * dst_w && src_h == 2 * dst_h) ? 1 : 0;
+  p.inner_h = dst_h; p.inner_w = dst_w; p.pad_top = 0; p.pad_left = 0;
+  p.pad_src[0] = p.pad_src[1] = p.pad_src[2] = p.pad_src[3] = 0;
+  if (keep_ratio_pad) {
+    // core/preprocess.py:191-219 `resize_pad`, rounding='trunc', center=True -- the same double arithmetic as Python's
+    if (!pad_rgb) return fail(MDE_ERR_INVALID, "preprocess: the pad colour is required");
+    const double sh = static_cast<double>(dst_h) / static_cast<double>(src_h), sw = static_cast<double>(dst_w) / static_cast<double>(src_w);
+    const double scale = sh < sw ? sh : sw;
+    p.inner_h = static_cast<int>(static_cast<double>(src_h) * scale);
+    p.inner_w = static_cast<int>(static_cast<double>(src_w) * scale);
+    if (p.inner_h < 1 || p.inner_w < 1 || p.inner_h > dst_h || p.inner_w > dst_w) return fail(MDE_ERR_INVALID, "preprocess: degenerate keep-ratio geometry");
+    p.pad_top = (dst_h - p.inner_h) / 2;
+    p.pad_left = (dst_w - p.inner_w) / 2;
+    for (int c = 0; c < 3; ++c) {
+      // cv2.copyMakeBorder saturate-casts the value: round half to even, clamp to 0..255; stored in SOURCE channel order
+      double v = nearbyint(pad_rgb[c]);
+      v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);
+      p.pad_src[swap_rb ? 2 - c : c] = static_cast<uint8_t>(v);
+    }
+  }
+  p.exact2x = (src_w == 2 * p.inner_w && src_h == 2 * p.inner_h) ? 1 : 0;
   const int smem = ((dst_w * 8 + 15) & ~15) + (d_cols ? (dst_w / patch) * kpad * 2 : 0);
   dim3 grid(dst_h / patch, batch);
   if (precision == MDE_BF16) {
@@ -797,13 +822,38 @@ int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int3
   return launch_im2col_f32(precision, d_nchw, batch, h, w, patch, kpad, d_cols, static_cast<cudaStream_t>(stream));
 }
 
+static int preprocess_entry(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
+                            int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
+                            const double* mean3, const double* std3, void* d_cols, float* d_nchw, void* stream,
+                            int keep_ratio_pad, const double* pad_rgb);
+
 int mde_k_preprocess_u8(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
                         int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
                         const double* mean3, const double* std3, void* d_cols, float* d_nchw, void* stream) {
   clear_error();
   if (!mean3 || !std3) return fail(MDE_ERR_INVALID, "mean/std are required");
+  return preprocess_entry(precision, d_src, batch, src_h, src_w, dst_h, dst_w, patch, kpad, swap_rb, mean3, std3, d_cols, d_nchw,
+                          stream, 0, nullptr);
+}
+
+int mde_k_preprocess_u8_pad(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
+                            int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
+                            const double* pad_rgb3, const double* mean3, const double* std3, void* d_cols, float* d_nchw,
+                            void* stream) {
+  clear_error();
+  if (!pad_rgb3) return fail(MDE_ERR_INVALID, "the pad colour is required");
+  if ((mean3 == nullptr) != (std3 == nullptr)) return fail(MDE_ERR_INVALID, "mean and std go together (both NULL: no normalisation)");
+  return preprocess_entry(precision, d_src, batch, src_h, src_w, dst_h, dst_w, patch, kpad, swap_rb, mean3, std3, d_cols, d_nchw,
+                          stream, 1, pad_rgb3);
+}
+
+static int preprocess_entry(int32_t precision, const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w,
+                            int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
+                            const double* mean3, const double* std3, void* d_cols, float* d_nchw, void* stream,
+                            int keep_ratio_pad, const double* pad_rgb) {
   float lut[768];
-  build_norm_lut(mean3, std3, lut);
+  if (mean3) build_norm_lut(mean3, std3, lut);
+  else build_raw_lut(lut);
   float* d_lut = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MDE_CUDA_TRY(cudaMalloc(&d_lut, sizeof(lut)));
@@ -812,7 +862,7 @@ int mde_k_preprocess_u8(int32_t precision, const uint8_t* d_src, int32_t batch, 
   if (e != cudaSuccess) rc = fail(MDE_ERR_CUDA, "LUT upload: %s", cudaGetErrorString(e));
   if (rc == MDE_OK)
     rc = launch_preprocess_u8(precision, d_src, static_cast<long long>(src_h) * src_w * 3, batch, src_h, src_w, dst_h,
-                              dst_w, patch, kpad, swap_rb, d_lut, d_cols, d_nchw, s);
+                              dst_w, patch, kpad, swap_rb, d_lut, d_cols, d_nchw, s, keep_ratio_pad, pad_rgb);
   cudaStreamSynchronize(s);   // test entry point: the temporary LUT must outlive the kernel
   cudaFree(d_lut);
   return rc;

@@ -5,7 +5,8 @@
 preprocess_golden.npz  outputs of the REFERENCE module itself (imported from /root/reference:
                        core.preprocess.preprocess_for(img, 'depth_anything_v2', size)) on the
                        reference's synthetic-input convention (tests/test_preprocess.py:47-51):
-                       full tensors at small target sizes, sha256 of the float32 bytes at 518x518.
+                       full tensors at small target sizes, sha256 of the float32 bytes at 518x518; the same for
+                       'metric3d_v2' (keep-ratio + pad, 616x1064) together with the geometry it reports.
 dav2_vits_golden.npz   the oracle's own ViT-S 518x518 batch-1 forward (BASELINE config 1) with the
                        seeded, calibrated init: a 7x-strided subsample of the depth map and summary
                        statistics.  It pins the oracle against drift between hosts; the oracle
@@ -46,6 +47,16 @@ def main():
         t, _ = ref.preprocess_for(img, "depth_anything_v2", (518, 518))
         digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
         blob[f"sha_seed{i}_{h}x{w}_to_518x518"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
+    # Metric3D V2: keep-ratio resize (truncated inner size) + centre pad with the mean colour, no normalisation
+    for i, (h, w) in enumerate(SOURCES):
+        img = synthetic(i, h, w)
+        for (th, tw) in [(70, 98), (56, 56)]:
+            t, _ = ref.preprocess_for(img, "metric3d_v2", (th, tw))
+            blob[f"m3d_full_seed{i}_{h}x{w}_to_{th}x{tw}"] = t
+        t, geom = ref.preprocess_for(img, "metric3d_v2", (616, 1064))
+        digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+        blob[f"m3d_sha_seed{i}_{h}x{w}_to_616x1064"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
+        blob[f"m3d_geom_seed{i}_{h}x{w}_to_616x1064"] = np.array([geom.inner_h, geom.inner_w, geom.pad_top, geom.pad_left], dtype=np.int64)
     np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), **blob)
     print("wrote preprocess_golden.npz", len(blob), "entries")
 

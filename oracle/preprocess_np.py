@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure, never shipped, never on the product path).
 
 numpy restatement of the reference's host preprocessing for the stretch + ImageNet family
-(Depth Anything V2/V3, Distill Any Depth): /root/reference/core/preprocess.py:412-430
+(Depth Anything V2/V3, Distill Any Depth) and the keep-ratio + pad form of Metric3D V2 (`preprocess_pad_none`): /root/reference/core/preprocess.py:412-430
 `preprocess` with MODELS['depth_anything_v2'] (:463-468):
 
     cvtColor BGR->RGB (:420) -> resize_stretch = cv2.resize(INTER_LINEAR) on uint8 (:144-154)
@@ -89,6 +89,30 @@ def preprocess_stretch_imagenet(img_bgr: np.ndarray, dst_h: int, dst_w: int) -> 
     x = small.astype(np.float64) / 255.0
     x = (x - np.asarray(IMAGENET_MEAN, np.float64)) / np.asarray(IMAGENET_STD, np.float64)
     return np.ascontiguousarray(x.transpose(2, 0, 1)[None]).astype(np.float32)
+
+
+IMAGENET_PAD = (123.675, 116.28, 103.53)   # core/preprocess.py `_IMAGENET_PAD`: metric3d_v2 pads with the mean colour
+
+
+def pad_geometry(src_h: int, src_w: int, dst_h: int, dst_w: int):
+    """core/preprocess.py:191-219 `resize_pad` with rounding='trunc', center=True (the metric3d_v2 spec, :487-491):
+    -> (inner_h, inner_w, top, left)."""
+    scale = min(dst_h / src_h, dst_w / src_w)
+    inner_h, inner_w = int(src_h * scale), int(src_w * scale)
+    return inner_h, inner_w, (dst_h - inner_h) // 2, (dst_w - inner_w) // 2
+
+
+def preprocess_pad_none(img_bgr: np.ndarray, dst_h: int, dst_w: int, pad_rgb=IMAGENET_PAD) -> np.ndarray:
+    """BGR uint8 HxWx3 -> float32 [1, 3, dst_h, dst_w] in 0..255 units, byte-exact with
+    core.preprocess.preprocess_for(img, 'metric3d_v2', (dst_h, dst_w))[0]: BGR->RGB, keep-ratio INTER_LINEAR resize to the
+    truncated inner size, centre pad with the mean colour (cv2.copyMakeBorder saturate-casts it: round half to even),
+    no normalisation (the model's own first op does it), float32."""
+    rgb = np.ascontiguousarray(img_bgr[:, :, ::-1])
+    inner_h, inner_w, top, left = pad_geometry(rgb.shape[0], rgb.shape[1], dst_h, dst_w)
+    canvas = np.empty((dst_h, dst_w, 3), dtype=np.uint8)
+    canvas[:] = np.clip(np.rint(np.asarray(pad_rgb, np.float64)), 0, 255).astype(np.uint8)
+    canvas[top:top + inner_h, left:left + inner_w] = resize_linear_u8(rgb, inner_h, inner_w)
+    return np.ascontiguousarray(canvas.transpose(2, 0, 1)[None]).astype(np.float32)
 
 
 def im2col(x_nchw: np.ndarray, patch: int = 14, kpad: int | None = None) -> np.ndarray:

@@ -157,6 +157,22 @@ def preprocess_u8(precision, src_u8, dst_h, dst_w, patch=14, kpad=640, swap_rb=T
     return cols, nchw
 
 
+def preprocess_u8_pad(precision, src_u8, dst_h, dst_w, patch=14, kpad=640, swap_rb=True, pad_rgb=(123.675, 116.28, 103.53),
+                      mean=None, std=None, want_cols=True, want_nchw=True):
+    """Keep-ratio + centre pad (Metric3D V2's input contract); mean/std None = no normalisation."""
+    lib = _lib.load()
+    B, H, W_, _ = src_u8.shape
+    rows = B * (dst_h // patch) * (dst_w // patch)
+    cols = torch.empty(rows, kpad, dtype=TORCH_DT[precision], device=src_u8.device) if want_cols else None
+    nchw = torch.full((B, 3, dst_h, dst_w), float("nan"), dtype=torch.float32, device=src_u8.device) if want_nchw else None
+    p3 = (C.c_double * 3)(*pad_rgb)
+    m3 = (C.c_double * 3)(*mean) if mean is not None else None
+    s3 = (C.c_double * 3)(*std) if std is not None else None
+    _lib.check(lib.mde_k_preprocess_u8_pad(_lib.PRECISIONS[precision], ptr(src_u8), B, H, W_, dst_h, dst_w, patch, kpad,
+                                           int(swap_rb), p3, m3, s3, ptr(cols), ptr(nchw), stream()), "mde_k_preprocess_u8_pad")
+    return cols, nchw
+
+
 def rel_err(got, ref):
     got, ref = got.float(), ref.float()
     return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))

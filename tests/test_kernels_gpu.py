@@ -343,3 +343,20 @@ def test_gemm_fused_gather_single_rank(lib, prec):
     for t in g:
         assert K.rel_err(t[row0:row0 + m], ref[:, D:]) < ULP[prec]
         assert torch.all(t[:row0] == 7.0) and torch.all(t[row0 + m:] == 7.0)
+
+
+# ------------------------------------------------------------------------------------------ Metric3D V2 input contract
+@pytest.mark.parametrize("src", [(480, 640), (720, 1280), (300, 777), (1036, 1036), (1232, 2128), (37, 41)])
+@pytest.mark.parametrize("dst", [(616, 1064), (518, 518)])
+def test_preprocess_keep_ratio_pad_bit_exact(lib, src, dst):
+    """uint8 BGR -> keep-ratio INTER_LINEAR resize (truncated inner size) -> centre pad with the mean colour -> float32
+    0..255, no normalisation: byte-exact with the oracle's restatement of core/preprocess.py MODELS['metric3d_v2']
+    (which tests/test_oracle_preprocess.py pins on the reference module's own outputs); im2col rows = that tensor's patches."""
+    from oracle import preprocess_np as P
+    img = np.random.default_rng(61).integers(0, 256, (*src, 3), dtype=np.uint8)
+    ref = P.preprocess_pad_none(img, *dst)
+    cols, nchw = K.preprocess_u8_pad("fp16", torch.from_numpy(img)[None].cuda(), dst[0], dst[1])
+    torch.cuda.synchronize()
+    assert np.array_equal(nchw.cpu().numpy(), ref)
+    ref_cols = torch.from_numpy(P.im2col(ref, 14, 640)).half()      # integers 0..255 are exact in fp16
+    assert torch.equal(cols.cpu(), ref_cols)

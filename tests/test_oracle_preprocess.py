@@ -92,3 +92,40 @@ def test_against_live_reference_module(model):
         r, geom = ref.preprocess_for(img, model, (518, 518))
         assert np.array_equal(r, P.preprocess_stretch_imagenet(img, 518, 518))
         assert (geom.src_h, geom.src_w, geom.dst_h, geom.dst_w) == (h, w, 518, 518)
+
+
+# ------------------------------------------------------------------ Metric3D V2: keep-ratio + centre pad, no normalisation
+def test_metric3d_variant_against_reference_golden_vectors():
+    g = np.load(GOLDEN)
+    for i, (h, w) in enumerate(SOURCES):
+        img = synthetic(i, h, w)
+        for th, tw in [(70, 98), (56, 56)]:
+            ref = g[f"m3d_full_seed{i}_{h}x{w}_to_{th}x{tw}"]
+            got = P.preprocess_pad_none(img, th, tw)
+            assert got.dtype == np.float32 and np.array_equal(got, ref)        # byte-exact
+        got = P.preprocess_pad_none(img, 616, 1064)
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).digest() == g[f"m3d_sha_seed{i}_{h}x{w}_to_616x1064"].tobytes()
+        assert list(P.pad_geometry(h, w, 616, 1064)) == list(g[f"m3d_geom_seed{i}_{h}x{w}_to_616x1064"])
+
+
+def test_metric3d_pad_uses_truncation_and_the_rounded_mean_colour():
+    # 300 x 777 -> 616 x 1064: scale = min(616/300, 1064/777) = 1.3694; int() truncates 410.81 -> 410 (round would give 411)
+    assert P.pad_geometry(300, 777, 616, 1064) == (410, 1064, 103, 0)
+    out = P.preprocess_pad_none(synthetic(4, 300, 777), 616, 1064)
+    assert out[0, :, 0, 0].tolist() == [124.0, 116.0, 104.0]                    # saturate_cast of (123.675, 116.28, 103.53)
+    assert out[0, :, 102, 5].tolist() == [124.0, 116.0, 104.0] and out.max() <= 255.0 and out.min() >= 0.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/core"), reason="reference checkout not present on this box")
+def test_metric3d_variant_against_live_reference_module():
+    sys.path.insert(0, "/root/reference")
+    try:
+        from core import preprocess as ref
+    finally:
+        sys.path.remove("/root/reference")
+    for i, (h, w) in enumerate(SOURCES):
+        img = synthetic(i, h, w)
+        for size in [(616, 1064), (518, 518)]:
+            r, geom = ref.preprocess_for(img, "metric3d_v2", size)
+            assert np.array_equal(r, P.preprocess_pad_none(img, *size))
+            assert (geom.inner_h, geom.inner_w, geom.pad_top, geom.pad_left) == P.pad_geometry(h, w, *size)
