@@ -360,3 +360,49 @@ def test_preprocess_keep_ratio_pad_bit_exact(lib, src, dst):
     assert np.array_equal(nchw.cpu().numpy(), ref)
     ref_cols = torch.from_numpy(P.im2col(ref, 14, 640)).half()      # integers 0..255 are exact in fp16
     assert torch.equal(cols.cpu(), ref_cols)
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("variant", ["tc", "2q", "kv64"])
+@pytest.mark.parametrize("B,ntok,heads", [(1, 1, 1), (2, 5, 2), (1, 31, 1), (1, 32, 1), (1, 33, 3), (1, 127, 1), (1, 128, 2), (3, 255, 1), (1, 256, 1), (1, 257, 1)])
+def test_attention_ragged_token_counts(lib, variant, B, ntok, heads):
+    """One token, tile boundaries and every +-1 around them: masking of the ragged last key tile, clipped query rows,
+    images that end inside another image's tile."""
+    dt = torch.float16
+    D = heads * 64
+    qkv = rnd((B * ntok, 3 * D), dt, seed=71)
+    out = K.attention("fp16", qkv, B, ntok, heads, variant)
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, i * D:(i + 1) * D].float().reshape(B, ntok, heads, 64).transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * ntok, D)
+    assert torch.isfinite(out).all()
+    assert K.rel_err(out, ref) < 4 * ULP["fp16"]
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 256, 64), (1, 1024, 1024), (127, 8, 8), (129, 264, 72), (256, 256, 4096), (5, 3072, 384)])
+def test_gemm_degenerate_shapes(lib, m, n, k):
+    """A single row, N / K that are not tile multiples, one tile with a long K loop."""
+    dt = torch.float16
+    a, b = rnd((m, k), dt, seed=72), rnd((n, k), dt, k ** -0.5, seed=73)
+    bias = torch.randn(n, device="cuda")
+    out = torch.full((m + 1, n), 7.0, dtype=dt, device="cuda")
+    x0 = torch.randn(m + 1, n, device="cuda")
+    x = x0.clone()
+    K.gemm("fp16", a, b, K.epilogue(bias=bias, out=out, ld_out=n))
+    K.gemm("fp16", a, b, K.epilogue(bias=bias, x=x, accumulate_x=True, ld_out=n))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias
+    assert K.rel_err(out[:m], ref) < ULP["fp16"] and torch.all(out[m:] == 7.0)
+    assert K.rel_err(x[:m], x0[:m] + ref) < 2e-5 and torch.equal(x[m:], x0[m:])
+
+
+def test_empty_problems_are_refused(lib):
+    """No rows / no tokens: an error through the ABI, never a launch."""
+    import ctypes as C
+    from monocular_depth_estimation_trt_b200 import _lib
+    t = torch.zeros(8, 64, dtype=torch.float16, device="cuda")
+    ep = K.epilogue(out=t, ld_out=64)
+    assert lib.mde_k_gemm(0, K.ptr(t), 0, 64, 64, K.ptr(t), 8, 64, C.byref(ep), None) != 0
+    assert "empty" in _lib.last_error()
+    assert lib.mde_k_attention(0, K.ptr(t), K.ptr(t), 1, 0, 1, None) != 0
+    assert lib.mde_k_layernorm(0, K.ptr(t), K.ptr(t), K.ptr(t), K.ptr(t), 0, 384, 1e-6, 0, 0, None) != 0
