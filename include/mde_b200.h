@@ -242,6 +242,12 @@ int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t bat
 int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t batch, int32_t hs, int32_t ws, int32_t ho,
                       int32_t wo, const float* d_bias, const float* d_head_w, float head_b, float head_scale,
                       float* d_out, void* stream);
+/* Depth Pro's patch merge (depth_pro/network/encoder.py `merge`; called from the model models/depth_pro/onnx_export.py:15-29
+ * builds): per_side x per_side crops of grid x grid tokens, d_tokens [per_side^2][grid^2][dim] 16-bit (a slice of the
+ * trunk-only engine's output) -> NHWC map [S][S][dim], S = per_side*grid - 2*padding*(per_side-1); each crop loses
+ * `padding` tokens at every edge it shares with a neighbour. */
+int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_side, int32_t grid, int32_t padding, int32_t dim,
+                        void* d_out, void* stream);
 /* The reference scripts' post-processing on the device (models/depth_anything_v2/onnx2trt.py:111-117):
  * F.interpolate(depth, (ho, wo), mode="bilinear", align_corners=True) then clamp(clamp_lo, clamp_hi); fp32 [B][h][w]. */
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

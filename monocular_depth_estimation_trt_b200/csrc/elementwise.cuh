@@ -332,6 +332,38 @@ __global__ void __launch_bounds__(256) resize_depth_kernel(const ResizeDepthPara
 }
 
 // ---------------------------------------------------------------------------------------------
+// Depth Pro's `merge`: per_side x per_side crops of grid x grid tokens each (row-major crops, [crop][token][D] 16-bit,
+// the layout the trunk-only engine writes) -> one NHWC feature map [S][S][D], S = per_side*grid - 2*pad*(per_side-1):
+// every crop loses `pad` tokens at each edge it shares with a neighbour.  16 bytes per thread.
+// ---------------------------------------------------------------------------------------------
+struct MergeParams {
+  const void* in;
+  void* out;
+  int per_side, grid, pad, D, S;
+};
+__device__ __forceinline__ void merge_axis(int o, int per_side, int grid, int pad, int& crop, int& tok) {
+  const int first = per_side > 1 ? grid - pad : grid, mid = grid - 2 * pad;
+  if (o < first) { crop = 0; tok = o; return; }
+  const int r = o - first;
+  crop = min(1 + r / mid, per_side - 1);
+  tok = pad + r - (crop - 1) * mid;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) merge_patches_kernel(const MergeParams p) {
+  const int cv = p.D / 8;
+  const long long total = static_cast<long long>(p.S) * p.S * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(i % cv);
+    const int x = static_cast<int>((i / cv) % p.S), y = static_cast<int>(i / cv / p.S);
+    int cy, ty, cx, tx;
+    merge_axis(y, p.per_side, p.grid, p.pad, cy, ty);
+    merge_axis(x, p.per_side, p.grid, p.pad, cx, tx);
+    const long long src = ((static_cast<long long>(cy) * p.per_side + cx) * p.grid * p.grid + ty * p.grid + tx) * p.D + c * 8;
+    reinterpret_cast<uint4*>(static_cast<T*>(p.out))[i] = *reinterpret_cast<const uint4*>(static_cast<const T*>(p.in) + src);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 3x3 / stride 2 / pad 1 gather: NHWC [B][H][W][C] -> rows [(b, oy, ox)][tap*C + c] for a plain GEMM
 // (resize_layers[3]: 37x37 -> 19x19; 0.5 % of the FLOPs, not worth a strided tensor map).
 // ---------------------------------------------------------------------------------------------

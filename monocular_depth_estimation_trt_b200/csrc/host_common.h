@@ -83,6 +83,7 @@ int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int h
                        cudaStream_t s);
 int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_out, int ho, int wo, float lo, float hi_clamp,
                         cudaStream_t s);
+int launch_merge_patches(int precision, const void* d_in, int per_side, int grid, int pad, int dim, void* d_out, cudaStream_t s);
 int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, int batch, int ntok, int dim, cudaStream_t s);
 // (v/255 - mean)/std in double, rounded once to float32: 3 x 256 entries (core/preprocess.py:294-328,337-342)
 void build_norm_lut(const double* mean3, const double* std3, float* lut768);

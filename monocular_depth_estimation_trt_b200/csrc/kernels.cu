@@ -577,6 +577,21 @@ int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_o
   return MDE_OK;
 }
 
+int launch_merge_patches(int precision, const void* d_in, int per_side, int grid, int pad, int dim, void* d_out, cudaStream_t s) {
+  if (per_side < 1 || grid < 1 || dim < 8 || dim % 8) return fail(MDE_ERR_INVALID, "merge_patches: bad geometry");
+  if (per_side == 1) pad = 0;
+  if (pad < 0 || pad > grid / 4) return fail(MDE_ERR_INVALID, "merge_patches: padding must be within [0, grid/4]");
+  if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) return fail(MDE_ERR_INVALID, "merge_patches: buffers must be 16-byte aligned");
+  MergeParams p;
+  p.in = d_in; p.out = d_out; p.per_side = per_side; p.grid = grid; p.pad = pad; p.D = dim;
+  p.S = per_side * grid - 2 * pad * (per_side - 1);
+  const long long total = static_cast<long long>(p.S) * p.S * (dim / 8);
+  if (precision == MDE_BF16) merge_patches_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(p);
+  else merge_patches_kernel<__half><<<grid_for(total, 256), 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s) {
   if (c % 8) return fail(MDE_ERR_INVALID, "im2col_s2: channels must be a multiple of 8");
   Im2colS2Params p;
@@ -798,6 +813,13 @@ int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t ba
                     void* stream) {
   clear_error();
   return launch_im2col_s2(precision, d_in, d_out, batch, h, w, c, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_side, int32_t grid, int32_t padding, int32_t dim,
+                        void* d_out, void* stream) {
+  clear_error();
+  if (!d_tokens || !d_out) return fail(MDE_ERR_INVALID, "merge_patches: null pointer");
+  return launch_merge_patches(precision, d_tokens, per_side, grid, padding, dim, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

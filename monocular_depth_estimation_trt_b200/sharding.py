@@ -193,3 +193,24 @@ class ShardedPatchEncoder:
     def close(self):
         self.ctx.close()
         self.buffers.close()
+
+
+def merge_features(taps, precision: str, stream_handle: int, hook_taps: Sequence[int] = (1, 0), final_tap: int = 3):
+    """The gathered taps of the 35 crops ([4, 35, 576, D] on the device, `ShardedPatchEncoder.gathered()`) -> Depth Pro's
+    five merged NHWC feature maps [f24, f48, f96, hook_a 96, hook_b 96] (the order transformers' DepthProPatchEncoder
+    returns them; hooks (11, 5) of the released ViT-L trunk are taps (1, 0)).  One small gather kernel per map."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    D = int(taps.shape[-1])
+    plan = [(final_tap, 34, 1, 0, 24), (final_tap, 25, 3, 6, 48), (final_tap, 0, 5, 3, 96)]
+    plan += [(t, 0, 5, 3, 96) for t in hook_taps]
+    out = []
+    for tap, first, per_side, pad, side in plan:
+        o = torch.empty(side, side, D, dtype=taps.dtype, device=taps.device)
+        src = taps[tap, first:first + per_side * per_side]
+        _lib.check(lib.mde_k_merge_patches(_lib.PRECISIONS[precision], C.c_void_p(src.data_ptr()), per_side, 24, pad, D,
+                                           C.c_void_p(o.data_ptr()), C.c_void_p(int(stream_handle))), "mde_k_merge_patches")
+        out.append(o)
+    return out

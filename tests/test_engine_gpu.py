@@ -356,3 +356,36 @@ def test_vitb_relative_head_parity(lib):
     print("vitb relative", m)
     assert m["abs_rel"] <= GATE["fp16"]["abs_rel"] and m["max_rel"] <= 2 * GATE["fp16"]["max_rel"]
     assert m["corr"] > 0.9995
+
+
+def test_depth_pro_patch_encoder_stage_end_to_end(lib, bitwise):
+    """Depth Pro's patch-encoder stage on one GPU: 35 crops of a 1536 x 1536 image -> trunk-only ViT/16 engine (fused
+    gather path, world 1) -> patch merge kernel -> the five feature maps.  Checked against the oracle
+    (oracle/depth_pro_torch.py, pinned on transformers' DepthProPatchEncoder); the merge itself is a copy and must be
+    bit-exact with the oracle's merge applied to the same taps."""
+    from oracle import dav2_torch as O, depth_pro_torch as DP
+    from monocular_depth_estimation_trt_b200 import sharding as S
+    torch.manual_seed(9)
+    image = torch.randn(3, 1536, 1536)
+    sd = O.init_state_dict("vits", seed=8, patch=16, pos_grid=24)
+    ref = DP.patch_encoder_features(sd, image, "vits", hook_taps=(2, 1))
+    crops = S.make_crops(image)
+    meta = W.describe("vits", 384, 384, max_depth=None, patch_size=16)
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=35, head="encoder_taps", tap_norm_mask=0x8), meta)
+    eng.load_state_dict({k: v for k, v in sd.items() if k.startswith("pretrained.")})
+    eng.finalize()
+    enc = S.ShardedPatchEncoder(eng, n_items=35, world=1, rank=0, mode="fused")
+    stream = torch.cuda.current_stream().cuda_stream
+    xd = crops.cuda()
+    enc.enqueue(xd.data_ptr(), stream)
+    enc.finish()
+    taps = enc.gathered()
+    maps = S.merge_features(taps, "fp16", stream, hook_taps=(2, 1))
+    torch.cuda.synchronize()
+    same = DP.merged_features([t.cpu() for t in taps], hook_taps=(2, 1))
+    assert [tuple(m.shape) for m in maps] == [(24, 24, 384), (48, 48, 384), (96, 96, 384), (96, 96, 384), (96, 96, 384)]
+    for m, s_, r in zip(maps, same, ref):
+        assert torch.equal(m.cpu(), s_)                              # the merge moves tokens, nothing else
+        assert rms_rel(m.float().cpu(), r) < INTER["fp16"]
+    enc.close()
+    eng.close()
