@@ -242,6 +242,14 @@ int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t bat
 int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t batch, int32_t hs, int32_t ws, int32_t ho,
                       int32_t wo, const float* d_bias, const float* d_head_w, float head_b, float head_scale,
                       float* d_out, void* stream);
+/* Stream-ordered hand-shake between the ranks of one box over peer memory, to follow / precede the fused gather kernels
+ * instead of a host barrier.  Every rank owns an array of n_ranks uint32 flags (zero-initialised, cudaIpc-mapped into
+ * every process).  signal: publish `epoch` in slot `rank` of every rank's array (system-scope release: all earlier work
+ * of this stream, including stores into peer buffers, is visible to an acquirer).  wait: block the stream until every
+ * slot of our own array has reached `epoch`.  Epochs must increase; the caller keeps a producer from overwriting a buffer
+ * a peer still reads (a second flag array used as acknowledgement, as monocular_depth_estimation_trt_b200/sharding.py does). */
+int mde_k_peer_signal(void* const* d_flags_of_every_rank, int32_t n_ranks, int32_t rank, uint32_t epoch, void* stream);
+int mde_k_peer_wait(void* d_own_flags, int32_t n_ranks, uint32_t epoch, void* stream);
 /* Depth Pro's patch merge (depth_pro/network/encoder.py `merge`; called from the model models/depth_pro/onnx_export.py:15-29
  * builds): per_side x per_side crops of grid x grid tokens, d_tokens [per_side^2][grid^2][dim] 16-bit (a slice of the
  * trunk-only engine's output) -> NHWC map [S][S][dim], S = per_side*grid - 2*padding*(per_side-1); each crop loses

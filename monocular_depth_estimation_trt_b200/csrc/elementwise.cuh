@@ -332,6 +332,36 @@ __global__ void __launch_bounds__(256) resize_depth_kernel(const ResizeDepthPara
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stream-ordered hand-shake between the ranks of one box over peer memory (no host barrier, no collective):
+// every rank owns a small flag array, mapped into every process.  `signal` runs after the kernel that wrote into the
+// peers' buffers (same stream): thread r publishes `epoch` into slot `rank` of rank r's flags with a system-scope
+// release, so everything this rank stored before is visible to whoever acquires the flag.  `wait` spins (system-scope
+// acquire) until every rank's slot of OUR flags has reached `epoch`; kernels enqueued behind it may read the gathered data.
+// ---------------------------------------------------------------------------------------------
+struct PeerFlagsParams {
+  unsigned int* flags[8];   // signal: every rank's array (peer pointers); wait: flags[0] = our own array
+  int n_ranks, rank;
+  unsigned int epoch;
+};
+__global__ void peer_signal_kernel(const PeerFlagsParams p) {
+  const int r = threadIdx.x;
+  if (r >= p.n_ranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[r] + p.rank), "r"(p.epoch) : "memory");
+}
+__global__ void peer_wait_kernel(const PeerFlagsParams p) {
+  const int r = threadIdx.x;
+  if (r >= p.n_ranks) return;
+  const long long t0 = clock64();
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags[0] + r) : "memory");
+    if (clock64() - t0 > 20LL * MDE_WATCHDOG_CYCLES) __trap();      // ~40 s: a rank died
+  } while (static_cast<int>(v - p.epoch) < 0);                      // wrap-safe "v >= epoch"
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Depth Pro's `merge`: per_side x per_side crops of grid x grid tokens each (row-major crops, [crop][token][D] 16-bit,
 // the layout the trunk-only engine writes) -> one NHWC feature map [S][S][D], S = per_side*grid - 2*pad*(per_side-1):
 // every crop loses `pad` tokens at each edge it shares with a neighbour.  16 bytes per thread.

@@ -815,6 +815,31 @@ int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t ba
   return launch_im2col_s2(precision, d_in, d_out, batch, h, w, c, static_cast<cudaStream_t>(stream));
 }
 
+int mde_k_peer_signal(void* const* d_flags_of_every_rank, int32_t n_ranks, int32_t rank, uint32_t epoch, void* stream) {
+  clear_error();
+  if (!d_flags_of_every_rank || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks) return fail(MDE_ERR_INVALID, "peer_signal: 1..8 ranks, 0 <= rank < n_ranks");
+  PeerFlagsParams p;
+  for (int r = 0; r < 8; ++r) p.flags[r] = r < n_ranks ? static_cast<unsigned int*>(d_flags_of_every_rank[r]) : nullptr;
+  for (int r = 0; r < n_ranks; ++r)
+    if (!p.flags[r]) return fail(MDE_ERR_INVALID, "peer_signal: flag array of rank %d is null", r);
+  p.n_ranks = n_ranks; p.rank = rank; p.epoch = epoch;
+  peer_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+int mde_k_peer_wait(void* d_own_flags, int32_t n_ranks, uint32_t epoch, void* stream) {
+  clear_error();
+  if (!d_own_flags || n_ranks < 1 || n_ranks > 8) return fail(MDE_ERR_INVALID, "peer_wait: 1..8 ranks and a flag array");
+  PeerFlagsParams p;
+  for (int r = 0; r < 8; ++r) p.flags[r] = nullptr;
+  p.flags[0] = static_cast<unsigned int*>(d_own_flags);
+  p.n_ranks = n_ranks; p.rank = 0; p.epoch = epoch;
+  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_side, int32_t grid, int32_t padding, int32_t dim,
                         void* d_out, void* stream) {
   clear_error();

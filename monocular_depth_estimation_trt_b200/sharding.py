@@ -131,6 +131,55 @@ class PeerBuffers:
             self.own = 0
 
 
+class PeerSync:
+    """Stream-ordered replacement for `torch.cuda.synchronize(); dist.barrier()` around the fused gather kernels:
+    two flag arrays per rank in peer-mapped memory -- "ready" (my stores into your buffer have landed) and "ack" (I have
+    finished reading what you sent me) -- driven by two one-warp kernels on the caller's stream.
+
+        sync.wait_acks(stream)      # before overwriting the peers' buffers again
+        ... producer kernels ...    # e.g. the trunk with the fused tap gather, or the QKV GEMM with the fused K|V gather
+        sync.signal_ready(stream); sync.wait_ready(stream)
+        ... consumer kernels ...    # read the gathered buffer
+        sync.signal_acks(stream)
+    """
+
+    def __init__(self, world: int, rank: int):
+        from . import _lib
+        self._lib, self._check = _lib.load(), _lib.check
+        self.world, self.rank = world, rank
+        self.ready = PeerBuffers(world, rank, (64,), "fp16")      # 128 zeroed bytes: room for 8 uint32 flags
+        self.acks = PeerBuffers(world, rank, (64,), "fp16")
+        self.epoch = 0
+
+    def _signal(self, bufs, epoch, stream_handle):
+        import ctypes as C
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in bufs.ptrs])
+        self._check(self._lib.mde_k_peer_signal(arr, self.world, self.rank, epoch, C.c_void_p(int(stream_handle))), "mde_k_peer_signal")
+
+    def _wait(self, bufs, epoch, stream_handle):
+        import ctypes as C
+        self._check(self._lib.mde_k_peer_wait(C.c_void_p(bufs.own), self.world, epoch, C.c_void_p(int(stream_handle))), "mde_k_peer_wait")
+
+    def wait_acks(self, stream_handle):
+        """Every peer has finished reading the previous round (a no-op in the first round)."""
+        if self.epoch > 0:
+            self._wait(self.acks, self.epoch, stream_handle)
+
+    def signal_ready(self, stream_handle):
+        self.epoch += 1
+        self._signal(self.ready, self.epoch, stream_handle)
+
+    def wait_ready(self, stream_handle):
+        self._wait(self.ready, self.epoch, stream_handle)
+
+    def signal_acks(self, stream_handle):
+        self._signal(self.acks, self.epoch, stream_handle)
+
+    def close(self):
+        self.ready.close()
+        self.acks.close()
+
+
 class GatherBuffers(PeerBuffers):
     """The patch encoder's gather buffers: [4][world * per_rank][T][D] per rank."""
 

@@ -87,6 +87,44 @@ for mode, proj in (("fused", run_fused), ("nccl", run_nccl)):
     result[f"{mode}_qkv_plus_gather_ms"] = sorted(ts_proj)[len(ts_proj) // 2]
     result[f"{mode}_attention_ms"] = sorted(ts_all)[len(ts_all) // 2]
     outs[mode] = out.clone()
+# ---- the whole layer stream-ordered, no host barrier anywhere: flags in peer memory (ready / ack) around the fused gather,
+# against the same pipeline with NCCL's (also stream-ordered) all-gather
+sync = S.PeerSync(world, rank)
+stream = torch.cuda.current_stream().cuda_stream
+
+
+def layer_flags():
+    sync.wait_acks(stream)
+    run_fused()
+    sync.signal_ready(stream)
+    sync.wait_ready(stream)
+    o = attend()
+    sync.signal_acks(stream)
+    return o
+
+
+def layer_nccl():
+    run_nccl()
+    return attend()
+
+
+for mode, layer in (("flags", layer_flags), ("nccl_stream", layer_nccl)):
+    kvbuf.view().zero_(); torch.cuda.synchronize(); dist.barrier()
+    for _ in range(2):
+        out = layer()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        out = layer()                                   # back to back: the hand-shake alone orders the ranks
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / a.reps], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    result[f"{mode}_layer_ms"] = float(t.item())
+    outs[mode] = out.clone()
+    dist.barrier()
+same_flags = torch.tensor([int(torch.equal(outs["flags"], outs["nccl"]))], device="cuda")
+dist.all_reduce(same_flags, op=dist.ReduceOp.MIN)
+result["flags_equals_nccl_on_every_rank"] = bool(same_flags.item())
 same = torch.tensor([int(torch.equal(outs["fused"], outs["nccl"]))], device="cuda")
 dist.all_reduce(same, op=dist.ReduceOp.MIN)
 result["fused_equals_nccl_on_every_rank"] = bool(same.item())
@@ -101,5 +139,6 @@ if rank == 0:
     result["rel_err_vs_fp32_reference"] = K.rel_err(outs["fused"], ref)
     print(json.dumps(result))
 dist.barrier()
+sync.close()
 kvbuf.close()
 dist.destroy_process_group()

@@ -406,3 +406,20 @@ def test_empty_problems_are_refused(lib):
     assert "empty" in _lib.last_error()
     assert lib.mde_k_attention(0, K.ptr(t), K.ptr(t), 1, 0, 1, None) != 0
     assert lib.mde_k_layernorm(0, K.ptr(t), K.ptr(t), K.ptr(t), K.ptr(t), 0, 384, 1e-6, 0, 0, None) != 0
+
+
+def test_peer_signal_and_wait_single_rank(lib):
+    """The stream-ordered hand-shake kernels with one rank (the multi-rank run is tests/mgpu/sharded_global_attention.py):
+    signal publishes the epoch in our own flag array, wait returns once every slot has reached it; epochs only grow."""
+    from monocular_depth_estimation_trt_b200 import sharding as S
+    sync = S.PeerSync(1, 0)
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        sync.wait_acks(s)
+        sync.signal_ready(s)
+        sync.wait_ready(s)
+        sync.signal_acks(s)
+    torch.cuda.synchronize()
+    flags = sync.ready.view().view(torch.int32)
+    assert int(flags[0]) == 3 and int(sync.acks.view().view(torch.int32)[0]) == 3
+    sync.close()
