@@ -96,8 +96,35 @@ class ExecutionContext:
         _lib.check(self._lib.mde_context_set_gather(self._h, int(n_ranks), int(rank), arr), "set_gather")
 
     def execute_async_v3(self, stream_handle) -> bool:
+        # core/profile.py:30-58 attaches a LayerTimer with `context.profiler = timer`; TensorRT then serialises the
+        # layers and calls timer.report_layer_time(name, ms) for each.  Same contract here: with a profiler attached the
+        # launches run one by one between CUDA events (no graph replay) and every launch is reported under its label.
+        prof = getattr(self, "profiler", None)
+        if prof is not None:
+            for label, ms, _, _ in self.execute_timed(stream_handle):
+                prof.report_layer_time(label, ms)
+            return True
         _lib.check(self._lib.mde_context_enqueue(self._h, C.c_void_p(int(stream_handle))), "enqueue")
         return True
+
+    def layer_information(self):
+        """One dict per launch of the plan, in execution order -- what core/profile.py:60-75 `inspect` collects from
+        TensorRT's engine inspector (keys Name / LayerType, plus the algorithmic FLOPs and bytes of the launch)."""
+        n = self.launches_per_enqueue
+        out = []
+        buf = C.create_string_buffer(192)
+        for i in range(n):
+            fl, by = C.c_double(), C.c_double()
+            _lib.check(self._lib.mde_context_op_info(self._h, i, buf, 192, C.byref(fl), C.byref(by)), "op_info")
+            label = buf.value.decode()
+            kind = label.split(" ")[0]
+            layer_type = ("Convolution" if kind.startswith("conv") else "MatrixMultiply" if kind.startswith("gemm") else
+                          "Attention" if kind == "attention" else "Normalization" if kind == "layernorm" else
+                          "Resize" if kind in ("bilinear", "resize_depth", "upconv_head") else "Shuffle")
+            prec = "Half" if self._engine._desc.precision == _lib.PRECISIONS["fp16"] else "BFloat16"
+            out.append({"Name": label, "LayerType": layer_type, "Outputs": [{"Format/Datatype": prec}],
+                        "AlgorithmicFlops": fl.value, "AlgorithmicBytes": by.value})
+        return out
 
     # -- extras (not part of the TensorRT surface)
     @property

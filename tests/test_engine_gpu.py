@@ -389,3 +389,38 @@ def test_depth_pro_patch_encoder_stage_end_to_end(lib, bitwise):
         assert rms_rel(m.float().cpu(), r) < INTER["fp16"]
     enc.close()
     eng.close()
+
+
+def test_profiler_surface_like_core_profile(lib, tmp_path, bitwise):
+    """tools/profile_model.py:120-135 attaches `context.profiler = LayerTimer()` and calls do_inference; core/profile.py
+    then builds rows {name, ms, calls_per_iter, share} and reads the engine's layer list.  The same flow here."""
+    from collections import OrderedDict
+
+    class LayerTimer:                         # core/profile.py:30-58, minus the tensorrt base class
+        def __init__(self):
+            self.total_ms, self.calls = OrderedDict(), OrderedDict()
+
+        def report_layer_time(self, layer_name, ms):
+            self.total_ms[layer_name] = self.total_ms.get(layer_name, 0.0) + ms
+            self.calls[layer_name] = self.calls.get(layer_name, 0) + 1
+
+    sd, x, depth, _ = R.reference("vits")
+    path = str(tmp_path / "dav2_vits.mdew")
+    W.save(path, sd, W.describe("vits", 518, 518, 20.0))
+    with common.get_engine(path, "", "fp16") as engine, engine.create_execution_context() as context:
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine, (1, 518, 518), profile_idx=0)
+        inputs[0].host = x.numpy()
+        plain = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)[0].copy()
+        timer = LayerTimer()
+        context.profiler = timer
+        for _ in range(2):
+            prof = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)[0].copy()
+        layers = context.layer_information()
+        common.free_buffers(inputs, outputs, stream)
+    assert np.array_equal(plain, prof)                                   # profiling changes the schedule, not the result
+    assert sum(timer.calls.values()) == 2 * len(layers) and all(v > 0 for v in timer.total_ms.values())
+    names = {l["Name"] for l in layers}
+    assert set(timer.total_ms) == names and any(n.startswith("attention") for n in names)
+    assert {l["LayerType"] for l in layers} >= {"MatrixMultiply", "Convolution", "Attention", "Normalization"}
+    total_flops = sum(l["AlgorithmicFlops"] for l in layers)
+    assert abs(total_flops / 115.3e9 - 1.0) < 0.12     # SURVEY section 8 d: 115.3 GFLOP per ViT-S image (the plan commutes two 1x1 / 3x3 maps with upsamplings)
