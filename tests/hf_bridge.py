@@ -57,3 +57,68 @@ def to_hf(sd, encoder):
     o["head.conv2.weight"], o["head.conv2.bias"] = sd[h + "scratch.output_conv2.0.weight"], sd[h + "scratch.output_conv2.0.bias"]
     o["head.conv3.weight"], o["head.conv3.bias"] = sd[h + "scratch.output_conv2.2.weight"], sd[h + "scratch.output_conv2.2.bias"]
     return o
+
+
+# ---------------------------------------------------------------------------------------------- Depth Pro (whole model)
+
+def depth_pro_hf_model(encoder, features, hook_ids):
+    from transformers import DepthProConfig, DepthProForDepthEstimation, Dinov2Config
+    c = O.MODEL_CONFIGS[encoder]
+    D = c["embed_dim"]
+    vit = Dinov2Config(hidden_size=D, num_hidden_layers=c["depth"], num_attention_heads=c["num_heads"], image_size=384, patch_size=16)
+    cfg = DepthProConfig(patch_model_config=vit, image_model_config=vit, fov_model_config=vit, intermediate_hook_ids=list(hook_ids),
+                         use_fov_model=True, fusion_hidden_size=features, scaled_images_feature_dims=[D, D, D // 2],
+                         intermediate_feature_dims=[features, features])
+    return DepthProForDepthEstimation(cfg).eval()
+
+
+def depth_pro_to_hf(sd, encoder):
+    """oracle/depth_pro_torch.py `init_full_state_dict` keys (upstream's module tree) -> transformers' DepthProForDepthEstimation."""
+    from oracle import depth_pro_torch as DP
+    o = {}
+    for pre, hf_pre in zip(DP.TRUNKS, ("depth_pro.encoder.patch_encoder.model.", "depth_pro.encoder.image_encoder.model.",
+                                       "fov_model.fov_encoder.model.")):
+        trunk = DP.trunk_state_dict(sd, pre)
+        full = {**init_heads_placeholder(encoder), **trunk}
+        for k, v in to_hf(full, encoder).items():
+            if k.startswith("backbone."):
+                o[hf_pre + k[len("backbone."):]] = v
+    up = "depth_pro.neck.feature_upsample."
+    for name, hf in (("upsample_latent0", "intermediate.1"), ("upsample_latent1", "intermediate.0"), ("upsample0", "scaled_images.2"),
+                     ("upsample1", "scaled_images.1"), ("upsample2", "scaled_images.0")):
+        j = 0
+        while f"encoder.{name}.{j}.weight" in sd:
+            o[up + f"{hf}.layers.{j}.weight"] = sd[f"encoder.{name}.{j}.weight"]
+            j += 1
+    o[up + "image_block.layers.0.weight"], o[up + "image_block.layers.0.bias"] = sd["encoder.upsample_lowres.weight"], sd["encoder.upsample_lowres.bias"]
+    o["depth_pro.neck.fuse_image_with_low_res.weight"] = sd["encoder.fuse_lowres.weight"]
+    o["depth_pro.neck.fuse_image_with_low_res.bias"] = sd["encoder.fuse_lowres.bias"]
+    for i in range(1, 5):
+        o[f"depth_pro.neck.feature_projection.projections.{4 - i}.weight"] = sd[f"decoder.convs.{i}.weight"]
+    for i in range(5):
+        f, hf = f"decoder.fusions.{i}.", (f"fusion_stage.intermediate.{4 - i}." if i > 0 else "fusion_stage.final.")
+        for r, hr in (("resnet1", "residual_layer1"), ("resnet2", "residual_layer2")):
+            for j, hc in ((1, "convolution1"), (3, "convolution2")):
+                for wb in ("weight", "bias"):
+                    if f + f"{r}.residual.{j}.{wb}" in sd:
+                        o[hf + f"{hr}.{hc}.{wb}"] = sd[f + f"{r}.residual.{j}.{wb}"]
+        if i > 0:
+            o[hf + "deconv.weight"] = sd[f + "deconv.weight"]
+        o[hf + "projection.weight"], o[hf + "projection.bias"] = sd[f + "out_conv.weight"], sd[f + "out_conv.bias"]
+    for j in (0, 1, 2, 4):
+        o[f"head.layers.{j}.weight"], o[f"head.layers.{j}.bias"] = sd[f"head.{j}.weight"], sd[f"head.{j}.bias"]
+    o["fov_model.fov_encoder.neck.weight"], o["fov_model.fov_encoder.neck.bias"] = sd["fov.encoder.1.weight"], sd["fov.encoder.1.bias"]
+    o["fov_model.conv.weight"], o["fov_model.conv.bias"] = sd["fov.downsample.0.weight"], sd["fov.downsample.0.bias"]
+    for j in (0, 2, 4):
+        o[f"fov_model.head.layers.{j}.weight"], o[f"fov_model.head.layers.{j}.bias"] = sd[f"fov.head.{j}.weight"], sd[f"fov.head.{j}.bias"]
+    return o
+
+
+_PLACEHOLDER = {}
+
+
+def init_heads_placeholder(encoder):
+    """to_hf() walks the DPT head keys too; give it any tensors of the right names (they are dropped afterwards)."""
+    if encoder not in _PLACEHOLDER:
+        _PLACEHOLDER[encoder] = {k: v for k, v in O.init_state_dict(encoder, seed=0).items() if k.startswith("depth_head.")}
+    return _PLACEHOLDER[encoder]

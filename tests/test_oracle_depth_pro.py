@@ -38,3 +38,33 @@ def test_patch_encoder_matches_transformers_depth_pro():
         r = r[0].permute(1, 2, 0)
         assert r.shape == g.shape
         assert float((r - g).abs().max()) < 3e-4 * float(r.abs().max())
+
+
+def test_full_model_matches_transformers_depth_pro():
+    """The whole restated model (three trunks, upsampling neck, fusion decoder, depth head, field-of-view head) against
+    transformers' independent DepthProForDepthEstimation on copied weights, at the exported 1536 x 1536 size."""
+    pytest.importorskip("transformers")
+    import hf_bridge as H
+    sd = DP.init_full_state_dict("vits", features=64, seed=11)
+    model = H.depth_pro_hf_model("vits", 64, hook_ids=(8, 5))
+    missing, unexpected = model.load_state_dict(H.depth_pro_to_hf(sd, "vits"), strict=False)
+    # transformers allocates a residual_layer1 for the first fusion layer that its forward never uses
+    assert not unexpected and all(k.startswith("fusion_stage.intermediate.0.residual_layer1.") for k in missing), (missing, unexpected)
+    torch.manual_seed(5)
+    x = torch.randn(1, 3, 1536, 1536)
+    with torch.no_grad():
+        ref = model(pixel_values=x)
+    inv, fov = DP.full_forward(sd, x, "vits", hook_taps=(2, 1))
+    assert inv.shape == (1, 1, 1536, 1536) and fov.shape == (1,)
+    r = ref.predicted_depth[:, None]
+    assert float(r.max()) > 0 and float((r > 0).float().mean()) > 0.2                 # not a dead ReLU map
+    assert float((inv - r).abs().max()) < 3e-4 * float(r.abs().max())
+    assert abs(float(fov) - float(ref.field_of_view)) < 3e-4 * max(1.0, abs(float(ref.field_of_view)))
+
+
+def test_postprocess_follows_the_reference_script():
+    """models/depth_pro/onnx2trt.py:118-134 on a constant map: f_px = 0.5 W / tan(fov / 2), depth = f_px / (W * inv)."""
+    inv = torch.full((1, 1, 8, 8), 0.5)
+    depth, f_px = DP.postprocess(inv, torch.tensor([90.0]), 4, 6)
+    assert depth.shape == (1, 1, 4, 6) and abs(float(f_px) - 3.0) < 1e-5
+    assert torch.allclose(depth, torch.full_like(depth, 1.0), atol=1e-6)              # 1 / (0.5 * 6 / 3)
