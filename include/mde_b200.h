@@ -256,6 +256,23 @@ int mde_k_peer_wait(void* d_own_flags, int32_t n_ranks, uint32_t epoch, void* st
  * `padding` tokens at every edge it shares with a neighbour. */
 int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_side, int32_t grid, int32_t padding, int32_t dim,
                         void* d_out, void* stream);
+/* torch.nn.functional.interpolate(mode="bilinear", align_corners=False) as Depth Pro uses it -- for the input
+ * (models/depth_pro/onnx2trt.py:56-74: ToTensor -> Normalize(0.5, 0.5) -> interpolate to 1536 x 1536) and for the crop
+ * pyramid inside the model (models/depth_pro/onnx_export.py:15-29).  Writes n_crops windows of out_h x out_w pixels, window
+ * i taken at (y0, x0) of the source resized to level_h x level_w; the resized images are never materialised.
+ * d_src: planar float32 [3][src_h][src_w], or (src_is_u8_hwc) uint8 [src_h][src_w][3] which is first divided by 255 and,
+ * when mean3 / std3 are given, normalised (v - mean) / std in fp32.  d_out: float32 [n_crops][3][out_h][out_w].
+ * `crops` is a host array (copied into the launch), at most 64 entries. */
+typedef struct mde_crop { int32_t level_h, level_w, y0, x0; } mde_crop;
+int mde_k_resize_crops(const void* d_src, int32_t src_is_u8_hwc, int32_t swap_rb, int32_t src_h, int32_t src_w,
+                       const mde_crop* crops, int32_t n_crops, int32_t out_h, int32_t out_w, const float* mean3,
+                       const float* std3, float* d_out, void* stream);
+/* Depth Pro's post-processing on the device (models/depth_pro/onnx2trt.py:118-134): f_px = 0.5 * src_w / tan(0.5 * rad(fov)),
+ * inverse = canonical_inverse_depth * (src_w / f_px), interpolate(bilinear, align_corners=False) to src_h x src_w (skipped
+ * when the sizes agree), depth = 1 / clamp(inverse, 1e-4, 1e4).  d_inv: float32 [h][w]; d_fov_deg: one float on the
+ * device (the engine's second output); d_depth: float32 [src_h][src_w]; d_f_px: one float or NULL. */
+int mde_k_depth_pro_post(const float* d_inv, const float* d_fov_deg, int32_t h, int32_t w, int32_t src_h, int32_t src_w,
+                         float* d_depth, float* d_f_px, void* stream);
 /* The reference scripts' post-processing on the device (models/depth_anything_v2/onnx2trt.py:111-117):
  * F.interpolate(depth, (ho, wo), mode="bilinear", align_corners=True) then clamp(clamp_lo, clamp_hi); fp32 [B][h][w]. */
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

@@ -424,4 +424,90 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const Im2colS2Params p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// torch.nn.functional.interpolate(mode="bilinear", align_corners=False), the resize Depth Pro uses everywhere
+// (models/depth_pro/onnx2trt.py:56-74 for the input, the crop pyramid inside the model, :124-128 for the output):
+// src = fma(scale, dst + 0.5, -0.5) clamped at 0, i0 = trunc(src), i1 = i0 + (i0 < size - 1), l1 = src - i0, l0 = 1 - l1,
+// out = h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d), every step a separately rounded fp32 operation.
+// One launch writes any number of crop windows of (virtually) resized copies of ONE source image: the 25 + 9 + 1 crops
+// of the pyramid never exist as resized images in memory.  The source is planar fp32 or uint8 HWC; the latter goes
+// through ToTensor (/ 255) and Normalize ((v - mean) / std) in fp32 first, as the script's transform does.
+// ---------------------------------------------------------------------------------------------
+struct HalfPixelCrop { int level_h, level_w, y0, x0; };
+struct ResizeCropsParams {
+  const void* src;
+  float* out;               // [n_crops][3][out_h][out_w]
+  int src_u8, swap_rb, normalise, src_h, src_w, out_h, out_w, n_crops;
+  float mean[3], std[3];
+  HalfPixelCrop crops[64];
+};
+__device__ __forceinline__ void halfpixel_coord(int dst, float scale, int size, int* i0, int* i1, float* l0, float* l1) {
+  float s = fmaf(scale, __fadd_rn(static_cast<float>(dst), 0.5f), -0.5f);   // fused, as torch's kernels compile it (x86 -mfma, nvcc)
+  s = s < 0.f ? 0.f : s;
+  const int i = min(static_cast<int>(s), size - 1);
+  *i0 = i;
+  *i1 = i + (i < size - 1 ? 1 : 0);
+  const float l = fminf(fmaxf(__fsub_rn(s, static_cast<float>(i)), 0.f), 1.f);
+  *l1 = l;
+  *l0 = __fsub_rn(1.f, l);
+}
+__global__ void __launch_bounds__(256) resize_crops_kernel(const ResizeCropsParams p) {
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
+  const int crop = blockIdx.z / 3, ch = blockIdx.z % 3;
+  if (ox >= p.out_w) return;
+  const HalfPixelCrop c = p.crops[crop];
+  int ya, yb, xa, xb;
+  float h0, h1, w0, w1;
+  halfpixel_coord(c.y0 + oy, __fdiv_rn(static_cast<float>(p.src_h), static_cast<float>(c.level_h)), p.src_h, &ya, &yb, &h0, &h1);
+  halfpixel_coord(c.x0 + ox, __fdiv_rn(static_cast<float>(p.src_w), static_cast<float>(c.level_w)), p.src_w, &xa, &xb, &w0, &w1);
+  float a, b, cc, d;
+  if (p.src_u8) {
+    const unsigned char* s = static_cast<const unsigned char*>(p.src);
+    const int sc = p.swap_rb ? 2 - ch : ch;
+    const float m = p.mean[ch], sd = p.std[ch];
+    auto px = [&](int y, int x) {
+      float v = __fdiv_rn(static_cast<float>(s[(static_cast<long long>(y) * p.src_w + x) * 3 + sc]), 255.f);
+      return p.normalise ? __fdiv_rn(__fsub_rn(v, m), sd) : v;
+    };
+    a = px(ya, xa); b = px(ya, xb); cc = px(yb, xa); d = px(yb, xb);
+  } else {
+    const float* s = static_cast<const float*>(p.src) + static_cast<long long>(ch) * p.src_h * p.src_w;
+    a = __ldg(s + static_cast<long long>(ya) * p.src_w + xa); b = __ldg(s + static_cast<long long>(ya) * p.src_w + xb);
+    cc = __ldg(s + static_cast<long long>(yb) * p.src_w + xa); d = __ldg(s + static_cast<long long>(yb) * p.src_w + xb);
+  }
+  const float top = __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b));
+  const float bot = __fadd_rn(__fmul_rn(w0, cc), __fmul_rn(w1, d));
+  p.out[((static_cast<long long>(crop) * 3 + ch) * p.out_h + oy) * p.out_w + ox] = __fadd_rn(__fmul_rn(h0, top), __fmul_rn(h1, bot));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depth Pro's post-processing (models/depth_pro/onnx2trt.py:118-134) on the device: f_px = 0.5 W / tan(0.5 rad(fov)),
+// inverse depth * (W / f_px), resized back to the source size (the interpolation above), depth = 1 / clamp(., 1e-4, 1e4).
+// ---------------------------------------------------------------------------------------------
+struct DepthProPostParams {
+  const float* inv;         // [h][w] canonical inverse depth
+  const float* fov_deg;     // [1] on the device
+  float* depth;             // [src_h][src_w]
+  float* f_px;              // [1] or NULL
+  int h, w, src_h, src_w;
+};
+__global__ void __launch_bounds__(256) depth_pro_post_kernel(const DepthProPostParams p) {
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
+  const float half_rad = __fmul_rn(0.5f, __fmul_rn(__ldg(p.fov_deg), 0.017453292519943295f));
+  const float f_px = __fdiv_rn(__fmul_rn(0.5f, static_cast<float>(p.src_w)), tanf(half_rad));
+  if (p.f_px && oy == 0 && ox == 0) *p.f_px = f_px;
+  if (ox >= p.src_w) return;
+  const float s = __fdiv_rn(static_cast<float>(p.src_w), f_px);
+  int ya, yb, xa, xb;
+  float h0, h1, w0, w1;
+  halfpixel_coord(oy, __fdiv_rn(static_cast<float>(p.h), static_cast<float>(p.src_h)), p.h, &ya, &yb, &h0, &h1);
+  halfpixel_coord(ox, __fdiv_rn(static_cast<float>(p.w), static_cast<float>(p.src_w)), p.w, &xa, &xb, &w0, &w1);
+  const float a = __fmul_rn(__ldg(p.inv + static_cast<long long>(ya) * p.w + xa), s), b = __fmul_rn(__ldg(p.inv + static_cast<long long>(ya) * p.w + xb), s);
+  const float c = __fmul_rn(__ldg(p.inv + static_cast<long long>(yb) * p.w + xa), s), d = __fmul_rn(__ldg(p.inv + static_cast<long long>(yb) * p.w + xb), s);
+  float v;
+  if (p.h == p.src_h && p.w == p.src_w) v = a;       // the script skips the interpolation when the sizes agree
+  else v = __fadd_rn(__fmul_rn(h0, __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b))), __fmul_rn(h1, __fadd_rn(__fmul_rn(w0, c), __fmul_rn(w1, d))));
+  p.depth[static_cast<long long>(oy) * p.src_w + ox] = __fdiv_rn(1.f, fminf(fmaxf(v, 1e-4f), 1e4f));
+}
+
 }  // namespace mde

@@ -577,6 +577,42 @@ int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_o
   return MDE_OK;
 }
 
+int launch_resize_crops(const void* d_src, int src_u8, int swap_rb, int src_h, int src_w, const mde_crop* crops, int n_crops,
+                        int out_h, int out_w, const float* mean3, const float* std3, float* d_out, cudaStream_t s) {
+  if (src_h < 1 || src_w < 1 || out_h < 1 || out_w < 1) return fail(MDE_ERR_INVALID, "resize_crops: empty problem");
+  if (n_crops < 1 || n_crops > 64) return fail(MDE_ERR_INVALID, "resize_crops: 1..64 crops per launch, not %d", n_crops);
+  if (out_h > 65535 || n_crops * 3 > 65535) return fail(MDE_ERR_INVALID, "resize_crops: output exceeds grid limits");
+  if ((mean3 == nullptr) != (std3 == nullptr)) return fail(MDE_ERR_INVALID, "resize_crops: mean and std go together (both NULL: no normalisation)");
+  if (mean3 && !src_u8) return fail(MDE_ERR_INVALID, "resize_crops: normalisation applies to the uint8 source only");
+  ResizeCropsParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = d_src; p.out = d_out; p.src_u8 = src_u8 ? 1 : 0; p.swap_rb = swap_rb ? 1 : 0; p.normalise = mean3 ? 1 : 0;
+  p.src_h = src_h; p.src_w = src_w; p.out_h = out_h; p.out_w = out_w; p.n_crops = n_crops;
+  for (int i = 0; i < 3; ++i) { p.mean[i] = mean3 ? mean3[i] : 0.f; p.std[i] = std3 ? std3[i] : 1.f; }
+  for (int i = 0; i < n_crops; ++i) {
+    const mde_crop& c = crops[i];
+    if (c.level_h < 1 || c.level_w < 1 || c.y0 < 0 || c.x0 < 0 || c.y0 + out_h > c.level_h || c.x0 + out_w > c.level_w)
+      return fail(MDE_ERR_INVALID, "resize_crops: crop %d (%d,%d)+(%dx%d) leaves its %dx%d level", i, c.y0, c.x0, out_h, out_w, c.level_h, c.level_w);
+    p.crops[i].level_h = c.level_h; p.crops[i].level_w = c.level_w; p.crops[i].y0 = c.y0; p.crops[i].x0 = c.x0;
+  }
+  dim3 grid((out_w + 255) / 256, out_h, n_crops * 3);
+  resize_crops_kernel<<<grid, 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+int launch_depth_pro_post(const float* d_inv, const float* d_fov, int h, int w, int src_h, int src_w, float* d_depth, float* d_f_px,
+                          cudaStream_t s) {
+  if (h < 1 || w < 1 || src_h < 1 || src_w < 1) return fail(MDE_ERR_INVALID, "depth_pro_post: empty problem");
+  if (src_h > 65535) return fail(MDE_ERR_INVALID, "depth_pro_post: height exceeds grid limits");
+  DepthProPostParams p;
+  p.inv = d_inv; p.fov_deg = d_fov; p.depth = d_depth; p.f_px = d_f_px; p.h = h; p.w = w; p.src_h = src_h; p.src_w = src_w;
+  dim3 grid((src_w + 255) / 256, src_h, 1);
+  depth_pro_post_kernel<<<grid, 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int launch_merge_patches(int precision, const void* d_in, int per_side, int grid, int pad, int dim, void* d_out, cudaStream_t s) {
   if (per_side < 1 || grid < 1 || dim < 8 || dim % 8) return fail(MDE_ERR_INVALID, "merge_patches: bad geometry");
   if (per_side == 1) pad = 0;
@@ -845,6 +881,22 @@ int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_sid
   clear_error();
   if (!d_tokens || !d_out) return fail(MDE_ERR_INVALID, "merge_patches: null pointer");
   return launch_merge_patches(precision, d_tokens, per_side, grid, padding, dim, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_resize_crops(const void* d_src, int32_t src_is_u8_hwc, int32_t swap_rb, int32_t src_h, int32_t src_w,
+                       const mde_crop* crops, int32_t n_crops, int32_t out_h, int32_t out_w, const float* mean3,
+                       const float* std3, float* d_out, void* stream) {
+  clear_error();
+  if (!d_src || !d_out || !crops) return fail(MDE_ERR_INVALID, "resize_crops: null pointer");
+  return launch_resize_crops(d_src, src_is_u8_hwc, swap_rb, src_h, src_w, crops, n_crops, out_h, out_w, mean3, std3, d_out,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_depth_pro_post(const float* d_inv, const float* d_fov_deg, int32_t h, int32_t w, int32_t src_h, int32_t src_w,
+                         float* d_depth, float* d_f_px, void* stream) {
+  clear_error();
+  if (!d_inv || !d_fov_deg || !d_depth) return fail(MDE_ERR_INVALID, "depth_pro_post: null pointer");
+  return launch_depth_pro_post(d_inv, d_fov_deg, h, w, src_h, src_w, d_depth, d_f_px, static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

@@ -238,3 +238,35 @@ def postprocess(inv: torch.Tensor, fov_deg: torch.Tensor, src_h: int, src_w: int
     if inv.shape[-2:] != (src_h, src_w):
         inverse = F.interpolate(inverse, size=(src_h, src_w), mode="bilinear", align_corners=False)
     return 1.0 / torch.clamp(inverse, min=1e-4, max=1e4), f_px.squeeze()
+
+
+def preprocess(image_rgb_u8, size: int = 1536) -> torch.Tensor:
+    """models/depth_pro/onnx2trt.py:56-74: Compose([ToTensor(), Normalize([0.5]*3, [0.5]*3)]) on the RGB uint8 image, then
+    F.interpolate(bilinear, align_corners=False) to size x size when the source is not already that size.
+    (ToTensor = HWC uint8 -> CHW float32 / 255; Normalize = (x - mean) / std, both in fp32.)"""
+    t = torch.from_numpy(image_rgb_u8).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+    t = (t - 0.5) / 0.5
+    t = t[None]
+    if t.shape[-2:] != (size, size):
+        t = F.interpolate(t, size=(size, size), mode="bilinear", align_corners=False)
+    return t
+
+
+@torch.no_grad()
+def calibrate_full(sd, x: torch.Tensor, encoder: str, hook_taps: Sequence[int] = (1, 0)):
+    """Random-init weights leave the final ReLU half dead and the field of view near zero; rescale the last 1x1 convolution
+    so the canonical inverse depth on `x` is ~N(3, 0.5^2) (positive everywhere, like the trained model's output) and shift
+    the last field-of-view bias so the prediction on `x` is 60 degrees.  Fixed once, before any kernel existed."""
+    trace = {}
+    full_forward(sd, x, encoder, hook_taps, trace)
+    h = trace["features"]
+    h = F.conv2d(h, sd["head.0.weight"], sd["head.0.bias"], padding=1)
+    h = F.conv_transpose2d(h, sd["head.1.weight"], sd["head.1.bias"], stride=2)
+    h = F.relu(F.conv2d(h, sd["head.2.weight"], sd["head.2.bias"], padding=1))
+    z = F.conv2d(h, sd["head.4.weight"], sd["head.4.bias"])
+    m, s = float(z.mean()), float(z.std())
+    sd["head.4.weight"] = (sd["head.4.weight"] * (0.5 / s)).contiguous()
+    sd["head.4.bias"] = ((sd["head.4.bias"] - m) * (0.5 / s) + 3.0).contiguous()
+    _, fov = full_forward(sd, x, encoder, hook_taps)
+    sd["fov.head.4.bias"] = (sd["fov.head.4.bias"] + (60.0 - float(fov))).contiguous()
+    return m, s

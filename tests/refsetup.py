@@ -39,3 +39,16 @@ def compare_depth(ref: np.ndarray, got: np.ndarray) -> dict:
     return {"compared": int(ok.sum()), "max_abs": float(d.max()), "rel_mean": float(d.mean() / np.abs(a).mean()),
             "abs_rel": float(rel.mean()), "max_rel": float(rel.max()), "positive": int(pos.sum()),
             "corr": float(np.corrcoef(a, b)[0, 1])}
+
+
+@functools.lru_cache(maxsize=2)
+def depth_pro_reference(encoder: str = "vits", features: int = 64, hook_taps=(2, 1)):
+    """-> (state_dict, x [1,3,1536,1536], canonical inverse depth, fov_deg, trace) of the oracle's whole Depth Pro model on
+    the reference's synthetic frame (seed 0, 480 x 640), weights seeded and calibrated (oracle/depth_pro_torch.py)."""
+    from oracle import depth_pro_torch as DP
+    x = DP.preprocess(synthetic_image(0), 1536)
+    sd = DP.init_full_state_dict(encoder, features=features, seed=21)
+    DP.calibrate_full(sd, x, encoder, hook_taps)
+    trace = {}
+    inv, fov = DP.full_forward(sd, x, encoder, hook_taps, trace)
+    return sd, x, inv, fov, trace

@@ -1,0 +1,102 @@
+"""Depth Pro (BASELINE.json configs[3]) on a B200: preprocessing and crop pyramid kernels against torch's interpolate,
+the post-processing kernel against the reference script's formulae, and the whole model -- through the reference-shaped
+host API (allocate_buffers / do_inference) -- against the oracle (oracle/depth_pro_torch.py, pinned on transformers'
+DepthProForDepthEstimation).
+
+Gates for the model outputs: the same as Depth Anything's (tests/test_engine_gpu.py): fp16 at north_star's numbers
+(max relative error <= 1e-2, AbsRel <= 2e-3), bf16 at the precision plan's own error; intermediate maps in RMS-relative
+error.  The field of view is one fp32 number out of a 16-bit pipeline: 0.05 degrees (fp16) / 0.5 degrees (bf16)."""
+import numpy as np
+import pytest
+import torch
+
+import refsetup as R
+from monocular_depth_estimation_trt_b200 import common, depth_pro as DPE, sharding as S
+
+pytestmark = pytest.mark.gpu
+
+GATE = {"fp16": dict(abs_rel=2e-3, max_rel=1e-2, fov=0.05), "bf16": dict(abs_rel=1.2e-2, max_rel=1.2e-1, fov=0.5)}
+INTER = {"fp16": 1.2e-3, "bf16": 9e-3}
+
+
+def rms_rel(got, ref):
+    got, ref = got.double(), ref.double()
+    return float(((got - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt())
+
+
+def test_crop_pyramid_matches_torch_interpolate(lib):
+    """One launch writes the 35 crops; torch builds the two lower levels with F.interpolate(align_corners=False) and
+    slices.  fp32 bilinear with separately rounded steps: within 2 ulp of 1.0 of torch's (FMA-contracted) CPU kernel."""
+    torch.manual_seed(4)
+    image = torch.randn(3, 1536, 1536)
+    ref = S.make_crops(image)
+    ops = DPE._Ops("fp16")
+    ops.stream = torch.cuda.current_stream().cuda_stream
+    import ctypes as C
+    ops.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.full((35, 3, 384, 384), float("nan"), device="cuda")
+    plan = [(side, side, y0, x0) for _, side, y0, x0 in S.pyramid_plan(1536)]
+    ops.crops(image.cuda().data_ptr(), False, False, 1536, 1536, plan, out)
+    torch.cuda.synchronize()
+    got = out.cpu()
+    assert torch.equal(got[:25], ref[:25])                            # full-resolution crops are copies
+    assert float((got - ref).abs().max()) <= 2.4e-7 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("hw", [(480, 640), (1536, 1536), (2268, 3024)])
+def test_preprocess_u8_matches_the_script_transform(lib, hw):
+    """uint8 frame -> ToTensor -> Normalize(0.5, 0.5) -> interpolate(1536): models/depth_pro/onnx2trt.py:56-74."""
+    from oracle import depth_pro_torch as DP
+    img = R.synthetic_image(3, *hw)
+    ref = DP.preprocess(img, 1536)
+    out = torch.full((1, 3, 1536, 1536), float("nan"), device="cuda")
+    DPE.preprocess_u8(torch.from_numpy(img).cuda(), 1536, out, stream_handle=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((out.cpu() - ref).abs().max()) <= 2.4e-7             # values in [-1, 1]: 2 ulp of 1.0
+
+
+@pytest.mark.parametrize("src", [(480, 640), (1536, 1536)])
+def test_postprocess_matches_the_script(lib, src):
+    from oracle import depth_pro_torch as DP
+    torch.manual_seed(6)
+    inv = torch.rand(1, 1, 1536, 1536) * 4 + 1e-5
+    inv[0, 0, :4, :4] = 0.0                                            # the clamp's lower end
+    fov = torch.tensor([57.3])
+    ref, f_px = DP.postprocess(inv, fov, *src)
+    depth = torch.full(src, float("nan"), device="cuda")
+    fpx = torch.zeros(1, device="cuda")
+    DPE.postprocess(inv.cuda().data_ptr(), fov.cuda().data_ptr(), 1536, src[0], src[1], depth, fpx,
+                    torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert abs(float(fpx) - float(f_px)) <= 2e-6 * float(f_px)
+    rel = ((depth.cpu() - ref[0, 0]).abs() / ref[0, 0]).max()
+    assert float(rel) <= 5e-6
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_whole_model_against_the_oracle(lib, prec):
+    sd, x, inv, fov, trace = R.depth_pro_reference()
+    with DPE.DepthProEngine(sd, encoder="vits", features=64, precision=prec, hook_blocks=(8, 5)) as engine, \
+            engine.create_execution_context() as context:
+        assert [engine.get_tensor_name(i) for i in range(engine.num_io_tensors)] == ["input", "canonical_inverse_depth", "fov_deg"]
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+        inputs[0].host = x.numpy()
+        outs = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        got_inv = outs[0].reshape(1536, 1536).copy()
+        got_fov = float(outs[1][0])
+        second = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        assert np.array_equal(second[0].reshape(1536, 1536), got_inv)                     # reproducible bit for bit
+        launches = context.launches_per_enqueue
+        # intermediates first: they localise a failure
+        def nchw(name, side, ch):
+            return context.get_buffer(name).float().cpu().reshape(side, side, ch).permute(2, 0, 1)[None]
+        assert rms_rel(nchw("proj4", 48, 64), trace["lowres"]) < INTER[prec]
+        for i, side in ((3, 96), (2, 192), (1, 384), (0, 768)):
+            assert rms_rel(nchw(f"feat{i}", side, 64), trace[f"fusion{i + 1}"]) < INTER[prec], i
+        assert rms_rel(nchw("features", 768, 64), trace["fusion0"]) < INTER[prec]
+        common.free_buffers(inputs, outputs, stream)
+    m = R.compare_depth(inv.numpy(), got_inv)
+    print(prec, launches, "launches", m, "fov", got_fov, float(fov))
+    assert m["positive"] == 1536 * 1536
+    assert m["abs_rel"] <= GATE[prec]["abs_rel"] and m["max_rel"] <= GATE[prec]["max_rel"], m
+    assert abs(got_fov - float(fov)) <= GATE[prec]["fov"]

@@ -1,0 +1,49 @@
+"""Host-side logic of the Depth Pro path (no GPU): tap selection, weight packing, the folded transposed convolution."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from monocular_depth_estimation_trt_b200 import depth_pro as DPE
+
+
+def test_tap_plan_keeps_hooks_and_last_block():
+    taps, (a, b) = DPE.tap_plan(24, (11, 5))
+    assert len(taps) == 4 and taps == sorted(taps) and taps[3] == 23 and taps[a] == 11 and taps[b] == 5
+    taps, (a, b) = DPE.tap_plan(12, (8, 5))
+    assert taps[3] == 11 and taps[a] == 8 and taps[b] == 5
+    with pytest.raises(ValueError):
+        DPE.tap_plan(12, (11, 5))                                      # the last block is not a hook
+    with pytest.raises(ValueError):
+        DPE.tap_plan(12, (5, 5))
+
+
+def test_deconv_packing_is_a_gemm_with_pixel_shuffle():
+    """ConvTranspose2d(k=2, s=2) == rows (y, x) x packed weight, column (ky*2+kx)*cout + o -> pixel (2y+ky, 2x+kx); with a
+    1x1 convolution folded in, the same GEMM gives conv1x1(conv_transpose(x))."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 16, 5, 7, generator=g)
+    w = torch.randn(16, 24, 2, 2, generator=g)
+    w1 = torch.randn(8, 24, generator=g)
+    for fold, ref in ((None, F.conv_transpose2d(x, w, stride=2)),
+                      (w1, F.conv2d(F.conv_transpose2d(x, w, stride=2), w1[:, :, None, None]))):
+        cout = ref.shape[1]
+        p = DPE.pack_deconv2(w, torch.float32, then_1x1=fold)           # [4*cout, cin]
+        rows = x[0].permute(1, 2, 0).reshape(35, 16) @ p.t()           # [(y, x), 4*cout]
+        got = rows.reshape(5, 7, 2, 2, cout).permute(4, 0, 2, 1, 3).reshape(1, cout, 10, 14)
+        assert torch.allclose(got, ref, atol=1e-4)
+
+
+def test_conv_packings():
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(8, 24, 3, 3, generator=g)
+    p = DPE.pack_conv3x3(w, torch.float32)
+    assert p.shape == (8, 9 * 64) and torch.equal(p.reshape(8, 9, 64)[:, 4, :24], w[:, :, 1, 1]) and float(p.reshape(8, 9, 64)[:, :, 24:].abs().max()) == 0
+    q = DPE.pack_conv3x3_s2(w, torch.float32)
+    assert q.shape == (8, 9 * 24) and torch.equal(q.reshape(8, 9, 24)[:, 2], w[:, :, 0, 2])
+
+
+def test_engine_refuses_other_sizes_and_precisions():
+    with pytest.raises(ValueError):
+        DPE.DepthProEngine({}, precision="fp32")
+    with pytest.raises(ValueError):
+        DPE.DepthProEngine({}, image_size=1024)
