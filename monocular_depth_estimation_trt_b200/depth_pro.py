@@ -33,7 +33,7 @@ TRUNKS = ("encoder.patch_encoder.", "encoder.image_encoder.", "fov.encoder.0.")
 
 def tap_plan(depth: int, hook_blocks: Sequence[int]) -> Tuple[List[int], Tuple[int, int]]:
     """The trunk engine taps four blocks; Depth Pro needs the two hooked blocks and the last one.  -> (sorted tap list,
-    positions of hook_blocks[0] / hook_blocks[1] in it).  (11, 5) on the 24-block trunk -> [5, 11, 17, 23], (1, 0)."""
+    positions of hook_blocks[0] / hook_blocks[1] in it).  (11, 5) on the 24-block trunk -> [5, 11, 22, 23], (1, 0)."""
     want = sorted(set(int(b) for b in hook_blocks) | {depth - 1})
     if len(want) != 3 or want[-1] != depth - 1 or want[0] < 0:
         raise ValueError(f"[MDET] hook blocks {tuple(hook_blocks)} must be two distinct blocks below the last one")
@@ -311,6 +311,13 @@ class DepthProContext:
         self.fov_out = torch.zeros(1, 8, dtype=torch.float32, device=dev)
         self.b = b
         self.launches_per_enqueue = 0
+        # the two batch-1 trunks fill a third of the SMs each: they run on side streams, beside each other and the patch trunk
+        from .common_runtime import cuda_call, cudart
+        self.side_streams = [cuda_call(cudart.cudaStreamCreateWithFlags(cudart.cudaStreamNonBlocking)) for _ in range(2)]
+        self.events = [cuda_call(cudart.cudaEventCreateWithFlags(cudart.cudaEventDisableTiming)) for _ in range(3)]
+        self.overlap_trunks = True
+        self.profile_stages = False       # True: CUDA events at the stage boundaries of the next execute (see stage_times())
+        self._marks = []
 
     # -- IExecutionContext surface
     def set_tensor_address(self, name: str, ptr: int) -> bool:
@@ -333,23 +340,41 @@ class DepthProContext:
         sh = int(stream_handle)
         o.stream = C.c_void_p(sh)
         o.launches = 0
+        from .common_runtime import cuda_call, cudart
+        self._marks = []
+
+        def mark(label):
+            if self.profile_stages:
+                ev = cuda_call(cudart.cudaEventCreate())
+                cuda_call(cudart.cudaEventRecord(ev, sh))
+                self._marks.append((label, ev))
+
+        mark("start")
         # 1. crops: this rank's share of the pyramid + the quarter-resolution image for the two batch-1 trunks
         first, count = e.bounds[e.rank]
         if count > 0:
             o.crops(self.addr["input"], False, False, e.S, e.S, e.plan[first:first + count], self.crops_in[:count])
         o.crops(self.addr["input"], False, False, e.S, e.S, e.plan[-1:], self.low_in)
+        mark("crops")
         # 2. trunks
+        if self.overlap_trunks:
+            cuda_call(cudart.cudaEventRecord(self.events[0], sh))
+            for st, ctx, done in ((self.side_streams[0], self.ctx_img, self.events[1]), (self.side_streams[1], self.ctx_fov, self.events[2])):
+                cuda_call(cudart.cudaStreamWaitEvent(st, self.events[0], 0))
+                ctx.execute_async_v3(int(st))
+                cuda_call(cudart.cudaEventRecord(done, st))
         if self.sync is not None:
             self.sync.wait_acks(sh)
         self.patch.enqueue(self.crops_in.data_ptr(), sh)
         if self.sync is not None:
             self.sync.signal_ready(sh)
-        self.ctx_img.execute_async_v3(sh)
-        self.ctx_fov.execute_async_v3(sh)
+        mark("patch trunk")
+        if not self.overlap_trunks:
+            self.ctx_img.execute_async_v3(sh)
+            self.ctx_fov.execute_async_v3(sh)
+        mark("image + fov trunks")
         if self.sync is not None:
-            self.sync.wait_ready(sh)
-        elif e.world > 1:
-            self.patch.finish()                                        # NCCL baseline: host-side ordering
+            self.sync.wait_ready(sh)                                   # (the NCCL baseline is ordered on the stream by NCCL itself)
         taps = self.patch.gathered()
         # 3. merge the crops' tokens into the five maps
         fin, (ha, hb) = taps[3], e.hook_taps
@@ -360,6 +385,7 @@ class DepthProContext:
         o.merge(taps[hb][0:25], 5, 3, D, self.hook_b)
         if self.sync is not None:
             self.sync.signal_acks(sh)
+        mark("merge")
         # 4. neck: 1x1 projection, then ConvTranspose2d layers (GEMM with the 2x2 pixel shuffle in the epilogue)
         def project(src, rows, wt, out):
             o.gemm(src, rows, D, D, wt, wt.shape[0], o.ep(out=out, ld_out=wt.shape[0]))
@@ -384,9 +410,12 @@ class DepthProContext:
         deconv(b["x1.p"], n // 2, D, u["upsample1"][1], b["enc3"])
         project(self.f24, n * n // 16, u["upsample2"][0], b["x2.p"])
         cat = b["cat"]
+        if self.overlap_trunks:
+            cuda_call(cudart.cudaStreamWaitEvent(sh, self.events[1], 0))      # image trunk done
         deconv(b["x2.p"], n // 4, D, u["upsample2"][1], cat, ld_out=2 * D)
         deconv(self.img_taps[3, 0], n // 4, D, w.up_lowres, cat[:, D:], ld_out=2 * D, bias=w.up_lowres_b)
         o.gemm(cat, side[4] ** 2, 2 * D, 2 * D, w.fuse, D, o.ep(bias=w.fuse_b, out=b["xg"], ld_out=D))
+        mark("neck")
         # 5. decoder: project every level to `features` channels, fuse from the lowest resolution up
         enc_dims = [Fd, Fd, D // 2, D, D]
         for i in range(1, 5):
@@ -410,14 +439,18 @@ class DepthProContext:
                 o.gemm(b[f"y{i}"], hw * hw, Fd, Fd, f["deconv.w"], 4 * Fd, o.ep(bias=f["out.b"], out=feat, ld_out=Fd, shuffle=(2, Fd, hw, hw)))
             else:
                 o.gemm(b["y0"], hw * hw, Fd, Fd, f["out.w"], Fd, o.ep(bias=f["out.b"], out=b["features"], ld_out=Fd))
+        mark("decoder")
         # 6. depth head
         hw = side[0]
         o.conv3x3(b["features"], hw, hw, Fd, w.h0, Fd // 2, o.ep(bias=w.h0_b, out=b["h0"], ld_out=Fd // 2))
         o.gemm(b["h0"], hw * hw, Fd // 2, Fd // 2, w.h1, 2 * Fd, o.ep(bias=w.h1_b, out=b["h1"], ld_out=Fd // 2, shuffle=(2, Fd // 2, hw, hw)))
         o.conv3x3(b["h1"], 2 * hw, 2 * hw, Fd // 2, w.h2, 32,
                   o.ep(bias=w.h2_b, head_w=w.h4, head_b=w.h4_b, head_out=self.addr["canonical_inverse_depth"], ld_out=32))
+        mark("depth head")
         # 7. field-of-view head
         g = GRID
+        if self.overlap_trunks:
+            cuda_call(cudart.cudaStreamWaitEvent(sh, self.events[2], 0))      # field-of-view trunk done
         o.gemm(self.fov_taps[3, 0], g * g, D, D, w.fov_lin, Fd // 2, o.ep(bias=w.fov_lin_b, out=b["fov.lin"], ld_out=Fd // 2))
         o.im2col_s2(b["proj4"], 2 * g, 2 * g, Fd, b["fov.col0"])
         o.gemm(b["fov.col0"], g * g, 9 * Fd, 9 * Fd, w.fov_down, Fd // 2, o.ep(bias=w.fov_down_b, act=2, res1=b["fov.lin"], out=b["fov.f0"], ld_out=Fd // 2))
@@ -427,11 +460,21 @@ class DepthProContext:
         o.gemm(b["fov.col2"], g * g // 16, 9 * Fd // 4, 9 * Fd // 4, w.fov2, Fd // 8, o.ep(bias=w.fov2_b, act=2, out=b["fov.f2"], ld_out=Fd // 8))
         k = (g // 4) ** 2 * (Fd // 8)
         o.gemm(b["fov.f2"], 1, k, k, w.fov4, 8, o.ep(bias=w.fov4_b, x=self.fov_out, ld_out=8))
-        from .common_runtime import cuda_call, cudart
         cuda_call(cudart.cudaMemcpyAsync(self.addr["fov_deg"], self.fov_out.data_ptr(), 4,
                                          cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, sh))
+        mark("fov head")
         self.launches_per_enqueue = o.launches + self.patch.ctx.launches_per_enqueue + self.ctx_img.launches_per_enqueue + self.ctx_fov.launches_per_enqueue
         return True
+
+    def stage_times(self):
+        """[(stage, ms)] of the last execute run with `profile_stages = True` (call after the stream has synchronised)."""
+        from .common_runtime import cuda_call, cudart
+        out = [(self._marks[i + 1][0], float(cuda_call(cudart.cudaEventElapsedTime(self._marks[i][1], self._marks[i + 1][1]))))
+               for i in range(len(self._marks) - 1)]
+        for _, ev in self._marks:
+            cuda_call(cudart.cudaEventDestroy(ev))
+        self._marks = []
+        return out
 
     def get_buffer(self, name: str):
         """Intermediate tensors for the per-stage parity gates (valid after execute + stream sync)."""
@@ -448,6 +491,12 @@ class DepthProContext:
             self.sync.close()
             self.sync = None
         self.ctx_img = self.ctx_fov = None
+        from .common_runtime import cudart
+        for st in getattr(self, "side_streams", []):
+            cudart.cudaStreamDestroy(st)
+        for ev in getattr(self, "events", []):
+            cudart.cudaEventDestroy(ev)
+        self.side_streams, self.events = [], []
 
     def __enter__(self):
         return self

@@ -221,9 +221,11 @@ class ShardedPatchEncoder:
         self.ctx.execute_async_v3(stream_handle)
         if self.mode == "nccl" and self.world > 1:
             g = self.buffers.view()
-            # per tap: the ranks' [per_rank, T, D] slabs are contiguous in the gathered layout
-            for i in range(4):
-                dist.all_gather_into_tensor(g[i], self.local[i])
+            # per tap: the ranks' [per_rank, T, D] slabs are contiguous in the gathered layout.  The collective is ordered
+            # on the caller's stream (behind the trunk, ahead of whatever the caller enqueues next).
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_handle))):
+                for i in range(4):
+                    dist.all_gather_into_tensor(g[i], self.local[i])
         elif self.mode == "nccl":
             self.buffers.view().copy_(self.local)
 
