@@ -119,10 +119,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     tmem_alloc(tmem_slot, kAtcTmemCols);
     tmem_relinquish();
   }
+  griddep_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                          // Q / K / V come from the previous kernel
 
   // Register re-partition per warpgroup: the single-thread roles need almost nothing, a softmax thread
   // holds a 128-wide score row.  2 CTAs x 256 threads start at 128 registers each.

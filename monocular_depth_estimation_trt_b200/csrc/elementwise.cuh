@@ -180,6 +180,8 @@ struct LayerNormParams {
 template <typename T, int D, bool kTap>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p) {
   constexpr int V = D / 128;   // float4 per lane
+  griddep_launch_dependents();
+  griddep_wait();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= p.rows) return;
   const int lane = threadIdx.x & 31;

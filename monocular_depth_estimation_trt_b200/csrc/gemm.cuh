@@ -192,11 +192,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (kCtas == 2) { tmem_alloc_pair(tmem_slot, Cfg::kTmemCols); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
+  griddep_launch_dependents();
   tc_fence_before();
   if (kCtas == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is sent to them
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                          // the prologue above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer

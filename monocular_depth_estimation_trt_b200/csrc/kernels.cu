@@ -1,3 +1,4 @@
+#include <utility>
 // Kernel instantiations, launchers and the single-kernel C-ABI entry points (mde_k_*).
 #include <math.h>
 #include <stdarg.h>
@@ -287,6 +288,34 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
   return pick_grid(op);
 }
 
+// Launch with programmatic stream serialisation (see ptx.cuh `griddep_wait`): the kernel may be scheduled while its
+// predecessor drains.  Only for kernels that call griddep_wait() before their first dependent access.  MDE_NO_PDL=1: off.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("MDE_NO_PDL") ? 0 : 1;
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int n = 0;
+  if (cluster > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster; attrs[n].val.clusterDim.y = 1; attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BN, typename T, int kCtas>
 static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
   static bool attr_set = false;
@@ -296,22 +325,7 @@ static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  if (kCtas == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(op.grid);
-    cfg.blockDim = dim3(Cfg::kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    MDE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, op.map_a, op.map_b, op.map_out, op.gather, op.p));
-  } else {
-    kern<<<op.grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(op.map_a, op.map_b, op.map_out, op.gather, op.p);
-  }
+  MDE_CUDA_TRY(launch_pdl(kern, dim3(op.grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, s, kCtas, op.map_a, op.map_b, op.map_out, op.gather, op.p));
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
@@ -440,7 +454,7 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
-  kern<<<grid, kAtcThreads, kAtcSmemBytes, s>>>(op.map_qkv, op.map_kv128, p);
+  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAtcThreads), kAtcSmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
@@ -516,11 +530,11 @@ template <typename T, bool kTap>
 static int launch_layernorm_t(const LayerNormParams& p, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((p.rows + 7) / 8);
   switch (p.D) {
-    case 384: layernorm_kernel<T, 384, kTap><<<grid, 256, 0, s>>>(p); break;
-    case 768: layernorm_kernel<T, 768, kTap><<<grid, 256, 0, s>>>(p); break;
-    case 1024: layernorm_kernel<T, 1024, kTap><<<grid, 256, 0, s>>>(p); break;
-    case 128: layernorm_kernel<T, 128, kTap><<<grid, 256, 0, s>>>(p); break;
-    case 1536: layernorm_kernel<T, 1536, kTap><<<grid, 256, 0, s>>>(p); break;
+    case 384: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 384, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
+    case 768: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 768, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
+    case 1024: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 1024, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
+    case 128: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 128, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
+    case 1536: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 1536, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
     default: return fail(MDE_ERR_INVALID, "layernorm: unsupported width %d", p.D);
   }
   MDE_CUDA_TRY(cudaGetLastError());

@@ -63,6 +63,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------ TMA
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still running.  `griddep_launch_dependents` lets the successor's CTAs be scheduled as
+// soon as every CTA of this grid has issued it (they only need free SM resources); `griddep_wait` blocks until the
+// predecessor grid has completed and its memory operations are visible.  Everything before the wait (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the predecessor's tail; nothing before it may touch memory the predecessor
+// writes, and nothing before it may write global memory at all.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
