@@ -273,6 +273,13 @@ int mde_k_resize_crops(const void* d_src, int32_t src_is_u8_hwc, int32_t swap_rb
  * device (the engine's second output); d_depth: float32 [src_h][src_w]; d_f_px: one float or NULL. */
 int mde_k_depth_pro_post(const float* d_inv, const float* d_fov_deg, int32_t h, int32_t w, int32_t src_h, int32_t src_w,
                          float* d_depth, float* d_f_px, void* stream);
+/* Metric3D V2's post-processing on the device (models/metric3d_v2/onnx2trt.py:148-158): the un-padded window of the canonical
+ * depth map -- d_in points at its first pixel, `pitch` is the padded map's width -- is resized to out_h x out_w with
+ * F.interpolate(mode="bilinear") (align_corners=False), multiplied by `mul` BEFORE the clamp (1 for the script's canonical
+ * output; real_focal * resize_scale / 1000 gives metres, tools/evaluate_gt.py:162-184 "multiply first, then clamp") and
+ * clamped to [clamp_lo, clamp_hi] (0, 300).  float32 in and out. */
+int mde_k_resize_depth_halfpixel(const float* d_in, int32_t pitch, int32_t h, int32_t w, float* d_out, int32_t out_h, int32_t out_w,
+                                 float mul, float clamp_lo, float clamp_hi, void* stream);
 /* The reference scripts' post-processing on the device (models/depth_anything_v2/onnx2trt.py:111-117):
  * F.interpolate(depth, (ho, wo), mode="bilinear", align_corners=True) then clamp(clamp_lo, clamp_hi); fp32 [B][h][w]. */
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

@@ -88,7 +88,10 @@ def get_engine(
     swap_rb: bool = True,
     device: int = 0,
     output: str = "model_grid",
-) -> Engine:
+    world: int = 1,
+    rank: int = 0,
+    gather: str = "fused",
+):
     """Build the engine for the exported model at `onnx_file_path` (an .mdew file here).
 
     Positional arguments keep the reference's order and meaning.  `precision` is "fp16" (the
@@ -111,6 +114,32 @@ def get_engine(
 
     begin = time.time()
     meta = W.read_meta(model_path)
+    if meta.get("family") == "depth_pro":
+        # models/depth_pro/onnx2trt.py:99: the same call, an engine with the same three bindings.  `world` / `rank` shard
+        # the 35 crops over one process per GPU (gather = "fused" | "nccl"); batch and input mode are fixed by the model.
+        from .depth_pro import DepthProEngine
+        if batch != 1 or input_mode != "f32_nchw" or output != "model_grid":
+            raise ValueError("[MDET] the Depth Pro engine is batch 1 with the float32 NCHW input of its spec.json")
+        print(f"[MDET] Build engine ({engine_file_path or model_path})")
+        sd, _ = W.load(model_path)
+        engine = DepthProEngine(sd, encoder=meta["encoder"], features=meta["features"], precision=precision,
+                                hook_blocks=tuple(meta["hook_blocks"]), image_size=meta["input_h"], world=world, rank=rank,
+                                gather=gather, device=device)
+        for i in range(engine.num_io_tensors):
+            name = engine.get_tensor_name(i)
+            kind = "input" if engine.get_tensor_mode(name) == TensorIOMode.INPUT else "output"
+            print(f"[MDET] {kind}({i}) name: {name}, shape= {engine.get_tensor_shape(name)}")
+        if engine_file_path:
+            os.makedirs(os.path.dirname(engine_file_path) or ".", exist_ok=True)
+            with open(engine_file_path, "w", encoding="utf-8") as f:
+                json.dump({"backend": "mde_b200", "abi": _lib.load().mde_abi_version(), "meta": meta, "precision": precision,
+                           "batch": 1, "input_mode": input_mode, "world": world}, f, indent=2)
+            if check_fingerprint:
+                with open(os.path.splitext(engine_file_path)[0] + ".fingerprint", "w", encoding="utf-8") as f:
+                    f.write(_engine_fingerprint(model_path, precision, workspace_gib, opt_level, obey_precision_constraints,
+                                                dynamic_input_shapes, 1, input_mode))
+        print(f"[MDET] Engine build done! ({time.time() - begin:.2f} [sec])")
+        return engine
     desc = make_desc(meta, precision=precision, batch=batch, input_mode=input_mode,
                      max_src_hw=max_src_hw, swap_rb=swap_rb, device=device, output=output)
 

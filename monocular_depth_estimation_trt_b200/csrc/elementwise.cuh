@@ -487,29 +487,35 @@ __global__ void __launch_bounds__(256) resize_crops_kernel(const ResizeCropsPara
 // inverse depth * (W / f_px), resized back to the source size (the interpolation above), depth = 1 / clamp(., 1e-4, 1e4).
 // ---------------------------------------------------------------------------------------------
 struct DepthProPostParams {
-  const float* inv;         // [h][w] canonical inverse depth
-  const float* fov_deg;     // [1] on the device
+  const float* inv;         // [h][pitch] map (Depth Pro: canonical inverse depth; Metric3D: the un-padded window of the canonical depth)
+  const float* fov_deg;     // [1] on the device, or NULL: `mul` is used instead of src_w / f_px
   float* depth;             // [src_h][src_w]
   float* f_px;              // [1] or NULL
-  int h, w, src_h, src_w;
+  int h, w, pitch, src_h, src_w;
+  float mul, lo, hi;
+  int reciprocal;           // 1: out = 1 / clamp(v, lo, hi);  0: out = clamp(v, lo, hi)
 };
 __global__ void __launch_bounds__(256) depth_pro_post_kernel(const DepthProPostParams p) {
   const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
-  const float half_rad = __fmul_rn(0.5f, __fmul_rn(__ldg(p.fov_deg), 0.017453292519943295f));
-  const float f_px = __fdiv_rn(__fmul_rn(0.5f, static_cast<float>(p.src_w)), tanf(half_rad));
-  if (p.f_px && oy == 0 && ox == 0) *p.f_px = f_px;
+  float s = p.mul;
+  if (p.fov_deg) {
+    const float half_rad = __fmul_rn(0.5f, __fmul_rn(__ldg(p.fov_deg), 0.017453292519943295f));
+    const float f_px = __fdiv_rn(__fmul_rn(0.5f, static_cast<float>(p.src_w)), tanf(half_rad));
+    if (p.f_px && oy == 0 && ox == 0) *p.f_px = f_px;
+    s = __fdiv_rn(static_cast<float>(p.src_w), f_px);
+  }
   if (ox >= p.src_w) return;
-  const float s = __fdiv_rn(static_cast<float>(p.src_w), f_px);
   int ya, yb, xa, xb;
   float h0, h1, w0, w1;
   halfpixel_coord(oy, __fdiv_rn(static_cast<float>(p.h), static_cast<float>(p.src_h)), p.h, &ya, &yb, &h0, &h1);
   halfpixel_coord(ox, __fdiv_rn(static_cast<float>(p.w), static_cast<float>(p.src_w)), p.w, &xa, &xb, &w0, &w1);
-  const float a = __fmul_rn(__ldg(p.inv + static_cast<long long>(ya) * p.w + xa), s), b = __fmul_rn(__ldg(p.inv + static_cast<long long>(ya) * p.w + xb), s);
-  const float c = __fmul_rn(__ldg(p.inv + static_cast<long long>(yb) * p.w + xa), s), d = __fmul_rn(__ldg(p.inv + static_cast<long long>(yb) * p.w + xb), s);
+  const float a = __fmul_rn(__ldg(p.inv + static_cast<long long>(ya) * p.pitch + xa), s), b = __fmul_rn(__ldg(p.inv + static_cast<long long>(ya) * p.pitch + xb), s);
+  const float c = __fmul_rn(__ldg(p.inv + static_cast<long long>(yb) * p.pitch + xa), s), d = __fmul_rn(__ldg(p.inv + static_cast<long long>(yb) * p.pitch + xb), s);
   float v;
   if (p.h == p.src_h && p.w == p.src_w) v = a;       // the script skips the interpolation when the sizes agree
   else v = __fadd_rn(__fmul_rn(h0, __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b))), __fmul_rn(h1, __fadd_rn(__fmul_rn(w0, c), __fmul_rn(w1, d))));
-  p.depth[static_cast<long long>(oy) * p.src_w + ox] = __fdiv_rn(1.f, fminf(fmaxf(v, 1e-4f), 1e4f));
+  v = fminf(fmaxf(v, p.lo), p.hi);
+  p.depth[static_cast<long long>(oy) * p.src_w + ox] = p.reciprocal ? __fdiv_rn(1.f, v) : v;
 }
 
 }  // namespace mde

@@ -620,8 +620,22 @@ int launch_depth_pro_post(const float* d_inv, const float* d_fov, int h, int w, 
   if (h < 1 || w < 1 || src_h < 1 || src_w < 1) return fail(MDE_ERR_INVALID, "depth_pro_post: empty problem");
   if (src_h > 65535) return fail(MDE_ERR_INVALID, "depth_pro_post: height exceeds grid limits");
   DepthProPostParams p;
-  p.inv = d_inv; p.fov_deg = d_fov; p.depth = d_depth; p.f_px = d_f_px; p.h = h; p.w = w; p.src_h = src_h; p.src_w = src_w;
+  p.inv = d_inv; p.fov_deg = d_fov; p.depth = d_depth; p.f_px = d_f_px; p.h = h; p.w = w; p.pitch = w; p.src_h = src_h; p.src_w = src_w;
+  p.mul = 1.f; p.lo = 1e-4f; p.hi = 1e4f; p.reciprocal = 1;
   dim3 grid((src_w + 255) / 256, src_h, 1);
+  depth_pro_post_kernel<<<grid, 256, 0, s>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+int launch_resize_depth_halfpixel(const float* d_in, int pitch, int h, int w, float* d_out, int out_h, int out_w, float mul, float lo,
+                                  float hi, cudaStream_t s) {
+  if (h < 1 || w < 1 || out_h < 1 || out_w < 1 || pitch < w) return fail(MDE_ERR_INVALID, "resize_depth_halfpixel: empty problem or pitch < width");
+  if (out_h > 65535) return fail(MDE_ERR_INVALID, "resize_depth_halfpixel: height exceeds grid limits");
+  DepthProPostParams p;
+  p.inv = d_in; p.fov_deg = nullptr; p.depth = d_out; p.f_px = nullptr; p.h = h; p.w = w; p.pitch = pitch; p.src_h = out_h; p.src_w = out_w;
+  p.mul = mul; p.lo = lo; p.hi = hi; p.reciprocal = 0;
+  dim3 grid((out_w + 255) / 256, out_h, 1);
   depth_pro_post_kernel<<<grid, 256, 0, s>>>(p);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -911,6 +925,13 @@ int mde_k_depth_pro_post(const float* d_inv, const float* d_fov_deg, int32_t h, 
   clear_error();
   if (!d_inv || !d_fov_deg || !d_depth) return fail(MDE_ERR_INVALID, "depth_pro_post: null pointer");
   return launch_depth_pro_post(d_inv, d_fov_deg, h, w, src_h, src_w, d_depth, d_f_px, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_resize_depth_halfpixel(const float* d_in, int32_t pitch, int32_t h, int32_t w, float* d_out, int32_t out_h, int32_t out_w,
+                                 float mul, float clamp_lo, float clamp_hi, void* stream) {
+  clear_error();
+  if (!d_in || !d_out) return fail(MDE_ERR_INVALID, "resize_depth_halfpixel: null pointer");
+  return launch_resize_depth_halfpixel(d_in, pitch, h, w, d_out, out_h, out_w, mul, clamp_lo, clamp_hi, static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

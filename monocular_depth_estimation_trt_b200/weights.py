@@ -49,6 +49,17 @@ def describe(encoder: str, input_h: int = 518, input_w: int = 518, max_depth: fl
     return meta
 
 
+def describe_depth_pro(encoder: str = "vitl", features: int = 256, hook_blocks=(11, 5), image_size: int = 1536) -> dict:
+    """Description stored next to a Depth Pro state dict (models/depth_pro/onnx_export.py:15-22: three `dinov2l16_384`
+    trunks, decoder_features 256, field-of-view head; 1536 x 1536 is upstream's fixed size, spec.json "caveats")."""
+    if encoder not in ENCODERS:
+        raise KeyError(f"unknown encoder {encoder!r}; available: {sorted(ENCODERS)}")
+    c = ENCODERS[encoder]
+    return dict(family="depth_pro", encoder=encoder, embed_dim=c["embed_dim"], depth=c["depth"], num_heads=c["num_heads"],
+                patch_size=16, features=int(features), hook_blocks=[int(b) for b in hook_blocks],
+                input_h=int(image_size), input_w=int(image_size))
+
+
 def resize_pos_embed(pos_embed: np.ndarray, gh: int, gw: int) -> np.ndarray:
     """DINOv2's position-embedding rule for a grid other than the trained square one: bicubic
     resize of the patch part with scale (g + 0.1) / m, cls part untouched.  At the trained grid

@@ -126,3 +126,20 @@ def im2col(x_nchw: np.ndarray, patch: int = 14, kpad: int | None = None) -> np.n
     out = np.zeros((t.shape[0], kpad), dtype=t.dtype)
     out[:, :t.shape[1]] = t
     return out
+
+
+def metric3d_postprocess(depth, src_h: int, src_w: int, size=(616, 1064), focal_px=None):
+    """models/metric3d_v2/onnx2trt.py:148-158 restated with torch, as the script runs it: un-pad with the geometry of
+    tools/evaluate_gt.py:133-139, F.interpolate(mode='bilinear') to the source size, clamp(0, 300); `focal_px` applies
+    canonical * focal * scale / 1000 before the clamp (evaluate_gt.py:162-184)."""
+    import torch
+    scale = min(size[0] / src_h, size[1] / src_w)
+    rh, rw = int(src_h * scale), int(src_w * scale)
+    pad_h, pad_w = size[0] - rh, size[1] - rw
+    pad = (pad_h // 2, pad_h - pad_h // 2, pad_w // 2, pad_w - pad_w // 2)
+    d = torch.as_tensor(depth, dtype=torch.float32).reshape(size)
+    d = d[pad[0]:d.shape[0] - pad[1], pad[2]:d.shape[1] - pad[3]]
+    d = torch.nn.functional.interpolate(d[None, None], (src_h, src_w), mode="bilinear").squeeze()
+    if focal_px is not None:
+        d = d * (focal_px * scale / 1000.0)
+    return torch.clamp(d, 0, 300)

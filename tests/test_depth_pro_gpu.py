@@ -100,3 +100,39 @@ def test_whole_model_against_the_oracle(lib, prec):
     assert m["positive"] == 1536 * 1536
     assert m["abs_rel"] <= GATE[prec]["abs_rel"] and m["max_rel"] <= GATE[prec]["max_rel"], m
     assert abs(got_fov - float(fov)) <= GATE[prec]["fov"]
+
+
+def test_get_engine_builds_depth_pro_from_an_exported_file(lib, tmp_path):
+    """models/depth_pro/onnx2trt.py:99-116 end to end: export file -> get_engine -> allocate_buffers -> do_inference, two
+    outputs in spec.json's order; the result equals the directly constructed engine's bit for bit."""
+    from monocular_depth_estimation_trt_b200 import weights as W
+    sd, x, inv, fov, _ = R.depth_pro_reference()
+    path = str(tmp_path / "depth_pro_1536x1536.mdew")
+    W.save(path, sd, W.describe_depth_pro("vits", features=64, hook_blocks=(8, 5)))
+    results = []
+    for make in (lambda: common.get_engine(path, str(tmp_path / "engine" / "depth_pro_fp16.engine"), "fp16"),
+                 lambda: DPE.DepthProEngine(sd, encoder="vits", features=64, precision="fp16", hook_blocks=(8, 5))):
+        with make() as engine, engine.create_execution_context() as context:
+            inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+            inputs[0].host = x.numpy()
+            outs = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+            results.append((outs[0].copy(), outs[1].copy()))
+            common.free_buffers(inputs, outputs, stream)
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
+    assert (tmp_path / "engine" / "depth_pro_fp16.fingerprint").exists()
+    with pytest.raises(ValueError):
+        common.get_engine(path, "", "fp16", batch=2)
+
+
+@pytest.mark.parametrize("src,focal", [((480, 640), None), ((768, 1024), 886.8), ((1064, 616), None)])
+def test_metric3d_postprocess_matches_the_script(lib, src, focal):
+    """models/metric3d_v2/onnx2trt.py:148-158 (un-pad, bilinear back to the source size, clamp 0..300) on the device."""
+    from oracle import preprocess_np as P
+    from monocular_depth_estimation_trt_b200 import postprocess as PP
+    torch.manual_seed(2)
+    depth = torch.rand(616, 1064) * 400 - 20                          # both ends of the clamp are hit
+    ref = P.metric3d_postprocess(depth, src[0], src[1], focal_px=focal)
+    out = torch.full(src, float("nan"), device="cuda")
+    PP.metric3d_postprocess(depth.cuda().data_ptr(), src[0], src[1], out, focal_px=focal, stream_handle=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((out.cpu() - ref).abs().max()) <= 1e-4               # values up to 300: 3 ulp

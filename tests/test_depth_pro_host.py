@@ -47,3 +47,12 @@ def test_engine_refuses_other_sizes_and_precisions():
         DPE.DepthProEngine({}, precision="fp32")
     with pytest.raises(ValueError):
         DPE.DepthProEngine({}, image_size=1024)
+
+
+def test_depth_pro_description_round_trips(tmp_path):
+    from monocular_depth_estimation_trt_b200 import weights as W
+    meta = W.describe_depth_pro("vitl")
+    assert meta["family"] == "depth_pro" and meta["hook_blocks"] == [11, 5] and meta["input_h"] == 1536 and meta["features"] == 256
+    path = str(tmp_path / "dp.mdew")
+    W.save(path, {"head.4.bias": torch.zeros(1)}, meta)
+    assert W.read_meta(path) == meta
