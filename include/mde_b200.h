@@ -256,6 +256,18 @@ int mde_k_peer_wait(void* d_own_flags, int32_t n_ranks, uint32_t epoch, void* st
  * `padding` tokens at every edge it shares with a neighbour. */
 int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_side, int32_t grid, int32_t padding, int32_t dim,
                         void* d_out, void* stream);
+/* VGGT's attention prologue (the frame / global blocks of the aggregator models/vggt/onnx_export.py:38-52 runs; un-vendored
+ * facebookresearch/vggt `layers/attention.py`, `layers/rope.py`): per-head LayerNorm of q and k over the 64 head features
+ * (weights d_qw/d_qb, d_kw/d_kb: [64] each), then the 2-D rotary embedding: features [0,32) of a head rotate with the token's y
+ * position, [32,64) with x; feature i of a half pairs with i +- 16.  In place on d_qkv [rows][3*heads*64] (q | k | v packed).
+ * d_pos: int32 [rows][2] (y, x) as core/export_compat.py:84-93 builds them (patch positions + 1, special tokens 0), or NULL
+ * for the normalisation alone; d_cos_sin: float32 [max_pos][32] = cos(p * f_j) for j < 16, then sin(p * f_j).
+ * gather_n > 0 (sequence-sharded global attention, SURVEY section 8 e row 3): the finished K row and the V row are also
+ * stored at [row][0, D) and [row][D, 2D) of each d_gather[r] (pitch gather_ld elements; every rank's gathered buffer,
+ * already offset to this rank's first row, cudaIpc-mapped): the K|V all-gather is this kernel's store. */
+int mde_k_qknorm_rope(int32_t precision, void* d_qkv, int64_t rows, int32_t heads, const float* d_qw, const float* d_qb,
+                      const float* d_kw, const float* d_kb, float eps, const int32_t* d_pos, const float* d_cos_sin,
+                      int32_t max_pos, int32_t gather_n, void* const* d_gather, int32_t gather_ld, void* stream);
 /* torch.nn.functional.interpolate(mode="bilinear", align_corners=False) as Depth Pro uses it -- for the input
  * (models/depth_pro/onnx2trt.py:56-74: ToTensor -> Normalize(0.5, 0.5) -> interpolate to 1536 x 1536) and for the crop
  * pyramid inside the model (models/depth_pro/onnx_export.py:15-29).  Writes n_crops windows of out_h x out_w pixels, window

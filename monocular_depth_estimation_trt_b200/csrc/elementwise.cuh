@@ -518,4 +518,84 @@ __global__ void __launch_bounds__(256) depth_pro_post_kernel(const DepthProPostP
   p.depth[static_cast<long long>(oy) * p.src_w + ox] = p.reciprocal ? __fdiv_rn(1.f, v) : v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// VGGT's attention prologue (vggt/layers/attention.py `Attention.forward`, the blocks the aggregator of
+// models/vggt/onnx_export.py:38-52 alternates): per-head LayerNorm of q and k over the 64 head features (`qk_norm`), then
+// the 2-D rotary embedding -- features [0,32) rotate with the token's y position, [32,64) with x; inside each half
+// feature i pairs with i +- 16 and frequency index i % 16 (positions as core/export_compat.py:84-93 builds them).
+// In place on the packed q|k|v rows the QKV GEMM wrote; cos/sin come from a small fp32 table [position][cos 16 | sin 16]
+// built on the host with upstream's formula.  One warp per token row, a lane holds two adjacent features of a head vector.
+// Sequence-sharded global attention: the finished K row and the V row are ALSO stored into every rank's gathered
+// [tokens, 2D] buffer (peer memory over NVLink) -- the all-gather of the exchange step is this kernel's store.
+// ---------------------------------------------------------------------------------------------
+struct QkNormRopeParams {
+  void* qkv;
+  const float *qw, *qb, *kw, *kb;
+  const int* pos;            // [rows][2] (y, x), or NULL: normalisation only
+  const float* cos_sin;      // [max_pos][32]
+  long long rows;
+  int heads, max_pos, gather_n, gather_ld;
+  float eps;
+  void* gather[8];           // each already offset to this rank's first row
+};
+template <typename T>
+__global__ void __launch_bounds__(256) qknorm_rope_kernel(const QkNormRopeParams p) {
+  using Tr = F16Traits<T>;
+  griddep_launch_dependents();
+  griddep_wait();
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  const int D = p.heads * 64;
+  T* base = static_cast<T*>(p.qkv) + row * 3 * D;
+  const int e0 = 2 * lane;
+  const float2 qw = make_float2(__ldg(p.qw + e0), __ldg(p.qw + e0 + 1)), qb = make_float2(__ldg(p.qb + e0), __ldg(p.qb + e0 + 1));
+  const float2 kw = make_float2(__ldg(p.kw + e0), __ldg(p.kw + e0 + 1)), kb = make_float2(__ldg(p.kb + e0), __ldg(p.kb + e0 + 1));
+  float c0 = 1.f, c1 = 1.f, s0 = 0.f, s1 = 0.f;
+  const bool lower = (e0 & 31) < 16;                 // first 16 features of a half pair with +16, the others with -16
+  if (p.pos) {
+    const int pp = min(max(__ldg(p.pos + row * 2 + (lane >> 4)), 0), p.max_pos - 1);
+    const float* t = p.cos_sin + static_cast<long long>(pp) * 32;
+    const int j = e0 & 15;
+    c0 = __ldg(t + j); c1 = __ldg(t + j + 1); s0 = __ldg(t + 16 + j); s1 = __ldg(t + 16 + j + 1);
+  }
+  for (int h = 0; h < p.heads; ++h) {
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t* ptr = reinterpret_cast<uint32_t*>(base + which * D + h * 64 + e0);
+      const float2 v = Tr::unpack2(*ptr);
+      float sum = v.x + v.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / 64.0f);
+      const float dx = v.x - mean, dy = v.y - mean;
+      float sq = dx * dx + dy * dy;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = __frsqrt_rn(sq * (1.0f / 64.0f) + p.eps);
+      const float2 w = which ? kw : qw, b = which ? kb : qb;
+      float y0 = dx * rstd * w.x + b.x, y1 = dy * rstd * w.y + b.y;
+      if (p.pos) {
+        const float o0 = __shfl_xor_sync(0xffffffffu, y0, 8), o1 = __shfl_xor_sync(0xffffffffu, y1, 8);
+        y0 = lower ? y0 * c0 - o0 * s0 : y0 * c0 + o0 * s0;
+        y1 = lower ? y1 * c1 - o1 * s1 : y1 * c1 + o1 * s1;
+      }
+      const uint32_t packed = Tr::pack2(y0, y1);
+      *ptr = packed;
+      if (which == 1) {
+        for (int r = 0; r < p.gather_n; ++r)
+          *reinterpret_cast<uint32_t*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld + h * 64 + e0) = packed;
+      }
+    }
+  }
+  if (p.gather_n > 0) {
+    const uint4* v = reinterpret_cast<const uint4*>(base + 2 * D);
+    for (int i = lane; i < D / 8; i += 32) {
+      const uint4 u = v[i];
+      for (int r = 0; r < p.gather_n; ++r)
+        *reinterpret_cast<uint4*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld + D + i * 8) = u;
+    }
+  }
+}
+
 }  // namespace mde

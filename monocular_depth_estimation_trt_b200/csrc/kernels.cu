@@ -591,6 +591,29 @@ int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_o
   return MDE_OK;
 }
 
+int launch_qknorm_rope(int precision, void* d_qkv, long long rows, int heads, const float* d_qw, const float* d_qb, const float* d_kw,
+                       const float* d_kb, float eps, const int* d_pos, const float* d_cos_sin, int max_pos, int gather_n,
+                       void* const* d_gather, int gather_ld, cudaStream_t s) {
+  if (rows <= 0 || heads <= 0) return fail(MDE_ERR_INVALID, "qknorm_rope: empty problem");
+  if (rows > 8LL * 0x7fffffffLL) return fail(MDE_ERR_INVALID, "qknorm_rope: too many rows");
+  if (d_pos && (!d_cos_sin || max_pos < 1)) return fail(MDE_ERR_INVALID, "qknorm_rope: positions need the cos / sin table");
+  if (gather_n < 0 || gather_n > 8 || (gather_n > 0 && (!d_gather || gather_ld < 2 * heads * 64 || gather_ld % 8)))
+    return fail(MDE_ERR_INVALID, "qknorm_rope: at most 8 gather destinations with a pitch >= 2 * D, a multiple of 8");
+  if (reinterpret_cast<uintptr_t>(d_qkv) & 15) return fail(MDE_ERR_INVALID, "qknorm_rope: rows must be 16-byte aligned");
+  QkNormRopeParams p;
+  memset(&p, 0, sizeof(p));
+  p.qkv = d_qkv; p.qw = d_qw; p.qb = d_qb; p.kw = d_kw; p.kb = d_kb; p.pos = d_pos; p.cos_sin = d_cos_sin; p.rows = rows;
+  p.heads = heads; p.max_pos = max_pos; p.gather_n = gather_n; p.gather_ld = gather_ld; p.eps = eps;
+  for (int r = 0; r < gather_n; ++r) {
+    if (!d_gather[r] || (reinterpret_cast<uintptr_t>(d_gather[r]) & 15)) return fail(MDE_ERR_INVALID, "qknorm_rope: gather destination %d is null or misaligned", r);
+    p.gather[r] = d_gather[r];
+  }
+  const dim3 grid(static_cast<unsigned>((rows + 7) / 8));
+  if (precision == MDE_BF16) MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, 1, p));
+  else MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__half>, grid, dim3(256), 0, s, 1, p));
+  return MDE_OK;
+}
+
 int launch_resize_crops(const void* d_src, int src_u8, int swap_rb, int src_h, int src_w, const mde_crop* crops, int n_crops,
                         int out_h, int out_w, const float* mean3, const float* std3, float* d_out, cudaStream_t s) {
   if (src_h < 1 || src_w < 1 || out_h < 1 || out_w < 1) return fail(MDE_ERR_INVALID, "resize_crops: empty problem");
@@ -909,6 +932,16 @@ int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_sid
   clear_error();
   if (!d_tokens || !d_out) return fail(MDE_ERR_INVALID, "merge_patches: null pointer");
   return launch_merge_patches(precision, d_tokens, per_side, grid, padding, dim, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_qknorm_rope(int32_t precision, void* d_qkv, int64_t rows, int32_t heads, const float* d_qw, const float* d_qb,
+                      const float* d_kw, const float* d_kb, float eps, const int32_t* d_pos, const float* d_cos_sin,
+                      int32_t max_pos, int32_t gather_n, void* const* d_gather, int32_t gather_ld, void* stream) {
+  clear_error();
+  if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
+  if (!d_qkv || !d_qw || !d_qb || !d_kw || !d_kb) return fail(MDE_ERR_INVALID, "qknorm_rope: null pointer");
+  return launch_qknorm_rope(precision, d_qkv, rows, heads, d_qw, d_qb, d_kw, d_kb, eps, d_pos, d_cos_sin, max_pos, gather_n, d_gather,
+                            gather_ld, static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_resize_crops(const void* d_src, int32_t src_is_u8_hwc, int32_t swap_rb, int32_t src_h, int32_t src_w,

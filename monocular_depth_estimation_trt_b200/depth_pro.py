@@ -57,9 +57,9 @@ class _Ops:
         self.launches = 0
 
     def ep(self, bias=None, act=0, x=None, res1=None, res2=None, out=None, out_relu=None, ld_out=0, shuffle=None,
-           head_w=None, head_b=0.0, head_out=None):
+           head_w=None, head_b=0.0, head_out=None, gamma=None, accumulate_x=False):
         e = _lib.Epilogue()
-        e.d_bias, e.act, e.d_x, e.accumulate_x = _p(bias), act, _p(x), 0
+        e.d_bias, e.act, e.d_x, e.accumulate_x, e.d_gamma = _p(bias), act, _p(x), int(accumulate_x), _p(gamma)
         e.d_res1, e.d_res2, e.d_out, e.d_out_relu, e.ld_out = _p(res1), _p(res2), _p(out), _p(out_relu), ld_out
         if shuffle:
             e.shuffle_s, e.shuffle_cout, e.shuffle_h, e.shuffle_w = shuffle
@@ -76,6 +76,25 @@ class _Ops:
 
     def im2col_s2(self, x, h, w, c, out):
         _lib.check(self.lib.mde_k_im2col_s2(self.prec, _p(x), _p(out), 1, h, w, c, self.stream), "mde_k_im2col_s2")
+        self.launches += 1
+
+    def layernorm(self, x, w, b, out, rows, dim, eps=1e-6):
+        _lib.check(self.lib.mde_k_layernorm(self.prec, _p(x), _p(w), _p(b), _p(out), rows, dim, eps, 0, 0, self.stream), "mde_k_layernorm")
+        self.launches += 1
+
+    def attention(self, qkv, out, batch, ntok, heads):
+        _lib.check(self.lib.mde_k_attention(self.prec, _p(qkv), _p(out), batch, ntok, heads, self.stream), "mde_k_attention")
+        self.launches += 1
+
+    def attention_kv(self, q, ldq, kv, ldkv, k_col0, v_col0, out, batch, ntok_q, ntok_kv, heads):
+        _lib.check(self.lib.mde_k_attention_kv(self.prec, _p(q), ldq, _p(kv), ldkv, k_col0, v_col0, _p(out), batch, ntok_q, ntok_kv, heads,
+                                               self.stream), "mde_k_attention_kv")
+        self.launches += 1
+
+    def qknorm_rope(self, qkv, rows, heads, qw, qb, kw, kb, eps, pos, cos_sin, max_pos, gather=(), gather_ld=0):
+        arr = (C.c_void_p * max(1, len(gather)))(*[C.c_void_p(int(g)) for g in gather])
+        _lib.check(self.lib.mde_k_qknorm_rope(self.prec, _p(qkv), rows, heads, _p(qw), _p(qb), _p(kw), _p(kb), eps, _p(pos), _p(cos_sin),
+                                              max_pos, len(gather), arr, gather_ld, self.stream), "mde_k_qknorm_rope")
         self.launches += 1
 
     def merge(self, src, per_side, pad, dim, out):

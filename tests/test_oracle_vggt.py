@@ -1,0 +1,84 @@
+"""Anchors for oracle/vggt_torch.py (parity unpinned against VGGT itself: see its header).  What can be checked:
+the position table against the reference's own re-implementation (core/export_compat.py:84-93, when the checkout is
+mounted), the rotary embedding against its complex-number form, the block's attention against torch's SDPA, and the
+product-side tables (monocular_depth_estimation_trt_b200/vggt.py) against the oracle's."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vggt_torch as V
+
+REF = "/root/reference/core/export_compat.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not mounted")
+def test_patch_positions_match_the_reference_export_patch():
+    spec = importlib.util.spec_from_file_location("ref_export_compat", REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class PositionGetter:                       # the two members the reference's patch touches
+        def __init__(self):
+            self.position_cache = {}
+
+    with mod.no_cartesian_prod(PositionGetter):
+        ref = PositionGetter()(2, 37, 37, torch.device("cpu"))          # [2, 1369, 2] rows of (y, x)
+    ours = V.positions(37, 37)
+    assert ours.shape == (5 + 1369, 2) and int(ours[:5].abs().max()) == 0
+    assert torch.equal(ours[5:] - 1, ref[0]) and torch.equal(ref[0], ref[1])
+
+
+def test_rope_is_a_rotation_by_position_times_frequency():
+    torch.manual_seed(0)
+    t = torch.randn(2, 3, 7, 64)
+    pos = torch.tensor([[0, 0], [1, 1], [1, 5], [2, 3], [7, 1], [4, 4], [9, 2]])
+    out = V.rope_2d(t, pos)
+    assert torch.equal(out[:, :, 0], t[:, :, 0])                         # position (0, 0): identity (special tokens)
+    f = 1.0 / (100.0 ** (torch.arange(16).float() / 16))                # frequency j of a 32-feature half
+    for half, axis in ((slice(0, 32), 0), (slice(32, 64), 1)):
+        x = t[..., half]
+        z = torch.complex(x[..., :16], x[..., 16:])                     # feature i pairs with i + 16
+        rot = z * torch.polar(torch.ones(7, 16), pos[:, axis, None].float() * f)
+        assert torch.allclose(out[..., half], torch.cat([rot.real, rot.imag], dim=-1), atol=1e-5)
+    assert torch.allclose(out.norm(dim=-1), t.norm(dim=-1), rtol=1e-5)  # rotations preserve length
+
+
+def test_block_attention_agrees_with_sdpa_and_global_mixes_frames():
+    torch.manual_seed(1)
+    D, H, S, gh, gw = 128, 2, 3, 2, 3
+    sd = V.init_aggregator(D, 1, seed=3)
+    N = 5 + gh * gw
+    tok = torch.randn(S, N, D)
+    pos = V.positions(gh, gw)
+    pre = "aggregator.frame_blocks.0."
+    out = V.block(sd, pre, tok, pos, H)
+    # the same block with torch's fused attention
+    y = F.layer_norm(tok, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
+    qkv = F.linear(y, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"]).reshape(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q = V.rope_2d(F.layer_norm(qkv[0], (64,), sd[pre + "attn.q_norm.weight"], sd[pre + "attn.q_norm.bias"]), pos)
+    k = V.rope_2d(F.layer_norm(qkv[1], (64,), sd[pre + "attn.k_norm.weight"], sd[pre + "attn.k_norm.bias"]), pos)
+    a = F.scaled_dot_product_attention(q, k, qkv[2]).transpose(1, 2).reshape(S, N, D)
+    t1 = tok + sd[pre + "ls1.gamma"] * F.linear(a, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+    y = F.layer_norm(t1, (D,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-6)
+    t2 = t1 + sd[pre + "ls2.gamma"] * F.linear(F.gelu(F.linear(y, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
+                                                sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    assert torch.allclose(out, t2, atol=2e-5)
+    # frame blocks keep frames independent, global blocks do not
+    layers = V.aggregate(sd, tok, gh, gw, H, 1)
+    tok2 = tok.clone(); tok2[2] += 1.0
+    layers2 = V.aggregate(sd, tok2, gh, gw, H, 1)
+    assert layers[0].shape == (S, N, 2 * D)
+    assert torch.equal(layers[0][:2, :, :D], layers2[0][:2, :, :D])      # frame halves of frames 0, 1 unchanged
+    assert not torch.allclose(layers[0][:2, :, D:], layers2[0][:2, :, D:])
+
+
+def test_product_tables_equal_the_oracle_tables():
+    from monocular_depth_estimation_trt_b200 import vggt as P
+    assert torch.equal(torch.from_numpy(P.token_positions(37, 37)).long(), V.positions(37, 37))
+    cos, sin = V.rope_tables(39)
+    t = P.cos_sin_table(39)
+    assert torch.equal(t[:, :16], cos[:, :16]) and torch.equal(t[:, 16:], sin[:, :16]) and torch.equal(cos[:, 16:], cos[:, :16])

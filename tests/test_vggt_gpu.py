@@ -1,0 +1,83 @@
+"""VGGT's aggregator blocks on a B200 against oracle/vggt_torch.py: the qk-norm + 2-D RoPE kernel on its own (fp32
+reference on the same 16-bit inputs), then frame / global blocks and the alternating stack at the real 37 x 37 token grid.
+Budgets as for the Depth Anything residual stream (tests/test_engine_gpu.py INTER), per block pair."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from monocular_depth_estimation_trt_b200 import vggt as P
+from oracle import vggt_torch as V
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+ULP = {"fp16": 2 ** -10, "bf16": 2 ** -7}
+INTER = {"fp16": 1.2e-3, "bf16": 9e-3}
+
+
+def rms_rel(got, ref):
+    got, ref = got.double(), ref.double()
+    return float(((got - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt())
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("heads,with_pos", [(6, True), (16, True), (2, False)])
+def test_qknorm_rope_kernel(lib, prec, heads, with_pos):
+    from monocular_depth_estimation_trt_b200.depth_pro import _Ops
+    import ctypes as C
+    torch.manual_seed(heads)
+    gh, gw = 5, 9
+    pos = V.positions(gh, gw)
+    rows, D = 3 * pos.shape[0] + 1, heads * 64                          # a ragged last CTA
+    posr = torch.cat([pos.repeat(3, 1), pos[-1:]])
+    qkv = (torch.randn(rows, 3 * D) * 2 + 0.3).to(DT[prec])
+    w = [1 + 0.1 * torch.randn(64), 0.1 * torch.randn(64), 1 + 0.1 * torch.randn(64), 0.1 * torch.randn(64)]
+    # fp32 reference on the same 16-bit inputs
+    r = qkv.float().reshape(rows, 3, heads, 64)
+    q = F.layer_norm(r[:, 0], (64,), w[0], w[1], 1e-5).permute(1, 0, 2)[None]
+    k = F.layer_norm(r[:, 1], (64,), w[2], w[3], 1e-5).permute(1, 0, 2)[None]
+    if with_pos:
+        q, k = V.rope_2d(q, posr), V.rope_2d(k, posr)
+    ref = torch.stack([q[0].permute(1, 0, 2), k[0].permute(1, 0, 2), r[:, 2]], dim=1).reshape(rows, 3 * D)
+    ops = _Ops(prec)
+    ops.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d = qkv.cuda()
+    gathered = torch.full((rows + 2, 2 * D + 8), 7.0, dtype=DT[prec], device="cuda")
+    table = P.cos_sin_table(int(pos.max()) + 1).cuda()
+    ops.qknorm_rope(d, rows, heads, *[t.cuda() for t in w], 1e-5, posr.int().cuda() if with_pos else None, table if with_pos else None,
+                    table.shape[0], gather=[gathered.data_ptr()], gather_ld=2 * D + 8)
+    torch.cuda.synchronize()
+    got = d.float().cpu()
+    assert torch.equal(got[:, 2 * D:], qkv.float()[:, 2 * D:])           # V untouched
+    assert float((got - ref).abs().max()) <= 1.01 * ULP[prec] * float(ref.abs().max())
+    g = gathered.cpu()
+    assert torch.equal(g[:rows, :2 * D], d.cpu()[:, D:]) and bool((g[rows:] == 7.0).all()) and bool((g[:, 2 * D:] == 7.0).all())
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_aggregator_against_the_oracle(lib, prec):
+    """Two layers of (frame block, global block), 3 frames of 5 + 37*37 tokens, ViT-S width: the taps [frame | global] of
+    both layers against the fp32 oracle."""
+    torch.manual_seed(5)
+    D, H, S, depth, gh, gw = 384, 6, 3, 2, 37, 37
+    sd = V.init_aggregator(D, depth, seed=4)
+    N = 5 + gh * gw
+    tok = torch.randn(S, N, D)
+    ref = V.aggregate(sd, tok, gh, gw, H, depth)
+    agg = P.Aggregator(sd, D, depth, H, gh, gw, frames_total=S, precision=prec, taps=(0, 1))
+    x = tok.cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    agg.forward(x.data_ptr(), stream)
+    torch.cuda.synchronize()
+    first = {t: agg.tap_out[t].clone() for t in (0, 1)}
+    agg.forward(x.data_ptr(), stream)
+    torch.cuda.synchronize()
+    for t in (0, 1):
+        got = agg.tap_out[t].cpu().reshape(S, N, 2 * D)
+        assert torch.equal(agg.tap_out[t], first[t])                     # reproducible bit for bit
+        e_frame, e_global = rms_rel(got[..., :D], ref[t][..., :D]), rms_rel(got[..., D:], ref[t][..., D:])
+        print(prec, "layer", t, "frame", e_frame, "global", e_global)
+        assert e_frame < INTER[prec] * (t + 1) and e_global < INTER[prec] * (t + 1)
+    assert agg.ops.launches == depth * 2 * 8
+    agg.close()
