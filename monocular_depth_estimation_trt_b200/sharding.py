@@ -67,6 +67,14 @@ def make_crops(image):
     return torch.stack(out)
 
 
+def torch_stream(stream_handle):
+    """The torch stream object of a raw CUDA stream handle, for ordering NCCL collectives on the caller's stream.  Handle 0
+    is the legacy default stream: torch.cuda.ExternalStream(0) would silently create a NEW pool stream instead."""
+    import torch
+    h = int(stream_handle)
+    return torch.cuda.default_stream() if h == 0 else torch.cuda.ExternalStream(h)
+
+
 def shard_bounds(n_items: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
     """Equal-size shards: every rank owns `per_rank = ceil(n / world)` slots so that one static engine serves all of
     them; the trailing slots of the last rank(s) are padding.  -> (per_rank, [(first_item, n_real_items)] per rank)."""
@@ -223,7 +231,7 @@ class ShardedPatchEncoder:
             g = self.buffers.view()
             # per tap: the ranks' [per_rank, T, D] slabs are contiguous in the gathered layout.  The collective is ordered
             # on the caller's stream (behind the trunk, ahead of whatever the caller enqueues next).
-            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_handle))):
+            with torch.cuda.stream(torch_stream(stream_handle)):
                 for i in range(4):
                     dist.all_gather_into_tensor(g[i], self.local[i])
         elif self.mode == "nccl":

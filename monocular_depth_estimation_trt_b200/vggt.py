@@ -121,7 +121,7 @@ class Aggregator:
             else:
                 import torch
                 import torch.distributed as dist
-                with torch.cuda.stream(torch.cuda.ExternalStream(sh)):
+                with torch.cuda.stream(S.torch_stream(sh)):
                     dist.all_gather_into_tensor(self.kv.view(), self.qkv[:, D:].contiguous())
             o.attention_kv(self.qkv, 3 * D, self.kv.own, 2 * D, 0, D, self.att, 1, rows, self.rows_total, self.heads)
             if self.sync is not None:
