@@ -250,6 +250,12 @@ int mde_k_upconv_head(int32_t precision, const void* d_z, int32_t ldz, int32_t b
  * a peer still reads (a second flag array used as acknowledgement, as monocular_depth_estimation_trt_b200/sharding.py does). */
 int mde_k_peer_signal(void* const* d_flags_of_every_rank, int32_t n_ranks, int32_t rank, uint32_t epoch, void* stream);
 int mde_k_peer_wait(void* d_own_flags, int32_t n_ranks, uint32_t epoch, void* stream);
+/* The same hand-shake with the epoch in device memory (one uint32, zero-initialised, private to this rank), so that the launch
+ * arguments are constant and a sharded forward can be captured into a CUDA graph: signal publishes *d_counter + advance
+ * (storing it back when advance != 0), wait blocks until every slot of our own array has reached *d_counter. */
+int mde_k_peer_signal_counter(void* const* d_flags_of_every_rank, int32_t n_ranks, int32_t rank, uint32_t* d_counter, int32_t advance,
+                              void* stream);
+int mde_k_peer_wait_counter(void* d_own_flags, int32_t n_ranks, const uint32_t* d_counter, void* stream);
 /* Depth Pro's patch merge (depth_pro/network/encoder.py `merge`; called from the model models/depth_pro/onnx_export.py:15-29
  * builds): per_side x per_side crops of grid x grid tokens, d_tokens [per_side^2][grid^2][dim] 16-bit (a slice of the
  * trunk-only engine's output) -> NHWC map [S][S][dim], S = per_side*grid - 2*padding*(per_side-1); each crop loses

@@ -363,6 +363,36 @@ __global__ void peer_wait_kernel(const PeerFlagsParams p) {
   __threadfence_system();
 }
 
+// The same hand-shake with the epoch kept in device memory, so that the launch arguments never change and a whole sharded
+// forward can be captured into a CUDA graph and replayed: `signal` publishes *counter + advance (and stores it back when it
+// advanced), `wait` blocks until every slot has reached *counter.
+struct PeerCounterParams {
+  unsigned int* flags[8];
+  unsigned int* counter;
+  int n_ranks, rank, advance;
+};
+__global__ void peer_signal_counter_kernel(const PeerCounterParams p) {
+  const int r = threadIdx.x;
+  const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(p.counter) + static_cast<unsigned int>(p.advance);
+  __syncwarp();
+  if (r == 0 && p.advance) *p.counter = epoch;
+  if (r >= p.n_ranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[r] + p.rank), "r"(epoch) : "memory");
+}
+__global__ void peer_wait_counter_kernel(const PeerCounterParams p) {
+  const int r = threadIdx.x;
+  if (r >= p.n_ranks) return;
+  const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(p.counter);
+  const long long t0 = clock64();
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags[0] + r) : "memory");
+    if (clock64() - t0 > 20LL * MDE_WATCHDOG_CYCLES) __trap();
+  } while (static_cast<int>(v - epoch) < 0);
+  __threadfence_system();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Depth Pro's `merge`: per_side x per_side crops of grid x grid tokens each (row-major crops, [crop][token][D] 16-bit,
 // the layout the trunk-only engine writes) -> one NHWC feature map [S][S][D], S = per_side*grid - 2*pad*(per_side-1):

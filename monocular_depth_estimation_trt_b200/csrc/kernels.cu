@@ -927,6 +927,33 @@ int mde_k_peer_wait(void* d_own_flags, int32_t n_ranks, uint32_t epoch, void* st
   return MDE_OK;
 }
 
+int mde_k_peer_signal_counter(void* const* d_flags_of_every_rank, int32_t n_ranks, int32_t rank, uint32_t* d_counter, int32_t advance,
+                              void* stream) {
+  clear_error();
+  if (!d_flags_of_every_rank || !d_counter || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks)
+    return fail(MDE_ERR_INVALID, "peer_signal_counter: 1..8 ranks, 0 <= rank < n_ranks, a counter");
+  PeerCounterParams p;
+  for (int r = 0; r < 8; ++r) p.flags[r] = r < n_ranks ? static_cast<unsigned int*>(d_flags_of_every_rank[r]) : nullptr;
+  for (int r = 0; r < n_ranks; ++r)
+    if (!p.flags[r]) return fail(MDE_ERR_INVALID, "peer_signal_counter: flag array of rank %d is null", r);
+  p.counter = d_counter; p.n_ranks = n_ranks; p.rank = rank; p.advance = advance ? 1 : 0;
+  peer_signal_counter_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+int mde_k_peer_wait_counter(void* d_own_flags, int32_t n_ranks, const uint32_t* d_counter, void* stream) {
+  clear_error();
+  if (!d_own_flags || !d_counter || n_ranks < 1 || n_ranks > 8) return fail(MDE_ERR_INVALID, "peer_wait_counter: 1..8 ranks, a flag array and a counter");
+  PeerCounterParams p;
+  for (int r = 0; r < 8; ++r) p.flags[r] = nullptr;
+  p.flags[0] = static_cast<unsigned int*>(d_own_flags);
+  p.counter = const_cast<uint32_t*>(d_counter); p.n_ranks = n_ranks; p.rank = 0; p.advance = 0;
+  peer_wait_counter_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int mde_k_merge_patches(int32_t precision, const void* d_tokens, int32_t per_side, int32_t grid, int32_t padding, int32_t dim,
                         void* d_out, void* stream) {
   clear_error();

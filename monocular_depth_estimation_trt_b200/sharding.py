@@ -157,35 +157,38 @@ class PeerSync:
         self.world, self.rank = world, rank
         self.ready = PeerBuffers(world, rank, (64,), "fp16")      # 128 zeroed bytes: room for 8 uint32 flags
         self.acks = PeerBuffers(world, rank, (64,), "fp16")
-        self.epoch = 0
+        # the round number lives in device memory (one uint32 of a private buffer): launch arguments never change, so a
+        # forward that uses the hand-shake can be captured into a CUDA graph and replayed
+        self.counter = PeerBuffers(1, 0, (64,), "fp16")
 
-    def _signal(self, bufs, epoch, stream_handle):
+    def _signal(self, bufs, advance, stream_handle):
         import ctypes as C
         arr = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in bufs.ptrs])
-        self._check(self._lib.mde_k_peer_signal(arr, self.world, self.rank, epoch, C.c_void_p(int(stream_handle))), "mde_k_peer_signal")
+        self._check(self._lib.mde_k_peer_signal_counter(arr, self.world, self.rank, C.c_void_p(self.counter.own), int(advance),
+                                                        C.c_void_p(int(stream_handle))), "mde_k_peer_signal_counter")
 
-    def _wait(self, bufs, epoch, stream_handle):
+    def _wait(self, bufs, stream_handle):
         import ctypes as C
-        self._check(self._lib.mde_k_peer_wait(C.c_void_p(bufs.own), self.world, epoch, C.c_void_p(int(stream_handle))), "mde_k_peer_wait")
+        self._check(self._lib.mde_k_peer_wait_counter(C.c_void_p(bufs.own), self.world, C.c_void_p(self.counter.own),
+                                                      C.c_void_p(int(stream_handle))), "mde_k_peer_wait_counter")
 
     def wait_acks(self, stream_handle):
-        """Every peer has finished reading the previous round (a no-op in the first round)."""
-        if self.epoch > 0:
-            self._wait(self.acks, self.epoch, stream_handle)
+        """Every peer has finished reading the previous round (trivially true in the first round: the counter is 0)."""
+        self._wait(self.acks, stream_handle)
 
     def signal_ready(self, stream_handle):
-        self.epoch += 1
-        self._signal(self.ready, self.epoch, stream_handle)
+        self._signal(self.ready, 1, stream_handle)
 
     def wait_ready(self, stream_handle):
-        self._wait(self.ready, self.epoch, stream_handle)
+        self._wait(self.ready, stream_handle)
 
     def signal_acks(self, stream_handle):
-        self._signal(self.acks, self.epoch, stream_handle)
+        self._signal(self.acks, 0, stream_handle)
 
     def close(self):
         self.ready.close()
         self.acks.close()
+        self.counter.close()
 
 
 class GatherBuffers(PeerBuffers):

@@ -154,7 +154,39 @@ class Aggregator:
             if i in self.tap_out:
                 self._tap(i, 1, sh)
 
+    def capture(self, tokens_ptr: int, stream_handle) -> None:
+        """Record one forward (every launch, copy and flag hand-shake; ~430 nodes at 24 + 24 blocks) into a CUDA graph on
+        `stream_handle`; `replay` then costs one launch on the host.  The hand-shake keeps its round number in device memory, so
+        the captured arguments stay valid for every replay.  Not for gather="nccl" on more than one rank."""
+        from .common_runtime import cuda_call, cudart
+        if self.world > 1 and self.sync is None:
+            raise RuntimeError("[MDET] the NCCL baseline is not captured; use gather='fused'")
+        sh = int(stream_handle)
+        if sh == 0:
+            raise ValueError("[MDET] capture needs a non-default stream")
+        self.release_graph()
+        cuda_call(cudart.cudaStreamBeginCapture(sh, cudart.cudaStreamCaptureMode.cudaStreamCaptureModeThreadLocal))
+        try:
+            self.forward(tokens_ptr, sh)
+        finally:
+            graph = cuda_call(cudart.cudaStreamEndCapture(sh))
+        self._graph_exec = cuda_call(cudart.cudaGraphInstantiate(graph, 0))
+        cuda_call(cudart.cudaGraphDestroy(graph))
+
+    def replay(self, stream_handle) -> None:
+        from .common_runtime import cuda_call, cudart
+        if getattr(self, "_graph_exec", None) is None:
+            raise RuntimeError("[MDET] replay before capture")
+        cuda_call(cudart.cudaGraphLaunch(self._graph_exec, int(stream_handle)))
+
+    def release_graph(self) -> None:
+        from .common_runtime import cudart
+        if getattr(self, "_graph_exec", None) is not None:
+            cudart.cudaGraphExecDestroy(self._graph_exec)
+        self._graph_exec = None
+
     def close(self) -> None:
+        self.release_graph()
         if self.sync is not None:
             self.sync.close()
             self.sync = None

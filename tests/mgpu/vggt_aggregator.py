@@ -28,6 +28,7 @@ ap.add_argument("--dim", type=int, default=1024); ap.add_argument("--depth", typ
 ap.add_argument("--frames", type=int, default=16); ap.add_argument("--grid", type=int, default=37)
 ap.add_argument("--precision", default="bf16"); ap.add_argument("--gather", default="fused")
 ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--graph", action="store_true", help="capture the forward into a CUDA graph and time replays")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -44,9 +45,20 @@ taps = tuple(range(a.depth)) if a.check else (4, 11, 17, 23)
 agg = P.Aggregator(sd, a.dim, a.depth, H, a.grid, a.grid, frames_total=a.frames, precision=a.precision, world=world, rank=rank,
                    gather=a.gather, taps=[t for t in taps if t < a.depth], device=local)
 x = tok[rank * per:(rank + 1) * per].contiguous().cuda()
-stream = torch.cuda.current_stream().cuda_stream
+ap_stream = torch.cuda.Stream()
+torch.cuda.set_stream(ap_stream)
+stream = ap_stream.cuda_stream
 for _ in range(2):
     agg.forward(x.data_ptr(), stream)
+torch.cuda.synchronize()
+graphed = a.graph and (world == 1 or a.gather == "fused")
+if graphed:
+    agg.capture(x.data_ptr(), stream)            # the whole sharded forward, hand-shakes included, as one graph launch
+    run = lambda: agg.replay(stream)
+else:
+    run = lambda: agg.forward(x.data_ptr(), stream)
+for _ in range(2):
+    run()
 torch.cuda.synchronize()
 ts = []
 for _ in range(a.reps):
@@ -54,7 +66,7 @@ for _ in range(a.reps):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); agg.forward(x.data_ptr(), stream); e1.record(); torch.cuda.synchronize()
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -62,7 +74,7 @@ for _ in range(a.reps):
 flops = a.depth * 2 * (24 * a.frames * N * a.dim ** 2) + a.depth * 4 * a.dim * (a.frames * N * N + (a.frames * N) ** 2)
 ms = sorted(ts)[len(ts) // 2]
 result = {"model": "vggt aggregator", "dim": a.dim, "depth": a.depth, "frames": a.frames, "tokens_per_frame": N, "precision": a.precision,
-          "world": world, "gather": a.gather, "ms_per_forward": ms, "launches": agg.ops.launches,
+          "world": world, "gather": a.gather, "cuda_graph": bool(graphed), "ms_per_forward": ms, "launches": agg.ops.launches,
           "algorithmic_tflop": flops / 1e12, "tflops_per_gpu": flops / 1e12 / (ms / 1e3) / world,
           "kv_bytes_gathered_per_global_layer": a.frames * N * 2 * a.dim * 2}
 ok = True

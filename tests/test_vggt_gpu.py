@@ -81,3 +81,26 @@ def test_aggregator_against_the_oracle(lib, prec):
         assert e_frame < INTER[prec] * (t + 1) and e_global < INTER[prec] * (t + 1)
     assert agg.ops.launches == depth * 2 * 8
     agg.close()
+
+
+def test_aggregator_graph_replay_equals_eager(lib):
+    """The forward captured into a CUDA graph (one host launch per forward) gives the eager launches' result bit for bit."""
+    torch.manual_seed(6)
+    D, H, S, depth, g = 384, 6, 2, 2, 9
+    sd = V.init_aggregator(D, depth, seed=9)
+    tok = torch.randn(S, 5 + g * g, D).cuda()
+    agg = P.Aggregator(sd, D, depth, H, g, g, frames_total=S, precision="fp16", taps=(1,))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        agg.forward(tok.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        eager = agg.tap_out[1].clone()
+        agg.capture(tok.data_ptr(), st.cuda_stream)
+        agg.tap_out[1].zero_()
+        for _ in range(2):
+            agg.replay(st.cuda_stream)
+        st.synchronize()
+        assert torch.equal(agg.tap_out[1], eager)
+    with pytest.raises(ValueError):
+        agg.capture(tok.data_ptr(), 0)
+    agg.close()
