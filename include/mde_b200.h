@@ -220,6 +220,10 @@ int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const vo
  * (csrc/attention_tc2q.cuh). */
 int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                        void* stream);
+/* The same op with the softmax of a query tile spread over eight warps, two per TMEM lane quarter, each taking half of the
+ * score columns (csrc/attention_tc8w.cuh).  The engine launches it when MDE_ATTN_KV=8 is set. */
+int mde_k_attention_8w(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       void* stream);
 /* The same op with 64-key tiles and four CTAs per SM (csrc/attention_tc64.cuh): the measured alternative to the
  * default kernel, kept for comparison; the engine launches it only when MDE_ATTN_KV=64 is set. */
 int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

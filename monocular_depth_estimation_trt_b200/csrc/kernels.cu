@@ -13,6 +13,7 @@
 #include "attention_tc.cuh"
 #include "attention_tc64.cuh"
 #include "attention_tc2q.cuh"
+#include "attention_tc8w.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -493,12 +494,42 @@ static int attn_kv() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MDE_ATTN_KV");
-    v = (e && atoi(e) == 64) ? 64 : ((e && atoi(e) == 256) ? 256 : 128);
+    v = (e && atoi(e) == 64) ? 64 : ((e && atoi(e) == 256) ? 256 : ((e && atoi(e) == 8) ? 8 : 128));
   }
   return v;
 }
+template <typename T, int kPoly>
+static int launch_attention_tc8w_t(const AttnOp& op, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = attention_tc8w_kernel<T, kPoly>;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kA8SmemBytes));
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("MDE_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kA8Threads, kA8SmemBytes);
+      fprintf(stderr, "[MDET] attention_tc8w: %d CTAs/SM (smem %d B, %d threads)\n", nb, kA8SmemBytes, kA8Threads);
+    }
+    attr_set = true;
+  }
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
+  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kA8Threads), kA8SmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
+  return MDE_OK;
+}
 template <typename T>
 static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s, int kv = 0) {
+  if ((kv ? kv : attn_kv()) == 8) {          // eight softmax warps per query tile (attention_tc8w.cuh)
+    switch (attn_poly()) {
+      case 0: return launch_attention_tc8w_t<T, 0>(op, s);
+      case 2: return launch_attention_tc8w_t<T, 2>(op, s);
+      case 4: return launch_attention_tc8w_t<T, 4>(op, s);
+      default: return launch_attention_tc8w_t<T, 3>(op, s);
+    }
+  }
   if ((kv ? kv : attn_kv()) == 256) {        // two query tiles per CTA, explicit ping-pong (attention_tc2q.cuh)
     switch (attn_poly()) {
       case 0: return launch_attention_tc2q_t<T, 0>(op, s);
@@ -867,6 +898,14 @@ int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
   return launch_attention_op(op, static_cast<cudaStream_t>(stream), 256);
+}
+
+int mde_k_attention_8w(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       void* stream) {
+  clear_error();
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 8);
 }
 
 int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
