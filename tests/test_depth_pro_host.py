@@ -56,3 +56,31 @@ def test_depth_pro_description_round_trips(tmp_path):
     path = str(tmp_path / "dp.mdew")
     W.save(path, {"head.4.bias": torch.zeros(1)}, meta)
     assert W.read_meta(path) == meta
+
+
+def test_vggt_aggregator_refuses_bad_configurations():
+    from monocular_depth_estimation_trt_b200 import vggt as V
+    with pytest.raises(ValueError):
+        V.Aggregator({}, 1024, 1, 16, 37, 37, frames_total=16, precision="fp32")
+    with pytest.raises(ValueError):
+        V.Aggregator({}, 1000, 1, 16, 37, 37, frames_total=16)          # head dimension must be 64
+    with pytest.raises(ValueError):
+        V.Aggregator({}, 1024, 1, 16, 37, 37, frames_total=15, world=2)
+    with pytest.raises(ValueError):
+        V.Aggregator({}, 1024, 1, 16, 37, 37, frames_total=16, gather="ring")
+
+
+def test_metric3d_geometry_matches_the_reference_helper():
+    """tools/evaluate_gt.py:133-139 `_metric3d_geometry`, restated; checked live when the checkout is mounted."""
+    import importlib.util, os
+    from monocular_depth_estimation_trt_b200 import postprocess as PP
+    cases = [(480, 640), (768, 1024), (1064, 616), (2268, 3024), (500, 500)]
+    assert PP.metric3d_geometry(480, 640) == (616 / 480, (616, 821), (0, 0, 121, 122))
+    ref = "/root/reference/tools/evaluate_gt.py"
+    if os.path.exists(ref):
+        src = open(ref).read()
+        start = src.index("def _metric3d_geometry"); end = src.index("\ndef ", start + 10)
+        ns = {"METRIC3D_SIZE": (616, 1064)}
+        exec(compile(src[start:end], ref, "exec"), ns)                  # the helper alone (the module imports cv2 / tensorrt tooling)
+        for h, w in cases:
+            assert PP.metric3d_geometry(h, w) == ns["_metric3d_geometry"](h, w)
