@@ -219,7 +219,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (ch < nch && (kFull || ch * 32 + i < nvalid)) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));
+          if (ch < nch && (kFull || ch < nch - 1 || ch * 32 + i < nvalid)) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[ch][i]));   // only the last live chunk can be ragged
       const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       // ---- lazy rescale: only when the maximum grew by more than 2^8 (always on the first tile)
       const bool grow = (mx - m_ref) * sl > kAtcRescaleThreshold;
@@ -242,7 +242,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             p0 = fast_exp2(x0);
             p1 = fast_exp2(x1);
           }
-          if (!kFull) {
+          if (!kFull && ch == nch - 1) {
             if (ch * 32 + i >= nvalid) p0 = 0.f;
             if (ch * 32 + i + 1 >= nvalid) p1 = 0.f;
           }
