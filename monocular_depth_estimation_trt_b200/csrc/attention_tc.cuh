@@ -284,12 +284,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       mbar_arrive(p_ready);
     };
 
-    for (int j = 0; j < nkv; ++j) {
+    using cuda::std::integral_constant;
+    const int n_full = p.ntok / 128;             // key tiles without a ragged end: no per-tile test inside the hot loop
+    for (int j = 0; j < n_full; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      using cuda::std::integral_constant;
-      if (j * 128 + 128 <= p.ntok) tile(integral_constant<int, 4>{}, cuda::std::true_type{}, j);
-      else if (last_chunks == 1) tile(integral_constant<int, 1>{}, cuda::std::false_type{}, j);
+      tile(integral_constant<int, 4>{}, cuda::std::true_type{}, j);
+    }
+    if (n_full < nkv) {
+      const int j = n_full;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (last_chunks == 1) tile(integral_constant<int, 1>{}, cuda::std::false_type{}, j);
       else if (last_chunks == 2) tile(integral_constant<int, 2>{}, cuda::std::false_type{}, j);
       else if (last_chunks == 3) tile(integral_constant<int, 3>{}, cuda::std::false_type{}, j);
       else tile(integral_constant<int, 4>{}, cuda::std::false_type{}, j);
