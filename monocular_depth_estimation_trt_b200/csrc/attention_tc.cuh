@@ -114,6 +114,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     }
     mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_ready, 128); mbar_init(o_full, 1);
     fence_mbar_init();
+    // the first loads go out before the TMEM allocation, the CTA-wide sync and the register re-partition: their latency
+    // (q|k|v was written by the previous kernel, mostly to HBM) is the longest item of the CTA's prologue
+    griddep_wait();
+    mbar_arrive_expect_tx(q_full, kAtcQBytes);
+    tma_load_2d(sQ, &map_qkv, q_full, head * 64, row_base + q0);
+    mbar_arrive_expect_tx(&k_full[0], kAtcQBytes);
+    tma_load_2d(sK, &map_kv, &k_full[0], p.k_col0 + head * 64, kv_base);
+    mbar_arrive_expect_tx(&v_full[0], kAtcQBytes);
+    tma_load_2d(sV, &map_kv, &v_full[0], p.v_col0 + head * 64, kv_base);
   }
   if (warp == 5) {
     tmem_alloc(tmem_slot, kAtcTmemCols);
@@ -132,9 +141,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     // ===================================================== TMA producer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kAtcQBytes);
-      tma_load_2d(sQ, &map_qkv, q_full, head * 64, row_base + q0);
-      for (int j = 0; j < nkv; ++j) {
+      for (int j = 1; j < nkv; ++j) {              // Q and key tile 0 were requested in the prologue
         const int st = j % kAtcStages;
         const uint32_t ph = (j / kAtcStages) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
