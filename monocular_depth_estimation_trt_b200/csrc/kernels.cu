@@ -290,10 +290,12 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
 }
 
 // Launch with programmatic stream serialisation (see ptx.cuh `griddep_wait`): the kernel may be scheduled while its
-// predecessor drains.  Only for kernels that call griddep_wait() before their first dependent access.  MDE_NO_PDL=1: off.
+// predecessor drains.  Only for kernels that call griddep_wait() before their first dependent access.  Opt-in (MDE_PDL=1):
+// it takes 3.4 % off the batch-1 latency (3.49 -> 3.37 ms), but Nsight Compute 2025.2 does not list or profile kernels
+// launched with this attribute, and a path that the profiler cannot see is not the default.
 static bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) v = getenv("MDE_NO_PDL") ? 0 : 1;
+  if (v < 0) { const char* e = getenv("MDE_PDL"); v = (e && atoi(e) != 0) ? 1 : 0; }
   return v != 0;
 }
 template <typename... KArgs, typename... Args>
@@ -482,8 +484,8 @@ static int attn_poly() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MDE_ATTN_POLY");
-    v = e ? atoi(e) : 3;
-    if (v != 0 && v != 2 && v != 3 && v != 4) v = 3;
+    v = e ? atoi(e) : 2;     // 2 of every 8 element pairs on the FMA pipe: the measured optimum (tools/attn_probe.py, MDE_ATTN_POLY sweep)
+    if (v != 0 && v != 1 && v != 2 && v != 3 && v != 4) v = 2;
   }
   return v;
 }
@@ -548,9 +550,11 @@ static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s, int kv = 0) {
   }
   switch (attn_poly()) {
     case 0: return launch_attention_tc_t<T, 0>(op, s);
+    case 1: return launch_attention_tc_t<T, 1>(op, s);
     case 2: return launch_attention_tc_t<T, 2>(op, s);
     case 4: return launch_attention_tc_t<T, 4>(op, s);
-    default: return launch_attention_tc_t<T, 3>(op, s);
+    case 3: return launch_attention_tc_t<T, 3>(op, s);
+    default: return launch_attention_tc_t<T, 2>(op, s);
   }
 }
 int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv) {
