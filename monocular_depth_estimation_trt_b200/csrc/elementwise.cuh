@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(256) depth_pro_post_kernel(const DepthProPostP
 // the 2-D rotary embedding -- features [0,32) rotate with the token's y position, [32,64) with x; inside each half
 // feature i pairs with i +- 16 and frequency index i % 16 (positions as core/export_compat.py:84-93 builds them).
 // In place on the packed q|k|v rows the QKV GEMM wrote; cos/sin come from a small fp32 table [position][cos 16 | sin 16]
-// built on the host with upstream's formula.  One warp per token row, a lane holds two adjacent features of a head vector.
+// built on the host with upstream's formula.  One warp per token row, a lane owns whole head vectors (no shuffles).
 // Sequence-sharded global attention: the finished K row and the V row are ALSO stored into every rank's gathered
 // [tokens, 2D] buffer (peer memory over NVLink) -- the all-gather of the exchange step is this kernel's store.
 // ---------------------------------------------------------------------------------------------
@@ -568,9 +568,11 @@ struct QkNormRopeParams {
   float eps;
   void* gather[8];           // each already offset to this rank's first row
 };
+constexpr int kRopeSmemBytes = 8 * 32 * 128;      // per warp: up to 32 head vectors of 128 bytes
 template <typename T>
-__global__ void __launch_bounds__(256) qknorm_rope_kernel(const QkNormRopeParams p) {
+__global__ void __launch_bounds__(256, 2) qknorm_rope_kernel(const QkNormRopeParams p) {
   using Tr = F16Traits<T>;
+  extern __shared__ __align__(16) uint8_t rope_smem[];
   griddep_launch_dependents();
   griddep_wait();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -578,45 +580,93 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(const QkNormRopeParams
   const int lane = threadIdx.x & 31;
   const int D = p.heads * 64;
   T* base = static_cast<T*>(p.qkv) + row * 3 * D;
-  const int e0 = 2 * lane;
-  const float2 qw = make_float2(__ldg(p.qw + e0), __ldg(p.qw + e0 + 1)), qb = make_float2(__ldg(p.qb + e0), __ldg(p.qb + e0 + 1));
-  const float2 kw = make_float2(__ldg(p.kw + e0), __ldg(p.kw + e0 + 1)), kb = make_float2(__ldg(p.kb + e0), __ldg(p.kb + e0 + 1));
-  float c0 = 1.f, c1 = 1.f, s0 = 0.f, s1 = 0.f;
-  const bool lower = (e0 & 31) < 16;                 // first 16 features of a half pair with +16, the others with -16
+  uint4* wb = reinterpret_cast<uint4*>(rope_smem) + (threadIdx.x >> 5) * 256;
+  // The q | k part of a row is one contiguous run of 2 * heads head vectors (128 bytes each).  The warp moves it between
+  // global and shared memory in fully coalesced 16-byte pieces (512 contiguous bytes per instruction); in between, lane v owns
+  // head vector v -- statistics and rotation partners stay inside the thread, no shuffles.  Chunk i of vector v lives at
+  // v * 8 + (i ^ (v & 7)): both the coalesced side (4 vectors x 8 chunks per instruction) and the per-vector side (32 vectors,
+  // one chunk index) touch every bank group the same number of times.
+  const float* cy = nullptr;
+  const float* cx = nullptr;
   if (p.pos) {
-    const int pp = min(max(__ldg(p.pos + row * 2 + (lane >> 4)), 0), p.max_pos - 1);
-    const float* t = p.cos_sin + static_cast<long long>(pp) * 32;
-    const int j = e0 & 15;
-    c0 = __ldg(t + j); c1 = __ldg(t + j + 1); s0 = __ldg(t + 16 + j); s1 = __ldg(t + 16 + j + 1);
+    cy = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2), 0), p.max_pos - 1)) * 32;
+    cx = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2 + 1), 0), p.max_pos - 1)) * 32;
   }
-  for (int h = 0; h < p.heads; ++h) {
+  const int nvec = 2 * p.heads;
+  for (int v0 = 0; v0 < nvec; v0 += 32) {
+    const int nv = min(32, nvec - v0);
+    const uint4* gsrc = reinterpret_cast<const uint4*>(base) + v0 * 8;
+    for (int c = lane; c < nv * 8; c += 32) wb[(c & ~7) + ((c & 7) ^ ((c >> 3) & 7))] = gsrc[c];
+    __syncwarp();
+    if (lane < nv) {
+      const int gv = v0 + lane;
+      const bool is_k = gv >= p.heads;
+      const float* wp = is_k ? p.kw : p.qw;
+      const float* bp = is_k ? p.kb : p.qb;
+      uint4* mine = wb + lane * 8;
+      const int sw = lane & 7;
+      float x[64];
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint32_t* ptr = reinterpret_cast<uint32_t*>(base + which * D + h * 64 + e0);
-      const float2 v = Tr::unpack2(*ptr);
-      float sum = v.x + v.y;
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = mine[i ^ sw];
+        const uint32_t* w = &u.x;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = sum * (1.0f / 64.0f);
-      const float dx = v.x - mean, dy = v.y - mean;
-      float sq = dx * dx + dy * dy;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      const float rstd = __frsqrt_rn(sq * (1.0f / 64.0f) + p.eps);
-      const float2 w = which ? kw : qw, b = which ? kb : qb;
-      float y0 = dx * rstd * w.x + b.x, y1 = dy * rstd * w.y + b.y;
-      if (p.pos) {
-        const float o0 = __shfl_xor_sync(0xffffffffu, y0, 8), o1 = __shfl_xor_sync(0xffffffffu, y1, 8);
-        y0 = lower ? y0 * c0 - o0 * s0 : y0 * c0 + o0 * s0;
-        y1 = lower ? y1 * c1 - o1 * s1 : y1 * c1 + o1 * s1;
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = Tr::unpack2(w[k]);
+          x[i * 8 + 2 * k] = f.x; x[i * 8 + 2 * k + 1] = f.y;
+        }
       }
-      const uint32_t packed = Tr::pack2(y0, y1);
-      *ptr = packed;
-      if (which == 1) {
-        for (int r = 0; r < p.gather_n; ++r)
-          *reinterpret_cast<uint32_t*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld + h * 64 + e0) = packed;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s4[i & 3] += x[i];
+      const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 64.0f);
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { x[i] -= mean; q4[i & 3] = fmaf(x[i], x[i], q4[i & 3]); }
+      const float rstd = __frsqrt_rn(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / 64.0f) + p.eps);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wp) + i), b = __ldg(reinterpret_cast<const float4*>(bp) + i);
+        x[4 * i] = x[4 * i] * rstd * w.x + b.x; x[4 * i + 1] = x[4 * i + 1] * rstd * w.y + b.y;
+        x[4 * i + 2] = x[4 * i + 2] * rstd * w.z + b.z; x[4 * i + 3] = x[4 * i + 3] * rstd * w.w + b.w;
+      }
+      if (p.pos) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float* t = half ? cx : cy;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(t) + j4), sn = __ldg(reinterpret_cast<const float4*>(t + 16) + j4);
+            const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = j4 * 4 + k;
+              const float lo = x[half * 32 + j], hi = x[half * 32 + 16 + j];
+              x[half * 32 + j] = lo * cc[k] - hi * ss[k];
+              x[half * 32 + 16 + j] = hi * cc[k] + lo * ss[k];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u;
+        u.x = Tr::pack2(x[i * 8], x[i * 8 + 1]); u.y = Tr::pack2(x[i * 8 + 2], x[i * 8 + 3]);
+        u.z = Tr::pack2(x[i * 8 + 4], x[i * 8 + 5]); u.w = Tr::pack2(x[i * 8 + 6], x[i * 8 + 7]);
+        mine[i ^ sw] = u;
       }
     }
+    __syncwarp();
+    uint4* gdst = reinterpret_cast<uint4*>(base) + v0 * 8;
+    for (int c = lane; c < nv * 8; c += 32) {
+      const uint4 u = wb[(c & ~7) + ((c & 7) ^ ((c >> 3) & 7))];
+      gdst[c] = u;
+      const int kc = v0 * 8 + c - p.heads * 8;           // 16-byte chunk index inside the K part, if this chunk is K
+      if (kc >= 0)
+        for (int r = 0; r < p.gather_n; ++r)
+          *(reinterpret_cast<uint4*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld) + kc) = u;
+    }
+    __syncwarp();
   }
   if (p.gather_n > 0) {
     const uint4* v = reinterpret_cast<const uint4*>(base + 2 * D);

@@ -644,8 +644,8 @@ int launch_qknorm_rope(int precision, void* d_qkv, long long rows, int heads, co
     p.gather[r] = d_gather[r];
   }
   const dim3 grid(static_cast<unsigned>((rows + 7) / 8));
-  if (precision == MDE_BF16) MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, 1, p));
-  else MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__half>, grid, dim3(256), 0, s, 1, p));
+  if (precision == MDE_BF16) MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__nv_bfloat16>, grid, dim3(256), kRopeSmemBytes, s, 1, p));
+  else MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__half>, grid, dim3(256), kRopeSmemBytes, s, 1, p));
   return MDE_OK;
 }
 
