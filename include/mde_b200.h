@@ -220,6 +220,10 @@ int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const vo
  * (csrc/attention_tc2q.cuh). */
 int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                        void* stream);
+/* The same op with every CTA working through two query tiles of one (image, head) one after the other, the second tile's Q
+ * and first S overlapped with the first tile's tail (csrc/attention_tcq.cuh).  Engine: MDE_ATTN_KV=2. */
+int mde_k_attention_q2(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       void* stream);
 /* The same op with the softmax of a query tile spread over eight warps, two per TMEM lane quarter, each taking half of the
  * score columns (csrc/attention_tc8w.cuh).  The engine launches it when MDE_ATTN_KV=8 is set. */
 int mde_k_attention_8w(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

@@ -14,6 +14,7 @@
 #include "attention_tc64.cuh"
 #include "attention_tc2q.cuh"
 #include "attention_tc8w.cuh"
+#include "attention_tcq.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -496,7 +497,8 @@ static int attn_kv() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MDE_ATTN_KV");
-    v = (e && atoi(e) == 64) ? 64 : ((e && atoi(e) == 256) ? 256 : ((e && atoi(e) == 8) ? 8 : 128));
+    const int x = e ? atoi(e) : 128;
+    v = (x == 64 || x == 256 || x == 8 || x == 2) ? x : 128;
   }
   return v;
 }
@@ -522,8 +524,34 @@ static int launch_attention_tc8w_t(const AttnOp& op, cudaStream_t s) {
   MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kA8Threads), kA8SmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
   return MDE_OK;
 }
+template <typename T, int kPoly>
+static int launch_attention_tcq_t(const AttnOp& op, cudaStream_t s) {
+  constexpr int kItems = 2;
+  static bool attr_set = false;
+  auto kern = attention_tcq_kernel<T, kPoly, kItems>;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
+    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  const int q_tiles = (op.ntok_q + 127) / 128;
+  dim3 grid((q_tiles + kItems - 1) / kItems, op.heads, op.batch);
+  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAtcThreads), kAtcSmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
+  return MDE_OK;
+}
 template <typename T>
 static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s, int kv = 0) {
+  if ((kv ? kv : attn_kv()) == 2) {          // two query tiles per CTA, one after the other (attention_tcq.cuh)
+    switch (attn_poly()) {
+      case 0: return launch_attention_tcq_t<T, 0>(op, s);
+      case 3: return launch_attention_tcq_t<T, 3>(op, s);
+      default: return launch_attention_tcq_t<T, 2>(op, s);
+    }
+  }
   if ((kv ? kv : attn_kv()) == 8) {          // eight softmax warps per query tile (attention_tc8w.cuh)
     switch (attn_poly()) {
       case 0: return launch_attention_tc8w_t<T, 0>(op, s);
@@ -902,6 +930,14 @@ int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
   return launch_attention_op(op, static_cast<cudaStream_t>(stream), 256);
+}
+
+int mde_k_attention_q2(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       void* stream) {
+  clear_error();
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 2);
 }
 
 int mde_k_attention_8w(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

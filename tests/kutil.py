@@ -68,7 +68,7 @@ def pack_conv3x3(w, dtype):
 def attention(precision, qkv, batch, ntok, heads, variant="tc"):
     lib = _lib.load()
     out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
-    fn = {"tc": lib.mde_k_attention, "kv64": lib.mde_k_attention_kv64, "2q": lib.mde_k_attention_2q, "8w": lib.mde_k_attention_8w, "mma": lib.mde_k_attention_mma}[variant]
+    fn = {"tc": lib.mde_k_attention, "kv64": lib.mde_k_attention_kv64, "2q": lib.mde_k_attention_2q, "8w": lib.mde_k_attention_8w, "q2": lib.mde_k_attention_q2, "mma": lib.mde_k_attention_mma}[variant]
     _lib.check(fn(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()), "mde_k_attention")
     return out
 
