@@ -220,6 +220,11 @@ int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const vo
  * (csrc/attention_tc2q.cuh). */
 int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                        void* stream);
+/* The default attention kernel with clock64 stamps of the softmax warps' phases (profiling aid, tools/attn_trace.py):
+ * d_trace int64 [2048 CTAs][4 warps][64 slots], zero-initialised by the caller; slot 0 kernel entry, 1 after the prologue sync,
+ * then per key tile: S available, S in registers, exponentials done, previous P V done, P stored; then O available, stored. */
+int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                          int64_t* d_trace, void* stream);
 /* The same op with every CTA working through two query tiles of one (image, head) one after the other, the second tile's Q
  * and first S overlapped with the first tile's tail (csrc/attention_tcq.cuh).  Engine: MDE_ATTN_KV=2. */
 int mde_k_attention_q2(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

@@ -75,7 +75,11 @@ __device__ __forceinline__ void exp2_fma2(f32x2 x, float& p0, float& p1) {
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
 
-template <typename T, int kPoly>
+// kTrace: the same kernel with clock64 stamps of every phase of the softmax warps written to p.trace (lane 0 of each warp,
+// the first kAtcTraceCtas CTAs): [cta][warp][0] kernel entry, [1] after the prologue sync, then 5 per key tile -- S available,
+// S in registers, exponentials done, previous P V done, P stored and announced -- and after the last tile: O available, stored.
+constexpr int kAtcTraceCtas = 2048, kAtcTraceSlots = 64;
+template <typename T, int kPoly, bool kTrace = false>
 __global__ void __launch_bounds__(kAtcThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {
   using Tr = F16Traits<T>;
@@ -103,6 +107,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   const int last_chunks = (p.ntok - (nkv - 1) * 128 + 31) / 32;   // 32-key chunks of the last key tile that hold real keys (1..4)
   const int row_base = img * p.ntok_q;     // first query row of this image
   const int kv_base = img * p.ntok;        // first key/value row of this image
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  int trace_n = 0;
+  auto stamp = [&]() {
+    if (kTrace) {
+      if (lane == 0 && warp < 4 && cta_lin < kAtcTraceCtas && trace_n < kAtcTraceSlots)
+        p.trace[(static_cast<long long>(cta_lin) * 4 + warp) * kAtcTraceSlots + trace_n] = clock64();
+      ++trace_n;
+    }
+  };
+  stamp();
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&map_qkv);
@@ -134,6 +148,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();                          // Q / K / V come from the previous kernel
+  stamp();
 
   // Register re-partition per warpgroup: the single-thread roles need almost nothing, a softmax thread
   // holds a 128-wide score row.  2 CTAs x 256 threads start at 128 registers each.
@@ -141,15 +156,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     // ===================================================== TMA producer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
-      for (int j = 1; j < nkv; ++j) {              // Q and key tile 0 were requested in the prologue
-        const int st = j % kAtcStages;
-        const uint32_t ph = (j / kAtcStages) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], kAtcQBytes);
-        tma_load_2d(sK + st * kAtcQBytes, &map_kv, &k_full[st], p.k_col0 + head * 64, kv_base + j * 128);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], kAtcQBytes);
-        tma_load_2d(sV + st * kAtcQBytes, &map_kv, &v_full[st], p.v_col0 + head * 64, kv_base + j * 128);
+      // Q and key tile 0 were requested in the prologue.  K runs one tile ahead of V: a K stage is free as soon as its
+      // S = Q K^T has been computed (early), a V stage only when its P V has (a whole softmax later); waiting for the V stage
+      // first would hold the next K back and S of the next key tile with it.
+      for (int j = 1; j <= nkv; ++j) {
+        if (j < nkv) {
+          const int st = j % kAtcStages;
+          mbar_wait(&k_empty[st], ((j / kAtcStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], kAtcQBytes);
+          tma_load_2d(sK + st * kAtcQBytes, &map_kv, &k_full[st], p.k_col0 + head * 64, kv_base + j * 128);
+        }
+        if (j >= 2) {
+          const int i = j - 1, st = i % kAtcStages;
+          mbar_wait(&v_empty[st], ((i / kAtcStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], kAtcQBytes);
+          tma_load_2d(sV + st * kAtcQBytes, &map_kv, &v_full[st], p.v_col0 + head * 64, kv_base + i * 128);
+        }
       }
     }
   } else if (warp == 5) {
@@ -220,6 +242,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_free);                       // the tensor core may overwrite S now
+      stamp();
       // ---- row maximum, four independent chains
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -258,11 +281,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         }
         }
       }
+      stamp();
       // ---- the previous product has read P (and, for a rescale, written O): only now may either change
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
+      stamp();
       if (__any_sync(0xffffffffu, grow)) {
         const float factor = grow ? fast_exp2((m_ref - mx) * sl) : 1.0f;
         if (grow) { m_ref = mx; l_run *= factor; }
@@ -289,6 +314,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       }
       tc_fence_before();            // TMEM stores (P, rescaled O) are ordered before the MMA that reads them
       mbar_arrive(p_ready);
+      stamp();
     };
 
     using cuda::std::integral_constant;
@@ -296,12 +322,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     for (int j = 0; j < n_full; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      stamp();
       tile(integral_constant<int, 4>{}, cuda::std::true_type{}, j);
     }
     if (n_full < nkv) {
       const int j = n_full;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      stamp();
       if (last_chunks == 1) tile(integral_constant<int, 1>{}, cuda::std::false_type{}, j);
       else if (last_chunks == 2) tile(integral_constant<int, 2>{}, cuda::std::false_type{}, j);
       else if (last_chunks == 3) tile(integral_constant<int, 3>{}, cuda::std::false_type{}, j);
@@ -310,6 +338,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     // ---- normalise and store this row (128 contiguous bytes)
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
+    stamp();
     const float inv = 1.0f / l_run;
     const int n = q0 + r;
     T* gout = static_cast<T*>(p.out) + (static_cast<long long>(row_base) + n) * p.D + head * 64;
@@ -330,6 +359,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         }
       }
     }
+    stamp();
   }
 
   tc_fence_before();

@@ -430,7 +430,7 @@ static int launch_attention_tc64_t(const AttnOp& op, cudaStream_t s) {
     attr_set = true;
   }
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
@@ -454,7 +454,7 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
     attr_set = true;
   }
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
@@ -471,7 +471,7 @@ static int launch_attention_tc2q_t(const AttnOp& op, cudaStream_t s) {
     attr_set = true;
   }
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 255) / 256, op.heads, op.batch);
@@ -517,7 +517,7 @@ static int launch_attention_tc8w_t(const AttnOp& op, cudaStream_t s) {
     attr_set = true;
   }
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
@@ -535,7 +535,7 @@ static int launch_attention_tcq_t(const AttnOp& op, cudaStream_t s) {
     attr_set = true;
   }
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   const int q_tiles = (op.ntok_q + 127) / 128;
@@ -585,6 +585,21 @@ static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s, int kv = 0) {
     default: return launch_attention_tc_t<T, 2>(op, s);
   }
 }
+template <typename T>
+static int launch_attention_trace_t(const AttnOp& op, long long* d_trace, cudaStream_t s) {
+  auto kern = attention_tc_kernel<T, 2, true>;
+  MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
+  MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = d_trace;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
+  kern<<<grid, kAtcThreads, kAtcSmemBytes, s>>>(op.map_qkv, op.map_kv128, p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv) {
   return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s, kv) : launch_attention_tc_p<__half>(op, s, kv);
 }
@@ -930,6 +945,16 @@ int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
   return launch_attention_op(op, static_cast<cudaStream_t>(stream), 256);
+}
+
+int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                          int64_t* d_trace, void* stream) {
+  clear_error();
+  if (!d_trace) return fail(MDE_ERR_INVALID, "attention_trace: the trace buffer is required");
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  return precision == MDE_BF16 ? launch_attention_trace_t<__nv_bfloat16>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream))
+                               : launch_attention_trace_t<__half>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream));
 }
 
 int mde_k_attention_q2(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
