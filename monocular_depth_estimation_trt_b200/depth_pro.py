@@ -20,7 +20,7 @@ only: every launch below is a kernel of libmde_b200.so, there is no eager fallba
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Mapping, Optional, Sequence, Tuple
+from typing import Dict, List, Mapping, Sequence, Tuple
 
 import numpy as np
 

@@ -17,7 +17,7 @@ The DINOv2-with-registers trunk in front of the aggregator and the DPT head behi
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Mapping, Optional, Sequence
+from typing import Mapping, Sequence
 
 import numpy as np
 

@@ -19,7 +19,7 @@ cross-checked against torch's scaled_dot_product_attention, the rotary embedding
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence
+from typing import Dict, List
 
 import torch
 import torch.nn.functional as F

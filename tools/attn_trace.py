@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where a softmax warp's time goes inside the default attention kernel: clock64 stamps of every phase
 (mde_k_attention_trace), averaged over the traced CTAs.  python tools/attn_trace.py [--batch 64] [--ntok 1370]"""
-import argparse, ctypes as C, os, sys
+import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

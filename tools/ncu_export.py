@@ -3,7 +3,7 @@
    <out>_raw.csv      the raw metric page of the first profiled launch
    <out>_stalls.txt   per-phase and per-instruction warp-stall samples from the source page (SASS)
     python tools/ncu_export.py gpurun_out/prof_attn.ncu-rep profiles/r01_ncu_attn_final [--top 30]"""
-import argparse, csv, io, subprocess, sys
+import argparse, csv, io, subprocess
 
 ap = argparse.ArgumentParser()
 ap.add_argument("report"); ap.add_argument("out"); ap.add_argument("--top", type=int, default=30)
