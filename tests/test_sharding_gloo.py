@@ -123,3 +123,74 @@ def test_two_ranks_shard_crops_and_all_gather_the_taps():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-5          # batch composition changes fp32 summation order at most
+
+
+# ------------------------------------------------------------------ VGGT: frames sharded by rank, K|V all-gathered per global block
+def _vggt_worker(rank, world, port, out):
+    """Each rank runs the ORACLE blocks on its frames.  Frame blocks are local.  In a global block every rank projects its
+    own tokens, finishes q and k (qk-norm + RoPE), all-gathers K|V into the layout the CUDA path uses ([frames_total * N, 2D],
+    rank r's rows at r * rows_local) and attends with its queries over all keys / values; rank 0 compares its frames with
+    the unsharded oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn.functional as F
+    from oracle import vggt_torch as V
+    from monocular_depth_estimation_trt_b200 import vggt as P
+    torch.set_num_threads(2)
+    D, H, S_total, depth, gh, gw = 128, 2, 4, 2, 3, 3
+    N = 5 + gh * gw
+    sd = V.init_aggregator(D, depth, seed=2)
+    torch.manual_seed(1)
+    tokens = torch.randn(S_total, N, D)
+    per = S_total // world
+    t = tokens[rank * per:(rank + 1) * per].clone()
+    pos = torch.from_numpy(P.token_positions(gh, gw)).long()            # the product's table, one frame
+    rows = per * N
+
+    def attend(pre, x, kv_from_all):
+        B, n, _ = x.shape
+        y = F.layer_norm(x, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], V.LN_EPS)
+        qkv = F.linear(y, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"]).reshape(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)
+        p_ = pos.repeat(n // N, 1)
+        q = V.rope_2d(F.layer_norm(qkv[0], (64,), sd[pre + "attn.q_norm.weight"], sd[pre + "attn.q_norm.bias"], V.QK_EPS), p_)
+        k = V.rope_2d(F.layer_norm(qkv[1], (64,), sd[pre + "attn.k_norm.weight"], sd[pre + "attn.k_norm.bias"], V.QK_EPS), p_)
+        v = qkv[2]
+        if kv_from_all:
+            local = torch.cat([k.permute(0, 2, 1, 3).reshape(n, D), v.permute(0, 2, 1, 3).reshape(n, D)], dim=1).contiguous()   # [rows, 2D]
+            gathered = torch.zeros(world * rows, 2 * D)
+            dist.all_gather_into_tensor(gathered, local)                 # rank r's rows land at r * rows: the CUDA path's layout
+            k = gathered[:, :D].reshape(1, world * rows, H, 64).permute(0, 2, 1, 3)
+            v = gathered[:, D:].reshape(1, world * rows, H, 64).permute(0, 2, 1, 3)
+        a = torch.softmax((q * 64 ** -0.5) @ k.transpose(-2, -1), dim=-1) @ v
+        a = a.transpose(1, 2).reshape(B, n, D)
+        x = x + sd[pre + "ls1.gamma"] * F.linear(a, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+        y = F.layer_norm(x, (D,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], V.LN_EPS)
+        return x + sd[pre + "ls2.gamma"] * F.linear(F.gelu(F.linear(y, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
+                                                     sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+
+    layers = []
+    with torch.no_grad():
+        for i in range(depth):
+            t = attend(f"aggregator.frame_blocks.{i}.", t, False)
+            frame = t
+            t = attend(f"aggregator.global_blocks.{i}.", t.reshape(1, rows, D), True).reshape(per, N, D)
+            layers.append(torch.cat([frame, t], dim=-1))
+    if rank == 0:
+        ref = V.aggregate(sd, tokens, gh, gw, H, depth)
+        out.put(max(float((layers[i] - ref[i][:per]).abs().max()) for i in range(depth)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_frames_and_all_gather_keys_and_values():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vggt_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 2e-5
