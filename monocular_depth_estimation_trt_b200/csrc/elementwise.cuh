@@ -568,37 +568,12 @@ struct QkNormRopeParams {
   float eps;
   void* gather[8];           // each already offset to this rank's first row
 };
-constexpr int kRopeSmemBytes = 8 * 32 * 128;      // per warp: up to 32 head vectors of 128 bytes
+constexpr int kRopeSmemBytes = 8 * 2 * 32 * 128;      // per warp: two buffers of up to 32 head vectors of 128 bytes
+// One head-vector pass over the swizzled warp buffer `wb`: lane v < nv owns vector v0 + v (see the kernel's comment).
 template <typename T>
-__global__ void __launch_bounds__(256, 2) qknorm_rope_kernel(const QkNormRopeParams p) {
+__device__ __forceinline__ void qknorm_rope_vectors(const QkNormRopeParams& p, uint4* wb, int v0, int nv, int lane, const float* cy, const float* cx) {
   using Tr = F16Traits<T>;
-  extern __shared__ __align__(16) uint8_t rope_smem[];
-  griddep_launch_dependents();
-  griddep_wait();
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
-  const int lane = threadIdx.x & 31;
-  const int D = p.heads * 64;
-  T* base = static_cast<T*>(p.qkv) + row * 3 * D;
-  uint4* wb = reinterpret_cast<uint4*>(rope_smem) + (threadIdx.x >> 5) * 256;
-  // The q | k part of a row is one contiguous run of 2 * heads head vectors (128 bytes each).  The warp moves it between
-  // global and shared memory in fully coalesced 16-byte pieces (512 contiguous bytes per instruction); in between, lane v owns
-  // head vector v -- statistics and rotation partners stay inside the thread, no shuffles.  Chunk i of vector v lives at
-  // v * 8 + (i ^ (v & 7)): both the coalesced side (4 vectors x 8 chunks per instruction) and the per-vector side (32 vectors,
-  // one chunk index) touch every bank group the same number of times.
-  const float* cy = nullptr;
-  const float* cx = nullptr;
-  if (p.pos) {
-    cy = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2), 0), p.max_pos - 1)) * 32;
-    cx = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2 + 1), 0), p.max_pos - 1)) * 32;
-  }
-  const int nvec = 2 * p.heads;
-  for (int v0 = 0; v0 < nvec; v0 += 32) {
-    const int nv = min(32, nvec - v0);
-    const uint4* gsrc = reinterpret_cast<const uint4*>(base) + v0 * 8;
-    for (int c = lane; c < nv * 8; c += 32) wb[(c & ~7) + ((c & 7) ^ ((c >> 3) & 7))] = gsrc[c];
-    __syncwarp();
-    if (lane < nv) {
+  if (lane < nv) {
       const int gv = v0 + lane;
       const bool is_k = gv >= p.heads;
       const float* wp = is_k ? p.kw : p.qw;
@@ -656,26 +631,77 @@ __global__ void __launch_bounds__(256, 2) qknorm_rope_kernel(const QkNormRopePar
         mine[i ^ sw] = u;
       }
     }
+}
+template <typename T>
+__global__ void __launch_bounds__(256, 2) qknorm_rope_kernel(const QkNormRopeParams p) {
+  extern __shared__ __align__(16) uint8_t rope_smem[];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int lane = threadIdx.x & 31;
+  const int D = p.heads * 64;
+  const int nvec = 2 * p.heads;
+  uint4* wbuf = reinterpret_cast<uint4*>(rope_smem) + (threadIdx.x >> 5) * 512;
+  // The q | k part of a row is one contiguous run of 2 * heads head vectors (128 bytes each).  The warp moves it between
+  // global and shared memory in fully coalesced 16-byte pieces (512 contiguous bytes per instruction); in between, lane v owns
+  // head vector v -- statistics and rotation partners stay inside the thread, no shuffles.  Chunk i of vector v lives at
+  // v * 8 + (i ^ (v & 7)): both the coalesced side (4 vectors x 8 chunks per instruction) and the per-vector side (32 vectors,
+  // one chunk index) touch every bank group the same number of times.  Warps are persistent (grid = 2 CTAs per SM): while a
+  // row is normalised and rotated, the next row of the warp is already on its way into the other buffer (cp.async).
+  const long long warps = static_cast<long long>(gridDim.x) * 8;
+  long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  auto slot = [](int c) { return (c & ~7) + ((c & 7) ^ ((c >> 3) & 7)); };
+  auto fetch = [&](long long r, uint4* wb) {
+    if (r < p.rows) {
+      const uint4* gsrc = reinterpret_cast<const uint4*>(static_cast<const T*>(p.qkv) + r * 3 * D);
+      const int chunks = min(nvec, 32) * 8;
+      for (int c = lane; c < chunks; c += 32) cp_async_16(wb + slot(c), gsrc + c, true);
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  fetch(row, wbuf);
+  for (; row < p.rows; row += warps, buf ^= 1) {
+    uint4* wb = wbuf + buf * 256;
+    fetch(row + warps, wbuf + (buf ^ 1) * 256);
+    const float* cy = nullptr;
+    const float* cx = nullptr;
+    if (p.pos) {
+      cy = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2), 0), p.max_pos - 1)) * 32;
+      cx = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2 + 1), 0), p.max_pos - 1)) * 32;
+    }
+    T* base = static_cast<T*>(p.qkv) + row * 3 * D;
+    cp_async_wait<1>();
     __syncwarp();
-    uint4* gdst = reinterpret_cast<uint4*>(base) + v0 * 8;
-    for (int c = lane; c < nv * 8; c += 32) {
-      const uint4 u = wb[(c & ~7) + ((c & 7) ^ ((c >> 3) & 7))];
-      gdst[c] = u;
-      const int kc = v0 * 8 + c - p.heads * 8;           // 16-byte chunk index inside the K part, if this chunk is K
-      if (kc >= 0)
+    for (int v0 = 0; v0 < nvec; v0 += 32) {
+      const int nv = min(32, nvec - v0);
+      if (v0 > 0) {                                  // more than 32 vectors per row: the later chunks are loaded in place
+        const uint4* gsrc = reinterpret_cast<const uint4*>(base) + v0 * 8;
+        for (int c = lane; c < nv * 8; c += 32) wb[slot(c)] = gsrc[c];
+        __syncwarp();
+      }
+      qknorm_rope_vectors<T>(p, wb, v0, nv, lane, cy, cx);
+      __syncwarp();
+      uint4* gdst = reinterpret_cast<uint4*>(base) + v0 * 8;
+      for (int c = lane; c < nv * 8; c += 32) {
+        const uint4 u = wb[slot(c)];
+        gdst[c] = u;
+        const int kc = v0 * 8 + c - p.heads * 8;           // 16-byte chunk index inside the K part, if this chunk is K
+        if (kc >= 0)
+          for (int r = 0; r < p.gather_n; ++r)
+            *(reinterpret_cast<uint4*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld) + kc) = u;
+      }
+      __syncwarp();
+    }
+    if (p.gather_n > 0) {
+      const uint4* v = reinterpret_cast<const uint4*>(base + 2 * D);
+      for (int i = lane; i < D / 8; i += 32) {
+        const uint4 u = v[i];
         for (int r = 0; r < p.gather_n; ++r)
-          *(reinterpret_cast<uint4*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld) + kc) = u;
-    }
-    __syncwarp();
-  }
-  if (p.gather_n > 0) {
-    const uint4* v = reinterpret_cast<const uint4*>(base + 2 * D);
-    for (int i = lane; i < D / 8; i += 32) {
-      const uint4 u = v[i];
-      for (int r = 0; r < p.gather_n; ++r)
-        *reinterpret_cast<uint4*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld + D + i * 8) = u;
+          *reinterpret_cast<uint4*>(static_cast<T*>(p.gather[r]) + row * p.gather_ld + D + i * 8) = u;
+      }
     }
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace mde

@@ -686,7 +686,15 @@ int launch_qknorm_rope(int precision, void* d_qkv, long long rows, int heads, co
     if (!d_gather[r] || (reinterpret_cast<uintptr_t>(d_gather[r]) & 15)) return fail(MDE_ERR_INVALID, "qknorm_rope: gather destination %d is null or misaligned", r);
     p.gather[r] = d_gather[r];
   }
-  const dim3 grid(static_cast<unsigned>((rows + 7) / 8));
+  const int sms = num_sms();
+  if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
+  const dim3 grid(static_cast<unsigned>(std::min<long long>((rows + 7) / 8, 2LL * sms)));   // persistent warps, two CTAs per SM
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDE_CUDA_TRY(cudaFuncSetAttribute(qknorm_rope_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRopeSmemBytes));
+    MDE_CUDA_TRY(cudaFuncSetAttribute(qknorm_rope_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRopeSmemBytes));
+    attr_set = true;
+  }
   if (precision == MDE_BF16) MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__nv_bfloat16>, grid, dim3(256), kRopeSmemBytes, s, 1, p));
   else MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__half>, grid, dim3(256), kRopeSmemBytes, s, 1, p));
   return MDE_OK;
