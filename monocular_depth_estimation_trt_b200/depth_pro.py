@@ -110,6 +110,79 @@ class _Ops:
         self.launches += 1
 
 
+# ------------------------------------------------------------------------------------------------ checkpoint contract
+def required_tensors(encoder: str = "vitl", features: int = 256) -> Dict[str, Tuple[int, ...]]:
+    """Name -> shape of every tensor the engine reads from a Depth Pro state dict, under the module tree the reference's
+    export script instantiates (models/depth_pro/onnx_export.py:15-29: `encoder` with its three up-sampling stacks and the
+    low-resolution fusion, `decoder`, `head`, `fov`; the three ViT trunks under timm's key names).  `export_checkpoint` checks a
+    checkpoint against it before anything is built, so a wrong file fails with the list of what is missing."""
+    c = W.ENCODERS[encoder]
+    D, L, Fd = c["embed_dim"], c["depth"], int(features)
+    s: Dict[str, Tuple[int, ...]] = {}
+    for pre in TRUNKS:
+        s[pre + "cls_token"] = (1, 1, D); s[pre + "pos_embed"] = (1, 1 + GRID * GRID, D)
+        s[pre + "patch_embed.proj.weight"] = (D, 3, 16, 16); s[pre + "patch_embed.proj.bias"] = (D,)
+        s[pre + "norm.weight"] = (D,); s[pre + "norm.bias"] = (D,)
+        for i in range(L):
+            b = f"{pre}blocks.{i}."
+            for n in ("norm1", "norm2"):
+                s[b + n + ".weight"] = (D,); s[b + n + ".bias"] = (D,)
+            s[b + "attn.qkv.weight"] = (3 * D, D); s[b + "attn.qkv.bias"] = (3 * D,)
+            s[b + "attn.proj.weight"] = (D, D); s[b + "attn.proj.bias"] = (D,)
+            s[b + "ls1.gamma"] = (D,); s[b + "ls2.gamma"] = (D,)
+            s[b + "mlp.fc1.weight"] = (4 * D, D); s[b + "mlp.fc1.bias"] = (4 * D,)
+            s[b + "mlp.fc2.weight"] = (D, 4 * D); s[b + "mlp.fc2.bias"] = (D,)
+    for name, mid, n_up in (("upsample_latent0", Fd, 3), ("upsample_latent1", Fd, 2), ("upsample0", D // 2, 1), ("upsample1", D, 1), ("upsample2", D, 1)):
+        s[f"encoder.{name}.0.weight"] = (mid, D, 1, 1)
+        for j in range(n_up):
+            s[f"encoder.{name}.{j + 1}.weight"] = (mid, mid, 2, 2)
+    s["encoder.upsample_lowres.weight"] = (D, D, 2, 2); s["encoder.upsample_lowres.bias"] = (D,)
+    s["encoder.fuse_lowres.weight"] = (D, 2 * D, 1, 1); s["encoder.fuse_lowres.bias"] = (D,)
+    dims = [Fd, Fd, D // 2, D, D]
+    for i in range(1, 5):
+        s[f"decoder.convs.{i}.weight"] = (Fd, dims[i], 3, 3)
+    for i in range(5):
+        f = f"decoder.fusions.{i}."
+        for r in (("resnet1",) if i < 4 else ()) + ("resnet2",):
+            for j in (1, 3):
+                s[f + f"{r}.residual.{j}.weight"] = (Fd, Fd, 3, 3); s[f + f"{r}.residual.{j}.bias"] = (Fd,)
+        if i > 0:
+            s[f + "deconv.weight"] = (Fd, Fd, 2, 2)
+        s[f + "out_conv.weight"] = (Fd, Fd, 1, 1); s[f + "out_conv.bias"] = (Fd,)
+    s["head.0.weight"] = (Fd // 2, Fd, 3, 3); s["head.0.bias"] = (Fd // 2,)
+    s["head.1.weight"] = (Fd // 2, Fd // 2, 2, 2); s["head.1.bias"] = (Fd // 2,)
+    s["head.2.weight"] = (32, Fd // 2, 3, 3); s["head.2.bias"] = (32,)
+    s["head.4.weight"] = (1, 32, 1, 1); s["head.4.bias"] = (1,)
+    s["fov.encoder.1.weight"] = (Fd // 2, D); s["fov.encoder.1.bias"] = (Fd // 2,)
+    s["fov.downsample.0.weight"] = (Fd // 2, Fd, 3, 3); s["fov.downsample.0.bias"] = (Fd // 2,)
+    s["fov.head.0.weight"] = (Fd // 4, Fd // 2, 3, 3); s["fov.head.0.bias"] = (Fd // 4,)
+    s["fov.head.2.weight"] = (Fd // 8, Fd // 4, 3, 3); s["fov.head.2.bias"] = (Fd // 8,)
+    s["fov.head.4.weight"] = (1, Fd // 8, 6, 6); s["fov.head.4.bias"] = (1,)
+    return s
+
+
+def export_checkpoint(checkpoint_path: str, out_path: str, encoder: str = "vitl", features: int = 256,
+                      hook_blocks: Sequence[int] = (11, 5)) -> dict:
+    """Stage `export` for an upstream Depth Pro checkpoint (models/depth_pro/onnx_export.py:15-22 loads
+    `ml-depth-pro/checkpoints/depth_pro.pt` into the model it then exports): read the state dict, check it against
+    `required_tensors`, keep those tensors and write the .mdew file `common.get_engine` builds the engine from."""
+    import torch
+    sd = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+    if isinstance(sd, dict) and "state_dict" in sd and "head.0.weight" not in sd:
+        sd = sd["state_dict"]
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    need = required_tensors(encoder, features)
+    missing = [k for k in need if k not in sd]
+    wrong = [f"{k}: {tuple(sd[k].shape)} != {shape}" for k, shape in need.items() if k in sd and tuple(sd[k].shape) != shape]
+    if missing or wrong:
+        raise ValueError(f"[MDET] {checkpoint_path} is not a Depth Pro ({encoder}, {features} decoder features) checkpoint: "
+                         f"{len(missing)} tensors missing (first: {missing[:3]}), {len(wrong)} with another shape (first: {wrong[:3]})")
+    meta = W.describe_depth_pro(encoder, features, hook_blocks)
+    meta["source_checkpoint_sha256"] = W.file_sha256(checkpoint_path)
+    W.save(out_path, {k: sd[k] for k in need}, meta)
+    return meta
+
+
 # ------------------------------------------------------------------------------------------------ weight packing
 def _t(v):
     import torch

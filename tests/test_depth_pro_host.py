@@ -1,4 +1,5 @@
 """Host-side logic of the Depth Pro path (no GPU): tap selection, weight packing, the folded transposed convolution."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -84,3 +85,24 @@ def test_metric3d_geometry_matches_the_reference_helper():
         exec(compile(src[start:end], ref, "exec"), ns)                  # the helper alone (the module imports cv2 / tensorrt tooling)
         for h, w in cases:
             assert PP.metric3d_geometry(h, w) == ns["_metric3d_geometry"](h, w)
+
+
+def test_required_tensors_are_exactly_what_the_oracle_model_holds(tmp_path):
+    """The engine's checkpoint contract against the oracle's parameter list (mask_token aside, which inference never reads),
+    and the export stage: a state dict saved as a checkpoint comes back as an .mdew file; a wrong file is refused by name."""
+    from oracle import depth_pro_torch as DP
+    from monocular_depth_estimation_trt_b200 import weights as W
+    for enc, feat in (("vits", 64), ("vitl", 256)):
+        need = DPE.required_tensors(enc, feat)
+        have = {k: v for k, v in DP.full_param_shapes(enc, feat).items() if not k.endswith("mask_token")}
+        assert need == have
+    sd = DP.init_full_state_dict("vits", features=64, seed=1)
+    ckpt = str(tmp_path / "depth_pro.pt")
+    torch.save({"module." + k: v for k, v in sd.items()}, ckpt)
+    meta = DPE.export_checkpoint(ckpt, str(tmp_path / "dp.mdew"), encoder="vits", features=64, hook_blocks=(8, 5))
+    back, meta2 = W.load(str(tmp_path / "dp.mdew"))
+    assert meta2 == meta and meta["family"] == "depth_pro" and len(meta["source_checkpoint_sha256"]) == 64
+    assert set(back) == set(DPE.required_tensors("vits", 64)) and np.array_equal(back["head.4.bias"], sd["head.4.bias"].numpy())
+    torch.save({k: v for k, v in sd.items() if not k.startswith("fov.")}, ckpt)
+    with pytest.raises(ValueError, match="tensors missing"):
+        DPE.export_checkpoint(ckpt, str(tmp_path / "x.mdew"), encoder="vits", features=64)
