@@ -660,14 +660,19 @@ __global__ void __launch_bounds__(256, 2) qknorm_rope_kernel(const QkNormRopePar
   };
   int buf = 0;
   fetch(row, wbuf);
+  // the token's (y, x) position is needed before the table rows can be addressed: loaded one row ahead as well
+  int2 pos_next = make_int2(0, 0);
+  if (p.pos && row < p.rows) pos_next = __ldg(reinterpret_cast<const int2*>(p.pos) + row);
   for (; row < p.rows; row += warps, buf ^= 1) {
     uint4* wb = wbuf + buf * 256;
     fetch(row + warps, wbuf + (buf ^ 1) * 256);
+    const int2 pos_cur = pos_next;
+    if (p.pos && row + warps < p.rows) pos_next = __ldg(reinterpret_cast<const int2*>(p.pos) + row + warps);
     const float* cy = nullptr;
     const float* cx = nullptr;
     if (p.pos) {
-      cy = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2), 0), p.max_pos - 1)) * 32;
-      cx = p.cos_sin + static_cast<long long>(min(max(__ldg(p.pos + row * 2 + 1), 0), p.max_pos - 1)) * 32;
+      cy = p.cos_sin + static_cast<long long>(min(max(pos_cur.x, 0), p.max_pos - 1)) * 32;
+      cx = p.cos_sin + static_cast<long long>(min(max(pos_cur.y, 0), p.max_pos - 1)) * 32;
     }
     T* base = static_cast<T*>(p.qkv) + row * 3 * D;
     cp_async_wait<1>();
