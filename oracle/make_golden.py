@@ -6,7 +6,8 @@ preprocess_golden.npz  outputs of the REFERENCE module itself (imported from /ro
                        core.preprocess.preprocess_for(img, 'depth_anything_v2', size)) on the
                        reference's synthetic-input convention (tests/test_preprocess.py:47-51):
                        full tensors at small target sizes, sha256 of the float32 bytes at 518x518; the same for
-                       'metric3d_v2' (keep-ratio + pad, 616x1064) together with the geometry it reports.
+                       'metric3d_v2' (keep-ratio + pad, 616x1064) together with the geometry it reports, and for 'vggt'
+                       (white square pad + cubic resize, IPP switched off: see oracle/preprocess_np.py resize_cubic_u8).
 dav2_vits_golden.npz   the oracle's own ViT-S 518x518 batch-1 forward (BASELINE config 1) with the
                        seeded, calibrated init: a 7x-strided subsample of the depth map and summary
                        statistics.  It pins the oracle against drift between hosts; the oracle
@@ -57,6 +58,20 @@ def main():
         digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
         blob[f"m3d_sha_seed{i}_{h}x{w}_to_616x1064"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
         blob[f"m3d_geom_seed{i}_{h}x{w}_to_616x1064"] = np.array([geom.inner_h, geom.inner_w, geom.pad_top, geom.pad_left], dtype=np.int64)
+    # VGGT / StreamVGGT: white square pad + ONE cubic resize + / 255 (float32, rank 5).  Generated with IPP off: the
+    # opencv-python wheel routes 8-bit cubic through Intel IPP by default, OpenCV's own path is what can be restated.
+    import cv2
+    cv2.ipp.setUseIPP(False)
+    for i, (h, w) in enumerate(SOURCES + [(501, 500), (33, 57)]):
+        img = synthetic(i, h, w)
+        for (th, tw) in [(70, 70), (56, 84)]:
+            t, _ = ref.preprocess_for(img, "vggt", (th, tw))
+            blob[f"vggt_full_seed{i}_{h}x{w}_to_{th}x{tw}"] = t
+        t, geom = ref.preprocess_for(img, "vggt", (518, 518))
+        digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+        blob[f"vggt_sha_seed{i}_{h}x{w}_to_518x518"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
+        blob[f"vggt_box_seed{i}_{h}x{w}_to_518x518"] = np.array(geom.box, dtype=np.float64)
+    cv2.ipp.setUseIPP(True)
     np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), **blob)
     print("wrote preprocess_golden.npz", len(blob), "entries")
 

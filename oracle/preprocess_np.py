@@ -143,3 +143,76 @@ def metric3d_postprocess(depth, src_h: int, src_w: int, size=(616, 1064), focal_
     if focal_px is not None:
         d = d * (focal_px * scale / 1000.0)
     return torch.clamp(d, 0, 300)
+
+
+# ------------------------------------------------------------------ VGGT / StreamVGGT: white square pad, then INTER_CUBIC
+def _cubic_tables(ssize: int, dsize: int):
+    """Source index of the second tap and the four 11-bit coefficients per destination index (cv2 `resize`, INTER_CUBIC on
+    8-bit data): fx = (float)((d + 0.5) * scale - 0.5), s = floor(fx), Keys kernel with A = -0.75 evaluated in fp32 in
+    `interpolateCubic`'s order, coefficients saturate_cast<short>(c * 2048) (round half to even), no re-normalisation."""
+    f32 = np.float32
+    A, one = f32(-0.75), f32(1)
+    d = np.arange(dsize, dtype=np.float64)
+    fx = ((d + 0.5) * (ssize / dsize) - 0.5).astype(f32)
+    s = np.floor(fx).astype(np.int64)
+    x = (fx - s.astype(f32)).astype(f32)
+    c0 = ((A * (x + one) - f32(5) * A) * (x + one) + f32(8) * A) * (x + one) - f32(4) * A
+    c1 = ((A + f32(2)) * x - (A + f32(3))) * x * x + one
+    c2 = ((A + f32(2)) * (one - x) - (A + f32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    co = np.rint(np.stack([c0, c1, c2, c3], axis=1).astype(f32) * f32(2048)).astype(np.int64)
+    return s, co
+
+
+def resize_cubic_u8(img: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+    """cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_CUBIC) for HxWxC uint8 -- OpenCV's OWN implementation
+    (imgproc/resize.cpp: integer horizontal pass with replicated borders, vertical pass in fp32 as `VResizeCubicVec_32s8u` does
+    it -- products of int rows and beta / 2^22, summed right to left without fusion, rounded half to even -- and the scalar
+    integer tail `(sum + 2^21) >> 22` for the last (W * C) % 8 elements of a row).  Bit-exact with cv2 4.13 when IPP is off
+    (`cv2.ipp.setUseIPP(False)`); opencv-python wheels route 8-bit cubic through Intel IPP by default, whose closed
+    implementation differs from this by one level in ~4.5 % of the pixels (tests/test_oracle_preprocess.py shows both)."""
+    assert img.dtype == np.uint8 and img.ndim == 3
+    src_h, src_w, cn = img.shape
+    if (src_h, src_w) == (dst_h, dst_w):
+        return img.copy()
+    xi, xa = _cubic_tables(src_w, dst_w)
+    yi, ya = _cubic_tables(src_h, dst_h)
+    S = img.astype(np.int64)
+    H = np.zeros((src_h, dst_w, cn), np.int64)
+    for k in range(4):
+        H += S[:, np.clip(xi + k - 1, 0, src_w - 1), :] * xa[:, k][None, :, None]
+    R = [H[np.clip(yi + k - 1, 0, src_h - 1)] for k in range(4)]
+    f32 = np.float32
+    scale = f32(1.0) / f32(2048 * 2048)
+    b = [(ya[:, k].astype(f32) * scale)[:, None, None] for k in range(4)]
+    Rf = [r.astype(f32) for r in R]
+    x = Rf[0] * b[0] + (Rf[1] * b[1] + (Rf[2] * b[2] + Rf[3] * b[3]))
+    out = np.clip(np.rint(x), 0, 255).astype(np.uint8)
+    tail = (dst_w * cn) % 8                                     # elements past the last full 8-lane vector: integer path
+    if tail:
+        O = sum(R[k] * ya[:, k][:, None, None] for k in range(4))
+        exact = np.clip((O + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+        flat, flat_exact = out.reshape(dst_h, dst_w * cn), exact.reshape(dst_h, dst_w * cn)
+        flat[:, dst_w * cn - tail:] = flat_exact[:, dst_w * cn - tail:]
+    return out
+
+
+def square_pad_geometry(src_h: int, src_w: int):
+    """core/preprocess.py:222-265 `resize_square_pad` with symmetric=True: (top, left) and the padded size -- the SAME count on
+    both sides, so an odd difference leaves the canvas one pixel short of square, as upstream does."""
+    m = max(src_h, src_w)
+    left, top = (m - src_w) // 2, (m - src_h) // 2
+    return top, left, src_h + 2 * top, src_w + 2 * left
+
+
+def preprocess_square_pad_cubic(img_bgr: np.ndarray, dst_h: int, dst_w: int, pad_value: int = 255) -> np.ndarray:
+    """BGR uint8 HxWx3 -> float32 [1, 1, 3, dst_h, dst_w] in 0..1: core.preprocess.preprocess_for(img, 'vggt', (dst_h, dst_w))[0]
+    (core/preprocess.py:493-498: BGR->RGB, white square pad at source resolution, ONE cubic resize, / 255 in float32, rank 5),
+    with cv2's own cubic (see resize_cubic_u8)."""
+    rgb = np.ascontiguousarray(img_bgr[:, :, ::-1])
+    top, left, ph, pw = square_pad_geometry(rgb.shape[0], rgb.shape[1])
+    canvas = np.full((ph, pw, 3), pad_value, dtype=np.uint8)
+    canvas[top:top + rgb.shape[0], left:left + rgb.shape[1]] = rgb
+    small = resize_cubic_u8(canvas, dst_h, dst_w)
+    x = small.astype(np.float32) / np.float32(255.0)
+    return np.ascontiguousarray(x.transpose(2, 0, 1)[None, None])
