@@ -164,6 +164,12 @@ int mde_k_preprocess_u8_pad(int32_t precision, const uint8_t* d_src, int32_t bat
                             int32_t dst_h, int32_t dst_w, int32_t patch, int32_t kpad, int32_t swap_rb,
                             const double* pad_rgb3, const double* mean3, const double* std3, void* d_cols, float* d_nchw,
                             void* stream);
+/* VGGT / StreamVGGT input contract (core/preprocess.py:222-265 `resize_square_pad`, symmetric, :493-498 `vggt`): white square
+ * pad at source resolution, ONE cv2.INTER_CUBIC resize (OpenCV's own 8-bit path, bit-exact: oracle/preprocess_np.py
+ * `resize_cubic_u8`), / 255 in float32.  d_src: uint8 [B][src_h][src_w][3]; d_nchw: float32 [B][3][dst_h][dst_w] (the rank-5
+ * binding [1, S, 3, H, W] of models/vggt/spec.json with B = S frames). */
+int mde_k_preprocess_u8_square_pad_cubic(const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w,
+                                         int32_t swap_rb, int32_t pad_value, float* d_nchw, void* stream);
 int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int32_t h, int32_t w, int32_t patch,
                      int32_t kpad, void* d_cols, void* stream);
 

@@ -709,4 +709,71 @@ __global__ void __launch_bounds__(256, 2) qknorm_rope_kernel(const QkNormRopePar
   cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// VGGT / StreamVGGT input contract (core/preprocess.py:222-265, 493-498): the RGB frame is padded to a square with white at
+// source resolution (the same count on both sides), resized ONCE with cv2.INTER_CUBIC, divided by 255 in float32.  The
+// padded image is never built: a tap outside the frame reads the pad value.  The resize is OpenCV's own 8-bit cubic
+// (oracle/preprocess_np.py `resize_cubic_u8`): Keys kernel (A = -0.75) in fp32 in `interpolateCubic`'s order, coefficients
+// rounded to 11 bits, integer horizontal pass with replicated borders, vertical pass in fp32 exactly as the vector unit does
+// it (int row * (beta * 2^-22), summed right to left, every step separately rounded, round half to even), and the scalar
+// integer tail for the last (W * 3) % 8 interleaved elements of a row.
+// ---------------------------------------------------------------------------------------------
+struct CubicPadParams {
+  const unsigned char* src;   // [B][src_h][src_w][3]
+  float* out;                 // [B][3][dst_h][dst_w]
+  int B, src_h, src_w, dst_h, dst_w, top, left, pad_h, pad_w, swap_rb, pad_value, tail;
+  double scale_y, scale_x;
+};
+__device__ __forceinline__ void cubic_taps(int d, double scale, int* s, int (&co)[4]) {
+  const float fx = static_cast<float>((d + 0.5) * scale - 0.5);
+  const float fl = floorf(fx);
+  *s = static_cast<int>(fl);
+  const float x = __fsub_rn(fx, fl), A = -0.75f;
+  const float x1 = __fadd_rn(x, 1.f), xm = __fsub_rn(1.f, x);
+  const float c0 = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), -3.75f), x1), -6.f), x1), -3.f);
+  const float c1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(1.25f, x), 2.25f), x), x), 1.f);
+  const float c2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(1.25f, xm), 2.25f), xm), xm), 1.f);
+  const float c3 = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c0), c1), c2);
+  co[0] = __float2int_rn(__fmul_rn(c0, 2048.f)); co[1] = __float2int_rn(__fmul_rn(c1, 2048.f));
+  co[2] = __float2int_rn(__fmul_rn(c2, 2048.f)); co[3] = __float2int_rn(__fmul_rn(c3, 2048.f));
+}
+__global__ void __launch_bounds__(256) preprocess_cubic_pad_kernel(const CubicPadParams p) {
+  const int dx = blockIdx.x * 256 + threadIdx.x, dy = blockIdx.y;
+  const int b = blockIdx.z / 3, c = blockIdx.z % 3;
+  if (dx >= p.dst_w) return;
+  int sy, sx, ya[4], xa[4];
+  cubic_taps(dy, p.scale_y, &sy, ya);
+  cubic_taps(dx, p.scale_x, &sx, xa);
+  const unsigned char* img = p.src + static_cast<long long>(b) * p.src_h * p.src_w * 3;
+  const int sc = p.swap_rb ? 2 - c : c;
+  int row[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int y = min(max(sy + k - 1, 0), p.pad_h - 1) - p.top;          // replicated border of the PADDED image, then into the frame
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = min(max(sx + j - 1, 0), p.pad_w - 1) - p.left;
+      const int v = (y >= 0 && y < p.src_h && x >= 0 && x < p.src_w) ? img[(static_cast<long long>(y) * p.src_w + x) * 3 + sc] : p.pad_value;
+      acc += v * xa[j];
+    }
+    row[k] = acc;
+  }
+  int level;
+  if (dx * 3 + c >= p.dst_w * 3 - p.tail) {
+    const long long sum = static_cast<long long>(row[0]) * ya[0] + static_cast<long long>(row[1]) * ya[1] +
+                          static_cast<long long>(row[2]) * ya[2] + static_cast<long long>(row[3]) * ya[3];
+    level = static_cast<int>((sum + (1LL << 21)) >> 22);
+  } else {
+    const float sc22 = 1.0f / 4194304.0f;
+    const float t3 = __fmul_rn(static_cast<float>(row[3]), __fmul_rn(static_cast<float>(ya[3]), sc22));
+    const float t2 = __fadd_rn(__fmul_rn(static_cast<float>(row[2]), __fmul_rn(static_cast<float>(ya[2]), sc22)), t3);
+    const float t1 = __fadd_rn(__fmul_rn(static_cast<float>(row[1]), __fmul_rn(static_cast<float>(ya[1]), sc22)), t2);
+    const float t0 = __fadd_rn(__fmul_rn(static_cast<float>(row[0]), __fmul_rn(static_cast<float>(ya[0]), sc22)), t1);
+    level = __float2int_rn(t0);
+  }
+  level = min(max(level, 0), 255);
+  p.out[((static_cast<long long>(b) * 3 + c) * p.dst_h + dy) * p.dst_w + dx] = __fdiv_rn(static_cast<float>(level), 255.f);
+}
+
 }  // namespace mde

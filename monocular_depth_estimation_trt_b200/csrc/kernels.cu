@@ -1083,6 +1083,26 @@ int mde_k_qknorm_rope(int32_t precision, void* d_qkv, int64_t rows, int32_t head
                             gather_ld, static_cast<cudaStream_t>(stream));
 }
 
+int mde_k_preprocess_u8_square_pad_cubic(const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w,
+                                         int32_t swap_rb, int32_t pad_value, float* d_nchw, void* stream) {
+  clear_error();
+  if (!d_src || !d_nchw) return fail(MDE_ERR_INVALID, "preprocess_cubic: null pointer");
+  if (batch < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return fail(MDE_ERR_INVALID, "preprocess_cubic: empty problem");
+  if (dst_h > 65535 || batch * 3 > 65535) return fail(MDE_ERR_INVALID, "preprocess_cubic: output exceeds grid limits");
+  if (pad_value < 0 || pad_value > 255) return fail(MDE_ERR_INVALID, "preprocess_cubic: the pad value is an 8-bit level");
+  CubicPadParams p;
+  p.src = d_src; p.out = d_nchw; p.B = batch; p.src_h = src_h; p.src_w = src_w; p.dst_h = dst_h; p.dst_w = dst_w;
+  const int m = std::max(src_h, src_w);
+  p.left = (m - src_w) / 2; p.top = (m - src_h) / 2;               // the same count on both sides (core/preprocess.py:239-243)
+  p.pad_h = src_h + 2 * p.top; p.pad_w = src_w + 2 * p.left;
+  p.swap_rb = swap_rb ? 1 : 0; p.pad_value = pad_value; p.tail = (dst_w * 3) % 8;
+  p.scale_y = static_cast<double>(p.pad_h) / dst_h; p.scale_x = static_cast<double>(p.pad_w) / dst_w;
+  dim3 grid((dst_w + 255) / 256, dst_h, batch * 3);
+  preprocess_cubic_pad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int mde_k_resize_crops(const void* d_src, int32_t src_is_u8_hwc, int32_t swap_rb, int32_t src_h, int32_t src_w,
                        const mde_crop* crops, int32_t n_crops, int32_t out_h, int32_t out_w, const float* mean3,
                        const float* std3, float* d_out, void* stream) {

@@ -181,3 +181,13 @@ def rel_err(got, ref):
 def rms_rel(got, ref):
     got, ref = got.double(), ref.double()
     return float(((got - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt().clamp_min(1e-30))
+
+
+def preprocess_u8_square_pad_cubic(src_u8, dst_h, dst_w, swap_rb=True, pad_value=255):
+    """VGGT's input contract: src_u8 [B, H, W, 3] uint8 cuda tensor -> float32 [B, 3, dst_h, dst_w]."""
+    lib = _lib.load()
+    B, H, W_, _ = src_u8.shape
+    out = torch.full((B, 3, dst_h, dst_w), float("nan"), dtype=torch.float32, device=src_u8.device)
+    _lib.check(lib.mde_k_preprocess_u8_square_pad_cubic(ptr(src_u8), B, H, W_, dst_h, dst_w, int(swap_rb), pad_value, ptr(out), stream()),
+               "mde_k_preprocess_u8_square_pad_cubic")
+    return out

@@ -104,3 +104,17 @@ def test_aggregator_graph_replay_equals_eager(lib):
     with pytest.raises(ValueError):
         agg.capture(tok.data_ptr(), 0)
     agg.close()
+
+
+@pytest.mark.parametrize("src", [(480, 640), (769, 1025), (500, 500), (33, 57), (1036, 720)])
+@pytest.mark.parametrize("dst", [(518, 518), (70, 70), (56, 84)])
+def test_vggt_preprocessing_kernel_is_byte_exact(lib, src, dst):
+    """uint8 frames -> white square pad -> cubic resize -> / 255: the kernel against the oracle (itself byte-exact with the
+    reference module and cv2's own cubic path), two frames per call, every bit."""
+    import kutil as K
+    from oracle import preprocess_np as Pn
+    frames = np.stack([np.random.default_rng(s).integers(0, 256, (*src, 3), dtype=np.uint8) for s in (3, 4)])
+    ref = np.concatenate([Pn.preprocess_square_pad_cubic(f, *dst)[0] for f in frames])
+    got = K.preprocess_u8_square_pad_cubic(torch.from_numpy(frames).cuda(), *dst)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), ref)
