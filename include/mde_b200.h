@@ -317,6 +317,12 @@ int mde_k_depth_pro_post(const float* d_inv, const float* d_fov_deg, int32_t h, 
  * clamped to [clamp_lo, clamp_hi] (0, 300).  float32 in and out. */
 int mde_k_resize_depth_halfpixel(const float* d_in, int32_t pitch, int32_t h, int32_t w, float* d_out, int32_t out_h, int32_t out_w,
                                  float mul, float clamp_lo, float clamp_hi, void* stream);
+/* VGGT / StreamVGGT post-processing on the device (tools/evaluate_gt.py:240-262 `_square_pad_depth`, transcribed there from the
+ * model scripts): the window of the network's output that the source frame occupies inside the padded square -- d_in points
+ * at its first pixel, `pitch` is the output's width -- is resized to the source size with half-pixel bilinear interpolation
+ * (cv2.INTER_LINEAR on a float map) and every value that is not above `floor_value` (1e-6) becomes NaN: "not a depth". */
+int mde_k_resize_depth_halfpixel_nan(const float* d_in, int32_t pitch, int32_t h, int32_t w, float* d_out, int32_t out_h, int32_t out_w,
+                                     float floor_value, void* stream);
 /* The reference scripts' post-processing on the device (models/depth_anything_v2/onnx2trt.py:111-117):
  * F.interpolate(depth, (ho, wo), mode="bilinear", align_corners=True) then clamp(clamp_lo, clamp_hi); fp32 [B][h][w]. */
 int mde_k_resize_depth(const float* d_in, int32_t batch, int32_t hi, int32_t wi, float* d_out, int32_t ho, int32_t wo,

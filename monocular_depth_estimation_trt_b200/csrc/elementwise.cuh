@@ -524,6 +524,7 @@ struct DepthProPostParams {
   int h, w, pitch, src_h, src_w;
   float mul, lo, hi;
   int reciprocal;           // 1: out = 1 / clamp(v, lo, hi);  0: out = clamp(v, lo, hi)
+  int nan_below;            // 1: out = v > lo ? min(v, hi) : NaN   (VGGT: "not a depth", tools/evaluate_gt.py:258-262)
 };
 __global__ void __launch_bounds__(256) depth_pro_post_kernel(const DepthProPostParams p) {
   const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
@@ -544,6 +545,10 @@ __global__ void __launch_bounds__(256) depth_pro_post_kernel(const DepthProPostP
   float v;
   if (p.h == p.src_h && p.w == p.src_w) v = a;       // the script skips the interpolation when the sizes agree
   else v = __fadd_rn(__fmul_rn(h0, __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b))), __fmul_rn(h1, __fadd_rn(__fmul_rn(w0, c), __fmul_rn(w1, d))));
+  if (p.nan_below) {
+    p.depth[static_cast<long long>(oy) * p.src_w + ox] = v > p.lo ? fminf(v, p.hi) : __int_as_float(0x7fc00000);
+    return;
+  }
   v = fminf(fmaxf(v, p.lo), p.hi);
   p.depth[static_cast<long long>(oy) * p.src_w + ox] = p.reciprocal ? __fdiv_rn(1.f, v) : v;
 }

@@ -730,7 +730,7 @@ int launch_depth_pro_post(const float* d_inv, const float* d_fov, int h, int w, 
   if (src_h > 65535) return fail(MDE_ERR_INVALID, "depth_pro_post: height exceeds grid limits");
   DepthProPostParams p;
   p.inv = d_inv; p.fov_deg = d_fov; p.depth = d_depth; p.f_px = d_f_px; p.h = h; p.w = w; p.pitch = w; p.src_h = src_h; p.src_w = src_w;
-  p.mul = 1.f; p.lo = 1e-4f; p.hi = 1e4f; p.reciprocal = 1;
+  p.mul = 1.f; p.lo = 1e-4f; p.hi = 1e4f; p.reciprocal = 1; p.nan_below = 0;
   dim3 grid((src_w + 255) / 256, src_h, 1);
   depth_pro_post_kernel<<<grid, 256, 0, s>>>(p);
   MDE_CUDA_TRY(cudaGetLastError());
@@ -738,12 +738,12 @@ int launch_depth_pro_post(const float* d_inv, const float* d_fov, int h, int w, 
 }
 
 int launch_resize_depth_halfpixel(const float* d_in, int pitch, int h, int w, float* d_out, int out_h, int out_w, float mul, float lo,
-                                  float hi, cudaStream_t s) {
+                                  float hi, cudaStream_t s, int nan_below = 0) {
   if (h < 1 || w < 1 || out_h < 1 || out_w < 1 || pitch < w) return fail(MDE_ERR_INVALID, "resize_depth_halfpixel: empty problem or pitch < width");
   if (out_h > 65535) return fail(MDE_ERR_INVALID, "resize_depth_halfpixel: height exceeds grid limits");
   DepthProPostParams p;
   p.inv = d_in; p.fov_deg = nullptr; p.depth = d_out; p.f_px = nullptr; p.h = h; p.w = w; p.pitch = pitch; p.src_h = out_h; p.src_w = out_w;
-  p.mul = mul; p.lo = lo; p.hi = hi; p.reciprocal = 0;
+  p.mul = mul; p.lo = lo; p.hi = hi; p.reciprocal = 0; p.nan_below = nan_below ? 1 : 0;
   dim3 grid((out_w + 255) / 256, out_h, 1);
   depth_pro_post_kernel<<<grid, 256, 0, s>>>(p);
   MDE_CUDA_TRY(cudaGetLastError());
@@ -1117,6 +1117,14 @@ int mde_k_depth_pro_post(const float* d_inv, const float* d_fov_deg, int32_t h, 
   clear_error();
   if (!d_inv || !d_fov_deg || !d_depth) return fail(MDE_ERR_INVALID, "depth_pro_post: null pointer");
   return launch_depth_pro_post(d_inv, d_fov_deg, h, w, src_h, src_w, d_depth, d_f_px, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_resize_depth_halfpixel_nan(const float* d_in, int32_t pitch, int32_t h, int32_t w, float* d_out, int32_t out_h, int32_t out_w,
+                                     float floor_value, void* stream) {
+  clear_error();
+  if (!d_in || !d_out) return fail(MDE_ERR_INVALID, "resize_depth_halfpixel_nan: null pointer");
+  return launch_resize_depth_halfpixel(d_in, pitch, h, w, d_out, out_h, out_w, 1.f, floor_value, 3.402823466e38f,
+                                       static_cast<cudaStream_t>(stream), 1);
 }
 
 int mde_k_resize_depth_halfpixel(const float* d_in, int32_t pitch, int32_t h, int32_t w, float* d_out, int32_t out_h, int32_t out_w,

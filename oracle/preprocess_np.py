@@ -216,3 +216,18 @@ def preprocess_square_pad_cubic(img_bgr: np.ndarray, dst_h: int, dst_w: int, pad
     small = resize_cubic_u8(canvas, dst_h, dst_w)
     x = small.astype(np.float32) / np.float32(255.0)
     return np.ascontiguousarray(x.transpose(2, 0, 1)[None, None])
+
+
+def vggt_postprocess(depth, net_h: int, net_w: int, src_h: int, src_w: int) -> np.ndarray:
+    """tools/evaluate_gt.py:240-262 `_square_pad_depth` as it stands there (numpy + cv2): crop the box the source frame occupies
+    inside the padded square (rounded corners of `_square_pad_geometry`, :192-208), cv2.INTER_LINEAR back to the source size on
+    float64, NaN where the value is not above 1e-6."""
+    import cv2
+    d = np.asarray(depth).reshape(net_h, net_w).astype(np.float64)
+    m = max(src_w, src_h)
+    left, top = (m - src_w) // 2, (m - src_h) // 2
+    s = net_w / m
+    x1, y1, x2, y2 = left * s, top * s, (left + src_w) * s, (top + src_h) * s
+    d = d[int(round(y1)):int(round(y2)), int(round(x1)):int(round(x2))]
+    d = cv2.resize(d, (src_w, src_h), interpolation=cv2.INTER_LINEAR)
+    return np.where(d > 1e-6, d, np.nan)

@@ -118,3 +118,21 @@ def test_vggt_preprocessing_kernel_is_byte_exact(lib, src, dst):
     got = K.preprocess_u8_square_pad_cubic(torch.from_numpy(frames).cuda(), *dst)
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("src", [(480, 640), (1025, 769), (500, 500)])
+def test_vggt_postprocessing_matches_the_reference_adapter(lib, src):
+    """tools/evaluate_gt.py:240-262 on the device: box crop, bilinear back to the source size, non-depths -> NaN."""
+    from oracle import preprocess_np as Pn
+    from monocular_depth_estimation_trt_b200 import postprocess as PP
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 518), torch.linspace(0, 1, 518), indexing="ij")
+    depth = 1.5 + torch.sin(6 * xx) * torch.cos(5 * yy) * 1.6           # smooth (the two sides compute the sampling coordinate
+    #                                                                     in fp32 vs fp64: ~3e-5 pixels apart), partly below the floor
+    ref = Pn.vggt_postprocess(depth.numpy(), 518, 518, *src)
+    out = torch.zeros(src, device="cuda")
+    PP.vggt_postprocess(depth.cuda().data_ptr(), 518, 518, src[0], src[1], out, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    both = np.isfinite(ref) & np.isfinite(got)
+    assert np.isnan(ref).any() and (np.isnan(ref) != np.isnan(got)).mean() < 1e-3      # the floor is crossed by the same pixels (fp32 vs fp64 at the edge)
+    assert np.abs(got[both] - ref[both]).max() <= 5e-5
