@@ -288,8 +288,9 @@ def run_ours(args):
     # wall clock of one do_inference incl. both copies, warm-up 20, 100 iterations, nearest-rank p50)
     latency = None
     if rank == 0 and world == 1 and not args.no_latency:
-        def b1_latency():
-            e1 = E.Engine(E.make_desc(meta, precision=args.precision, batch=1, input_mode="u8_hwc", max_src_hw=SRC_HW, device=local), meta)
+        def b1_latency(split_k=False):
+            e1 = E.Engine(E.make_desc(meta, precision=args.precision, batch=1, input_mode="u8_hwc", max_src_hw=SRC_HW, device=local,
+                                      split_k=split_k), meta)
             e1.load_state_dict(sd)
             e1.finalize()
             c1 = e1.create_execution_context()
@@ -311,15 +312,8 @@ def run_ours(args):
         latency = b1_latency()          # default configuration: bitwise reproducible
         latency["what"] = ("batch 1, wall clock of do_inference incl. H2D (uint8 frame) and D2H (float32 map), warm-up 20, "
                            "100 iterations")
-        prev = os.environ.get("MDE_SPLITK")
-        os.environ["MDE_SPLITK"] = "1"  # opt-in: split-K for the residual GEMMs (fp32 adds in arrival order, not bitwise reproducible)
-        try:
-            latency["with_split_k"] = b1_latency()
-        finally:
-            if prev is None:
-                del os.environ["MDE_SPLITK"]
-            else:
-                os.environ["MDE_SPLITK"] = prev
+        # opt-in engine flag: split-K for the residual GEMMs (fp32 adds in arrival order, not bitwise reproducible)
+        latency["with_split_k"] = b1_latency(split_k=True)
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

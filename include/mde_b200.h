@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MDE_ABI_VERSION 1
+#define MDE_ABI_VERSION 2
 
 /* operand precision of the tensor-core path (accumulation is always fp32) */
 #define MDE_FP16 0
@@ -53,6 +53,14 @@ extern "C" {
 #define MDE_HEAD_DPT 0          /* Depth Anything V2: DPT head, output float32 depth [B,H,W] */
 #define MDE_HEAD_ENCODER_TAPS 1 /* trunk only (the patch-encoder stage of Depth Pro, models/depth_pro/onnx_export.py:15-22):
                                  * output = the four tapped block outputs, cls dropped, 16-bit [4][B][T][D] */
+
+/* mde_engine_desc.flags: everything that changes which kernels run or how they are launched is part of the engine
+ * description (and of the fingerprint get_engine writes) -- nothing is read from the environment except MDE_PROFILE=1,
+ * which launches without PDL and without graph replay so that Nsight Compute lists every kernel (numerics unchanged). */
+#define MDE_FLAG_SPLIT_K 1  /* small batches: split K of the residual GEMMs over idle SMs; the partial products meet in the
+                             * L2's fp32 adds in arrival order, i.e. results are no longer bitwise reproducible run to run */
+#define MDE_FLAG_NO_PDL 2   /* launch without programmatic dependent launch (default: on for GEMM / attention / LayerNorm) */
+#define MDE_FLAG_NO_GRAPH 4 /* always launch kernel by kernel instead of replaying the captured CUDA graph */
 
 /* error codes */
 #define MDE_OK 0
@@ -93,6 +101,9 @@ typedef struct mde_engine_desc {
   int32_t head_mode;       /* MDE_HEAD_* */
   int32_t tap_norm_mask;   /* bit i: tap i goes through the trunk's final LayerNorm (0xF for Depth Anything; 0x8 for
                             * Depth Pro's hooks, which take raw block outputs and normalise only the last one) */
+  int32_t flags;           /* MDE_FLAG_* */
+  int32_t attn_poly;       /* eighths of the softmax exponentials evaluated by a polynomial on the FMA pipe instead of the
+                            * SFU: 0..4, or -1 for the library default (2).  Changes the last bits of the probabilities. */
 } mde_engine_desc;
 
 const char* mde_last_error(void);
@@ -222,27 +233,14 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
  * V at v_col0; d_out: [batch*ntok_q][heads*64]. */
 int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
                        int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream);
-/* The same op with two query tiles per CTA and explicit turn-taking of the two softmax groups on the SFU
- * (csrc/attention_tc2q.cuh). */
-int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                       void* stream);
+/* mde_k_attention with an explicit share of polynomial exponentials (poly_eighths 0..4; tools/attn_probe.py sweeps it). */
+int mde_k_attention_poly(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                         int32_t poly_eighths, void* stream);
 /* The default attention kernel with clock64 stamps of the softmax warps' phases (profiling aid, tools/attn_trace.py):
  * d_trace int64 [2048 CTAs][4 warps][64 slots], zero-initialised by the caller; slot 0 kernel entry, 1 after the prologue sync,
  * then per key tile: S available, S in registers, exponentials done, previous P V done, P stored; then O available, stored. */
 int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                           int64_t* d_trace, void* stream);
-/* The same op with every CTA working through two query tiles of one (image, head) one after the other, the second tile's Q
- * and first S overlapped with the first tile's tail (csrc/attention_tcq.cuh).  Engine: MDE_ATTN_KV=2. */
-int mde_k_attention_q2(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                       void* stream);
-/* The same op with the softmax of a query tile spread over eight warps, two per TMEM lane quarter, each taking half of the
- * score columns (csrc/attention_tc8w.cuh).  The engine launches it when MDE_ATTN_KV=8 is set. */
-int mde_k_attention_8w(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                       void* stream);
-/* The same op with 64-key tiles and four CTAs per SM (csrc/attention_tc64.cuh): the measured alternative to the
- * default kernel, kept for comparison; the engine launches it only when MDE_ATTN_KV=64 is set. */
-int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                         void* stream);
 /* The same op on warp-level mma.sync tensor-core instructions: an independent cross-check of the
  * tcgen05 kernel for the tests; the engine never launches it. */
 int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

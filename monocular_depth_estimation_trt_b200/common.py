@@ -41,8 +41,9 @@ def _gpu_name() -> Optional[str]:
 
 
 def _engine_fingerprint(model_file_path, precision, workspace_gib, opt_level,
-                        obey_precision_constraints, dynamic_input_shapes, batch=1, input_mode="f32_nchw"):
-    """What an engine was built from, so a stale stub is not trusted."""
+                        obey_precision_constraints, dynamic_input_shapes, batch=1, input_mode="f32_nchw", extra=None):
+    """What an engine was built from, so a stale stub is not trusted.  `extra`: every further option that changes what the
+    engine computes or which kernels it launches (output, max_src_hw, swap_rb, world, gather, split_k, pdl, graph, attn_poly)."""
     parts = [
         W.file_sha256(model_file_path),
         f"mde_b200_abi={_lib.load().mde_abi_version()}",
@@ -54,6 +55,8 @@ def _engine_fingerprint(model_file_path, precision, workspace_gib, opt_level,
         f"batch={batch}",
         f"input_mode={input_mode}",
     ]
+    for k in sorted(extra or {}):
+        parts.append(f"{k}={extra[k]}")
     gpu = _gpu_name()
     if gpu:
         parts.append(f"gpu={gpu}")
@@ -91,6 +94,10 @@ def get_engine(
     world: int = 1,
     rank: int = 0,
     gather: str = "fused",
+    split_k: bool = False,
+    pdl: bool = True,
+    graph: bool = True,
+    attn_poly: int = -1,
 ):
     """Build the engine for the exported model at `onnx_file_path` (an .mdew file here).
 
@@ -104,8 +111,11 @@ def get_engine(
     float32 contract fed by core/preprocess.py; "u8_hwc" = raw source frames, preprocessing fused
     on the GPU), `max_src_hw` for the latter; `output` ("model_grid" = spec.json's [B, H, W] map; "source_grid" =
     the scripts' post-processing fused in: resized back to `max_src_hw` / the bound source size and clamped,
-    models/depth_anything_v2/onnx2trt.py:111-117).
+    models/depth_anything_v2/onnx2trt.py:111-117); `split_k` / `pdl` / `graph` / `attn_poly` = the engine's tuning surface
+    (mde_engine_desc.flags, attn_poly).  Every keyword enters the fingerprint.
     """
+    extra = dict(output=output, max_src_hw=tuple(max_src_hw), swap_rb=bool(swap_rb), world=world, gather=gather,
+                 split_k=bool(split_k), pdl=bool(pdl), graph=bool(graph), attn_poly=int(attn_poly))
     model_path = os.fspath(onnx_file_path)
     if not os.path.exists(model_path):
         raise FileNotFoundError(f"[MDET] model file {model_path} not found.")
@@ -137,17 +147,18 @@ def get_engine(
             if check_fingerprint:
                 with open(os.path.splitext(engine_file_path)[0] + ".fingerprint", "w", encoding="utf-8") as f:
                     f.write(_engine_fingerprint(model_path, precision, workspace_gib, opt_level, obey_precision_constraints,
-                                                dynamic_input_shapes, 1, input_mode))
+                                                dynamic_input_shapes, 1, input_mode, extra))
         print(f"[MDET] Engine build done! ({time.time() - begin:.2f} [sec])")
         return engine
     desc = make_desc(meta, precision=precision, batch=batch, input_mode=input_mode,
-                     max_src_hw=max_src_hw, swap_rb=swap_rb, device=device, output=output)
+                     max_src_hw=max_src_hw, swap_rb=swap_rb, device=device, output=output,
+                     split_k=split_k, pdl=pdl, graph=graph, attn_poly=attn_poly)
 
     fingerprint = None
     fingerprint_path = os.path.splitext(engine_file_path)[0] + ".fingerprint" if engine_file_path else ""
     if check_fingerprint:
         fingerprint = _engine_fingerprint(model_path, precision, workspace_gib, opt_level,
-                                          obey_precision_constraints, dynamic_input_shapes, batch, input_mode)
+                                          obey_precision_constraints, dynamic_input_shapes, batch, input_mode, extra)
     if engine_file_path:
         stale = engine_staleness(engine_file_path, fingerprint_path, fingerprint, True)
         if stale is None:

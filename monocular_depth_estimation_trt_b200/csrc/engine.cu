@@ -124,6 +124,40 @@ struct mde_context {
   std::vector<cudaEvent_t> events;
 };
 
+// MDE_PROFILE=1: profiling runs launch kernel by kernel without PDL, so that Nsight Compute lists every launch.  It does
+// not change what is computed; everything that does lives in mde_engine_desc (flags, attn_poly).
+static bool profile_mode() {
+  static const bool v = [] { const char* e = getenv("MDE_PROFILE"); return e && atoi(e) != 0; }();
+  return v;
+}
+
+namespace {
+// Makes the engine's device current and installs its launch options for the calling thread; restores both on exit.
+// One process may hold engines on several GPUs (mde_engine_desc.device).
+struct EngineScope {
+  int prev_dev = -1;
+  bool switched = false;
+  LaunchOpts prev_opts;
+  int rc = MDE_OK;
+  explicit EngineScope(const mde_engine_desc& d) {
+    prev_opts = launch_opts();
+    LaunchOpts o;
+    o.pdl = !(d.flags & MDE_FLAG_NO_PDL) && !profile_mode();
+    o.split_k = (d.flags & MDE_FLAG_SPLIT_K) != 0;
+    set_launch_opts(o);
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) { rc = fail(MDE_ERR_CUDA, "cudaGetDevice failed (no CUDA device?)"); return; }
+    if (prev_dev != d.device) {
+      if (cudaSetDevice(d.device) != cudaSuccess) { rc = fail(MDE_ERR_CUDA, "cudaSetDevice(%d) failed", d.device); return; }
+      switched = true;
+    }
+  }
+  ~EngineScope() {
+    set_launch_opts(prev_opts);
+    if (switched) cudaSetDevice(prev_dev);
+  }
+};
+}  // namespace
+
 // =============================================================================================== engine
 static int require(const mde_engine* e, const std::string& name, std::vector<int64_t> dims, const HostTensor** out) {
   auto it = e->raw.find(name);
@@ -223,6 +257,8 @@ static int validate_desc(const mde_engine_desc* d) {
     if (d->taps[i] < 0 || d->taps[i] >= d->depth || (i > 0 && d->taps[i] <= d->taps[i - 1]))
       return fail(MDE_ERR_INVALID, "taps must be increasing block indices below depth");
   }
+  if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
+  if (d->attn_poly < -1 || d->attn_poly > 4) return fail(MDE_ERR_INVALID, "attn_poly must be -1 (default) or 0..4 eighths");
   if (d->input_mode == MDE_INPUT_U8_HWC) {
     if (d->max_src_h <= 0 || d->max_src_w <= 0) return fail(MDE_ERR_INVALID, "max_src_h/max_src_w are required for the uint8 input");
     for (int c = 0; c < 3; ++c)
@@ -300,7 +336,8 @@ extern "C" int mde_engine_finalize(mde_engine* e) {
   if (!e) return fail(MDE_ERR_INVALID, "null engine");
   if (e->finalized) return MDE_OK;
   const mde_engine_desc& d = e->d;
-  MDE_CUDA_TRY(cudaSetDevice(d.device));
+  EngineScope scope(d);
+  MDE_TRY(scope.rc);
   int major = 0;
   MDE_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d.device));
   if (major != 10) return fail(MDE_ERR_CUDA, "device %d has compute capability %d.x; this library only runs on sm_100a (B200)", d.device, major);
@@ -565,6 +602,7 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
       pl.gemm("qkv", ln, rows, D, D, b.qkv_w, 3 * D, D, ep); }
     { Op a; a.kind = Op::ATTENTION; a.in = qkv; a.out = att;
       if (!dry && pl.rc == MDE_OK) pl.rc = make_attention_op(&a.attn, d.precision, qkv, att, B, NT, d.num_heads);
+      if (d.attn_poly >= 0) a.attn.poly = d.attn_poly;
       pl.push(a, "attention", 8.0 * rows * D, 4.0 * static_cast<double>(B) * NT * NT * D); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.proj_b; ep.d_gamma = b.ls1; ep.d_x = x; ep.accumulate_x = 1; ep.ld_out = D;
       pl.gemm("proj+ls+res", att, rows, D, D, b.proj_w, D, D, ep); }
@@ -700,7 +738,8 @@ extern "C" int mde_context_create(mde_engine* e, mde_context** out) {
   if (!e || !out) return fail(MDE_ERR_INVALID, "bad argument to mde_context_create");
   *out = nullptr;
   if (!e->finalized) return fail(MDE_ERR_STATE, "mde_engine_finalize must succeed before a context is created");
-  MDE_CUDA_TRY(cudaSetDevice(e->d.device));
+  EngineScope scope(e->d);
+  MDE_TRY(scope.rc);
   mde_context* c = new mde_context();
   c->e = e;
   int64_t bytes = 0;
@@ -867,7 +906,9 @@ extern "C" int mde_context_enqueue(mde_context* c, void* stream) {
   clear_error();
   if (!c) return fail(MDE_ERR_INVALID, "null context");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static const bool no_graph = getenv("MDE_NO_GRAPH") != nullptr;
+  EngineScope scope(c->e->d);
+  MDE_TRY(scope.rc);
+  const bool no_graph = (c->e->d.flags & MDE_FLAG_NO_GRAPH) != 0 || profile_mode();
   // the legacy default stream cannot be captured; a failed capture falls back to plain launches for good
   if (no_graph || c->graph_failed || s == nullptr || s == cudaStreamLegacy) return enqueue_impl(c, s, false);
   if (!c->d_input || (!c->d_output && c->gather_ranks == 0)) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'input' and 'output' before enqueue");
@@ -920,6 +961,8 @@ extern "C" int mde_context_enqueue_timed(mde_context* c, void* stream, float* ms
     c->events.push_back(ev);
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  EngineScope scope(c->e->d);
+  MDE_TRY(scope.rc);
   MDE_TRY(enqueue_impl(c, s, true));
   MDE_CUDA_TRY(cudaStreamSynchronize(s));
   for (int i = 0; i < n; ++i) MDE_CUDA_TRY(cudaEventElapsedTime(&ms[i], c->events[i], c->events[i + 1]));

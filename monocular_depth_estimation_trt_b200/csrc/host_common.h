@@ -26,7 +26,16 @@ void clear_error();
     if (r__ != MDE_OK) return r__; \
   } while (0)
 
-int num_sms();   // SM count of the current device (cached), 0 on failure
+int num_sms();   // SM count of the current device (cached per device), 0 on failure
+
+// Per-thread launch options.  The engine sets them from mde_engine_desc.flags around plan building and enqueue; the
+// single-kernel entry points (mde_k_*) run with the defaults.
+struct LaunchOpts {
+  bool pdl = false;       // programmatic dependent launch for the kernels that call griddep_wait()
+  bool split_k = false;   // small-batch split-K of the residual GEMMs (arrival-order fp32 adds in the L2)
+};
+void set_launch_opts(const LaunchOpts& o);
+LaunchOpts launch_opts();
 
 // One tensor-core GEMM / implicit-GEMM conv launch, fully described at plan-build time.
 struct GemmOp {
@@ -51,19 +60,19 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream);
 
 // tcgen05 attention launch, described at plan-build time (tensor map over the packed q|k|v rows)
 struct AttnOp {
-  alignas(64) CUtensorMap map_qkv;   // 128-row boxes (query tiles; key/value tiles of the two-CTA-per-SM kernel)
-  alignas(64) CUtensorMap map_kv;    // 64-row boxes (key/value tiles of the four-CTA-per-SM kernel)
-  alignas(64) CUtensorMap map_kv128; // key/value source with 128-row boxes (== map_qkv for self-attention)
+  alignas(64) CUtensorMap map_qkv;   // 128-row boxes: query tiles
+  alignas(64) CUtensorMap map_kv128; // key/value source with 128-row boxes (the same tensor as map_qkv for self-attention)
   const void* qkv;
   void* out;
   int batch, ntok, heads, precision;
   int ntok_q, k_col0, v_col0;        // queries per image; first K / V column of head 0 in the key/value source
+  int poly;                          // eighths of the exponentials evaluated on the FMA pipe (0..4; make_* sets the default, 2)
 };
 int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads);
 // queries from d_q ([batch*ntok_q][ldq], q columns first), keys/values from d_kv ([batch*ntok_kv][ldkv], K at k_col0, V at v_col0)
 int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, const void* d_kv, int ldkv, int k_col0, int v_col0,
                          void* d_out, int batch, int ntok_q, int ntok_kv, int heads);
-int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv = 0);   // kv: 0 = default kernel, 64 / 128 = key-tile variant
+int launch_attention_op(const AttnOp& op, cudaStream_t s);
 // warp-level mma.sync variant (kept as an independent cross-check of the tcgen05 kernel in the tests)
 int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s);
 int launch_layernorm(int precision, const float* d_x, const float* d_w, const float* d_b, void* d_out, long long rows,

@@ -7,14 +7,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
-#include "attention_tc64.cuh"
-#include "attention_tc2q.cuh"
-#include "attention_tc8w.cuh"
-#include "attention_tcq.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -37,16 +35,38 @@ int fail(int code, const char* fmt, ...) {
 void clear_error() { g_last_error.clear(); }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs).
 int num_sms() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] <= 0) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    cached = n;
+    cached[dev] = n;
   }
-  return cached;
+  return cached[dev];
 }
+
+// Function attributes (dynamic shared memory limit, carve-out) are per DEVICE: set once per (kernel, device ordinal).
+static int ensure_func_attrs(const void* kern, int smem_bytes, bool max_carveout) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  MDE_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kern, dev})) return MDE_OK;
+  MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (max_carveout) MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  done.insert({kern, dev});
+  return MDE_OK;
+}
+
+// Launch options of the calling thread, set by the engine around an enqueue from its description (mde_engine_desc.flags);
+// the single-kernel entry points run with the defaults.
+static thread_local LaunchOpts g_opts;
+void set_launch_opts(const LaunchOpts& o) { g_opts = o; }
+LaunchOpts launch_opts() { return g_opts; }
 
 // ------------------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -81,7 +101,6 @@ static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long
   p.gather_n = 0;
   p.gather_col0 = 0;
   if (ep->gather_n < 0 || ep->gather_n > 8) return fail(MDE_ERR_INVALID, "gemm: at most 8 gather destinations");
-  if (getenv("MDE_NO_TMA_OUT")) return MDE_OK;
   // residual-stream update on plain rows: fp32 boxes of gamma * (acc + bias) are added to x by bulk tensor reductions
   if (ep->d_x && ep->accumulate_x && !ep->d_out && !ep->d_out_relu && !ep->d_res1 && !ep->d_res2 && !ep->d_pos && !ep->d_head_w &&
       ep->act == 0 && !p.conv && p.row_map == ROW_IDENTITY && op->block_n >= 128 && n % op->block_n == 0 && ep->ld_out % 4 == 0 &&
@@ -148,11 +167,11 @@ static int pick_block_n(int n) {
   return best;
 }
 
-// One persistent CTA per SM -- or, for wide tiles with enough rows, one CTA pair per TPC (MDE_NO_PAIR=1 turns pairs off).
+// One persistent CTA per SM -- or, for wide tiles with enough rows, one CTA pair per TPC.
 static void pick_ctas(GemmOp* op) {
   // pairs pay off for 256-wide tiles with a real K loop; short K (a few k-blocks per tile) is epilogue-bound either way
   const bool wide = op->block_n == 256 || (op->block_n == 128 && op->p.num_k_blocks >= 8);
-  op->ctas = (wide && op->p.m_tiles >= 2 && op->p.num_k_blocks >= 4 && !getenv("MDE_NO_PAIR")) ? 2 : 1;
+  op->ctas = (wide && op->p.m_tiles >= 2 && op->p.num_k_blocks >= 4) ? 2 : 1;
 }
 static int pick_grid(GemmOp* op) {
   const int sms = num_sms();
@@ -163,10 +182,10 @@ static int pick_grid(GemmOp* op) {
   pw.kb_per_split = p.num_k_blocks;
   const int units = op->ctas == 2 ? sms / 2 : sms;                                        // CTAs or CTA pairs that can run at once
   const int tiles = op->ctas == 2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
-  if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && getenv("MDE_SPLITK")) {
+  if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && g_opts.split_k) {
     // small batch: a handful of tiles on 148 SMs.  Split K so that every SM gets a piece (at least 8 k-blocks each);
-    // the reduction epilogue adds the partial products in the L2.  Opt-in (MDE_SPLITK=1): the fp32 adds happen in arrival
-    // order, so results are no longer reproducible bit for bit from run to run.
+    // the reduction epilogue adds the partial products in the L2.  Opt-in (MDE_FLAG_SPLIT_K in mde_engine_desc.flags, part
+    // of the engine fingerprint): the fp32 adds happen in arrival order, so results are no longer reproducible bit for bit.
     int splits = std::min(std::min(units / tiles, p.num_k_blocks / 8), 8);
     pw.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
     pw.splits = (p.num_k_blocks + pw.kb_per_split - 1) / pw.kb_per_split;
@@ -291,14 +310,11 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
 }
 
 // Launch with programmatic stream serialisation (see ptx.cuh `griddep_wait`): the kernel may be scheduled while its
-// predecessor drains.  Only for kernels that call griddep_wait() before their first dependent access.  Opt-in (MDE_PDL=1):
-// it takes 3.4 % off the batch-1 latency (3.49 -> 3.37 ms), but Nsight Compute 2025.2 does not list or profile kernels
-// launched with this attribute, and a path that the profiler cannot see is not the default.
-static bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MDE_PDL"); v = (e && atoi(e) != 0) ? 1 : 0; }
-  return v != 0;
-}
+// predecessor drains, so barrier initialisation, TMEM allocation and descriptor prefetch overlap the predecessor's tail.
+// Only for kernels that call griddep_wait() before their first dependent access.  On for engine enqueues unless
+// MDE_FLAG_NO_PDL is set or the process runs under MDE_PROFILE=1 (Nsight Compute 2025.2 does not list kernels launched
+// with the attribute; numerics are identical either way).
+static bool pdl_enabled() { return g_opts.pdl; }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -322,13 +338,9 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 template <int BN, typename T, int kCtas>
 static int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
-  static bool attr_set = false;
   auto kern = gemm_tcgen05_kernel<BN, T, kCtas>;
   using Cfg = GemmCfg<BN, kCtas>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), Cfg::kSmemBytes, false));
   MDE_CUDA_TRY(launch_pdl(kern, dim3(op.grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, s, kCtas, op.map_a, op.map_b, op.map_out, op.gather, op.p));
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -359,12 +371,8 @@ int launch_gemm(const GemmOp& op, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------- other launchers
 template <typename T>
 static int launch_attention_t(const void* d_qkv, void* d_out, int batch, int ntok, int heads, cudaStream_t s) {
-  static bool attr_set = false;
   auto kern = attention_mma_kernel<T>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    attr_set = true;
-  }
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAttnSmemBytes, false));
   AttnParams p;
   p.qkv = d_qkv; p.out = d_out; p.ntok = ntok; p.heads = heads; p.D = heads * 64;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
@@ -402,9 +410,9 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(ldkv), static_cast<cuuint64_t>(rows_kv)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(ldkv) * 2};
-  cuuint32_t box128[2] = {64, 128}, box64[2] = {64, 64};
-  MDE_TRY(encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128));
-  return encode_map(&op->map_kv, precision, d_kv, 2, dims, str, box64);
+  cuuint32_t box128[2] = {64, 128};
+  op->poly = 2;      // the measured optimum (tools/attn_probe.py sweep); engines override it from mde_engine_desc.attn_poly
+  return encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128);
 }
 
 int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads) {
@@ -413,46 +421,9 @@ int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out,
 }
 
 template <typename T, int kPoly>
-static int launch_attention_tc64_t(const AttnOp& op, cudaStream_t s) {
-  static bool attr_set = false;
-  auto kern = attention_tc64_kernel<T, kPoly>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kA64SmemBytes));
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (getenv("MDE_DEBUG")) {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAtcThreads, kA64SmemBytes);
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, kern);
-      fprintf(stderr, "[MDET] attention_tc64: %d CTAs/SM (smem %d B, %d threads, %d regs, %zu B local, %zu B static smem), %d/8 of the exponentials on the FMA pipe\n",
-              nb, kA64SmemBytes, kAtcThreads, fa.numRegs, fa.localSizeBytes, fa.sharedSizeBytes, kPoly);
-    }
-    attr_set = true;
-  }
-  AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
-  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
-  p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
-  kern<<<grid, kAtcThreads, kA64SmemBytes, s>>>(op.map_qkv, op.map_kv, p);
-  MDE_CUDA_TRY(cudaGetLastError());
-  return MDE_OK;
-}
-
-template <typename T, int kPoly>
 static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
-  static bool attr_set = false;
   auto kern = attention_tc_kernel<T, kPoly>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (getenv("MDE_DEBUG")) {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAtcThreads, kAtcSmemBytes);
-      fprintf(stderr, "[MDET] attention_tc: %d CTAs/SM (smem %d B, %d threads), %d/8 of the exponentials on the FMA pipe\n", nb, kAtcSmemBytes, kAtcThreads, kPoly);
-    }
-    attr_set = true;
-  }
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAtcSmemBytes, true));
   AttnParams p;
   p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
@@ -462,134 +433,23 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
-template <typename T, int kPoly>
-static int launch_attention_tc2q_t(const AttnOp& op, cudaStream_t s) {
-  static bool attr_set = false;
-  auto kern = attention_tc2q_kernel<T, kPoly>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes));
-    attr_set = true;
-  }
-  AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
-  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
-  p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok_q + 255) / 256, op.heads, op.batch);
-  kern<<<grid, kA2Threads, kA2SmemBytes, s>>>(op.map_qkv, op.map_kv128, p);
-  MDE_CUDA_TRY(cudaGetLastError());
-  return MDE_OK;
-}
-
-// Share of the exponentials evaluated on the FMA pipe instead of the SFU, in eighths (tuning knob: MDE_ATTN_POLY).
-static int attn_poly() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDE_ATTN_POLY");
-    v = e ? atoi(e) : 2;     // 2 of every 8 element pairs on the FMA pipe: the measured optimum (tools/attn_probe.py, MDE_ATTN_POLY sweep)
-    if (v != 0 && v != 1 && v != 2 && v != 3 && v != 4) v = 2;
-  }
-  return v;
-}
-// Default: 128-key tiles, two CTAs per SM (attention_tc.cuh).  MDE_ATTN_KV=64 (or kv == 64 from mde_k_attention_kv64)
-// selects the four-CTAs-per-SM kernel with 64-key tiles (attention_tc64.cuh): measured slower on B200 (0.84 vs 0.70 ms
-// at B=64, N=1370: both sit at ~60 % of the SFU bound, see profiles/), kept as the measured alternative.
-static int attn_kv() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MDE_ATTN_KV");
-    const int x = e ? atoi(e) : 128;
-    v = (x == 64 || x == 256 || x == 8 || x == 2) ? x : 128;
-  }
-  return v;
-}
-template <typename T, int kPoly>
-static int launch_attention_tc8w_t(const AttnOp& op, cudaStream_t s) {
-  static bool attr_set = false;
-  auto kern = attention_tc8w_kernel<T, kPoly>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kA8SmemBytes));
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (getenv("MDE_DEBUG")) {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kA8Threads, kA8SmemBytes);
-      fprintf(stderr, "[MDET] attention_tc8w: %d CTAs/SM (smem %d B, %d threads)\n", nb, kA8SmemBytes, kA8Threads);
-    }
-    attr_set = true;
-  }
-  AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
-  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
-  p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
-  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kA8Threads), kA8SmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
-  return MDE_OK;
-}
-template <typename T, int kPoly>
-static int launch_attention_tcq_t(const AttnOp& op, cudaStream_t s) {
-  constexpr int kItems = 2;
-  static bool attr_set = false;
-  auto kern = attention_tcq_kernel<T, kPoly, kItems>;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
-    MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
-  }
-  AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
-  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
-  p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  const int q_tiles = (op.ntok_q + 127) / 128;
-  dim3 grid((q_tiles + kItems - 1) / kItems, op.heads, op.batch);
-  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAtcThreads), kAtcSmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
-  return MDE_OK;
-}
+// kPoly of every 8 element pairs of the softmax take the FMA-pipe polynomial instead of the SFU (op.poly, 0..4; the
+// engine's default is 2, the measured optimum).
 template <typename T>
-static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s, int kv = 0) {
-  if ((kv ? kv : attn_kv()) == 2) {          // two query tiles per CTA, one after the other (attention_tcq.cuh)
-    switch (attn_poly()) {
-      case 0: return launch_attention_tcq_t<T, 0>(op, s);
-      case 3: return launch_attention_tcq_t<T, 3>(op, s);
-      default: return launch_attention_tcq_t<T, 2>(op, s);
-    }
-  }
-  if ((kv ? kv : attn_kv()) == 8) {          // eight softmax warps per query tile (attention_tc8w.cuh)
-    switch (attn_poly()) {
-      case 0: return launch_attention_tc8w_t<T, 0>(op, s);
-      case 2: return launch_attention_tc8w_t<T, 2>(op, s);
-      case 4: return launch_attention_tc8w_t<T, 4>(op, s);
-      default: return launch_attention_tc8w_t<T, 3>(op, s);
-    }
-  }
-  if ((kv ? kv : attn_kv()) == 256) {        // two query tiles per CTA, explicit ping-pong (attention_tc2q.cuh)
-    switch (attn_poly()) {
-      case 0: return launch_attention_tc2q_t<T, 0>(op, s);
-      case 2: return launch_attention_tc2q_t<T, 2>(op, s);
-      case 4: return launch_attention_tc2q_t<T, 4>(op, s);
-      default: return launch_attention_tc2q_t<T, 3>(op, s);
-    }
-  }
-  if ((kv ? kv : attn_kv()) == 64) {
-    switch (attn_poly()) {
-      case 0: return launch_attention_tc64_t<T, 0>(op, s);
-      case 2: return launch_attention_tc64_t<T, 2>(op, s);
-      case 4: return launch_attention_tc64_t<T, 4>(op, s);
-      default: return launch_attention_tc64_t<T, 3>(op, s);
-    }
-  }
-  switch (attn_poly()) {
+static int launch_attention_tc_p(const AttnOp& op, cudaStream_t s) {
+  switch (op.poly) {
     case 0: return launch_attention_tc_t<T, 0>(op, s);
     case 1: return launch_attention_tc_t<T, 1>(op, s);
     case 2: return launch_attention_tc_t<T, 2>(op, s);
-    case 4: return launch_attention_tc_t<T, 4>(op, s);
     case 3: return launch_attention_tc_t<T, 3>(op, s);
-    default: return launch_attention_tc_t<T, 2>(op, s);
+    case 4: return launch_attention_tc_t<T, 4>(op, s);
   }
+  return fail(MDE_ERR_INVALID, "attention: the polynomial share is 0..4 eighths, not %d", op.poly);
 }
 template <typename T>
 static int launch_attention_trace_t(const AttnOp& op, long long* d_trace, cudaStream_t s) {
   auto kern = attention_tc_kernel<T, 2, true>;
-  MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
-  MDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAtcSmemBytes, true));
   AttnParams p;
   p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = d_trace;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
@@ -600,8 +460,8 @@ static int launch_attention_trace_t(const AttnOp& op, long long* d_trace, cudaSt
   return MDE_OK;
 }
 
-int launch_attention_op(const AttnOp& op, cudaStream_t s, int kv) {
-  return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s, kv) : launch_attention_tc_p<__half>(op, s, kv);
+int launch_attention_op(const AttnOp& op, cudaStream_t s) {
+  return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s) : launch_attention_tc_p<__half>(op, s);
 }
 
 template <typename T, bool kTap>
@@ -689,12 +549,8 @@ int launch_qknorm_rope(int precision, void* d_qkv, long long rows, int heads, co
   const int sms = num_sms();
   if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
   const dim3 grid(static_cast<unsigned>(std::min<long long>((rows + 7) / 8, 2LL * sms)));   // persistent warps, two CTAs per SM
-  static bool attr_set = false;
-  if (!attr_set) {
-    MDE_CUDA_TRY(cudaFuncSetAttribute(qknorm_rope_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRopeSmemBytes));
-    MDE_CUDA_TRY(cudaFuncSetAttribute(qknorm_rope_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRopeSmemBytes));
-    attr_set = true;
-  }
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(qknorm_rope_kernel<__nv_bfloat16>), kRopeSmemBytes, false));
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(qknorm_rope_kernel<__half>), kRopeSmemBytes, false));
   if (precision == MDE_BF16) MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__nv_bfloat16>, grid, dim3(256), kRopeSmemBytes, s, 1, p));
   else MDE_CUDA_TRY(launch_pdl(qknorm_rope_kernel<__half>, grid, dim3(256), kRopeSmemBytes, s, 1, p));
   return MDE_OK;
@@ -939,20 +795,21 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
 }
 
+int mde_k_attention_poly(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                         int32_t poly_eighths, void* stream) {
+  clear_error();
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  op.poly = poly_eighths;
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream));
+}
+
 int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
                        int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream) {
   clear_error();
   AttnOp op;
   MDE_TRY(make_attention_op_kv(&op, precision, d_q, ldq, d_kv, ldkv, k_col0, v_col0, d_out, batch, ntok_q, ntok_kv, heads));
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
-}
-
-int mde_k_attention_2q(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                       void* stream) {
-  clear_error();
-  AttnOp op;
-  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
-  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 256);
 }
 
 int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
@@ -963,30 +820,6 @@ int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
   return precision == MDE_BF16 ? launch_attention_trace_t<__nv_bfloat16>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream))
                                : launch_attention_trace_t<__half>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream));
-}
-
-int mde_k_attention_q2(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                       void* stream) {
-  clear_error();
-  AttnOp op;
-  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
-  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 2);
-}
-
-int mde_k_attention_8w(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                       void* stream) {
-  clear_error();
-  AttnOp op;
-  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
-  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 8);
-}
-
-int mde_k_attention_kv64(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                         void* stream) {
-  clear_error();
-  AttnOp op;
-  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
-  return launch_attention_op(op, static_cast<cudaStream_t>(stream), 64);
 }
 
 int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,

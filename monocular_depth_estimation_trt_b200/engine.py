@@ -37,7 +37,10 @@ _NP_DTYPES = {_lib.MDE_DT_F32: np.dtype(np.float32), _lib.MDE_DT_U8: np.dtype(np
 def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode: str = "f32_nchw",
               max_src_hw: Tuple[int, int] = (0, 0), swap_rb: bool = True,
               mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
-              device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF, output: str = "model_grid") -> _lib.EngineDesc:
+              device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF, output: str = "model_grid",
+              split_k: bool = False, pdl: bool = True, graph: bool = True, attn_poly: int = -1) -> _lib.EngineDesc:
+    """`split_k`, `pdl`, `graph` and `attn_poly` are the engine's tuning surface (mde_engine_desc.flags / attn_poly): they are
+    part of the description -- and of the fingerprint `get_engine` records -- not environment variables."""
     if precision not in _lib.PRECISIONS:
         # The reference also builds "fp32" engines (core/common.py:141-150).  The B200 path is a
         # 16-bit tensor-core path with fp32 accumulation; refuse instead of silently downgrading.
@@ -67,6 +70,9 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
     if output not in ("model_grid", "source_grid"):
         raise ValueError(f"[MDET] unknown output {output!r}")
     d.output_mode = _lib.MDE_OUTPUT_SOURCE_GRID if output == "source_grid" else _lib.MDE_OUTPUT_MODEL_GRID
+    d.flags = ((_lib.MDE_FLAG_SPLIT_K if split_k else 0) | (0 if pdl else _lib.MDE_FLAG_NO_PDL) |
+               (0 if graph else _lib.MDE_FLAG_NO_GRAPH))
+    d.attn_poly = int(attn_poly)
     return d
 
 
@@ -204,9 +210,11 @@ class Engine:
         _lib.check(self._lib.mde_engine_load_weights(self._h, path.encode()), f"load_weights({path})")
         gh = self._desc.input_h // self._desc.patch_size
         gw = self._desc.input_w // self._desc.patch_size
-        if (gh, gw) != (37, 37):
-            sd, _ = W.load(path)
-            self.set_weight("pretrained.pos_embed", W.resize_pos_embed(sd["pretrained.pos_embed"], gh, gw))
+        # the trained grid is whatever the stored table holds (37 x 37 for the /14 checkpoints, 24 x 24 for ViT/16 at 384):
+        # only that one tensor is read again, and only when this engine's grid differs from it
+        pos = W.load_tensor(path, "pretrained.pos_embed")
+        if pos.shape[1] != gh * gw + 1 or gh != gw:
+            self.set_weight("pretrained.pos_embed", W.resize_pos_embed(pos, gh, gw))
 
     def finalize(self) -> "Engine":
         _lib.check(self._lib.mde_engine_finalize(self._h), "mde_engine_finalize")

@@ -136,6 +136,26 @@ def load(path: str) -> Tuple[Dict[str, np.ndarray], dict]:
     return out, meta
 
 
+def load_tensor(path: str, wanted: str) -> np.ndarray:
+    """Read ONE tensor of an .mdew file, seeking past the data of the others."""
+    with open(path, "rb") as f:
+        if f.read(8) != MAGIC:
+            raise ValueError(f"[MDET] {path} is not an MDEW0001 weights file")
+        (n,) = struct.unpack("<I", f.read(4))
+        f.seek(n, 1)
+        (count,) = struct.unpack("<I", f.read(4))
+        for _ in range(count):
+            (ln,) = struct.unpack("<I", f.read(4))
+            name = f.read(ln).decode("utf-8")
+            (nd,) = struct.unpack("<I", f.read(4))
+            dims = struct.unpack(f"<{nd}q", f.read(8 * nd))
+            cnt = int(np.prod(dims)) if nd else 1
+            if name == wanted:
+                return np.frombuffer(f.read(4 * cnt), dtype="<f4").reshape(dims).copy()
+            f.seek(4 * cnt, 1)
+    raise KeyError(f"[MDET] {path} holds no tensor named {wanted!r}")
+
+
 def file_sha256(path: str) -> str:
     h = hashlib.sha256()
     with open(path, "rb") as f:

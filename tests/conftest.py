@@ -39,7 +39,8 @@ def lib():
 
 
 @pytest.fixture
-def bitwise(monkeypatch):
-    """Tests that compare two runs with `torch.equal` need the default, bitwise-reproducible configuration: split-K for
-    small batches (MDE_SPLITK=1: partial products meet in the L2's fp32 adds, in arrival order) must be off."""
-    monkeypatch.delenv("MDE_SPLITK", raising=False)
+def bitwise():
+    """Tests that compare two runs with `torch.equal` rely on the default, bitwise-reproducible configuration.  Everything
+    that could break it (split-K for small batches) is an explicit field of the engine description now, off by default;
+    the fixture is kept as the marker of that requirement."""
+    yield

@@ -66,9 +66,15 @@ def pack_conv3x3(w, dtype):
 
 
 def attention(precision, qkv, batch, ntok, heads, variant="tc"):
+    """variant: "tc" (the engine's kernel), "tc:<n>" (the same with n/8 of the exponentials on the FMA pipe), "mma" (the
+    independent mma.sync cross-check)."""
     lib = _lib.load()
     out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
-    fn = {"tc": lib.mde_k_attention, "kv64": lib.mde_k_attention_kv64, "2q": lib.mde_k_attention_2q, "8w": lib.mde_k_attention_8w, "q2": lib.mde_k_attention_q2, "mma": lib.mde_k_attention_mma}[variant]
+    if variant.startswith("tc:"):
+        _lib.check(lib.mde_k_attention_poly(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, int(variant[3:]), stream()),
+                   "mde_k_attention_poly")
+        return out
+    fn = {"tc": lib.mde_k_attention, "mma": lib.mde_k_attention_mma}[variant]
     _lib.check(fn(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()), "mde_k_attention")
     return out
 

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
-    assert lib.mde_abi_version() == 1
+    assert lib.mde_abi_version() == _lib.MDE_ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header(tmp_path):

@@ -305,19 +305,15 @@ def test_graph_replay_matches_plain_launches(lib, bitwise):
     eng.close()
 
 
-def test_split_k_changes_only_the_last_bits(lib, monkeypatch):
-    """Batch 1 with MDE_SPLITK=1: FC2 / projection split K over the SMs and meet in the L2's fp32 adds (arrival order).  Against the
+def test_split_k_changes_only_the_last_bits(lib):
+    """Batch 1 with split_k=True (MDE_FLAG_SPLIT_K in the engine description): FC2 / projection split K over the SMs and meet in the L2's fp32 adds (arrival order).  Against the
     unsplit engine the depth map moves the way any re-association of fp32 sums moves a 16-bit pipeline (some 16-bit
     roundings flip downstream); both stay inside the parity gate on the oracle."""
     sd, x, depth, _ = R.reference("vits")
     outs = []
-    for split in ("1", ""):
-        if split:
-            monkeypatch.setenv("MDE_SPLITK", "1")
-        else:
-            monkeypatch.delenv("MDE_SPLITK", raising=False)
+    for split in (True, False):
         meta = W.describe("vits", 518, 518, 20.0)
-        eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1), meta)
+        eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1, split_k=split), meta)
         eng.load_state_dict(sd)
         eng.finalize()
         out = torch.full((1, 518, 518), float("nan"), device="cuda")
