@@ -1,0 +1,133 @@
+"""The reference's measurement and parity harness, restated.  TEST INFRASTRUCTURE ONLY (tests/, bench.py's checker legs,
+__graft_entry__.smoke()); the product package never imports this file.
+
+  compare()       core/golden.py:101-174 `compare` for one output: pairwise finite mask, max_abs / mean_abs / rel_mean, and
+                  the per-pixel depth metrics (abs_rel, abs_rel_median, rmse, delta1) over pixels where both maps exceed 1e-6
+                  -- plus `max_rel`, the per-pixel maximum north_star gates on (the reference does not report it)
+  measure()       core/bench.py:182-210 `measure`: warm-up, then perf_counter around fn() + sync() per iteration
+  pct()/stats()   core/bench.py:113-150 `Bench.pct` / `Bench.stats`: nearest-rank percentiles (rank = ceil(q/100 * N))
+
+Pinned: tests/test_oracle_harness.py checks every function against the live reference modules where /root/reference is
+mounted, and against tests/golden/harness_golden.json (produced by the reference's own functions, oracle/make_golden.py)
+everywhere else.  Where the reference is mounted `reference_modules()` hands out the real `core.bench` / `core.golden`,
+and callers use those instead of the restatement.
+"""
+from __future__ import annotations
+
+import importlib
+import math
+import os
+import statistics
+import sys
+import time
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("MDE_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_modules():
+    """(core.bench, core.golden) of the reference checkout, or (None, None) when it is not mounted (the GPU box)."""
+    if not os.path.isfile(os.path.join(REFERENCE_ROOT, "core", "golden.py")):
+        return None, None
+    added = REFERENCE_ROOT not in sys.path
+    if added:
+        sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        return importlib.import_module("core.bench"), importlib.import_module("core.golden")
+    except Exception:
+        return None, None
+    finally:
+        if added:
+            sys.path.remove(REFERENCE_ROOT)
+
+
+def compare(ref: np.ndarray, got: np.ndarray, valid_mask: Optional[np.ndarray] = None) -> dict:
+    """One entry of core/golden.py `compare` (depth_metrics=True), plus max_rel."""
+    a, b = np.asarray(ref, np.float64), np.asarray(got, np.float64)
+    if a.shape != b.shape:
+        return {"status": "shape_mismatch", "ref_shape": list(a.shape), "new_shape": list(b.shape)}
+    finite = np.isfinite(a) & np.isfinite(b)
+    if valid_mask is not None and valid_mask.shape == a.shape:
+        finite &= valid_mask.astype(bool)
+    n = int(finite.sum())
+    if n == 0:
+        return {"status": "no_finite_overlap"}
+    av, bv = a[finite], b[finite]
+    d = np.abs(av - bv)
+    scale = np.abs(av).mean()
+    entry = {"status": "ok", "compared": n, "excluded": int(a.size - n), "max_abs": float(d.max()),
+             "mean_abs": float(d.mean()), "rel_mean": float(d.mean() / scale) if scale > 0 else None,
+             "identical": bool(d.max() == 0)}
+    pos = (av > 1e-6) & (bv > 1e-6)
+    k = int(pos.sum())
+    if k:
+        ap, bp = av[pos], bv[pos]
+        rel = np.abs(ap - bp) / ap
+        ratio = np.maximum(ap / bp, bp / ap)
+        entry.update({"abs_rel": float(rel.mean()), "abs_rel_median": float(np.median(rel)),
+                      "rmse": float(np.sqrt(((ap - bp) ** 2).mean())), "delta1": float((ratio < 1.25).mean()),
+                      "positive": k, "max_rel": float(rel.max())})
+    return entry
+
+
+def compare_depth(ref: np.ndarray, got: np.ndarray) -> dict:
+    """Parity record of one depth map: the reference's `compare` entry (its own function where the checkout is mounted)
+    with `max_rel` and the Pearson correlation added."""
+    _, golden = reference_modules()
+    entry = compare(ref, got)
+    if golden is not None and entry.get("status") == "ok":
+        theirs = golden.compare({"depth": np.asarray(ref)}, {"depth": np.asarray(got)})["depth"]
+        for key, val in theirs.items():
+            if isinstance(val, float):
+                assert math.isclose(val, entry[key], rel_tol=1e-12, abs_tol=0.0), (key, val, entry[key])
+            else:
+                assert val == entry[key], (key, val, entry[key])
+        entry = {**theirs, "max_rel": entry.get("max_rel")}
+    a, b = np.asarray(ref, np.float64).ravel(), np.asarray(got, np.float64).ravel()
+    ok = np.isfinite(a) & np.isfinite(b)
+    entry["corr"] = float(np.corrcoef(a[ok], b[ok])[0, 1]) if ok.sum() > 1 else float("nan")
+    return entry
+
+
+def measure(fn: Callable[[], object], *, warmup: int = 10, iterations: int = 100, sync: Optional[Callable[[], None]] = None):
+    """core/bench.py `measure`: (last return value, per-iteration wall-clock milliseconds incl. sync)."""
+    bench, _ = reference_modules()
+    if bench is not None:
+        return bench.measure(fn, warmup=warmup, iterations=iterations, sync=sync if sync is not None else (lambda: None))
+    if sync is None:
+        sync = lambda: None
+    for _ in range(warmup):
+        fn()
+    sync()
+    out, samples = None, []
+    for _ in range(iterations):
+        t0 = time.perf_counter()
+        out = fn()
+        sync()
+        samples.append((time.perf_counter() - t0) * 1000.0)
+    return out, samples
+
+
+def pct(samples_ms: List[float], q: float) -> float:
+    """Nearest-rank percentile, q in [0, 100] (core/bench.py `Bench.pct`)."""
+    if not samples_ms:
+        return 0.0
+    s = sorted(samples_ms)
+    return s[min(len(s) - 1, max(0, math.ceil(q / 100.0 * len(s)) - 1))]
+
+
+def stats(samples_ms: List[float], warmup: int = 0) -> Dict[str, float]:
+    """core/bench.py `Bench.stats` without the stage breakdown."""
+    bench, _ = reference_modules()
+    if bench is not None:
+        return bench.Bench(model="_", samples_ms=list(samples_ms), warmup=warmup).stats()
+    if not samples_ms:
+        return {}
+    mean = statistics.fmean(samples_ms)
+    return {"iterations": len(samples_ms), "warmup": warmup, "mean_ms": round(mean, 4), "min_ms": round(min(samples_ms), 4),
+            "p50_ms": round(pct(samples_ms, 50), 4), "p90_ms": round(pct(samples_ms, 90), 4),
+            "p99_ms": round(pct(samples_ms, 99), 4), "max_ms": round(max(samples_ms), 4),
+            "stdev_ms": round(statistics.stdev(samples_ms), 4) if len(samples_ms) > 1 else 0.0,
+            "fps": round(1000.0 / mean if mean else 0.0, 2)}

@@ -180,8 +180,16 @@ def preprocess_u8_pad(precision, src_u8, dst_h, dst_w, patch=14, kpad=640, swap_
 
 
 def rel_err(got, ref):
+    """The larger of two error measures: the global one (max |d| / max |ref|) and the per-element one
+    (max_i |d_i| / (|ref_i| + rms(ref))), which a localised error in a small-magnitude output cannot hide behind -- an
+    element is held to its own magnitude plus one rms of the tensor (the floor that fp32 accumulation-order noise of a
+    cancelling sum needs)."""
     got, ref = got.float(), ref.float()
-    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    d = (got - ref).abs()
+    glob = d.max() / ref.abs().max().clamp_min(1e-30)
+    rms = (ref.double() ** 2).mean().sqrt().float().clamp_min(1e-30)
+    elem = (d / (ref.abs() + rms)).max()
+    return float(torch.maximum(glob, elem))
 
 
 def rms_rel(got, ref):

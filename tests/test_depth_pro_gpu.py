@@ -3,9 +3,10 @@ the post-processing kernel against the reference script's formulae, and the whol
 host API (allocate_buffers / do_inference) -- against the oracle (oracle/depth_pro_torch.py, pinned on transformers'
 DepthProForDepthEstimation).
 
-Gates for the model outputs: the same as Depth Anything's (tests/test_engine_gpu.py): fp16 at north_star's numbers
-(max relative error <= 1e-2, AbsRel <= 2e-3), bf16 at the precision plan's own error; intermediate maps in RMS-relative
-error.  The field of view is one fp32 number out of a 16-bit pipeline: 0.05 degrees (fp16) / 0.5 degrees (bf16)."""
+Gate for the model outputs: the same single gate as Depth Anything's (tests/test_engine_gpu.py), north_star's numbers (max
+relative error <= 1e-2, AbsRel <= 2e-3) for every precision.  fp16 must meet it; bf16 asserts a regression guard (the
+precision plan's own error) and reports itself as xfail against the gate with the measured numbers.  Intermediate maps are
+gated in RMS-relative error.  The field of view is one fp32 number out of a 16-bit pipeline: 0.05 degrees (fp16) / 0.5 (bf16)."""
 import numpy as np
 import pytest
 import torch
@@ -15,7 +16,9 @@ from monocular_depth_estimation_trt_b200 import common, depth_pro as DPE, shardi
 
 pytestmark = pytest.mark.gpu
 
-GATE = {"fp16": dict(abs_rel=2e-3, max_rel=1e-2, fov=0.05), "bf16": dict(abs_rel=1.2e-2, max_rel=1.2e-1, fov=0.5)}
+GATE = dict(abs_rel=2e-3, max_rel=1e-2)                        # north_star, every precision
+BF16_REGRESSION_GUARD = dict(abs_rel=1.2e-2, max_rel=1.2e-1)     # not a parity claim: keeps a broken bf16 kernel from hiding behind the xfail
+FOV_DEG = {"fp16": 0.05, "bf16": 0.5}
 INTER = {"fp16": 1.2e-3, "bf16": 9e-3}
 
 
@@ -98,8 +101,13 @@ def test_whole_model_against_the_oracle(lib, prec):
     m = R.compare_depth(inv.numpy(), got_inv)
     print(prec, launches, "launches", m, "fov", got_fov, float(fov))
     assert m["positive"] == 1536 * 1536
-    assert m["abs_rel"] <= GATE[prec]["abs_rel"] and m["max_rel"] <= GATE[prec]["max_rel"], m
-    assert abs(got_fov - float(fov)) <= GATE[prec]["fov"]
+    assert abs(got_fov - float(fov)) <= FOV_DEG[prec]
+    if prec == "bf16":
+        assert m["abs_rel"] <= BF16_REGRESSION_GUARD["abs_rel"] and m["max_rel"] <= BF16_REGRESSION_GUARD["max_rel"], m
+        if not (m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= GATE["max_rel"]):
+            pytest.xfail(f"bf16 operands miss north_star's gate on the fp32 oracle: abs_rel {m['abs_rel']:.2e}, max_rel {m['max_rel']:.2e}")
+    else:
+        assert m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= GATE["max_rel"], m
 
 
 def test_get_engine_builds_depth_pro_from_an_exported_file(lib, tmp_path):

@@ -3,14 +3,14 @@
 Oracle: oracle/dav2_torch.py fp32 forward on the same synthetic input and the same seeded,
 calibrated random-init weights (BASELINE.json configs[0]: ViT-S 518x518 batch 1; configs[1]: ViT-L).
 
-Gates (north_star): final depth max relative error <= 1e-2 and AbsRel <= 2e-3.
-  * precision "fp16" (the reference's own build target, models/depth_anything_v2/onnx2trt.py:61)
-    must meet that gate.
-  * precision "bf16" cannot on this oracle: rounding only the *weights* to bf16 and running
-    everything else in fp32 already gives AbsRel 3.0e-3 / max-rel 2.7e-2 (tests/test_precision_plan.py
-    reproduces this on the CPU).  bf16 is therefore gated at the error of the precision plan itself:
-    the CPU emulation of the plan (tests/bf16_emulation.py) scores AbsRel 7.3e-3 / max-rel 7.6e-2 on
-    this input, and the gate is that with 1.6x head-room for different rounding realisations.
+ONE gate (north_star): final depth max relative error <= 1e-2 and AbsRel <= 2e-3, for every precision.
+  * precision "fp16" (the reference's own build target, models/depth_anything_v2/onnx2trt.py:61, and the default /
+    benchmarked precision of this runtime) must meet it.
+  * precision "bf16" does not on this oracle, and cannot: rounding only the *weights* to bf16 and running everything else
+    in fp32 already gives AbsRel 3.0e-3 / max-rel 2.7e-2 (tests/test_precision_plan.py reproduces this on the CPU).  The
+    bf16 cases therefore run the same checks, assert a REGRESSION GUARD (the emulated error of the bf16 plan itself,
+    tests/bf16_emulation.py: AbsRel 7.3e-3 / max-rel 7.6e-2, x1.6) so that a broken kernel still fails, and then report
+    themselves as xfail against the gate with the measured numbers -- the gate is never widened.
   * intermediate tensors (residual stream after blocks 5 and 11, the four layer_rn maps, path_1)
     are gated in RMS-relative error at 2x what the same emulation measures for each precision.
 """
@@ -25,7 +25,20 @@ from monocular_depth_estimation_trt_b200 import common, engine as E, weights as 
 
 pytestmark = pytest.mark.gpu
 
-GATE = {"fp16": dict(abs_rel=2e-3, max_rel=1e-2), "bf16": dict(abs_rel=1.2e-2, max_rel=1.2e-1)}
+GATE = dict(abs_rel=2e-3, max_rel=1e-2)                      # north_star, every precision
+BF16_REGRESSION_GUARD = dict(abs_rel=1.2e-2, max_rel=1.2e-1)   # the bf16 plan's own emulated error x1.6: not a parity claim
+
+
+def gate(m, prec):
+    """Assert north_star's gate; bf16 is reported against the same gate as an expected failure (after its regression guard)."""
+    if prec == "bf16":
+        assert m["abs_rel"] <= BF16_REGRESSION_GUARD["abs_rel"] and m["max_rel"] <= BF16_REGRESSION_GUARD["max_rel"], m
+        if not (m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= GATE["max_rel"]):
+            pytest.xfail(f"bf16 operands miss north_star's gate on the fp32 oracle: abs_rel {m['abs_rel']:.2e} (<= 2e-3), "
+                         f"max_rel {m['max_rel']:.2e} (<= 1e-2); fp16 is the precision that meets it")
+        return
+    assert m["abs_rel"] <= GATE["abs_rel"], m
+    assert m["max_rel"] <= GATE["max_rel"], m
 # RMS-relative budgets: emulation gives 4.3e-4 (fp16) / 3.6e-3 (bf16) on the residual stream and
 # 7.5e-4 / 5.9e-3 on the head's maps
 INTER = {"fp16": 9e-4, "bf16": 7.5e-3}
@@ -86,9 +99,8 @@ def test_vits_518_b1_parity_and_intermediates(lib, prec):
         r = fetch(ctx, f"r{i}", (1, hh, hh, 64), prec).permute(0, 3, 1, 2)
         assert rms_rel(r, trace[f"layer{i + 1}_rn"]) < 1.7 * INTER[prec]
     assert m["compared"] == 518 * 518
-    assert m["abs_rel"] <= GATE[prec]["abs_rel"]
-    assert m["max_rel"] <= GATE[prec]["max_rel"]
     assert m["corr"] > 0.9995
+    gate(m, prec)
 
 
 def test_embed_tokens_match_oracle(lib):
@@ -123,8 +135,10 @@ def test_vitl_518_b2_parity(lib, prec):
     for b in range(2):
         m = R.compare_depth(ref[b].numpy(), out[b].cpu().numpy())
         print(prec, b, m)
-        assert m["abs_rel"] <= GATE[prec]["abs_rel"]
-        assert m["max_rel"] <= GATE[prec]["max_rel"]
+        if prec == "fp16" or b == 1:       # bf16: image 0 runs the regression guard only; the xfail report comes with the last image
+            gate(m, prec)
+        else:
+            assert m["abs_rel"] <= BF16_REGRESSION_GUARD["abs_rel"] and m["max_rel"] <= BF16_REGRESSION_GUARD["max_rel"], m
 
 
 @pytest.mark.parametrize("h,w", [(616, 1064), (518, 700), (266, 518)])
@@ -141,8 +155,8 @@ def test_vits_non_square_token_grids(lib, h, w):
     m = R.compare_depth(depth.numpy(), out.cpu().numpy())
     print(h, w, m)
     assert m["compared"] == h * w
-    assert m["abs_rel"] <= GATE["fp16"]["abs_rel"]
-    assert m["max_rel"] <= GATE["fp16"]["max_rel"]
+    assert m["abs_rel"] <= GATE["abs_rel"]
+    assert m["max_rel"] <= GATE["max_rel"]
 
 
 def test_batch_entries_are_independent(lib, bitwise):
@@ -207,7 +221,7 @@ def test_reference_call_shape_do_inference(lib, tmp_path):
         timer.free()
         common.free_buffers(inputs, outputs, stream)
     m = R.compare_depth(depth.numpy(), got)
-    assert m["abs_rel"] <= GATE["fp16"]["abs_rel"] and m["max_rel"] <= GATE["fp16"]["max_rel"]
+    assert m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= GATE["max_rel"]
     assert (tmp_path / "engine" / "dav2_vits_fp16.fingerprint").exists()
 
 
@@ -325,10 +339,10 @@ def test_split_k_changes_only_the_last_bits(lib):
     # fp32 re-association upstream flips 16-bit roundings downstream, and twelve blocks later the two runs carry two
     # independent realisations of the pipeline's rounding noise: they differ from each other by about as much as each
     # differs from the fp32 oracle (measured AbsRel 7.0e-4 / max-rel 9.5e-3), i.e. inside north_star's gate, not bitwise
-    assert m["abs_rel"] < GATE["fp16"]["abs_rel"] and m["max_rel"] < 1.5 * GATE["fp16"]["max_rel"]
+    assert m["abs_rel"] < GATE["abs_rel"] and m["max_rel"] < 1.5 * GATE["max_rel"]
     for o in outs:
         g = R.compare_depth(depth.numpy(), o.numpy())
-        assert g["abs_rel"] <= GATE["fp16"]["abs_rel"] and g["max_rel"] <= GATE["fp16"]["max_rel"]
+        assert g["abs_rel"] <= GATE["abs_rel"] and g["max_rel"] <= GATE["max_rel"]
 
 
 def test_vitb_relative_head_parity(lib):
@@ -350,7 +364,7 @@ def test_vitb_relative_head_parity(lib):
     assert float(got.min()) >= 0.0
     m = R.compare_depth(depth.numpy(), got)
     print("vitb relative", m)
-    assert m["abs_rel"] <= GATE["fp16"]["abs_rel"] and m["max_rel"] <= 2 * GATE["fp16"]["max_rel"]
+    assert m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= 2 * GATE["max_rel"]
     assert m["corr"] > 0.9995
 
 
