@@ -76,6 +76,9 @@ def compare_depth(ref: np.ndarray, got: np.ndarray) -> dict:
     """Parity record of one depth map: the reference's `compare` entry (its own function where the checkout is mounted)
     with `max_rel` and the Pearson correlation added."""
     _, golden = reference_modules()
+    ref, got = np.asarray(ref), np.asarray(got)
+    if ref.shape != got.shape and ref.size == got.size:      # [1, H, W] against [H, W]: the callers' reshape, done here
+        ref, got = np.squeeze(ref), np.squeeze(got)
     entry = compare(ref, got)
     if golden is not None and entry.get("status") == "ok":
         theirs = golden.compare({"depth": np.asarray(ref)}, {"depth": np.asarray(got)})["depth"]

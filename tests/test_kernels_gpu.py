@@ -168,7 +168,7 @@ def test_conv3x3_fused_depth_head(lib, prec, max_depth):
 
 
 # ------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("variant", ["tc", "tc:0", "tc:4", "mma"])
+@pytest.mark.parametrize("variant", ["tc", "k0:0", "k0:4", "k1", "k1:0", "k2", "k2:4", "mma"])
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,ntok,heads", [(2, 1370, 6), (1, 577, 16), (3, 64, 2), (1, 129, 1), (1, 3349, 2),
                                           (2, 256, 3), (1, 257, 2), (2, 128, 1)])
@@ -222,7 +222,7 @@ def test_im2col_stride2_matches_conv(lib, prec):
     w = rnd((64, c, 3, 3), dt, seed=20)
     got = (cols.float() @ w.permute(0, 2, 3, 1).reshape(64, 9 * c).float().t()).reshape(B, 19, 19, 64)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1).permute(0, 2, 3, 1)
-    assert K.rel_err(got, ref) < 1e-5     # the gather itself is exact; fp32 matmul order only
+    assert K.rel_err(got, ref) < 3e-5     # the gather itself is exact; fp32 matmul order only (K = 9 * c products per element)
 
 
 # ------------------------------------------------------------------------------------------ kernel (1)
@@ -363,7 +363,7 @@ def test_preprocess_keep_ratio_pad_bit_exact(lib, src, dst):
 
 
 # ------------------------------------------------------------------------------------------ edge cases
-@pytest.mark.parametrize("variant", ["tc", "tc:0", "tc:3"])
+@pytest.mark.parametrize("variant", ["tc", "k0:3", "k1", "k1:3", "k2", "k2:0"])
 @pytest.mark.parametrize("B,ntok,heads", [(1, 1, 1), (2, 5, 2), (1, 31, 1), (1, 32, 1), (1, 33, 3), (1, 127, 1), (1, 128, 2), (3, 255, 1), (1, 256, 1), (1, 257, 1)])
 def test_attention_ragged_token_counts(lib, variant, B, ntok, heads):
     """One token, tile boundaries and every +-1 around them: masking of the ragged last key tile, clipped query rows,
