@@ -391,6 +391,15 @@ def run_ours(args):
                    "sample": f"{len(idx)} images of the batch (the first and the last), oracle/dav2_torch.py fp32 forward, batch 1 per call, "
                              f"torch {threads} threads"}
 
+    # ---------------- the partitioned configurations (strong scaling over the ranks; every rank takes part)
+    partitioned = None
+    if not args.no_partitioned:
+        import bench_partitioned
+        ctx.close(); eng.close()          # idempotent: free the batch-64 workspace before the other models are built
+        d_in = d_out = None
+        torch.cuda.empty_cache()
+        partitioned = bench_partitioned.run_all(world, rank, local, args.precision)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -405,7 +414,7 @@ def run_ours(args):
                        "b1_note": "batch-1 latency: `latency_b1` (or python bench.py --batch 1)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "latency_b1": latency, "other_precision": other,
-            "breakdown_ms_per_step": breakdown,
+            "partitioned": partitioned, "breakdown_ms_per_step": breakdown,
         }
         print(json.dumps(line))
     if world > 1:
@@ -423,6 +432,7 @@ def main():
     # bf16 does not; both use the same tensor-core rate.  The other one is measured beside it.
     ap.add_argument("--precision", default="fp16", choices=["bf16", "fp16"])
     ap.add_argument("--no-other-precision", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the VGGT-aggregator / Depth Pro legs (strong scaling over the ranks)")
     ap.add_argument("--encoder", default="vitl", choices=["vits", "vitb", "vitl"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -104,7 +104,6 @@ typedef struct mde_engine_desc {
   int32_t flags;           /* MDE_FLAG_* */
   int32_t attn_poly;       /* eighths of the softmax exponentials evaluated by a polynomial on the FMA pipe instead of the
                             * SFU: 0..4, or -1 for the library default (2).  Changes the last bits of the probabilities. */
-  int32_t attn_kernel;     /* attention kernel, see mde_k_attention_tuned; -1 for the library default */
 } mde_engine_desc;
 
 const char* mde_last_error(void);
@@ -234,11 +233,10 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
  * V at v_col0; d_out: [batch*ntok_q][heads*64]. */
 int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
                        int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream);
-/* mde_k_attention with an explicit kernel (0: 128-key tiles, one S buffer in TMEM; 1: 96-key tiles, S double-buffered, P
- * stored over its S; 2: the same with the speculative row maximum; -1: the library default) and an explicit share of
- * polynomial exponentials (poly_eighths 0..4, -1: default).  tools/attn_probe.py sweeps both. */
-int mde_k_attention_tuned(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                          int32_t kernel, int32_t poly_eighths, void* stream);
+/* mde_k_attention with an explicit share of polynomial exponentials (poly_eighths 0..4, -1: the library default;
+ * tools/attn_sweep.py sweeps it). */
+int mde_k_attention_poly(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                         int32_t poly_eighths, void* stream);
 /* The default attention kernel with clock64 stamps of the softmax warps' phases (profiling aid, tools/attn_trace.py):
  * d_trace int64 [2048 CTAs][4 warps][64 slots], zero-initialised by the caller; slot 0 kernel entry, 1 after the prologue sync,
  * then per key tile: S available, S in registers, exponentials done, previous P V done, P stored; then O available, stored. */

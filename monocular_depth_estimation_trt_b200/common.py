@@ -98,7 +98,6 @@ def get_engine(
     pdl: bool = True,
     graph: bool = True,
     attn_poly: int = -1,
-    attn_kernel: int = -1,
 ):
     """Build the engine for the exported model at `onnx_file_path` (an .mdew file here).
 
@@ -116,7 +115,7 @@ def get_engine(
     (mde_engine_desc.flags, attn_poly).  Every keyword enters the fingerprint.
     """
     extra = dict(output=output, max_src_hw=tuple(max_src_hw), swap_rb=bool(swap_rb), world=world, gather=gather,
-                 split_k=bool(split_k), pdl=bool(pdl), graph=bool(graph), attn_poly=int(attn_poly), attn_kernel=int(attn_kernel))
+                 split_k=bool(split_k), pdl=bool(pdl), graph=bool(graph), attn_poly=int(attn_poly))
     model_path = os.fspath(onnx_file_path)
     if not os.path.exists(model_path):
         raise FileNotFoundError(f"[MDET] model file {model_path} not found.")
@@ -153,7 +152,7 @@ def get_engine(
         return engine
     desc = make_desc(meta, precision=precision, batch=batch, input_mode=input_mode,
                      max_src_hw=max_src_hw, swap_rb=swap_rb, device=device, output=output,
-                     split_k=split_k, pdl=pdl, graph=graph, attn_poly=attn_poly, attn_kernel=attn_kernel)
+                     split_k=split_k, pdl=pdl, graph=graph, attn_poly=attn_poly)
 
     fingerprint = None
     fingerprint_path = os.path.splitext(engine_file_path)[0] + ".fingerprint" if engine_file_path else ""

@@ -259,7 +259,6 @@ static int validate_desc(const mde_engine_desc* d) {
   }
   if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
   if (d->attn_poly < -1 || d->attn_poly > 4) return fail(MDE_ERR_INVALID, "attn_poly must be -1 (default) or 0..4 eighths");
-  if (d->attn_kernel < -1 || d->attn_kernel > 2) return fail(MDE_ERR_INVALID, "attn_kernel must be -1 (default) or 0..2");
   if (d->input_mode == MDE_INPUT_U8_HWC) {
     if (d->max_src_h <= 0 || d->max_src_w <= 0) return fail(MDE_ERR_INVALID, "max_src_h/max_src_w are required for the uint8 input");
     for (int c = 0; c < 3; ++c)
@@ -604,7 +603,6 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     { Op a; a.kind = Op::ATTENTION; a.in = qkv; a.out = att;
       if (!dry && pl.rc == MDE_OK) pl.rc = make_attention_op(&a.attn, d.precision, qkv, att, B, NT, d.num_heads);
       if (d.attn_poly >= 0) a.attn.poly = d.attn_poly;
-      if (d.attn_kernel >= 0) a.attn.kernel = d.attn_kernel;
       pl.push(a, "attention", 8.0 * rows * D, 4.0 * static_cast<double>(B) * NT * NT * D); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.proj_b; ep.d_gamma = b.ls1; ep.d_x = x; ep.accumulate_x = 1; ep.ld_out = D;
       pl.gemm("proj+ls+res", att, rows, D, D, b.proj_w, D, D, ep); }
@@ -965,6 +963,12 @@ extern "C" int mde_context_enqueue_timed(mde_context* c, void* stream, float* ms
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   EngineScope scope(c->e->d);
   MDE_TRY(scope.rc);
+  {
+    // per-launch times need launches that do not overlap: no programmatic dependent launch while the events are recorded
+    LaunchOpts o = launch_opts();
+    o.pdl = false;
+    set_launch_opts(o);
+  }
   MDE_TRY(enqueue_impl(c, s, true));
   MDE_CUDA_TRY(cudaStreamSynchronize(s));
   for (int i = 0; i < n; ++i) MDE_CUDA_TRY(cudaEventElapsedTime(&ms[i], c->events[i], c->events[i + 1]));

@@ -103,8 +103,10 @@ __device__ __forceinline__ float gelu_erf(float v) {
 //   GELU(v) = v * Phi(v) = 0.5 * (v + |v| * erf(|v| / sqrt 2)),   erf(x) = 1 - poly(t) * exp(-x^2),  t = 1 / (1 + p x)
 // i.e. den (FFMA2) - 2 rcp - poly - 2 ex2 - one FFMA2 for erf - one FFMA2 + one FMUL2 for the result; |v| rides on
 // operand modifiers.  kShort picks Abramowitz & Stegun 7.1.25 (three terms, |erf error| <= 2.5e-5: relative error of
-// the result <= 2.5e-5 for v > 0, absolute error <= 1.3e-5 |v| everywhere -- below one bf16 rounding step) instead of
-// 7.1.26 (five terms, 1.5e-7).  About 13 / 15 issue slots per pair against 20 for the select-based form.
+// the result <= 2.5e-5 for v > 0, absolute error <= 1.3e-5 |v| everywhere -- a twentieth of the fp16 rounding step
+// 2.4e-4 |v| of the value that is stored, less still for bf16) instead of 7.1.26 (five terms, 1.5e-7).  About 13 / 15 issue
+// slots per pair against 20 for the select-based form.  The 16-bit bulk-store epilogues use the short form for both
+// operand types; the fp32 residual path (`gelu_erf`) keeps the five-term form.
 template <bool kShort>
 __device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
   const f32x2 v = f2_pack(v0, v1);
@@ -360,7 +362,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_erf2<Tr::kFmt == 1>(v[j], v[j + 1]);
+            for (int j = 0; j < 32; j += 2) gelu_erf2<true>(v[j], v[j + 1]);
           } else if (p.act == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -632,7 +634,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               }
               if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) gelu_erf2<Tr::kFmt == 1>(v[j], v[j + 1]);
+                for (int j = 0; j < 8; j += 2) gelu_erf2<true>(v[j], v[j + 1]);
               } else if (p.act == ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);

@@ -62,16 +62,12 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream);
 struct AttnOp {
   alignas(64) CUtensorMap map_qkv;   // 128-row boxes: query tiles
   alignas(64) CUtensorMap map_kv128; // key/value source with 128-row boxes (the same tensor as map_qkv for self-attention)
-  alignas(64) CUtensorMap map_kv96;  // key/value source with 96-row boxes (attention_db.cuh)
   const void* qkv;
   void* out;
   int batch, ntok, heads, precision;
   int ntok_q, k_col0, v_col0;        // queries per image; first K / V column of head 0 in the key/value source
   int poly;                          // eighths of the exponentials evaluated on the FMA pipe (0..4; make_* sets the default, 2)
-  int kernel;                        // 0: attention_tc.cuh (128-key tiles, one S buffer); 1 / 2: attention_db.cuh (96-key tiles, S
-                                     // double-buffered; 2 = speculative maximum).  make_* sets kAttnKernelDefault
 };
-constexpr int kAttnKernelDefault = 0;
 int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads);
 // queries from d_q ([batch*ntok_q][ldq], q columns first), keys/values from d_kv ([batch*ntok_kv][ldkv], K at k_col0, V at v_col0)
 int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, const void* d_kv, int ldkv, int k_col0, int v_col0,

@@ -13,7 +13,6 @@
 
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
-#include "attention_db.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -411,10 +410,8 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(ldkv), static_cast<cuuint64_t>(rows_kv)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(ldkv) * 2};
-  cuuint32_t box128[2] = {64, 128}, box96[2] = {64, kAdbKeys};
-  op->poly = 2;      // the measured optimum (tools/attn_probe.py sweep); engines override it from mde_engine_desc.attn_poly
-  op->kernel = kAttnKernelDefault;
-  MDE_TRY(encode_map(&op->map_kv96, precision, d_kv, 2, dims, str, box96));
+  cuuint32_t box128[2] = {64, 128};
+  op->poly = 2;      // the measured optimum (tools/attn_sweep.py); engines override it from mde_engine_desc.attn_poly
   return encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128);
 }
 
@@ -435,30 +432,6 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAtcThreads), kAtcSmemBytes, s, 1, op.map_qkv, op.map_kv128, p));
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
-}
-template <typename T, int kPoly, bool kSpec>
-static int launch_attention_db_t(const AttnOp& op, cudaStream_t s) {
-  auto kern = attention_db_kernel<T, kPoly, kSpec>;
-  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAdbSmemBytes, true));
-  AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
-  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
-  p.scale_log2 = 0.125f * 1.44269504088896340736f;
-  dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
-  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAtcThreads), kAdbSmemBytes, s, 1, op.map_qkv, op.map_kv96, p));
-  MDE_CUDA_TRY(cudaGetLastError());
-  return MDE_OK;
-}
-template <typename T, bool kSpec>
-static int launch_attention_db_p(const AttnOp& op, cudaStream_t s) {
-  switch (op.poly) {
-    case 0: return launch_attention_db_t<T, 0, kSpec>(op, s);
-    case 1: return launch_attention_db_t<T, 1, kSpec>(op, s);
-    case 2: return launch_attention_db_t<T, 2, kSpec>(op, s);
-    case 3: return launch_attention_db_t<T, 3, kSpec>(op, s);
-    case 4: return launch_attention_db_t<T, 4, kSpec>(op, s);
-  }
-  return fail(MDE_ERR_INVALID, "attention: the polynomial share is 0..4 eighths, not %d", op.poly);
 }
 // kPoly of every 8 element pairs of the softmax take the FMA-pipe polynomial instead of the SFU (op.poly, 0..4; the
 // engine's default is 2, the measured optimum).
@@ -488,13 +461,7 @@ static int launch_attention_trace_t(const AttnOp& op, long long* d_trace, cudaSt
 }
 
 int launch_attention_op(const AttnOp& op, cudaStream_t s) {
-  const bool bf = op.precision == MDE_BF16;
-  switch (op.kernel) {
-    case 0: return bf ? launch_attention_tc_p<__nv_bfloat16>(op, s) : launch_attention_tc_p<__half>(op, s);
-    case 1: return bf ? launch_attention_db_p<__nv_bfloat16, false>(op, s) : launch_attention_db_p<__half, false>(op, s);
-    case 2: return bf ? launch_attention_db_p<__nv_bfloat16, true>(op, s) : launch_attention_db_p<__half, true>(op, s);
-  }
-  return fail(MDE_ERR_INVALID, "attention: unknown kernel %d", op.kernel);
+  return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s) : launch_attention_tc_p<__half>(op, s);
 }
 
 template <typename T, bool kTap>
@@ -828,12 +795,11 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int mde_k_attention_tuned(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
-                          int32_t kernel, int32_t poly_eighths, void* stream) {
+int mde_k_attention_poly(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                         int32_t poly_eighths, void* stream) {
   clear_error();
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
-  if (kernel >= 0) op.kernel = kernel;
   if (poly_eighths >= 0) op.poly = poly_eighths;
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
 }

@@ -66,15 +66,13 @@ def pack_conv3x3(w, dtype):
 
 
 def attention(precision, qkv, batch, ntok, heads, variant="tc"):
-    """variant: "tc" (the engine's default kernel), "k<kernel>" or "k<kernel>:<n>" (an explicit kernel -- 0: 128-key tiles, one S
-    buffer; 1: 96-key tiles, S double-buffered; 2: the same with the speculative maximum -- with n/8 of the exponentials on the
-    FMA pipe), "mma" (the independent mma.sync cross-check)."""
+    """variant: "tc" (the engine's kernel), "tc:<n>" (the same with n/8 of the exponentials on the FMA pipe), "mma" (the
+    independent mma.sync cross-check)."""
     lib = _lib.load()
     out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
-    if variant.startswith("k"):
-        kern, _, poly = variant[1:].partition(":")
-        _lib.check(lib.mde_k_attention_tuned(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, int(kern),
-                                             int(poly) if poly else -1, stream()), "mde_k_attention_tuned")
+    if variant.startswith("tc:"):
+        _lib.check(lib.mde_k_attention_poly(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, int(variant[3:]), stream()),
+                   "mde_k_attention_poly")
         return out
     fn = {"tc": lib.mde_k_attention, "mma": lib.mde_k_attention_mma}[variant]
     _lib.check(fn(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, stream()), "mde_k_attention")

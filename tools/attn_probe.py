@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Time the attention kernels alone (CUDA events).  python tools/attn_probe.py [--batch 64] [--variant tc|k<kernel>[:<poly eighths>]|mma]"""
+"""Time the attention kernels alone (CUDA events).  python tools/attn_probe.py [--batch 64] [--variant tc|tc:<poly eighths>|mma]"""
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time every attention kernel / polynomial share in one process (CUDA events, median of --reps).
-python tools/attn_sweep.py [--batch 64] [--ntok 1370] [--precisions fp16,bf16] [--variants k0:2,k1:2,...]"""
+python tools/attn_sweep.py [--batch 64] [--ntok 1370] [--precisions fp16,bf16] [--variants tc:1,tc:2,...]"""
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,7 +9,7 @@ import kutil as K
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64); ap.add_argument("--ntok", type=int, default=1370)
 ap.add_argument("--heads", type=int, default=16); ap.add_argument("--precisions", default="fp16,bf16")
-ap.add_argument("--variants", default=",".join(f"k{k}:{p}" for k in (0, 1, 2) for p in (1, 2, 3, 4)))
+ap.add_argument("--variants", default=",".join(f"tc:{p}" for p in (0, 1, 2, 3, 4)))
 ap.add_argument("--reps", type=int, default=7)
 a = ap.parse_args()
 fl = 4.0 * a.batch * a.heads * a.ntok * a.ntok * 64
