@@ -202,6 +202,8 @@ def depth_pro(world: int, rank: int, local: int, precision: str, reps: int = 10)
 
 
 def run_all(world: int, rank: int, local: int, precision: str) -> dict | None:
+    import torch
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))      # torchrun pins OMP_NUM_THREADS=1: the oracle legs need more
     res = {"vggt_aggregator": vggt_aggregator(world, rank, local, precision),
            "depth_pro": depth_pro(world, rank, local, precision)}
     return res if rank == 0 else None

@@ -24,7 +24,7 @@ import numpy as np
 from . import _lib, sharding as S
 from .depth_pro import _Ops, _t
 
-LN_EPS = 1e-6
+LN_EPS = 1e-5          # aggregator blocks: nn.LayerNorm's default (the DINOv2 trunk in front uses 1e-6)
 QK_EPS = 1e-5
 ROPE_FREQUENCY = 100.0
 

@@ -6,6 +6,8 @@ __graft_entry__.smoke()); the product package never imports this file.
                   -- plus `max_rel`, the per-pixel maximum north_star gates on (the reference does not report it)
   measure()       core/bench.py:182-210 `measure`: warm-up, then perf_counter around fn() + sync() per iteration
   pct()/stats()   core/bench.py:113-150 `Bench.pct` / `Bench.stats`: nearest-rank percentiles (rank = ceil(q/100 * N))
+  record()        core/bench.py:345-404 `record` + :316-334 `save` + :247-272 `summarize_outputs` + :275-313 `collect_env`:
+                  the result file `<model>_<HxW>_<profile>_<variant>_<precision>.json` in the reference's schema 1
 
 Pinned: tests/test_oracle_harness.py checks every function against the live reference modules where /root/reference is
 mounted, and against tests/golden/harness_golden.json (produced by the reference's own functions, oracle/make_golden.py)
@@ -134,3 +136,86 @@ def stats(samples_ms: List[float], warmup: int = 0) -> Dict[str, float]:
             "p99_ms": round(pct(samples_ms, 99), 4), "max_ms": round(max(samples_ms), 4),
             "stdev_ms": round(statistics.stdev(samples_ms), 4) if len(samples_ms) > 1 else 0.0,
             "fps": round(1000.0 / mean if mean else 0.0, 2)}
+
+
+SCHEMA = 1      # core/bench.py:43
+
+
+def summarize_outputs(outputs) -> Dict[str, dict]:
+    """core/bench.py:247-272: shape / dtype / finite counts / min / max / mean over the finite values of every output."""
+    out = {}
+    for name, arr in outputs.items():
+        a = np.asarray(arr)
+        finite = np.isfinite(a)
+        v = a[finite]
+        out[name] = {"shape": list(a.shape), "dtype": str(a.dtype), "finite": int(finite.sum()), "nonfinite": int(a.size - finite.sum()),
+                     "min": float(v.min()) if v.size else None, "max": float(v.max()) if v.size else None,
+                     "mean": float(v.mean()) if v.size else None}
+    return out
+
+
+def collect_env() -> dict:
+    """core/bench.py:275-313: versions, GPU name, driver, graphics clock and its maximum."""
+    import platform
+    env, device, driver, clock, clock_max = {}, "", "", 0, 0
+    try:
+        import torch
+        env["torch"] = torch.__version__
+        if torch.cuda.is_available():
+            device = torch.cuda.get_device_name(0)
+            env["cuda"] = torch.version.cuda or ""
+    except ImportError:
+        pass
+    try:
+        import subprocess
+        line = subprocess.check_output(["nvidia-smi", "--query-gpu=driver_version,clocks.gr,clocks.max.gr", "--format=csv,noheader,nounits"],
+                                       stderr=subprocess.DEVNULL, text=True, timeout=10).strip().splitlines()[0]
+        driver, clock, clock_max = (p.strip() for p in line.split(","))
+        clock, clock_max = int(clock), int(clock_max)
+    except Exception:
+        pass
+    env["python"] = platform.python_version()
+    return {"versions": env, "device": device, "driver": driver, "clock_mhz": clock, "clock_max_mhz": clock_max}
+
+
+def record(model: str, samples_ms, *, outputs=None, model_input=None, extra_inputs=None, out_dir: Optional[str] = None,
+           echo: bool = True, warmup: int = 0, backend: str = "tensorrt", precision: str = "fp32", profile: str = "bench",
+           variant: str = "single", encoder: str = "", input_h: int = 0, input_w: int = 0, engine_path: str = "", notes: str = "",
+           stage_samples_ms=None, inputs_dir: Optional[str] = None) -> dict:
+    """core/bench.py `record`: write the result file and return the record (the reference returns its Bench object; callers
+    in the model scripts ignore the return value).  Where the reference checkout is mounted its own function does the work."""
+    import json
+    import platform
+    bench, _ = reference_modules()
+    if out_dir is None:
+        raise ValueError("record(): out_dir is required here (the reference defaults to its own reports/bench)")
+    if bench is not None:
+        b = bench.record(model, samples_ms, outputs=outputs, out_dir=out_dir, echo=echo, warmup=warmup, backend=backend,
+                         precision=precision, profile=profile, variant=variant, encoder=encoder, input_h=input_h, input_w=input_w,
+                         notes=notes, **({"stage_samples_ms": stage_samples_ms} if stage_samples_ms else {}))
+        d = b.to_dict()
+    else:
+        samples = list(samples_ms)
+        d = {"model": model, "samples_ms": [round(x, 4) for x in samples], "warmup": warmup,
+             "stage_samples_ms": dict(stage_samples_ms or {}), "backend": backend, "precision": precision, "profile": profile,
+             "variant": variant, "encoder": encoder, "input_h": input_h, "input_w": input_w, **collect_env(),
+             "host": platform.node(), "outputs": summarize_outputs(outputs) if outputs else {}, "engine_path": "",
+             "engine_bytes": 0, "engine_mtime": 0, "onnx_sha256": "", "timestamp": time.strftime("%Y-%m-%dT%H:%M:%S"), "notes": notes,
+             "schema": SCHEMA, "stats": stats(samples, warmup)}
+        parts = [model, profile, variant, precision]
+        if input_h and input_w:
+            parts.insert(1, f"{input_h}x{input_w}")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "_".join(str(p) for p in parts if p) + ".json"), "w", encoding="utf-8") as f:
+            json.dump(d, f, indent=2, ensure_ascii=False)
+        if echo:
+            st = d["stats"]
+            print(f"[MDET] {st['iterations']} iterations time: {sum(samples) / 1000.0:.4f} [sec]")
+            print(f"[MDET] Average FPS: {st['fps']:.2f} [fps]")
+            print(f"[MDET] Average inference time: {st['mean_ms']:.2f} [msec]")
+            print(f"[MDET] p50 {st['p50_ms']:.2f} / p90 {st['p90_ms']:.2f} / p99 {st['p99_ms']:.2f} [msec], min {st['min_ms']:.2f}, "
+                  f"stdev {st['stdev_ms']:.2f}")
+    if model_input is not None and inputs_dir:
+        os.makedirs(inputs_dir, exist_ok=True)
+        np.save(os.path.join(inputs_dir, f"{model}.npy"), np.ascontiguousarray(model_input))
+    return d

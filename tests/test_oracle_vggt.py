@@ -82,3 +82,67 @@ def test_product_tables_equal_the_oracle_tables():
     cos, sin = V.rope_tables(39)
     t = P.cos_sin_table(39)
     assert torch.equal(t[:, :16], cos[:, :16]) and torch.equal(t[:, 16:], sin[:, :16]) and torch.equal(cos[:, 16:], cos[:, :16])
+
+
+# ------------------------------------------------------------------------------------------------ the whole model's pieces
+def test_trunk_with_registers_matches_transformers_dinov2_with_registers():
+    """VGGT's (and Metric3D V2's) trunk is DINOv2 *with registers*: four learned tokens between cls and the patches, without a
+    position embedding, dropped at the output.  transformers' Dinov2WithRegistersModel is an independent implementation."""
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
+    import hf_bridge as HB
+    from oracle import dav2_torch as O
+    enc = "vits"
+    c = O.MODEL_CONFIGS[enc]
+    sd = O.init_state_dict(enc, seed=3, registers=4)
+    cfg = Dinov2WithRegistersConfig(hidden_size=c["embed_dim"], num_hidden_layers=c["depth"], num_attention_heads=c["num_heads"],
+                                    image_size=518, patch_size=14, num_register_tokens=4)
+    model = Dinov2WithRegistersModel(cfg).eval()
+    hf = {k[len("backbone."):]: v for k, v in HB.to_hf({**HB.init_heads_placeholder(enc), **sd}, enc).items() if k.startswith("backbone.")}
+    hf["embeddings.register_tokens"] = sd["pretrained.register_tokens"]
+    missing, unexpected = model.load_state_dict(hf, strict=False)
+    assert not unexpected and all("mask_token" in m or "pooler" in m for m in missing), (missing, unexpected)
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 518, 518)
+    with torch.no_grad():
+        want = model(pixel_values=x).last_hidden_state            # [2, 1 + 4 + 1369, D], final LayerNorm applied
+        cfg1 = dict(c); cfg1["taps"] = [c["depth"] - 1]
+        got = O.encoder_taps(sd, x, cfg1, norm_mask=0x1)[0]
+    assert want.shape == (2, 1374, c["embed_dim"]) and got.shape == (2, 1369, c["embed_dim"])
+    assert float((got - want[:, 5:]).abs().max() / want.abs().max()) < 5e-5
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not mounted")
+def test_head_position_embedding_matches_the_reference_export_patch():
+    """core/export_compat.py:145-152 is the reference's own float32 restatement of upstream's make_sincos_pos_embed."""
+    import sys
+    import types
+    spec = importlib.util.spec_from_file_location("ref_export_compat2", REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    holder = types.ModuleType("fake.heads.utils")
+    holder.make_sincos_pos_embed = lambda *a, **k: None
+    with mod.float32_sincos_pos_embed(holder):
+        ref_fn = holder.make_sincos_pos_embed
+        pos = torch.linspace(-0.7, 0.7, 37)
+        for dim in (128, 512):
+            assert torch.equal(ref_fn(dim, pos), V.make_sincos_pos_embed(dim, pos))
+    pe = V.head_pos_embed(256, 37, 37, 518, 518)
+    assert pe.shape == (256, 37, 37) and float(pe.abs().max()) <= 0.1 + 1e-6
+    # u varies along x only and feeds the first half of the channels, v along y and the second half
+    assert torch.equal(pe[:128, 0], pe[:128, 5]) and torch.equal(pe[128:, :, 0], pe[128:, :, 7])
+    assert not torch.equal(pe[:128, :, 0], pe[:128, :, 1])
+
+
+def test_whole_model_shapes_and_special_tokens():
+    sd = V.init_vggt("vits", depth=2, features=64, out_channels=(48, 96, 192, 384), seed=0)
+    sp = V.special_tokens(sd, 3)
+    assert sp.shape == (3, 5, 384) and torch.equal(sp[1], sp[2]) and not torch.equal(sp[0], sp[1])
+    torch.manual_seed(0)
+    img = torch.rand(3, 3, 70, 84)
+    tr = {}
+    d = V.vggt_depth(sd, img, "vits", 2, (0, 0, 1, 1), trace=tr)
+    assert d.shape == (3, 70, 84) and bool((d > 0).all()) and tr["tokens"].shape == (3, 5 + 30, 384)
+    assert tr["aggregated"][0].shape == (3, 35, 768) and tr["logits"].shape == (3, 2, 70, 84)
+    # frames interact through the global blocks only: changing frame 2 changes frame 0's depth
+    img2 = img.clone(); img2[2] = torch.rand(3, 70, 84)
+    assert not torch.allclose(V.vggt_depth(sd, img2, "vits", 2, (0, 0, 1, 1))[0], d[0])
