@@ -101,6 +101,8 @@ typedef struct mde_engine_desc {
   int32_t head_mode;       /* MDE_HEAD_* */
   int32_t tap_norm_mask;   /* bit i: tap i goes through the trunk's final LayerNorm (0xF for Depth Anything; 0x8 for
                             * Depth Pro's hooks, which take raw block outputs and normalise only the last one) */
+  int32_t num_registers;   /* DINOv2 "with registers" trunks (Metric3D V2, VGGT): learned tokens between cls and the patch tokens
+                            * ("pretrained.register_tokens" [1, R, D]), dropped again from the taps; 0 for Depth Anything / Depth Pro */
   int32_t flags;           /* MDE_FLAG_* */
   int32_t attn_poly;       /* eighths of the softmax exponentials evaluated by a polynomial on the FMA pipe instead of the
                             * SFU: 0..4, or -1 for the library default (2).  Changes the last bits of the probabilities. */
@@ -214,6 +216,11 @@ typedef struct mde_epilogue {
    * gather_col0 must be a multiple of 64 and N a multiple of the tile width. */
   int32_t gather_n, gather_col0, gather_ld;
   void* d_gather[8];
+  /* token remap with more rows in front of the patch tokens than the cls row (DINOv2 with registers): row b*T+t ->
+   * b*(T+token_skip)+token_skip+t, plus pos[(1+t)][:].  0 means 1 (cls only). */
+  int32_t token_skip;
+  /* fused depth head: 0 = head_scale decides (sigmoid * scale / ReLU), 1 = exp(z) (VGGT's depth head, activation "exp") */
+  int32_t head_act;
 } mde_epilogue;
 
 /* D[M,N] = A[M,K] * B[N,K]^T.  A: 16-bit row-major, pitch lda elements; B: 16-bit row-major, pitch ldb.
@@ -246,13 +253,24 @@ int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int
  * tcgen05 kernel for the tests; the engine never launches it. */
 int mde_k_attention_mma(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                         void* stream);
-/* LayerNorm of fp32 rows -> 16-bit.  drop_cls != 0: rows are [B][ntok]; token 0 of each image is
- * skipped and the output is dense [B][ntok-1]. */
+/* LayerNorm of fp32 rows -> 16-bit.  drop_cls = n > 0: rows are [B][ntok]; the first n tokens of each image (cls, or cls +
+ * registers, or VGGT's camera + register tokens) are skipped and the output is dense [B][ntok-n].  dim: 128, 384, 768, 1024,
+ * 1536 or 2048. */
 int mde_k_layernorm(int32_t precision, const float* d_x, const float* d_w, const float* d_b, void* d_out,
                     int64_t rows, int32_t dim, float eps, int32_t drop_cls, int32_t ntok, void* stream);
 /* bilinear, align_corners=True, NHWC 16-bit, c multiple of 8 */
 int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t hi, int32_t wi, int32_t ho,
                    int32_t wo, int32_t c, void* stream);
+/* mde_k_bilinear with a per-pixel, per-channel addend (fp32 [ho][wo][c], the same for every image) added after the
+ * interpolation: VGGT's depth head adds its position embedding to the up-sampled map (reports/profile/vggt.json layers 705-706). */
+int mde_k_bilinear_add(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t hi, int32_t wi, int32_t ho,
+                       int32_t wo, int32_t c, const float* d_addend, void* stream);
+/* VGGT's aggregator input (models/vggt/onnx_export.py:38-52 -> vggt `Aggregator.forward`): per frame the camera token and the
+ * four register tokens (d_special: float32 [2][n_special][dim]; global frame 0 takes variant 0, every other frame variant 1)
+ * followed by the trunk's normalised patch tokens (d_patch: 16-bit [frames][tokens][dim]) -> float32
+ * [frames][n_special + tokens][dim].  first_frame: global index of this rank's first frame. */
+int mde_k_assemble_tokens(int32_t precision, const void* d_patch, const float* d_special, int32_t frames, int32_t tokens,
+                          int32_t n_special, int32_t dim, int32_t first_frame, float* d_out, void* stream);
 /* Tail of the DPT head (models/depth_anything_v2: output_conv1 -> interpolate(align_corners=True) -> output_conv2)
  * with the 3x3 conv's channel contraction done before the interpolation.  d_z: [B][hs][ws][ldz] 16-bit with
  * z[.., (ky*3+kx)*32 + o] = sum_c W2[o][c][ky][kx] * o1[.., c] (no bias); d_bias: [32] conv bias; d_head_w: [32]

@@ -26,7 +26,7 @@ SYMBOLS = [
     "mde_context_set_input_shape", "mde_context_enqueue", "mde_context_set_gather", "mde_context_launches_per_enqueue",
     "mde_context_get_buffer", "mde_context_snapshot_block", "mde_context_enqueue_timed", "mde_context_op_info",
     "mde_k_preprocess_u8", "mde_k_preprocess_u8_pad", "mde_k_preprocess_u8_square_pad_cubic", "mde_k_im2col_f32", "mde_k_gemm", "mde_k_conv3x3", "mde_k_attention", "mde_k_attention_poly", "mde_k_attention_trace", "mde_k_attention_kv", "mde_k_attention_mma",
-    "mde_k_layernorm", "mde_k_bilinear", "mde_k_im2col_s2", "mde_k_upconv_head", "mde_k_resize_depth", "mde_k_merge_patches", "mde_k_peer_signal", "mde_k_peer_wait",
+    "mde_k_layernorm", "mde_k_bilinear", "mde_k_bilinear_add", "mde_k_assemble_tokens", "mde_k_im2col_s2", "mde_k_upconv_head", "mde_k_resize_depth", "mde_k_merge_patches", "mde_k_peer_signal", "mde_k_peer_wait",
     "mde_k_resize_crops", "mde_k_depth_pro_post", "mde_k_resize_depth_halfpixel", "mde_k_resize_depth_halfpixel_nan", "mde_k_qknorm_rope", "mde_k_peer_signal_counter", "mde_k_peer_wait_counter",
 ]
 
@@ -42,7 +42,7 @@ class EngineDesc(C.Structure):
         ("norm_mean", C.c_double * 3), ("norm_std", C.c_double * 3),
         ("max_depth", C.c_float), ("device", C.c_int32),
         ("output_mode", C.c_int32), ("head_mode", C.c_int32), ("tap_norm_mask", C.c_int32),
-        ("flags", C.c_int32), ("attn_poly", C.c_int32),
+        ("num_registers", C.c_int32), ("flags", C.c_int32), ("attn_poly", C.c_int32),
     ]
 
 
@@ -59,6 +59,7 @@ class Epilogue(C.Structure):
         ("shuffle_s", C.c_int32), ("shuffle_cout", C.c_int32), ("shuffle_h", C.c_int32), ("shuffle_w", C.c_int32),
         ("d_head_w", C.c_void_p), ("head_b", C.c_float), ("head_scale", C.c_float), ("d_head_out", C.c_void_p),
         ("gather_n", C.c_int32), ("gather_col0", C.c_int32), ("gather_ld", C.c_int32), ("d_gather", C.c_void_p * 8),
+        ("token_skip", C.c_int32), ("head_act", C.c_int32),
     ]
 
 
@@ -117,6 +118,8 @@ def load() -> C.CDLL:
         "mde_k_attention_trace": (C.c_int, [i32, vp, vp, i32, i32, i32, vp, vp]),
         "mde_k_layernorm": (C.c_int, [i32, vp, vp, vp, vp, i64, i32, f32, i32, i32, vp]),
         "mde_k_bilinear": (C.c_int, [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "mde_k_bilinear_add": (C.c_int, [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "mde_k_assemble_tokens": (C.c_int, [i32, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "mde_k_im2col_s2": (C.c_int, [i32, vp, vp, i32, i32, i32, i32, vp]),
         "mde_k_peer_signal": (C.c_int, [P(vp), i32, i32, C.c_uint32, vp]),
         "mde_k_peer_wait": (C.c_int, [vp, i32, C.c_uint32, vp]),

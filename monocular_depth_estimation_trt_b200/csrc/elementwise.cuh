@@ -166,7 +166,7 @@ struct LayerNormParams {
   const float* b;
   void* out;           // 16-bit
   long long rows;
-  int D;               // multiple of 128, <= 1024
+  int D;               // multiple of 128, <= 2048
   float eps;
   int drop_cls;
   int ntok;
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
   if (row >= p.rows) return;
   const int lane = threadIdx.x & 31;
   long long orow = row;
-  if (p.drop_cls) {
+  if (p.drop_cls) {       // number of leading tokens of every image that are skipped: cls (1), cls + registers (5), ...
     const long long b = row / p.ntok;
     const int t = static_cast<int>(row % p.ntok);
-    if (t == 0) return;
-    orow = b * (p.ntok - 1) + (t - 1);
+    if (t < p.drop_cls) return;
+    orow = b * (p.ntok - p.drop_cls) + (t - p.drop_cls);
   }
   const float4* xr = reinterpret_cast<const float4*>(p.x + row * D);
   float4 v[V];
@@ -254,10 +254,47 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
   }
 }
 
-// x[b][0][:] = cls + pos[0]   (the patch-embed GEMM epilogue writes rows 1..T)
-__global__ void cls_row_kernel(float* x, const float* cls, const float* pos, int ntok, int D) {
+// x[b][0][:] = cls + pos[0], x[b][1 + r][:] = register r (DINOv2 with registers: no position embedding on them); the
+// patch-embed GEMM epilogue writes the rows behind them
+__global__ void cls_row_kernel(float* x, const float* cls, const float* pos, const float* reg, int n_reg, int ntok, int D) {
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) x[static_cast<long long>(b) * ntok * D + i] = cls[i] + pos[i];
+  float* xb = x + static_cast<long long>(b) * ntok * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) xb[i] = cls[i] + pos[i];
+  for (int i = threadIdx.x; i < n_reg * D; i += blockDim.x) xb[D + i] = reg[i];
+}
+
+// VGGT's aggregator input (vggt/models/aggregator.py: camera token, four register tokens, then the trunk's normalised patch
+// tokens; frame 0 of the scene takes variant 0 of the special tokens, every other frame variant 1):
+// out[s][j][:] = special[variant(s)][j][:] for j < n_special, float(patch[s][j - n_special][:]) behind them.
+struct AssembleTokensParams {
+  const void* patch;      // [frames][tokens][D] 16-bit
+  const float* special;   // [2][n_special][D]
+  float* out;             // [frames][n_special + tokens][D]
+  int frames, tokens, n_special, D, first_frame;   // first_frame: global index of this rank's frame 0
+};
+template <typename T>
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const AssembleTokensParams p) {
+  const int ntok = p.n_special + p.tokens;
+  const long long row = blockIdx.x;                    // (frame, token)
+  const int s = static_cast<int>(row / ntok), j = static_cast<int>(row % ntok);
+  float* o = p.out + row * p.D;
+  if (j < p.n_special) {
+    const float* src = p.special + (static_cast<long long>((p.first_frame + s) == 0 ? 0 : 1) * p.n_special + j) * p.D;
+    for (int i = threadIdx.x * 4; i < p.D; i += blockDim.x * 4) *reinterpret_cast<float4*>(o + i) = *reinterpret_cast<const float4*>(src + i);
+    return;
+  }
+  const T* src = static_cast<const T*>(p.patch) + (static_cast<long long>(s) * p.tokens + (j - p.n_special)) * p.D;
+  for (int i = threadIdx.x * 8; i < p.D; i += blockDim.x * 8) {
+    const uint4 q = *reinterpret_cast<const uint4*>(src + i);
+    const uint32_t* u = &q.x;
+    float4 a, b;
+    float2 v = F16Traits<T>::unpack2(u[0]); a.x = v.x; a.y = v.y;
+    v = F16Traits<T>::unpack2(u[1]); a.z = v.x; a.w = v.y;
+    v = F16Traits<T>::unpack2(u[2]); b.x = v.x; b.y = v.y;
+    v = F16Traits<T>::unpack2(u[3]); b.z = v.x; b.w = v.y;
+    *reinterpret_cast<float4*>(o + i) = a;
+    *reinterpret_cast<float4*>(o + i + 4) = b;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,6 +306,7 @@ struct BilinearParams {
   void* out;        // [B][Ho][Wo][C]
   int B, Hi, Wi, Ho, Wo, C;
   float sy, sx;     // (Hi-1)/(Ho-1), (Wi-1)/(Wo-1)
+  const float* addend;   // optional fp32 [Ho][Wo][C] added to every image after the interpolation (VGGT's position embedding)
 };
 // grid = (Ho, B): one output row per CTA, so the vertical taps and weight are CTA-uniform and the two source
 // rows (Wi*C*2 bytes each) stay in L1 while the row is produced; no 64-bit index arithmetic per element.
@@ -297,12 +335,18 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const BilinearParams
     const uint4 q11 = *reinterpret_cast<const uint4*>(row1 + x1 * p.C + c);
     const uint32_t* a = &q00.x; const uint32_t* bb = &q01.x; const uint32_t* cc = &q10.x; const uint32_t* d = &q11.x;
     uint4 r; uint32_t* ro = &r.x;
+    float add[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p.addend) {
+      const float4* ad = reinterpret_cast<const float4*>(p.addend + (static_cast<long long>(y) * p.Wo + x) * p.C + c);
+      const float4 a0 = __ldg(ad), a1 = __ldg(ad + 1);
+      add[0] = a0.x; add[1] = a0.y; add[2] = a0.z; add[3] = a0.w; add[4] = a1.x; add[5] = a1.y; add[6] = a1.z; add[7] = a1.w;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 v00 = Tr::unpack2(a[k]), v01 = Tr::unpack2(bb[k]), v10 = Tr::unpack2(cc[k]), v11 = Tr::unpack2(d[k]);
       const float tx0 = v00.x + wx * (v01.x - v00.x), tx1 = v00.y + wx * (v01.y - v00.y);
       const float bx0 = v10.x + wx * (v11.x - v10.x), bx1 = v10.y + wx * (v11.y - v10.y);
-      ro[k] = Tr::pack2(tx0 + wy * (bx0 - tx0), tx1 + wy * (bx1 - tx1));
+      ro[k] = Tr::pack2(tx0 + wy * (bx0 - tx0) + add[2 * k], tx1 + wy * (bx1 - tx1) + add[2 * k + 1]);
     }
     *reinterpret_cast<uint4*>(orow + static_cast<long long>(i) * 8) = r;
   }

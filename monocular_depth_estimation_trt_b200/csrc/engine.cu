@@ -66,7 +66,7 @@ struct mde_engine {
   int lvl_h[4] = {0, 0, 0, 0}, lvl_w[4] = {0, 0, 0, 0};
   // packed device weights
   void* pe_w = nullptr;
-  float *pe_b = nullptr, *cls = nullptr, *pos = nullptr, *norm_w = nullptr, *norm_b = nullptr, *lut = nullptr;
+  float *pe_b = nullptr, *cls = nullptr, *pos = nullptr, *norm_w = nullptr, *norm_b = nullptr, *lut = nullptr, *reg = nullptr;
   std::vector<Block> blocks;
   void* proj_w[4] = {nullptr, nullptr, nullptr, nullptr};
   float* proj_b[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -258,6 +258,7 @@ static int validate_desc(const mde_engine_desc* d) {
       return fail(MDE_ERR_INVALID, "taps must be increasing block indices below depth");
   }
   if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
+  if (d->num_registers < 0 || d->num_registers > 16) return fail(MDE_ERR_INVALID, "num_registers must be 0..16");
   if (d->attn_poly < -1 || d->attn_poly > 4) return fail(MDE_ERR_INVALID, "attn_poly must be -1 (default) or 0..4 eighths");
   if (d->input_mode == MDE_INPUT_U8_HWC) {
     if (d->max_src_h <= 0 || d->max_src_w <= 0) return fail(MDE_ERR_INVALID, "max_src_h/max_src_w are required for the uint8 input");
@@ -277,7 +278,7 @@ extern "C" int mde_engine_create(const mde_engine_desc* desc, mde_engine** out) 
   e->gh = desc->input_h / desc->patch_size;
   e->gw = desc->input_w / desc->patch_size;
   e->T = e->gh * e->gw;
-  e->ntok = e->T + 1;
+  e->ntok = e->T + 1 + desc->num_registers;
   e->kpad = round_up(3 * desc->patch_size * desc->patch_size, 64);
   e->lvl_h[0] = 4 * e->gh; e->lvl_w[0] = 4 * e->gw;
   e->lvl_h[1] = 2 * e->gh; e->lvl_w[1] = 2 * e->gw;
@@ -349,7 +350,8 @@ extern "C" int mde_engine_finalize(mde_engine* e) {
   MDE_TRY(upload_mat16(e, t->data.data(), D, 3 * P * P, e->kpad, &e->pe_w));
   MDE_TRY(upload_f32(e, "pretrained.patch_embed.proj.bias", {D}, &e->pe_b));
   MDE_TRY(upload_f32(e, "pretrained.cls_token", {1, 1, D}, &e->cls));
-  MDE_TRY(upload_f32(e, "pretrained.pos_embed", {1, e->ntok, D}, &e->pos));   // already resized to this grid by the host
+  MDE_TRY(upload_f32(e, "pretrained.pos_embed", {1, e->T + 1, D}, &e->pos));   // already resized to this grid by the host
+  if (d.num_registers > 0) MDE_TRY(upload_f32(e, "pretrained.register_tokens", {1, d.num_registers, D}, &e->reg));
   MDE_TRY(upload_f32(e, "pretrained.norm.weight", {D}, &e->norm_w));
   MDE_TRY(upload_f32(e, "pretrained.norm.bias", {D}, &e->norm_b));
   // ---- blocks
@@ -587,10 +589,10 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     else
       pl.push(op, "im2col_f32", 4.0 * B * 3 * d.input_h * d.input_w + 2.0 * prow * e->kpad);
     mde_epilogue ep = ep_zero();
-    ep.d_bias = e->pe_b; ep.d_x = x; ep.ld_out = D; ep.tokens = T; ep.d_pos = e->pos;
+    ep.d_bias = e->pe_b; ep.d_x = x; ep.ld_out = D; ep.tokens = T; ep.d_pos = e->pos; ep.token_skip = 1 + d.num_registers;
     pl.gemm("patch_embed", cols, prow, e->kpad, e->kpad, e->pe_w, D, e->kpad, ep, kreal);
     Op cr; cr.kind = Op::CLS_ROW; cr.out = x;
-    pl.push(cr, "cls_row", 12.0 * D * B);
+    pl.push(cr, "cls_row", (12.0 + 8.0 * d.num_registers) * D * B);
   }
   // ---- encoder
   int next_tap = 0;
@@ -614,7 +616,8 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
       pl.gemm("fc2+ls+res", hid, rows, 4 * D, 4 * D, b.fc2_w, D, 4 * D, ep); }
     { Op s; s.kind = Op::SNAPSHOT; s.block = i; pl.push(s, "snapshot"); }
     if (next_tap < 4 && d.taps[next_tap] == i) {
-      Op t; t.kind = Op::LAYERNORM; t.in = x; t.out = tap[next_tap]; t.w = e->norm_w; t.b = e->norm_b; t.rows = rows; t.i0 = 1;
+      Op t; t.kind = Op::LAYERNORM; t.in = x; t.out = tap[next_tap]; t.w = e->norm_w; t.b = e->norm_b; t.rows = rows;
+      t.i0 = 1 + d.num_registers;                              // cls and the registers are dropped from the taps
       t.i1 = ((d.tap_norm_mask >> next_tap) & 1) ? 0 : 1;     // identity: raw block output
       t.i2 = taps_only ? next_tap : -1;                        // which slice of the output binding
       pl.push(t, "layernorm tap", 4.0 * rows * D + 2.0 * prow * D);
@@ -851,7 +854,7 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         MDE_TRY(launch_im2col_f32(prec, static_cast<const float*>(c->d_input), d.batch, d.input_h, d.input_w, d.patch_size, e->kpad, op.out, s));
         break;
       case Op::CLS_ROW:
-        MDE_TRY(launch_cls_row(static_cast<float*>(op.out), e->cls, e->pos, d.batch, e->ntok, d.embed_dim, s));
+        MDE_TRY(launch_cls_row(static_cast<float*>(op.out), e->cls, e->pos, e->reg, d.num_registers, d.batch, e->ntok, d.embed_dim, s));
         break;
       case Op::GEMM:
         if (op.g.p.head_w) op.g.p.head_out = static_cast<float*>(c->d_output);

@@ -31,7 +31,8 @@ struct GemmParams {
   int cin_blocks;       // conv: 64-channel blocks per tap
   // ---- epilogue
   int row_map;
-  int tokens;           // ROW_TOKENS: T patch tokens per image (output rows per image = T + 1)
+  int tokens;           // ROW_TOKENS: T patch tokens per image
+  int tok_skip;         // ROW_TOKENS: rows in front of the patch tokens in every image of the output (1 = cls; 1 + registers)
   int shuffle_s;        // ROW_SHUFFLE: ConvTranspose kernel == stride
   int shuffle_cout;     // ROW_SHUFFLE: N = s*s*cout, column = (ky*s + kx)*cout + o
   int act;
@@ -55,6 +56,7 @@ struct GemmParams {
   const float* head_w;
   float head_b;
   float head_scale;     // metric: sigmoid(z) * head_scale; relative (head_scale < 0): relu(z)
+  int head_act;         // 1: exp(z) (VGGT's depth head) instead of the two above
   float* head_out;      // [M] fp32
 };
 
@@ -470,7 +472,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         valid = m < p.M;
         orow = m;
         if (p.row_map == ROW_TOKENS) {
-          orow = (m / p.tokens) * (p.tokens + 1) + 1 + (m % p.tokens);
+          orow = (m / p.tokens) * (p.tokens + p.tok_skip) + p.tok_skip + (m % p.tokens);
         } else if (p.row_map == ROW_SHUFFLE) {
           const int hw = p.H * p.W;
           const long long b = m / hw;
@@ -505,7 +507,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           xin[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (rx[pass] >= 0 && n < p.N) {
             if (p.accumulate_x) xin[pass] = *reinterpret_cast<const float4*>(p.x + static_cast<long long>(rx[pass]) * p.ld_out + n);
-            else if (p.pos) xin[pass] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(rx[pass] % (p.tokens + 1)) * p.ld_out + n));
+            else if (p.pos) xin[pass] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(rx[pass] % (p.tokens + p.tok_skip) - p.tok_skip + 1) * p.ld_out + n));
           }
         }
       };
@@ -556,7 +558,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float v = __uint_as_float(raw[j]) + __ldg(p.bias + n_base + j);
             z = fmaf(fmaxf(v, 0.f), __ldg(p.head_w + n_base + j), z);
           }
-          if (valid) p.head_out[orow] = p.head_scale < 0.f ? fmaxf(z, 0.f) : p.head_scale / (1.0f + __expf(-z));
+          if (valid) p.head_out[orow] = p.head_act == 1 ? expf(z) : (p.head_scale < 0.f ? fmaxf(z, 0.f) : p.head_scale / (1.0f + __expf(-z)));
           continue;
         }
         // ---- phase 1

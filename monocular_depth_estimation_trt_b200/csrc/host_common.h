@@ -79,7 +79,7 @@ int launch_layernorm(int precision, const float* d_x, const float* d_w, const fl
                      int dim, float eps, int drop_cls, int ntok, cudaStream_t s, int identity = 0, int n_dst = 0,
                      void* const* dst = nullptr, long long dst_row0 = 0);
 int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int hi, int wi, int ho, int wo, int c,
-                    cudaStream_t s);
+                    cudaStream_t s, const float* d_addend = nullptr);
 int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s);
 int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int w, int patch, int kpad, void* d_cols,
                       cudaStream_t s);
@@ -93,7 +93,8 @@ int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int h
 int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_out, int ho, int wo, float lo, float hi_clamp,
                         cudaStream_t s);
 int launch_merge_patches(int precision, const void* d_in, int per_side, int grid, int pad, int dim, void* d_out, cudaStream_t s);
-int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, int batch, int ntok, int dim, cudaStream_t s);
+int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, const float* d_reg, int n_reg, int batch, int ntok, int dim,
+                   cudaStream_t s);
 // (v/255 - mean)/std in double, rounded once to float32: 3 x 256 entries (core/preprocess.py:294-328,337-342)
 void build_norm_lut(const double* mean3, const double* std3, float* lut768);
 

@@ -196,7 +196,7 @@ static int pick_grid(GemmOp* op) {
 
 static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_out) {
   p.row_map = ROW_IDENTITY;
-  p.tokens = 0; p.shuffle_s = 0; p.shuffle_cout = 0;
+  p.tokens = 0; p.tok_skip = 1; p.shuffle_s = 0; p.shuffle_cout = 0;
   p.act = ep->act;
   p.ld_out = ep->ld_out;
   p.accumulate_x = ep->accumulate_x;
@@ -204,6 +204,9 @@ static int fill_epilogue(GemmParams& p, const mde_epilogue* ep, long long rows_o
   p.x = ep->d_x; p.res1 = ep->d_res1; p.res2 = ep->d_res2; p.out = ep->d_out; p.out_relu = ep->d_out_relu;
   p.head_w = ep->d_head_w; p.head_b = ep->head_b;
   p.head_scale = ep->head_scale > 0.f ? ep->head_scale : -1.f;
+  p.head_act = ep->head_act;
+  if (ep->head_act != 0 && ep->head_act != 1) return fail(MDE_ERR_INVALID, "unknown head activation %d", ep->head_act);
+  if (ep->token_skip < 0) return fail(MDE_ERR_INVALID, "token_skip must not be negative");
   p.head_out = ep->d_head_out;
   if (ep->ld_out % 8 != 0 && !ep->d_head_w) return fail(MDE_ERR_INVALID, "ld_out must be a multiple of 8");
   if (rows_out > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "more than 2^31 output rows");
@@ -220,7 +223,8 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
     return fail(MDE_ERR_INVALID, "gemm: operands must be 16-byte aligned");
   memset(&op->p, 0, sizeof(op->p));
   GemmParams& p = op->p;
-  MDE_TRY(fill_epilogue(p, ep, ep->shuffle_s > 0 ? m * ep->shuffle_s * ep->shuffle_s : (ep->tokens > 0 ? m + m / ep->tokens : m)));
+  const int tok_skip = ep->token_skip > 0 ? ep->token_skip : 1;
+  MDE_TRY(fill_epilogue(p, ep, ep->shuffle_s > 0 ? m * ep->shuffle_s * ep->shuffle_s : (ep->tokens > 0 ? m + m / ep->tokens * tok_skip : m)));
   p.M = static_cast<int>(m); p.N = n; p.K = k;
   if (m > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "gemm: m too large");
   p.num_k_blocks = (k + 63) / 64;
@@ -230,7 +234,7 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
   p.n_tiles = (n + op->block_n - 1) / op->block_n;
   p.conv = 0;
   if (ep->tokens > 0) {
-    p.row_map = ROW_TOKENS; p.tokens = ep->tokens;
+    p.row_map = ROW_TOKENS; p.tokens = ep->tokens; p.tok_skip = tok_skip;
     if (m % ep->tokens) return fail(MDE_ERR_INVALID, "gemm: m not a multiple of tokens");
   } else if (ep->shuffle_s > 0) {
     p.row_map = ROW_SHUFFLE; p.shuffle_s = ep->shuffle_s; p.shuffle_cout = ep->shuffle_cout;
@@ -473,6 +477,7 @@ static int launch_layernorm_t(const LayerNormParams& p, cudaStream_t s) {
     case 1024: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 1024, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
     case 128: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 128, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
     case 1536: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 1536, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
+    case 2048: MDE_CUDA_TRY(launch_pdl(layernorm_kernel<T, 2048, kTap>, dim3(grid), dim3(256), 0, s, 1, p)); break;
     default: return fail(MDE_ERR_INVALID, "layernorm: unsupported width %d", p.D);
   }
   MDE_CUDA_TRY(cudaGetLastError());
@@ -482,7 +487,7 @@ int launch_layernorm(int precision, const float* d_x, const float* d_w, const fl
                      int dim, float eps, int drop_cls, int ntok, cudaStream_t s, int identity, int n_dst, void* const* dst,
                      long long dst_row0) {
   if (rows <= 0) return fail(MDE_ERR_INVALID, "layernorm: no rows");
-  if (drop_cls && (ntok < 2 || rows % ntok)) return fail(MDE_ERR_INVALID, "layernorm: rows not a multiple of ntok");
+  if (drop_cls < 0 || (drop_cls && (ntok <= drop_cls || rows % ntok))) return fail(MDE_ERR_INVALID, "layernorm: rows not a multiple of ntok, or nothing left after dropping %d tokens", drop_cls);
   if (n_dst < 0 || n_dst > 8 || (n_dst > 0 && !dst)) return fail(MDE_ERR_INVALID, "layernorm: at most 8 gather destinations");
   LayerNormParams p;
   p.x = d_x; p.w = d_w; p.b = d_b; p.out = d_out; p.rows = rows; p.D = dim; p.eps = eps; p.drop_cls = drop_cls; p.ntok = ntok;
@@ -500,11 +505,12 @@ static unsigned grid_for(long long total, int per_block) {
 }
 
 int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int hi, int wi, int ho, int wo, int c,
-                    cudaStream_t s) {
+                    cudaStream_t s, const float* d_addend) {
   if (c % 8) return fail(MDE_ERR_INVALID, "bilinear: channels must be a multiple of 8");
   if (batch <= 0 || hi <= 0 || wi <= 0 || ho <= 0 || wo <= 0) return fail(MDE_ERR_INVALID, "bilinear: empty problem");
   BilinearParams p;
-  p.in = d_in; p.out = d_out; p.B = batch; p.Hi = hi; p.Wi = wi; p.Ho = ho; p.Wo = wo; p.C = c;
+  p.in = d_in; p.out = d_out; p.B = batch; p.Hi = hi; p.Wi = wi; p.Ho = ho; p.Wo = wo; p.C = c; p.addend = d_addend;
+  if (d_addend && (reinterpret_cast<uintptr_t>(d_addend) & 15)) return fail(MDE_ERR_INVALID, "bilinear: the addend must be 16-byte aligned");
   p.sy = ho > 1 ? static_cast<float>(hi - 1) / static_cast<float>(ho - 1) : 0.f;
   p.sx = wo > 1 ? static_cast<float>(wi - 1) / static_cast<float>(wo - 1) : 0.f;
   if (batch > 65535) return fail(MDE_ERR_INVALID, "bilinear: batch exceeds grid limits");
@@ -753,8 +759,9 @@ int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int h
   return MDE_OK;
 }
 
-int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, int batch, int ntok, int dim, cudaStream_t s) {
-  cls_row_kernel<<<batch, 256, 0, s>>>(d_x, d_cls, d_pos, ntok, dim);
+int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, const float* d_reg, int n_reg, int batch, int ntok, int dim,
+                   cudaStream_t s) {
+  cls_row_kernel<<<batch, 256, 0, s>>>(d_x, d_cls, d_pos, d_reg, n_reg, ntok, dim);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
@@ -839,6 +846,31 @@ int mde_k_bilinear(int32_t precision, const void* d_in, void* d_out, int32_t bat
                    int32_t wo, int32_t c, void* stream) {
   clear_error();
   return launch_bilinear(precision, d_in, d_out, batch, hi, wi, ho, wo, c, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_bilinear_add(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t hi, int32_t wi, int32_t ho,
+                       int32_t wo, int32_t c, const float* d_addend, void* stream) {
+  clear_error();
+  if (!d_addend) return fail(MDE_ERR_INVALID, "bilinear_add: the addend is required");
+  return launch_bilinear(precision, d_in, d_out, batch, hi, wi, ho, wo, c, static_cast<cudaStream_t>(stream), d_addend);
+}
+
+int mde_k_assemble_tokens(int32_t precision, const void* d_patch, const float* d_special, int32_t frames, int32_t tokens,
+                          int32_t n_special, int32_t dim, int32_t first_frame, float* d_out, void* stream) {
+  clear_error();
+  if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
+  if (!d_patch || !d_special || !d_out) return fail(MDE_ERR_INVALID, "assemble_tokens: null pointer");
+  if (frames < 1 || tokens < 1 || n_special < 1 || dim < 8 || dim % 8 || first_frame < 0) return fail(MDE_ERR_INVALID, "assemble_tokens: bad geometry");
+  if ((reinterpret_cast<uintptr_t>(d_patch) | reinterpret_cast<uintptr_t>(d_special) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+    return fail(MDE_ERR_INVALID, "assemble_tokens: buffers must be 16-byte aligned");
+  AssembleTokensParams p;
+  p.patch = d_patch; p.special = d_special; p.out = d_out; p.frames = frames; p.tokens = tokens; p.n_special = n_special; p.D = dim;
+  p.first_frame = first_frame;
+  const unsigned grid = static_cast<unsigned>(frames) * static_cast<unsigned>(n_special + tokens);
+  if (precision == MDE_BF16) assemble_tokens_kernel<__nv_bfloat16><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else assemble_tokens_kernel<__half><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
 }
 
 int mde_k_im2col_s2(int32_t precision, const void* d_in, void* d_out, int32_t batch, int32_t h, int32_t w, int32_t c,

@@ -57,29 +57,42 @@ class _Ops:
         self.launches = 0
 
     def ep(self, bias=None, act=0, x=None, res1=None, res2=None, out=None, out_relu=None, ld_out=0, shuffle=None,
-           head_w=None, head_b=0.0, head_out=None, gamma=None, accumulate_x=False):
+           head_w=None, head_b=0.0, head_out=None, gamma=None, accumulate_x=False, head_act=0):
         e = _lib.Epilogue()
         e.d_bias, e.act, e.d_x, e.accumulate_x, e.d_gamma = _p(bias), act, _p(x), int(accumulate_x), _p(gamma)
         e.d_res1, e.d_res2, e.d_out, e.d_out_relu, e.ld_out = _p(res1), _p(res2), _p(out), _p(out_relu), ld_out
         if shuffle:
             e.shuffle_s, e.shuffle_cout, e.shuffle_h, e.shuffle_w = shuffle
         e.d_head_w, e.head_b, e.head_scale, e.d_head_out = _p(head_w), head_b, 0.0, _p(head_out)
+        e.head_act = int(head_act)
         return e
 
     def gemm(self, a, m, k, lda, b, n, ep):
         _lib.check(self.lib.mde_k_gemm(self.prec, _p(a), m, k, lda, _p(b), n, b.stride(0), C.byref(ep), self.stream), "mde_k_gemm")
         self.launches += 1
 
-    def conv3x3(self, x, h, w, cin, wt, cout, ep):
-        _lib.check(self.lib.mde_k_conv3x3(self.prec, _p(x), 1, h, w, cin, _p(wt), cout, C.byref(ep), self.stream), "mde_k_conv3x3")
+    def conv3x3(self, x, h, w, cin, wt, cout, ep, batch=1):
+        _lib.check(self.lib.mde_k_conv3x3(self.prec, _p(x), batch, h, w, cin, _p(wt), cout, C.byref(ep), self.stream), "mde_k_conv3x3")
         self.launches += 1
 
-    def im2col_s2(self, x, h, w, c, out):
-        _lib.check(self.lib.mde_k_im2col_s2(self.prec, _p(x), _p(out), 1, h, w, c, self.stream), "mde_k_im2col_s2")
+    def im2col_s2(self, x, h, w, c, out, batch=1):
+        _lib.check(self.lib.mde_k_im2col_s2(self.prec, _p(x), _p(out), batch, h, w, c, self.stream), "mde_k_im2col_s2")
         self.launches += 1
 
-    def layernorm(self, x, w, b, out, rows, dim, eps=1e-6):
-        _lib.check(self.lib.mde_k_layernorm(self.prec, _p(x), _p(w), _p(b), _p(out), rows, dim, eps, 0, 0, self.stream), "mde_k_layernorm")
+    def layernorm(self, x, w, b, out, rows, dim, eps=1e-6, drop=0, ntok=0):
+        _lib.check(self.lib.mde_k_layernorm(self.prec, _p(x), _p(w), _p(b), _p(out), rows, dim, eps, drop, ntok, self.stream), "mde_k_layernorm")
+        self.launches += 1
+
+    def bilinear(self, x, out, batch, hi, wi, ho, wo, c, addend=None):
+        if addend is None:
+            _lib.check(self.lib.mde_k_bilinear(self.prec, _p(x), _p(out), batch, hi, wi, ho, wo, c, self.stream), "mde_k_bilinear")
+        else:
+            _lib.check(self.lib.mde_k_bilinear_add(self.prec, _p(x), _p(out), batch, hi, wi, ho, wo, c, _p(addend), self.stream), "mde_k_bilinear_add")
+        self.launches += 1
+
+    def assemble_tokens(self, patch, special, frames, tokens, n_special, dim, first_frame, out):
+        _lib.check(self.lib.mde_k_assemble_tokens(self.prec, _p(patch), _p(special), frames, tokens, n_special, dim, first_frame, _p(out),
+                                                  self.stream), "mde_k_assemble_tokens")
         self.launches += 1
 
     def attention(self, qkv, out, batch, ntok, heads):

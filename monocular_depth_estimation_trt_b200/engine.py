@@ -38,7 +38,8 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
               max_src_hw: Tuple[int, int] = (0, 0), swap_rb: bool = True,
               mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
               device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF, output: str = "model_grid",
-              split_k: bool = False, pdl: bool = True, graph: bool = True, attn_poly: int = -1) -> _lib.EngineDesc:
+              split_k: bool = False, pdl: bool = True, graph: bool = True, attn_poly: int = -1,
+              registers: int = 0) -> _lib.EngineDesc:
     """`split_k`, `pdl`, `graph` and `attn_poly` are the engine's tuning surface (mde_engine_desc.flags / attn_poly): they are
     part of the description -- and of the fingerprint `get_engine` records -- not environment variables."""
     if precision not in _lib.PRECISIONS:
@@ -73,6 +74,7 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
     d.flags = ((_lib.MDE_FLAG_SPLIT_K if split_k else 0) | (0 if pdl else _lib.MDE_FLAG_NO_PDL) |
                (0 if graph else _lib.MDE_FLAG_NO_GRAPH))
     d.attn_poly = int(attn_poly)
+    d.num_registers = int(registers if registers else meta.get("registers", 0))
     return d
 
 

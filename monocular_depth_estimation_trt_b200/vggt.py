@@ -12,7 +12,13 @@ process per GPU.
 
 A block is eight launches: LayerNorm, QKV GEMM, qk-norm + RoPE, attention, projection GEMM (LayerScale + residual in the
 epilogue), LayerNorm, FC1 GEMM (+GELU), FC2 GEMM (LayerScale + residual).  torch provides device memory only.
-The DINOv2-with-registers trunk in front of the aggregator and the DPT head behind it are not built.
+
+`VGGTEngine` is the whole exported model (models/vggt/onnx_export.py:38-52 `VGGTDepthOnlyWrapper`; spec.json: images float32
+[1, S, 3, 518, 518] scaled by 1/255, output `depth`) behind the engine / context surface `allocate_buffers` / `do_inference`
+drive: the DINOv2-with-registers trunk (a trunk-only C-ABI engine with four register tokens, the ImageNet normalisation folded
+into its patch-embed weights), camera / register tokens (`mde_k_assemble_tokens`), the aggregator above, and the depth head --
+LayerNorm over the 2D-wide [frame | global] taps, DPT reassemble with the head's sin / cos position embedding added after each
+projection and again after the final up-sampling, RefineNets, `exp` -- composed from the GEMM / conv kernels.
 """
 from __future__ import annotations
 
@@ -21,8 +27,8 @@ from typing import Mapping, Sequence
 
 import numpy as np
 
-from . import _lib, sharding as S
-from .depth_pro import _Ops, _t
+from . import _lib, engine as E, sharding as S, weights as W
+from .depth_pro import _Ops, _t, pack_conv3x3, pack_conv3x3_s2
 
 LN_EPS = 1e-5          # aggregator blocks: nn.LayerNorm's default (the DINOv2 trunk in front uses 1e-6)
 QK_EPS = 1e-5
@@ -193,3 +199,294 @@ class Aggregator:
         if self.kv is not None:
             self.kv.close()
             self.kv = None
+
+
+# ================================================================================================ the whole model
+TRUNK = "aggregator.patch_embed."
+RESNET_MEAN, RESNET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # reports/profile/vggt.json layer 2 (`Sub`, `Div`)
+HEAD_LN_EPS = 1e-5
+N_SPECIAL = 5
+
+
+def head_pos_embed(channels: int, h: int, w: int, image_w: int, image_h: int):
+    """float32 [h, w, channels]: what `DPTHead._apply_pos_embed` adds -- 0.1 * [sincos(u) | sincos(v)] of the h x w grid whose
+    (u, v) span the image with its diagonal normalised to 1; sin / cos table as the reference exports it
+    (core/export_compat.py:145-152: float32 frequencies 1 / 100 ** (i / (channels / 4)), sines first)."""
+    import torch
+    aspect = image_w / image_h
+    diag = (aspect ** 2 + 1.0) ** 0.5
+    sx, sy = aspect / diag, 1.0 / diag
+    xs = torch.linspace(-sx * (w - 1) / w, sx * (w - 1) / w, steps=w, dtype=torch.float32)
+    ys = torch.linspace(-sy * (h - 1) / h, sy * (h - 1) / h, steps=h, dtype=torch.float32)
+
+    def sincos(pos, dim):
+        omega = torch.arange(dim // 2, dtype=torch.float32)
+        omega /= dim / 2.0
+        omega = 1.0 / 100.0 ** omega
+        out = torch.einsum("m,d->md", pos.to(torch.float32), omega)
+        return torch.cat([torch.sin(out), torch.cos(out)], dim=1)
+
+    eu, ev = sincos(xs, channels // 2), sincos(ys, channels // 2)                  # [w, C/2], [h, C/2]
+    return (torch.cat([eu[None].expand(h, -1, -1), ev[:, None].expand(-1, w, -1)], dim=-1) * 0.1).contiguous()
+
+
+def pack_deconv(w, s: int, dtype):
+    """ConvTranspose2d(kernel == stride == s) [cin, cout, s, s] -> GEMM B [s*s*cout, cin], row (ky*s + kx)*cout + o."""
+    cin, cout = w.shape[:2]
+    return w.permute(2, 3, 1, 0).reshape(s * s * cout, cin).to(dtype).contiguous()
+
+
+class _HeadWeights:
+    def __init__(self, sd: Mapping, D: int, F: int, oc, gh: int, gw: int, H: int, Wd: int, frames: int, dtype, device):
+        import torch
+        g = lambda k: _t(sd["depth_head." + k])
+        dev = lambda t: t.contiguous().to(device)
+        self.norm_w, self.norm_b = dev(g("norm.weight")), dev(g("norm.bias"))
+        self.proj, self.proj_b, self.pe, self.rn = [], [], [], []
+        for i in range(4):
+            self.proj.append(dev(g(f"projects.{i}.weight").flatten(1).to(dtype)))
+            self.proj_b.append(dev(g(f"projects.{i}.bias")))
+            pe = head_pos_embed(oc[i], gh, gw, Wd, H).reshape(gh * gw, oc[i])
+            self.pe.append(dev(pe.repeat(frames, 1).to(dtype)))             # added as a 16-bit residual in the projection's epilogue
+            self.rn.append(dev(pack_conv3x3(g(f"scratch.layer{i + 1}_rn.weight"), dtype)))
+        self.ct0, self.ct0_b = dev(pack_deconv(g("resize_layers.0.weight"), 4, dtype)), dev(g("resize_layers.0.bias"))
+        self.ct1, self.ct1_b = dev(pack_deconv(g("resize_layers.1.weight"), 2, dtype)), dev(g("resize_layers.1.bias"))
+        self.rs3, self.rs3_b = dev(pack_conv3x3_s2(g("resize_layers.3.weight"), dtype)), dev(g("resize_layers.3.bias"))
+        self.ref = []
+        for i in range(4):
+            r = f"scratch.refinenet{i + 1}."
+            d = {"out.w": dev(g(r + "out_conv.weight").flatten(1).to(dtype)), "out.b": dev(g(r + "out_conv.bias"))}
+            for u in (("resConfUnit2",) if i == 3 else ("resConfUnit1", "resConfUnit2")):
+                for cv in ("conv1", "conv2"):
+                    d[f"{u}.{cv}.w"] = dev(pack_conv3x3(g(r + f"{u}.{cv}.weight"), dtype))
+                    d[f"{u}.{cv}.b"] = dev(g(r + f"{u}.{cv}.bias"))
+            self.ref.append(d)
+        self.oc1, self.oc1_b = dev(pack_conv3x3(g("scratch.output_conv1.weight"), dtype)), dev(g("scratch.output_conv1.bias"))
+        self.oc2, self.oc2_b = dev(pack_conv3x3(g("scratch.output_conv2.0.weight"), dtype)), dev(g("scratch.output_conv2.0.bias"))
+        last_w, last_b = g("scratch.output_conv2.2.weight"), g("scratch.output_conv2.2.bias")
+        self.head_w, self.head_b = dev(last_w[0].flatten()), float(last_b[0])    # channel 0 = log depth (channel 1, the confidence, is not exported)
+        self.pe_out = dev(head_pos_embed(F // 2, H, Wd, Wd, H).reshape(H * Wd, F // 2))   # fp32, added by the up-sampling kernel
+
+
+class VGGTEngine:
+    """Stands in for the tensorrt.ICudaEngine models/vggt/onnx2trt.py builds: bindings `images` float32 [1, S, 3, H, W] (values
+    0..1) and `depth` float32 [1, S, H, W, 1].  With `world` > 1 (one process per GPU) the S frames of the scene are sharded by
+    rank: the bindings then hold this rank's `S / world` frames."""
+
+    TensorIOMode = E.TensorIOMode
+    IO = (("images", True), ("depth", False))
+
+    def __init__(self, state_dict: Mapping, encoder: str = "vitl", depth: int = 24, features: int = 256,
+                 out_channels: Sequence[int] = (256, 512, 1024, 1024), taps: Sequence[int] = (4, 11, 17, 23), frames: int = 16,
+                 image_hw=(518, 518), precision: str = "fp16", world: int = 1, rank: int = 0, gather: str = "fused", device: int = 0):
+        import torch
+        cfg = W.ENCODERS[encoder]
+        H, Wd = int(image_hw[0]), int(image_hw[1])
+        if H % 14 or Wd % 14:
+            raise ValueError(f"[MDET] image size {H}x{Wd} is not a multiple of the patch size 14")
+        if frames % world:
+            raise ValueError(f"[MDET] {frames} frames do not divide over {world} ranks")
+        if features % 64 or any(c % 8 for c in out_channels):
+            raise ValueError("[MDET] decoder widths must be multiples of 64 (features) / 8 (out_channels)")
+        self.encoder, self.depth, self.F, self.oc, self.taps = encoder, int(depth), int(features), [int(c) for c in out_channels], [int(t) for t in taps]
+        self.D, self.heads, self.H, self.W, self.gh, self.gw = cfg["embed_dim"], cfg["num_heads"], H, Wd, H // 14, Wd // 14
+        self.S_total, self.S, self.world, self.rank, self.precision = int(frames), int(frames) // int(world), int(world), int(rank), precision
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float16
+        self.device = torch.device("cuda", device)
+        self.trunk = None
+        self.agg = None
+        try:
+            # ---- trunk: DINOv2 with four registers; (x - mean) / std folded into the patch embedding (two linear maps, one rounding)
+            sd = {"pretrained." + k[len(TRUNK):]: _t(v) for k, v in state_dict.items() if k.startswith(TRUNK)}
+            if not sd:
+                raise ValueError(f"[MDET] the state dict holds no '{TRUNK}*' tensors")
+            w = sd["pretrained.patch_embed.proj.weight"].double()
+            mean, std = torch.tensor(RESNET_MEAN, dtype=torch.float64), torch.tensor(RESNET_STD, dtype=torch.float64)
+            sd["pretrained.patch_embed.proj.bias"] = (sd["pretrained.patch_embed.proj.bias"].double()
+                                                      - (w * (mean / std).view(1, 3, 1, 1)).sum(dim=(1, 2, 3))).float()
+            sd["pretrained.patch_embed.proj.weight"] = (w / std.view(1, 3, 1, 1)).float()
+            L = cfg["depth"]
+            meta = W.describe(encoder, H, Wd, None)
+            meta["taps"] = [L - 4, L - 3, L - 2, L - 1]
+            meta["registers"] = int(sd["pretrained.register_tokens"].shape[1])
+            self.trunk = E.Engine(E.make_desc(meta, precision=precision, batch=self.S, head="encoder_taps", tap_norm_mask=0x8, device=device), meta)
+            self.trunk.load_state_dict(sd)
+            self.trunk.finalize()
+            # ---- aggregator + head
+            self.agg = Aggregator(state_dict, self.D, self.depth, self.heads, self.gh, self.gw, frames_total=self.S_total, precision=precision,
+                                  world=world, rank=rank, gather=gather, taps=self.taps, device=device)
+            self.special = torch.cat([_t(state_dict["aggregator.camera_token"])[0], _t(state_dict["aggregator.register_token"])[0]],
+                                     dim=1).contiguous().to(self.device)                      # [2, 5, D]
+            self.head = _HeadWeights(state_dict, self.D, self.F, self.oc, self.gh, self.gw, H, Wd, self.S, self.dtype, self.device)
+        except Exception:
+            self.close()
+            raise
+
+    @property
+    def num_io_tensors(self) -> int:
+        return len(self.IO)
+
+    def get_tensor_name(self, i: int) -> str:
+        return self.IO[i][0]
+
+    def get_tensor_shape(self, name: str):
+        return {"images": (1, self.S, 3, self.H, self.W), "depth": (1, self.S, self.H, self.W, 1)}[name]
+
+    def get_tensor_profile_shape(self, name: str, profile_idx: int):
+        s = self.get_tensor_shape(name)
+        return (s, s, s)
+
+    def get_tensor_dtype(self, name: str) -> np.dtype:
+        self.get_tensor_shape(name)
+        return np.dtype(np.float32)
+
+    def get_tensor_mode(self, name: str):
+        return E.TensorIOMode.INPUT if dict(self.IO)[name] else E.TensorIOMode.OUTPUT
+
+    def create_execution_context(self) -> "VGGTContext":
+        return VGGTContext(self)
+
+    def close(self) -> None:
+        if getattr(self, "agg", None) is not None:
+            self.agg.close()
+            self.agg = None
+        if getattr(self, "trunk", None) is not None:
+            self.trunk.close()
+            self.trunk = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+class VGGTContext:
+    """`set_tensor_address` for the two bindings, `execute_async_v3(stream)`: trunk engine (its own CUDA graph), token assembly,
+    aggregator (captured into a CUDA graph at the first call), depth head.  Every buffer is allocated here."""
+
+    def __init__(self, engine: VGGTEngine):
+        import torch
+        e = self.e = engine
+        self.ops = e.agg.ops
+        self.addr = {}
+        dev, dt = e.device, e.dtype
+        S_, T, D, F, oc, gh, gw = e.S, e.gh * e.gw, e.D, e.F, e.oc, e.gh, e.gw
+        z16 = lambda *shape: torch.zeros(*shape, dtype=dt, device=dev)
+        self.trunk_ctx = e.trunk.create_execution_context()
+        self.trunk_out = z16(4, S_, T, D)
+        self.tokens = torch.zeros(S_, N_SPECIAL + T, D, dtype=torch.float32, device=dev)
+        self.lvl = [(4 * gh, 4 * gw), (2 * gh, 2 * gw), (gh, gw), ((gh - 1) // 2 + 1, (gw - 1) // 2 + 1)]
+        b = {"ln": z16(S_ * T, 2 * D)}
+        for i in range(4):
+            b[f"pr{i}"] = z16(S_ * T, oc[i])
+            h, w = self.lvl[i]
+            b[f"l{i}"] = b[f"pr{i}"] if i == 2 else z16(S_ * h * w, oc[i])
+            for name in ("r", "r.relu", "a", "s", "s.relu", "a2", "u", "q"):
+                b[f"{name}{i}"] = z16(S_ * h * w, F)
+            ho, wo = (self.lvl[i - 1] if i > 0 else (2 * h, 2 * w))
+            b[f"path{i}"] = z16(S_ * ho * wo, F)
+        b["cols3"] = z16(S_ * self.lvl[3][0] * self.lvl[3][1], 9 * oc[3])
+        h1, w1 = 2 * self.lvl[0][0], 2 * self.lvl[0][1]
+        b["o1"] = z16(S_ * h1 * w1, F // 2)
+        b["up"] = z16(S_ * e.H * e.W, F // 2)
+        self.b = b
+        self.launches_per_enqueue = 0
+        self._captured = False
+
+    def set_tensor_address(self, name: str, ptr: int) -> bool:
+        self.e.get_tensor_shape(name)
+        self.addr[name] = int(ptr)
+        return True
+
+    def set_input_shape(self, name: str, shape) -> bool:
+        if tuple(int(s) for s in shape) != self.e.get_tensor_shape(name):
+            raise ValueError(f"[MDET] {name}: engines are static, shape {tuple(shape)} != {self.e.get_tensor_shape(name)}")
+        return True
+
+    def get_buffer(self, name: str):
+        return self.b[name]
+
+    def execute_async_v3(self, stream_handle) -> bool:
+        missing = [n for n, _ in self.e.IO if not self.addr.get(n)]
+        if missing:
+            raise RuntimeError(f"[MDET] execute before set_tensor_address for {missing}")
+        e, o, b, hw = self.e, self.ops, self.b, self.e.head
+        sh = int(stream_handle)
+        S_, T, D, F, oc, gh, gw = e.S, e.gh * e.gw, e.D, e.F, e.oc, e.gh, e.gw
+        # 1. trunk: normalised patch tokens of every frame (slice 3 of the trunk-only engine's output)
+        self.trunk_ctx.set_tensor_address("input", self.addr["images"])
+        self.trunk_ctx.set_tensor_address("output", self.trunk_out.data_ptr())
+        self.trunk_ctx.execute_async_v3(sh)
+        o.stream = C.c_void_p(sh)
+        o.launches = 0
+        # 2. camera + register tokens in front
+        o.assemble_tokens(self.trunk_out[3], e.special, S_, T, N_SPECIAL, D, e.rank * S_, self.tokens)
+        # 3. aggregator (graph replay after the first call on a capturable stream)
+        if sh != 0 and (e.world == 1 or e.agg.sync is not None):
+            if not self._captured:
+                e.agg.forward(self.tokens.data_ptr(), sh)              # warm run: every kernel's attributes are set outside the capture
+                self._agg_launches = o.launches
+                e.agg.capture(self.tokens.data_ptr(), sh)
+                self._captured = True
+            else:
+                e.agg.replay(sh)
+        else:
+            e.agg.forward(self.tokens.data_ptr(), sh)
+            self._agg_launches = o.launches
+        agg_launches = self._agg_launches
+        o.stream = C.c_void_p(sh)
+        o.launches = 0
+        # 4. depth head
+        N = N_SPECIAL + T
+        for i, layer in enumerate(e.taps):
+            o.layernorm(e.agg.tap_out[layer], hw.norm_w, hw.norm_b, b["ln"], S_ * N, 2 * D, HEAD_LN_EPS, drop=N_SPECIAL, ntok=N)
+            o.gemm(b["ln"], S_ * T, 2 * D, 2 * D, hw.proj[i], oc[i], o.ep(bias=hw.proj_b[i], res1=hw.pe[i], out=b[f"pr{i}"], ld_out=oc[i]))
+            if i == 0:
+                o.gemm(b["pr0"], S_ * T, oc[0], oc[0], hw.ct0, 16 * oc[0], o.ep(bias=hw.ct0_b, out=b["l0"], ld_out=oc[0], shuffle=(4, oc[0], gh, gw)))
+            elif i == 1:
+                o.gemm(b["pr1"], S_ * T, oc[1], oc[1], hw.ct1, 4 * oc[1], o.ep(bias=hw.ct1_b, out=b["l1"], ld_out=oc[1], shuffle=(2, oc[1], gh, gw)))
+            elif i == 3:
+                o.im2col_s2(b["pr3"], gh, gw, oc[3], b["cols3"], batch=S_)
+                h4, w4 = self.lvl[3]
+                o.gemm(b["cols3"], S_ * h4 * w4, 9 * oc[3], 9 * oc[3], hw.rs3, oc[3], o.ep(bias=hw.rs3_b, out=b["l3"], ld_out=oc[3]))
+        for i in range(4):
+            h, w = self.lvl[i]
+            o.conv3x3(b[f"l{i}"], h, w, oc[i], hw.rn[i], F, o.ep(out=b[f"r{i}"], out_relu=b[f"r.relu{i}"], ld_out=F), batch=S_)
+        path = None
+        for i in (3, 2, 1, 0):
+            h, w = self.lvl[i]
+            rf = hw.ref[i]
+            s_relu, s_raw = b[f"r.relu{i}"], b[f"r{i}"]
+            if i != 3:      # s = path + RCU1(r_i)
+                o.conv3x3(b[f"r.relu{i}"], h, w, F, rf["resConfUnit1.conv1.w"], F, o.ep(bias=rf["resConfUnit1.conv1.b"], act=2, out=b[f"a{i}"], ld_out=F), batch=S_)
+                o.conv3x3(b[f"a{i}"], h, w, F, rf["resConfUnit1.conv2.w"], F,
+                          o.ep(bias=rf["resConfUnit1.conv2.b"], res1=b[f"r{i}"], res2=path, out=b[f"s{i}"], out_relu=b[f"s.relu{i}"], ld_out=F), batch=S_)
+                s_relu, s_raw = b[f"s.relu{i}"], b[f"s{i}"]
+            o.conv3x3(s_relu, h, w, F, rf["resConfUnit2.conv1.w"], F, o.ep(bias=rf["resConfUnit2.conv1.b"], act=2, out=b[f"a2{i}"], ld_out=F), batch=S_)
+            o.conv3x3(b[f"a2{i}"], h, w, F, rf["resConfUnit2.conv2.w"], F, o.ep(bias=rf["resConfUnit2.conv2.b"], res1=s_raw, out=b[f"u{i}"], ld_out=F), batch=S_)
+            # 1x1 out_conv before the bilinear up-sampling (both linear, interpolation weights sum to 1: they commute)
+            o.gemm(b[f"u{i}"], S_ * h * w, F, F, rf["out.w"], F, o.ep(bias=rf["out.b"], out=b[f"q{i}"], ld_out=F))
+            ho, wo = (self.lvl[i - 1] if i > 0 else (2 * h, 2 * w))
+            o.bilinear(b[f"q{i}"], b[f"path{i}"], S_, h, w, ho, wo, F)
+            path = b[f"path{i}"]
+        h1, w1 = 2 * self.lvl[0][0], 2 * self.lvl[0][1]
+        o.conv3x3(path, h1, w1, F, hw.oc1, F // 2, o.ep(bias=hw.oc1_b, out=b["o1"], ld_out=F // 2), batch=S_)
+        o.bilinear(b["o1"], b["up"], S_, h1, w1, e.H, e.W, F // 2, addend=hw.pe_out)
+        o.conv3x3(b["up"], e.H, e.W, F // 2, hw.oc2, 32,
+                  o.ep(bias=hw.oc2_b, ld_out=32, head_w=hw.head_w, head_b=hw.head_b, head_out=self.addr["depth"], head_act=1), batch=S_)
+        self.launches_per_enqueue = self.trunk_ctx.launches_per_enqueue + 1 + agg_launches + o.launches
+        return True
+
+    def close(self) -> None:
+        if getattr(self, "trunk_ctx", None) is not None:
+            self.trunk_ctx.close()
+            self.trunk_ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -1,6 +1,8 @@
 """VGGT's aggregator blocks on a B200 against oracle/vggt_torch.py: the qk-norm + 2-D RoPE kernel on its own (fp32
 reference on the same 16-bit inputs), then frame / global blocks and the alternating stack at the real 37 x 37 token grid.
 Budgets as for the Depth Anything residual stream (tests/test_engine_gpu.py INTER), per block pair."""
+import functools
+
 import numpy as np
 import pytest
 import torch
@@ -136,3 +138,87 @@ def test_vggt_postprocessing_matches_the_reference_adapter(lib, src):
     both = np.isfinite(ref) & np.isfinite(got)
     assert np.isnan(ref).any() and (np.isnan(ref) != np.isnan(got)).mean() < 1e-3      # the floor is crossed by the same pixels (fp32 vs fp64 at the edge)
     assert np.abs(got[both] - ref[both]).max() <= 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ the whole model
+@functools.lru_cache(maxsize=1)
+def vggt_reference(frames=3, depth=4, seed=0):
+    """(state dict, images [frames, 3, 518, 518] in 0..1, oracle depth, trace): ViT-S trunk with four registers, `depth`
+    (frame, global) block pairs, DPT head at ViT-S widths; the frames are the reference's synthetic images through its own
+    VGGT preprocessing (white square pad + cubic resize + / 255, oracle/preprocess_np.py)."""
+    from oracle import preprocess_np as PP
+    sd = V.init_vggt("vits", depth=depth, features=64, out_channels=(48, 96, 192, 384), seed=seed)
+    imgs = torch.cat([torch.from_numpy(PP.preprocess_square_pad_cubic(
+        np.random.default_rng(i).integers(0, 256, (480, 640, 3), dtype=np.uint8), 518, 518))[0] for i in range(frames)])
+    taps = tuple(range(depth))[-4:] if depth >= 4 else (0, 0, depth - 1, depth - 1)
+    V.calibrate_vggt(sd, imgs, "vits", depth, taps)
+    trace = {}
+    ref = V.vggt_depth(sd, imgs, "vits", depth, taps, trace)
+    return sd, imgs, ref, trace, taps
+
+
+def test_assemble_tokens_and_layernorm_drop(lib):
+    from monocular_depth_estimation_trt_b200.depth_pro import _Ops
+    import ctypes as C
+    torch.manual_seed(2)
+    S, T, D = 3, 11, 384
+    patch = torch.randn(S, T, D).half().cuda()
+    special = torch.randn(2, 5, D).cuda()
+    ops = _Ops("fp16")
+    ops.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for first in (0, 4):
+        out = torch.full((S, 5 + T, D), float("nan"), device="cuda")
+        ops.assemble_tokens(patch, special, S, T, 5, D, first, out)
+        torch.cuda.synchronize()
+        want = torch.cat([torch.stack([special[0 if first + s == 0 else 1] for s in range(S)]), patch.float()], dim=1)
+        assert torch.equal(out, want)
+    # LayerNorm over 2 * 1024 features, dropping the five special tokens of every frame
+    x = torch.randn(S * (5 + T), 2048, device="cuda") * 3 + 0.5
+    w, b = 1 + 0.1 * torch.randn(2048, device="cuda"), 0.1 * torch.randn(2048, device="cuda")
+    y = torch.empty(S * T, 2048, dtype=torch.float16, device="cuda")
+    ops.layernorm(x, w, b, y, S * (5 + T), 2048, 1e-5, drop=5, ntok=5 + T)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.reshape(S, 5 + T, 2048)[:, 5:], (2048,), w, b, 1e-5).reshape(S * T, 2048)
+    assert float((y.float() - ref).abs().max()) <= 2.0 ** -10 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_whole_model_against_the_oracle(lib, prec):
+    """models/vggt/onnx_export.py:38-52 as one engine: images [1, S, 3, 518, 518] -> depth [1, S, 518, 518, 1], through the
+    reference-shaped host API, against the oracle's fp32 forward.  One gate (north_star); bf16 reports against it as xfail."""
+    from monocular_depth_estimation_trt_b200 import common
+    import refsetup as R
+    sd, imgs, ref, trace, taps = vggt_reference()
+    S = imgs.shape[0]
+    with P.VGGTEngine(sd, encoder="vits", depth=4, features=64, out_channels=(48, 96, 192, 384), taps=taps, frames=S, precision=prec) as engine, \
+            engine.create_execution_context() as context:
+        assert [engine.get_tensor_name(i) for i in range(engine.num_io_tensors)] == ["images", "depth"]
+        assert engine.get_tensor_shape("images") == (1, S, 3, 518, 518) and engine.get_tensor_shape("depth") == (1, S, 518, 518, 1)
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+        inputs[0].host = imgs.numpy()
+        out = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        got = out[0].reshape(S, 518, 518).copy()
+        again = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        assert np.array_equal(again[0].reshape(S, 518, 518), got)             # graph replay of the aggregator: bit-identical
+        # intermediates localise a failure: aggregator input, the four [frame | global] taps, path_1
+        tok = context.tokens.cpu()
+        assert rms_rel(tok, trace["tokens"]) < INTER[prec]
+        for i, layer in enumerate(taps):
+            t = engine.agg.tap_out[layer].cpu().reshape(S, 1374, -1)
+            assert rms_rel(t, trace["aggregated"][i]) < INTER[prec] * (layer + 2), layer
+        p1 = context.get_buffer("path0").float().cpu().reshape(S, 296, 296, 64).permute(0, 3, 1, 2)
+        assert rms_rel(p1, trace["path_1"]) < 3 * INTER[prec]
+        launches = context.launches_per_enqueue
+        common.free_buffers(inputs, outputs, stream)
+    worst = {"abs_rel": 0.0, "max_rel": 0.0}
+    for s in range(S):
+        m = R.compare_depth(ref[s].numpy(), got[s])
+        worst = {k: max(worst[k], m[k]) for k in worst}
+    print(prec, launches, "launches", worst)
+    assert np.isfinite(got).all() and (got > 0).all()
+    if prec == "bf16":
+        assert worst["abs_rel"] <= 1.2e-2 and worst["max_rel"] <= 1.2e-1, worst             # regression guard, not a parity claim
+        if not (worst["abs_rel"] <= 2e-3 and worst["max_rel"] <= 1e-2):
+            pytest.xfail(f"bf16 operands miss north_star's gate on the fp32 oracle: {worst}")
+    else:
+        assert worst["abs_rel"] <= 2e-3 and worst["max_rel"] <= 1e-2, worst
