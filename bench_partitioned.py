@@ -7,6 +7,8 @@ oracle provides seeded weights in set-up and is the checker after the timed regi
                       K|V all-gather of every global block fused into the qk-norm + RoPE kernel's stores (peer memory over
                       NVLink, flag hand-shake on the stream, whole forward replayed as one CUDA graph); "nccl" = the same
                       pipeline with all_gather_into_tensor
+    vggt_model        the whole exported model around that aggregator (DINOv2-L-with-registers trunk, camera / register tokens,
+                      depth head), 16 frames of 518 x 518
     depth_pro         the whole model at 1536 x 1536 (ViT-L/16 trunks): 35 crops sharded by rank, taps all-gathered by the
                       kernel that produces them (or NCCL), decoder on every rank
 
@@ -128,6 +130,87 @@ def vggt_aggregator(world: int, rank: int, local: int, precision: str, reps: int
     return out
 
 
+def vggt_model(world: int, rank: int, local: int, precision: str, reps: int = 5) -> dict:
+    """The WHOLE exported VGGT model (trunk with registers -> camera / register tokens -> aggregator -> depth head), frames
+    sharded by rank: parity of every rank's depth maps against the unsharded oracle at ViT-S widths, then device time of one
+    16-frame scene at the model's size (ViT-L, 24 + 24 blocks)."""
+    import numpy as np
+    import torch
+    import refsetup as R
+    from cuda.bindings import runtime as cudart
+    from monocular_depth_estimation_trt_b200 import common, vggt as P
+    from oracle import preprocess_np as PP, vggt_torch as V
+    out = {"precision": precision, "world": world, "scaling": "strong"}
+
+    def run(sd, imgs_local, cfg, frames, timed):
+        with P.VGGTEngine(sd, frames=frames, precision=precision, world=world, rank=rank, device=local, **cfg) as engine, \
+                engine.create_execution_context() as context:
+            inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+            inputs[0].host = imgs_local.numpy()
+            for _ in range(2):
+                res = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+            got = res[0].reshape(imgs_local.shape[0], 518, 518).copy()
+            ms = None
+            if timed:
+                ev0, ev1 = common.cuda_call(cudart.cudaEventCreate()), common.cuda_call(cudart.cudaEventCreate())
+                ts = []
+                for _ in range(reps):
+                    _barrier(world)
+                    common.cuda_call(cudart.cudaEventRecord(ev0, stream))
+                    context.execute_async_v3(stream_handle=stream)
+                    common.cuda_call(cudart.cudaEventRecord(ev1, stream))
+                    common.cuda_call(cudart.cudaStreamSynchronize(stream))
+                    ts.append(_max_over_ranks(float(common.cuda_call(cudart.cudaEventElapsedTime(ev0, ev1))), world))
+                ms = float(np.median(ts))
+            launches = context.launches_per_enqueue
+            common.free_buffers(inputs, outputs, stream)
+        return got, ms, launches
+
+    # ---- parity (ViT-S widths, 4 + 4 blocks): rank 0 runs the CPU oracle and hands weights, frames and reference to the others
+    frames = {1: 3, 2: 4}.get(world, world)
+    small = dict(encoder="vits", depth=4, features=64, out_channels=(48, 96, 192, 384), taps=(0, 1, 2, 3))
+
+    def reference():
+        sd = V.init_vggt("vits", depth=4, features=64, out_channels=(48, 96, 192, 384), seed=0)
+        imgs = torch.cat([torch.from_numpy(PP.preprocess_square_pad_cubic(
+            np.random.default_rng(i).integers(0, 256, (480, 640, 3), dtype=np.uint8), 518, 518))[0] for i in range(frames)])
+        V.calibrate_vggt(sd, imgs, "vits", 4, small["taps"])
+        return sd, imgs, V.vggt_depth(sd, imgs, "vits", 4, small["taps"])
+
+    if world > 1:
+        import torch.distributed as dist
+        box = [reference() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sd, imgs, ref = box[0]
+    else:
+        sd, imgs, ref = reference()
+    per = frames // world
+    got, _, _ = run(sd, imgs[rank * per:(rank + 1) * per].contiguous(), small, frames, False)
+    worst_abs = worst_max = 0.0
+    for s in range(per):
+        m = R.compare_depth(ref[rank * per + s].numpy(), got[s])
+        worst_abs, worst_max = max(worst_abs, m["abs_rel"]), max(worst_max, m["max_rel"])
+    worst_abs, worst_max = _max_over_ranks(worst_abs, world), _max_over_ranks(worst_max, world)
+    out["parity"] = {"abs_rel": worst_abs, "max_rel": worst_max, "gate": {"abs_rel": 2e-3, "max_rel": 1e-2},
+                     "meets_gate": bool(worst_abs <= 2e-3 and worst_max <= 1e-2),
+                     "what": f"ViT-S widths, 4 + 4 blocks, {frames} frames of 518 x 518 sharded over {world} rank(s): every rank's depth maps "
+                             f"vs the unsharded fp32 oracle (oracle/vggt_torch.py, parity unpinned against upstream VGGT)"}
+    _barrier(world)
+    # ---- timing at the model's size
+    frames = 16
+    per = frames // world
+    sd = V.init_vggt("vitl", depth=24, features=256, out_channels=(256, 512, 1024, 1024), seed=0)
+    torch.manual_seed(1)
+    imgs = torch.rand(per, 3, 518, 518)
+    big = dict(encoder="vitl", depth=24, features=256, out_channels=(256, 512, 1024, 1024), taps=(4, 11, 17, 23))
+    _, ms, launches = run(sd, imgs, big, frames, True)
+    out.update(frames=frames, image=[518, 518], ms=ms, frames_per_s=frames / (ms / 1e3), launches_per_rank=launches,
+               what="trunk (DINOv2-L with registers) + 24 x (frame, global) blocks + depth head, device time, CUDA events, max over ranks")
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
 def depth_pro(world: int, rank: int, local: int, precision: str, reps: int = 10) -> dict:
     import numpy as np
     import torch
@@ -205,5 +288,6 @@ def run_all(world: int, rank: int, local: int, precision: str) -> dict | None:
     import torch
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))      # torchrun pins OMP_NUM_THREADS=1: the oracle legs need more
     res = {"vggt_aggregator": vggt_aggregator(world, rank, local, precision),
+           "vggt_model": vggt_model(world, rank, local, precision),
            "depth_pro": depth_pro(world, rank, local, precision)}
     return res if rank == 0 else None
