@@ -51,6 +51,10 @@ extern "C" {
 
 /* what the engine computes behind the shared DINOv2 trunk */
 #define MDE_HEAD_DPT 0          /* Depth Anything V2: DPT head, output float32 depth [B,H,W] */
+#define MDE_HEAD_DPT_EXP_SKY 2  /* Depth Anything V3 (models/depth_anything_v3/onnx_export.py:31-55, reports/profile/depth_anything_v3.json
+                                 * layers 221-227): the same DPT head ending in exp(), plus a parallel sky branch
+                                 * (`sky_output_conv2`: conv3x3 -> ReLU -> conv1x1 -> ReLU) on the same up-sampled features.
+                                 * Bindings: "image" in, "depth" and "sky" out, float32 [B][H][W] each */
 #define MDE_HEAD_ENCODER_TAPS 1 /* trunk only (the patch-encoder stage of Depth Pro, models/depth_pro/onnx_export.py:15-22):
                                  * output = the four tapped block outputs, cls dropped, 16-bit [4][B][T][D] */
 
@@ -61,6 +65,8 @@ extern "C" {
                              * L2's fp32 adds in arrival order, i.e. results are no longer bitwise reproducible run to run */
 #define MDE_FLAG_NO_PDL 2   /* launch without programmatic dependent launch (default: on for GEMM / attention / LayerNorm) */
 #define MDE_FLAG_NO_GRAPH 4 /* always launch kernel by kernel instead of replaying the captured CUDA graph */
+#define MDE_FLAG_SCALE_F32 8 /* MDE_INPUT_U8_HWC: v / 255 evaluated in float32 before the float64 (v - mean) / std -- depth_anything_ac's
+                              * input contract (core/preprocess.py:294-305, :470-476); default: float64 throughout (depth_anything_v2) */
 
 /* error codes */
 #define MDE_OK 0

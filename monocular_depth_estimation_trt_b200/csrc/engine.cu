@@ -74,9 +74,9 @@ struct mde_engine {
   float *ct0_b = nullptr, *ct1_b = nullptr, *rs3_b = nullptr;
   void* rn_w[4] = {nullptr, nullptr, nullptr, nullptr};
   Refine refine[4];   // index i = refinenet{i+1}
-  void *oc1_w = nullptr, *oc2_w = nullptr;
-  float *oc1_b = nullptr, *oc2_b = nullptr, *head_w = nullptr;
-  float head_b = 0.f;
+  void *oc1_w = nullptr, *oc2_w = nullptr, *sky2_w = nullptr;
+  float *oc1_b = nullptr, *oc2_b = nullptr, *head_w = nullptr, *sky2_b = nullptr, *sky_head_w = nullptr;
+  float head_b = 0.f, sky_head_b = 0.f;
   int64_t weight_bytes = 0;
 };
 
@@ -108,6 +108,7 @@ struct mde_context {
   std::map<std::string, int> named_dtype;
   void* d_input = nullptr;
   void* d_output = nullptr;
+  void* d_output2 = nullptr;       // MDE_HEAD_DPT_EXP_SKY: the sky map
   int src_h = 0, src_w = 0;
   int snapshot_block = -1;
   int gather_ranks = 0, gather_rank = 0;       // mde_context_set_gather
@@ -248,16 +249,17 @@ static int validate_desc(const mde_engine_desc* d) {
   if (d->output_mode != MDE_OUTPUT_MODEL_GRID && d->output_mode != MDE_OUTPUT_SOURCE_GRID) return fail(MDE_ERR_INVALID, "unknown output_mode %d", d->output_mode);
   if (d->output_mode == MDE_OUTPUT_SOURCE_GRID && (d->head_mode != MDE_HEAD_DPT || d->max_src_h <= 0 || d->max_src_w <= 0))
     return fail(MDE_ERR_INVALID, "MDE_OUTPUT_SOURCE_GRID needs the DPT head and max_src_h / max_src_w");
-  if (d->head_mode != MDE_HEAD_DPT && d->head_mode != MDE_HEAD_ENCODER_TAPS) return fail(MDE_ERR_INVALID, "unknown head_mode %d", d->head_mode);
+  if (d->head_mode != MDE_HEAD_DPT && d->head_mode != MDE_HEAD_ENCODER_TAPS && d->head_mode != MDE_HEAD_DPT_EXP_SKY)
+    return fail(MDE_ERR_INVALID, "unknown head_mode %d", d->head_mode);
   if (d->tap_norm_mask < 0 || d->tap_norm_mask > 0xF) return fail(MDE_ERR_INVALID, "tap_norm_mask must be a 4-bit mask");
-  if (d->head_mode == MDE_HEAD_DPT && d->tap_norm_mask != 0xF) return fail(MDE_ERR_INVALID, "the DPT head takes all four taps through the final LayerNorm (tap_norm_mask 0xF)");
-  if (d->head_mode == MDE_HEAD_DPT && (d->features <= 0 || d->features % 16)) return fail(MDE_ERR_INVALID, "features must be a positive multiple of 16");
+  if (d->head_mode != MDE_HEAD_ENCODER_TAPS && d->tap_norm_mask != 0xF) return fail(MDE_ERR_INVALID, "the DPT head takes all four taps through the final LayerNorm (tap_norm_mask 0xF)");
+  if (d->head_mode != MDE_HEAD_ENCODER_TAPS && (d->features <= 0 || d->features % 16)) return fail(MDE_ERR_INVALID, "features must be a positive multiple of 16");
   for (int i = 0; i < 4; ++i) {
-    if (d->head_mode == MDE_HEAD_DPT && (d->out_channels[i] <= 0 || d->out_channels[i] % 8)) return fail(MDE_ERR_INVALID, "out_channels must be positive multiples of 8");
+    if (d->head_mode != MDE_HEAD_ENCODER_TAPS && (d->out_channels[i] <= 0 || d->out_channels[i] % 8)) return fail(MDE_ERR_INVALID, "out_channels must be positive multiples of 8");
     if (d->taps[i] < 0 || d->taps[i] >= d->depth || (i > 0 && d->taps[i] <= d->taps[i - 1]))
       return fail(MDE_ERR_INVALID, "taps must be increasing block indices below depth");
   }
-  if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
+  if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH | MDE_FLAG_SCALE_F32)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
   if (d->num_registers < 0 || d->num_registers > 16) return fail(MDE_ERR_INVALID, "num_registers must be 0..16");
   if (d->attn_poly < -1 || d->attn_poly > 4) return fail(MDE_ERR_INVALID, "attn_poly must be -1 (default) or 0..4 eighths");
   if (d->input_mode == MDE_INPUT_U8_HWC) {
@@ -377,7 +379,7 @@ extern "C" int mde_engine_finalize(mde_engine* e) {
   if (d.head_mode == MDE_HEAD_ENCODER_TAPS) {
     if (d.input_mode == MDE_INPUT_U8_HWC) {
       float lut[768];
-      build_norm_lut(d.norm_mean, d.norm_std, lut);
+      build_norm_lut(d.norm_mean, d.norm_std, lut, (d.flags & MDE_FLAG_SCALE_F32) != 0);
       MDE_TRY(upload(e, lut, sizeof(lut), reinterpret_cast<void**>(&e->lut)));
     }
     e->raw.clear();
@@ -423,9 +425,25 @@ extern "C" int mde_engine_finalize(mde_engine* e) {
   MDE_TRY(upload_f32(e, h + "scratch.output_conv2.2.weight", {1, 32, 1, 1}, &e->head_w));
   MDE_TRY(require(e, h + "scratch.output_conv2.2.bias", {1}, &t));
   e->head_b = t->data[0];
+  if (d.head_mode == MDE_HEAD_DPT_EXP_SKY) {
+    // the sky branch: a second conv3x3 (F/2 -> 32) + ReLU + conv1x1 (32 -> 1) + ReLU on the same up-sampled map, packed like
+    // output_conv2 (nine 1x1 contractions applied before the up-sampling)
+    MDE_TRY(require(e, h + "scratch.sky_output_conv2.0.weight", {32, F / 2, 3, 3}, &t));
+    const int cin = F / 2;
+    std::vector<uint16_t> wz(static_cast<size_t>(384) * cin, 0);
+    for (int o = 0; o < 32; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int tap = 0; tap < 9; ++tap)
+          wz[(static_cast<size_t>(tap) * 32 + o) * cin + c] = to16(t->data[(static_cast<size_t>(o) * cin + c) * 9 + tap], d.precision);
+    MDE_TRY(upload(e, wz.data(), wz.size() * 2, &e->sky2_w));
+    MDE_TRY(upload_f32(e, h + "scratch.sky_output_conv2.0.bias", {32}, &e->sky2_b));
+    MDE_TRY(upload_f32(e, h + "scratch.sky_output_conv2.2.weight", {1, 32, 1, 1}, &e->sky_head_w));
+    MDE_TRY(require(e, h + "scratch.sky_output_conv2.2.bias", {1}, &t));
+    e->sky_head_b = t->data[0];
+  }
   if (d.input_mode == MDE_INPUT_U8_HWC) {
     float lut[768];
-    build_norm_lut(d.norm_mean, d.norm_std, lut);
+    build_norm_lut(d.norm_mean, d.norm_std, lut, (d.flags & MDE_FLAG_SCALE_F32) != 0);
     MDE_TRY(upload(e, lut, sizeof(lut), reinterpret_cast<void**>(&e->lut)));
   }
   e->raw.clear();
@@ -439,14 +457,16 @@ extern "C" void mde_engine_destroy(mde_engine* e) {
   delete e;
 }
 
-extern "C" int mde_engine_num_io(const mde_engine* e) { return e ? 2 : 0; }
+static int io_count(const mde_engine* e) { return e->d.head_mode == MDE_HEAD_DPT_EXP_SKY ? 3 : 2; }
+extern "C" int mde_engine_num_io(const mde_engine* e) { return e ? io_count(e) : 0; }
 extern "C" const char* mde_engine_io_name(const mde_engine* e, int32_t i) {
-  if (!e || i < 0 || i > 1) return nullptr;
+  if (!e || i < 0 || i >= io_count(e)) return nullptr;
+  if (e->d.head_mode == MDE_HEAD_DPT_EXP_SKY) return i == 0 ? "image" : (i == 1 ? "depth" : "sky");   // models/depth_anything_v3/spec.json
   return i == 0 ? "input" : "output";   // models/depth_anything_v2/spec.json input.name / outputs[0].name
 }
 extern "C" int mde_engine_io_shape(const mde_engine* e, int32_t i, int32_t* ndim, int64_t* dims) {
   clear_error();
-  if (!e || !ndim || !dims || i < 0 || i > 1) return fail(MDE_ERR_INVALID, "bad argument to mde_engine_io_shape");
+  if (!e || !ndim || !dims || i < 0 || i >= io_count(e)) return fail(MDE_ERR_INVALID, "bad argument to mde_engine_io_shape");
   if (i == 0) {
     *ndim = 4;
     if (e->d.input_mode == MDE_INPUT_F32_NCHW) {
@@ -467,12 +487,12 @@ extern "C" int mde_engine_io_shape(const mde_engine* e, int32_t i, int32_t* ndim
   return MDE_OK;
 }
 extern "C" int mde_engine_io_dtype(const mde_engine* e, int32_t i) {
-  if (!e || i < 0 || i > 1) return -1;
+  if (!e || i < 0 || i >= io_count(e)) return -1;
   if (i == 1 && e->d.head_mode == MDE_HEAD_ENCODER_TAPS) return e->d.precision == MDE_BF16 ? MDE_DT_BF16 : MDE_DT_F16;
   return (i == 0 && e->d.input_mode == MDE_INPUT_U8_HWC) ? MDE_DT_U8 : MDE_DT_F32;
 }
 extern "C" int mde_engine_io_is_input(const mde_engine* e, int32_t i) {
-  if (!e || i < 0 || i > 1) return -1;
+  if (!e || i < 0 || i >= io_count(e)) return -1;
   return i == 0 ? 1 : 0;
 }
 
@@ -721,6 +741,14 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     } else {
       pl.push(uh, "upconv_head interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
     }
+    if (d.head_mode == MDE_HEAD_DPT_EXP_SKY) {
+      // the sky branch on the same o1: its own tap contraction into the same z buffer (the depth branch has consumed it), then
+      // the same interpolate + sum + ReLU + 1x1 kernel with a ReLU at the end, into the second output binding
+      { mde_epilogue ep = ep_zero(); ep.d_out = z; ep.ld_out = 384;
+        pl.gemm("sky_output_conv2 taps", o1, px1, F / 2, F / 2, e->sky2_w, 384, F / 2, ep, 0, 288); }
+      Op us = uh; us.i4 = 1;      // i4 == 1: the sky variant (weights, activation, destination)
+      pl.push(us, "upconv_head sky interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
+    }
   }
   if (bytes_out) *bytes_out = pl.bytes;
   return pl.rc;
@@ -771,8 +799,10 @@ extern "C" int mde_context_set_tensor_address(mde_context* c, const char* name, 
   if (!c || !name) return fail(MDE_ERR_INVALID, "bad argument to mde_context_set_tensor_address");
   if (!d_ptr) return fail(MDE_ERR_INVALID, "null device address for tensor '%s'", name);
   if (reinterpret_cast<uintptr_t>(d_ptr) & 15) return fail(MDE_ERR_INVALID, "tensor '%s' must be 16-byte aligned", name);
-  if (!strcmp(name, "input")) c->d_input = d_ptr;
-  else if (!strcmp(name, "output")) c->d_output = d_ptr;
+  const bool sky = c->e->d.head_mode == MDE_HEAD_DPT_EXP_SKY;
+  if (!strcmp(name, sky ? "image" : "input")) c->d_input = d_ptr;
+  else if (!strcmp(name, sky ? "depth" : "output")) c->d_output = d_ptr;
+  else if (sky && !strcmp(name, "sky")) c->d_output2 = d_ptr;
   else return fail(MDE_ERR_INVALID, "engine has no tensor named '%s'", name);
   return MDE_OK;
 }
@@ -780,7 +810,7 @@ extern "C" int mde_context_set_tensor_address(mde_context* c, const char* name, 
 extern "C" int mde_context_set_input_shape(mde_context* c, const char* name, int32_t ndim, const int64_t* dims) {
   clear_error();
   if (!c || !name || !dims) return fail(MDE_ERR_INVALID, "bad argument to mde_context_set_input_shape");
-  if (strcmp(name, "input")) return fail(MDE_ERR_INVALID, "engine has no input named '%s'", name);
+  if (strcmp(name, c->e->d.head_mode == MDE_HEAD_DPT_EXP_SKY ? "image" : "input")) return fail(MDE_ERR_INVALID, "engine has no input named '%s'", name);
   const mde_engine_desc& d = c->e->d;
   if (d.input_mode == MDE_INPUT_F32_NCHW) {
     if (ndim != 4 || dims[0] != d.batch || dims[1] != 3 || dims[2] != d.input_h || dims[3] != d.input_w)
@@ -838,6 +868,7 @@ extern "C" int mde_context_set_gather(mde_context* c, int32_t n_ranks, int32_t r
 
 static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
   if (!c->d_input || (!c->d_output && c->gather_ranks == 0)) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'input' and 'output' before enqueue");
+  if (c->e->d.head_mode == MDE_HEAD_DPT_EXP_SKY && !c->d_output2) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'sky' before enqueue");
   mde_engine* e = c->e;
   const mde_engine_desc& d = e->d;
   const int prec = d.precision;
@@ -885,8 +916,13 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         MDE_TRY(launch_bilinear(prec, op.in, op.out, d.batch, op.i0, op.i1, op.i2, op.i3, op.i4, s));
         break;
       case Op::UPCONV_HEAD:
-        MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->oc2_b, e->head_w, e->head_b,
-                                   d.max_depth > 0.f ? d.max_depth : 0.f, static_cast<float*>(op.out ? op.out : c->d_output), s));
+        if (op.i4 == 1)
+          MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->sky2_b, e->sky_head_w, e->sky_head_b, 0.f,
+                                     static_cast<float*>(c->d_output2), s));
+        else
+          MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->oc2_b, e->head_w, e->head_b,
+                                     d.max_depth > 0.f ? d.max_depth : 0.f, static_cast<float*>(op.out ? op.out : c->d_output), s,
+                                     d.head_mode == MDE_HEAD_DPT_EXP_SKY));
         break;
       case Op::RESIZE_DEPTH:
         MDE_TRY(launch_resize_depth(static_cast<const float*>(op.in), d.batch, d.input_h, d.input_w, static_cast<float*>(c->d_output),
@@ -918,7 +954,7 @@ extern "C" int mde_context_enqueue(mde_context* c, void* stream) {
   unsigned long long key[8] = {reinterpret_cast<unsigned long long>(c->d_input), reinterpret_cast<unsigned long long>(c->d_output),
                                static_cast<unsigned long long>(c->src_h), static_cast<unsigned long long>(c->src_w),
                                static_cast<unsigned long long>(c->snapshot_block + 1), static_cast<unsigned long long>(c->gather_ranks),
-                               static_cast<unsigned long long>(c->gather_rank), 0ull};
+                               static_cast<unsigned long long>(c->gather_rank), reinterpret_cast<unsigned long long>(c->d_output2)};
   for (int r = 0; r < c->gather_ranks; ++r) key[7] = key[7] * 1000003ull + reinterpret_cast<unsigned long long>(c->gather_dst[r]);
   if (!c->graph_exec || memcmp(key, c->graph_key, sizeof(key)) != 0) {
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }

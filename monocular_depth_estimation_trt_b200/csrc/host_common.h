@@ -89,13 +89,13 @@ int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batc
 // bilinear upsample -> 3x3 conv (tap-contracted z, see upconv_head.cuh) -> ReLU -> 1x1 -> activation
 int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int hs, int ws, int ho, int wo,
                        const float* d_bias, const float* d_head_w, float head_b, float head_scale, float* d_out,
-                       cudaStream_t s);
+                       cudaStream_t s, int head_exp = 0);
 int launch_resize_depth(const float* d_in, int batch, int hi, int wi, float* d_out, int ho, int wo, float lo, float hi_clamp,
                         cudaStream_t s);
 int launch_merge_patches(int precision, const void* d_in, int per_side, int grid, int pad, int dim, void* d_out, cudaStream_t s);
 int launch_cls_row(float* d_x, const float* d_cls, const float* d_pos, const float* d_reg, int n_reg, int batch, int ntok, int dim,
                    cudaStream_t s);
 // (v/255 - mean)/std in double, rounded once to float32: 3 x 256 entries (core/preprocess.py:294-328,337-342)
-void build_norm_lut(const double* mean3, const double* std3, float* lut768);
+void build_norm_lut(const double* mean3, const double* std3, float* lut768, bool scale_f32 = false);
 
 }  // namespace mde

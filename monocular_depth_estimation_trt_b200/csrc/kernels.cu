@@ -663,10 +663,11 @@ int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int 
   return MDE_OK;
 }
 
-void build_norm_lut(const double* mean3, const double* std3, float* lut768) {
+void build_norm_lut(const double* mean3, const double* std3, float* lut768, bool scale_f32) {
   for (int c = 0; c < 3; ++c)
     for (int v = 0; v < 256; ++v) {
-      volatile double x = static_cast<double>(v) / 255.0;   // volatile: no fused/reassociated evaluation
+      volatile float xf = static_cast<float>(v) / 255.0f;   // depth_anything_ac divides in float32 (core/preprocess.py:294-305)
+      volatile double x = scale_f32 ? static_cast<double>(xf) : static_cast<double>(v) / 255.0;   // volatile: no fused/reassociated evaluation
       volatile double y = x - mean3[c];
       volatile double z = y / std3[c];
       lut768[c * 256 + v] = static_cast<float>(z);
@@ -722,13 +723,14 @@ int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batc
 
 int launch_upconv_head(int precision, const void* d_z, int ldz, int batch, int hs, int ws, int ho, int wo,
                        const float* d_bias, const float* d_head_w, float head_b, float head_scale, float* d_out,
-                       cudaStream_t s) {
+                       cudaStream_t s, int head_exp) {
   if (batch <= 0 || hs <= 0 || ws <= 0 || ho <= 0 || wo <= 0) return fail(MDE_ERR_INVALID, "upconv_head: empty problem");
   if (ldz < kUpZc || ldz % 8 || (reinterpret_cast<uintptr_t>(d_z) & 15)) return fail(MDE_ERR_INVALID, "upconv_head: z needs >= 288 channels, a pitch that is a multiple of 8 and 16-byte alignment");
   if (batch > 65535) return fail(MDE_ERR_INVALID, "upconv_head: batch exceeds grid limits");
   UpconvHeadParams p;
   p.z = d_z; p.out = d_out; p.bias = d_bias; p.head_w = d_head_w; p.head_b = head_b;
   p.head_scale = head_scale > 0.f ? head_scale : -1.f;
+  p.head_exp = head_exp ? 1 : 0;
   p.B = batch; p.Hs = hs; p.Ws = ws; p.Ho = ho; p.Wo = wo; p.ldz = ldz;
   p.sy = ho > 1 ? static_cast<float>(hs - 1) / static_cast<float>(ho - 1) : 0.f;
   p.sx = wo > 1 ? static_cast<float>(ws - 1) / static_cast<float>(wo - 1) : 0.f;

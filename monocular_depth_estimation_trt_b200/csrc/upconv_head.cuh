@@ -34,6 +34,7 @@ struct UpconvHeadParams {
   const float* head_w;  // [32]  output_conv2[2].weight
   float head_b;
   float head_scale;     // > 0: head_scale * sigmoid(v);  < 0: relu(v)
+  int head_exp;         // 1: exp(v) (Depth Anything V3's depth branch) instead of the two above
   int B, Hs, Ws, Ho, Wo, ldz;
   float sy, sx;         // (Hs-1)/(Ho-1), (Ws-1)/(Wo-1)
   int fh, fw;           // rows / columns of z staged per tile (upper bound computed on the host)
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256, 2) upconv_head_kernel(const UpconvHeadPar
     v = fmaf(fmaxf(a1, 0.f), __ldg(p.head_w + 2 * j + 1), v);
   }
   if (oy < p.Ho && ox < p.Wo)
-    p.out[(static_cast<long long>(b) * p.Ho + oy) * p.Wo + ox] = p.head_scale < 0.f ? fmaxf(v, 0.f) : p.head_scale / (1.0f + __expf(-v));
+    p.out[(static_cast<long long>(b) * p.Ho + oy) * p.Wo + ox] = p.head_exp ? expf(v) : (p.head_scale < 0.f ? fmaxf(v, 0.f) : p.head_scale / (1.0f + __expf(-v)));
 }
 
 }  // namespace mde

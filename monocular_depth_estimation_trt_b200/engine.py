@@ -39,7 +39,7 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
               mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
               device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF, output: str = "model_grid",
               split_k: bool = False, pdl: bool = True, graph: bool = True, attn_poly: int = -1,
-              registers: int = 0) -> _lib.EngineDesc:
+              registers: int = 0, scale_dtype: str = "float64") -> _lib.EngineDesc:
     """`split_k`, `pdl`, `graph` and `attn_poly` are the engine's tuning surface (mde_engine_desc.flags / attn_poly): they are
     part of the description -- and of the fingerprint `get_engine` records -- not environment variables."""
     if precision not in _lib.PRECISIONS:
@@ -64,15 +64,18 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
         d.norm_mean[i], d.norm_std[i] = float(mean[i]), float(std[i])
     d.max_depth = float(meta["max_depth"]) if meta.get("max_depth") else 0.0
     d.device = int(device)
-    if head not in ("dpt", "encoder_taps"):
+    heads = {"dpt": _lib.MDE_HEAD_DPT, "encoder_taps": _lib.MDE_HEAD_ENCODER_TAPS, "dpt_exp_sky": _lib.MDE_HEAD_DPT_EXP_SKY}
+    if head not in heads:
         raise ValueError(f"[MDET] unknown head {head!r}")
-    d.head_mode = _lib.MDE_HEAD_ENCODER_TAPS if head == "encoder_taps" else _lib.MDE_HEAD_DPT
+    d.head_mode = heads[head]
     d.tap_norm_mask = int(tap_norm_mask)
     if output not in ("model_grid", "source_grid"):
         raise ValueError(f"[MDET] unknown output {output!r}")
     d.output_mode = _lib.MDE_OUTPUT_SOURCE_GRID if output == "source_grid" else _lib.MDE_OUTPUT_MODEL_GRID
+    if scale_dtype not in ("float64", "float32"):
+        raise ValueError(f"[MDET] scale_dtype {scale_dtype!r}: float64 (depth_anything_v2) or float32 (depth_anything_ac)")
     d.flags = ((_lib.MDE_FLAG_SPLIT_K if split_k else 0) | (0 if pdl else _lib.MDE_FLAG_NO_PDL) |
-               (0 if graph else _lib.MDE_FLAG_NO_GRAPH))
+               (0 if graph else _lib.MDE_FLAG_NO_GRAPH) | (_lib.MDE_FLAG_SCALE_F32 if scale_dtype == "float32" else 0))
     d.attn_poly = int(attn_poly)
     d.num_registers = int(registers if registers else meta.get("registers", 0))
     return d

@@ -60,6 +60,28 @@ def describe_depth_pro(encoder: str = "vitl", features: int = 256, hook_blocks=(
                 input_h=int(image_size), input_w=int(image_size))
 
 
+def keep_ratio_size(src_h: int, src_w: int, target: int = 518, multiple: int = 14, rounding: str = "ceil") -> Tuple[int, int]:
+    """The engine size for a source frame under the keep-ratio rule of the Depth Anything family (core/preprocess.py:157-171
+    `resize_keep_ratio`, bound "lower", with :112-137 `_round_to_multiple`): short side to `target`, both sides snapped to
+    a multiple of the patch size -- "ceil" for depth_anything_ac (4:3 -> 518 x 700), "constrain" for depth_anything_v2 (nearest,
+    never below the target: 4:3 -> 518 x 686)."""
+    scale = target / min(src_h, src_w)
+
+    def snap(x: float) -> int:
+        if rounding == "constrain":
+            y = int(round(x / multiple)) * multiple if abs(x / multiple - round(x / multiple)) != 0.5 else int(np.round(x / multiple) * multiple)
+            if y < target:
+                y = int(math.ceil(x / multiple) * multiple)
+            return max(y, multiple)
+        if rounding == "ceil":
+            return max(int(math.ceil(x / multiple)) * multiple, multiple)
+        if rounding == "floor":
+            return max(int(math.floor(x / multiple)) * multiple, multiple)
+        raise ValueError(f"[MDET] unknown rounding {rounding!r}")
+
+    return snap(src_h * scale), snap(src_w * scale)
+
+
 def resize_pos_embed(pos_embed: np.ndarray, gh: int, gw: int) -> np.ndarray:
     """DINOv2's position-embedding rule for a grid other than the trained square one: bicubic
     resize of the patch part with scale (g + 0.1) / m, cls part untouched.  At the trained grid

@@ -7,7 +7,8 @@ preprocess_golden.npz  outputs of the REFERENCE module itself (imported from /ro
                        reference's synthetic-input convention (tests/test_preprocess.py:47-51):
                        full tensors at small target sizes, sha256 of the float32 bytes at 518x518; the same for
                        'metric3d_v2' (keep-ratio + pad, 616x1064) together with the geometry it reports, and for 'vggt'
-                       (white square pad + cubic resize, IPP switched off: see oracle/preprocess_np.py resize_cubic_u8).
+                       (white square pad + cubic resize, IPP switched off: see oracle/preprocess_np.py resize_cubic_u8), and for
+                       'depth_anything_ac' (float32 division by 255) with its keep-ratio network sizes.
 dav2_vits_golden.npz   the oracle's own ViT-S 518x518 batch-1 forward (BASELINE config 1) with the
                        seeded, calibrated init: a 7x-strided subsample of the depth map and summary
                        statistics.  It pins the oracle against drift between hosts; the oracle
@@ -72,6 +73,21 @@ def main():
         blob[f"vggt_sha_seed{i}_{h}x{w}_to_518x518"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
         blob[f"vggt_box_seed{i}_{h}x{w}_to_518x518"] = np.array(geom.box, dtype=np.float64)
     cv2.ipp.setUseIPP(True)
+    # Depth-Anything-AC at the square bench size: the stretch of depth_anything_v2 with the division by 255 in float32
+    # (core/preprocess.py:470-476), and the network size its keep-ratio rule ("ceil") gives for each source frame
+    for i, (h, w) in enumerate(SOURCES):
+        img = synthetic(i, h, w)
+        t, _ = ref.preprocess_for(img, "depth_anything_ac", (56, 56))
+        blob[f"ac_full_seed{i}_{h}x{w}_to_56x56"] = t
+        t, _ = ref.preprocess_for(img, "depth_anything_ac", (518, 518))
+        digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+        blob[f"ac_sha_seed{i}_{h}x{w}_to_518x518"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
+        sizes = []
+        for rounding in ("ceil", "constrain"):
+            kw = {"min_val": 518} if rounding == "constrain" else {}
+            sc = 518 / min(h, w)
+            sizes += [ref._round_to_multiple(h * sc, 14, rounding, **kw), ref._round_to_multiple(w * sc, 14, rounding, **kw)]
+        blob[f"ac_keep_ratio_seed{i}_{h}x{w}"] = np.array(sizes, dtype=np.int64)        # [ceil h, ceil w, constrain h, constrain w]
     np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), **blob)
     print("wrote preprocess_golden.npz", len(blob), "entries")
 

@@ -81,14 +81,36 @@ def norm_lut(mean=IMAGENET_MEAN, std=IMAGENET_STD) -> np.ndarray:
     return np.stack([((v - np.float64(m)) / np.float64(s)) for m, s in zip(mean, std)]).astype(np.float32)
 
 
-def preprocess_stretch_imagenet(img_bgr: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+def preprocess_stretch_imagenet(img_bgr: np.ndarray, dst_h: int, dst_w: int, scale_dtype: str = "float64") -> np.ndarray:
     """BGR uint8 HxWx3 -> float32 [1, 3, dst_h, dst_w], byte-exact with
-    core.preprocess.preprocess_for(img, 'depth_anything_v2', (dst_h, dst_w))[0]."""
+    core.preprocess.preprocess_for(img, 'depth_anything_v2', (dst_h, dst_w))[0]; with scale_dtype="float32" (the division by
+    255 happens in float32, core/preprocess.py:294-305, :470-476 `da_ac`) with ...(img, 'depth_anything_ac', (dst_h, dst_w))[0]
+    at the square bench size, where the model's keep-ratio post-resize is the identity."""
     rgb = img_bgr[:, :, ::-1]
     small = resize_linear_u8(np.ascontiguousarray(rgb), dst_h, dst_w)
-    x = small.astype(np.float64) / 255.0
+    x = small.astype(np.dtype(scale_dtype)) / 255.0
     x = (x - np.asarray(IMAGENET_MEAN, np.float64)) / np.asarray(IMAGENET_STD, np.float64)
     return np.ascontiguousarray(x.transpose(2, 0, 1)[None]).astype(np.float32)
+
+
+def keep_ratio_size(src_h: int, src_w: int, target: int = 518, multiple: int = 14, rounding: str = "ceil"):
+    """Network input size of the keep-ratio rule (core/preprocess.py:157-171 `resize_keep_ratio`, bound="lower", with
+    :112-137 `_round_to_multiple`): the short side goes to `target`, both sides snap to a multiple -- always up for
+    depth_anything_ac ("ceil": 4:3 -> 518 x 700), to the nearest but not below the target for depth_anything_v2 ("constrain":
+    4:3 -> 518 x 686)."""
+    scale = target / min(src_h, src_w)
+
+    def snap(x):
+        if rounding == "constrain":
+            y = int(np.round(x / multiple) * multiple)
+            if y < target:
+                y = int(np.ceil(x / multiple) * multiple)
+            return max(y, multiple)
+        q = x / multiple
+        q = np.ceil(q) if rounding == "ceil" else np.floor(q) if rounding == "floor" else np.round(q)
+        return max(int(q) * multiple, multiple)
+
+    return snap(src_h * scale), snap(src_w * scale)
 
 
 IMAGENET_PAD = (123.675, 116.28, 103.53)   # core/preprocess.py `_IMAGENET_PAD`: metric3d_v2 pads with the mean colour

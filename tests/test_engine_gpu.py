@@ -434,3 +434,89 @@ def test_profiler_surface_like_core_profile(lib, tmp_path, bitwise):
     assert {l["LayerType"] for l in layers} >= {"MatrixMultiply", "Convolution", "Attention", "Normalization"}
     total_flops = sum(l["AlgorithmicFlops"] for l in layers)
     assert abs(total_flops / 115.3e9 - 1.0) < 0.12     # SURVEY section 8 d: 115.3 GFLOP per ViT-S image (the plan commutes two 1x1 / 3x3 maps with upsamplings)
+
+
+def test_depth_anything_v3_exp_and_sky_heads(lib):
+    """MDE_HEAD_DPT_EXP_SKY (models/depth_anything_v3/onnx_export.py:31-55: outputs `depth`, `sky`): the DPT head ending in
+    exp(), and the parallel sky branch on the same up-sampled map, against the oracle's restatement of the profile's layer list."""
+    from oracle import dav2_torch as O
+    import torch.nn.functional as F
+    sd, x, _, _ = R.reference("vits")
+    sd = dict(sd)
+    O.add_sky_branch(sd, "vits", seed=0)
+    # calibrate the sky logit to straddle zero (median 0, unit spread) so that the final ReLU is exercised on both sides
+    tr = {}
+    O.forward_da3(sd, x, "vits", tr)
+    h = "depth_head.scratch."
+    up = F.interpolate(F.conv2d(tr["path_1"], sd[h + "output_conv1.weight"], sd[h + "output_conv1.bias"], padding=1), (518, 518),
+                       mode="bilinear", align_corners=True)
+    pre = F.conv2d(F.relu(F.conv2d(up, sd[h + "sky_output_conv2.0.weight"], sd[h + "sky_output_conv2.0.bias"], padding=1)),
+                   sd[h + "sky_output_conv2.2.weight"], sd[h + "sky_output_conv2.2.bias"])
+    sd[h + "sky_output_conv2.2.weight"] = sd[h + "sky_output_conv2.2.weight"] / float(pre.std())
+    sd[h + "sky_output_conv2.2.bias"] = (sd[h + "sky_output_conv2.2.bias"] - float(pre.median())) / float(pre.std())
+    depth_ref, sky_ref = O.forward_da3(sd, x, "vits")
+    assert 0.3 < float((sky_ref > 0).float().mean()) < 0.7
+    meta = W.describe("vits", 518, 518, None)
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1, head="dpt_exp_sky"), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    assert [eng.get_tensor_name(i) for i in range(eng.num_io_tensors)] == ["image", "depth", "sky"]
+    assert eng.get_tensor_shape("depth") == (1, 518, 518) == eng.get_tensor_shape("sky")
+    inputs, outputs, bindings, stream = common.allocate_buffers(eng)
+    inputs[0].host = x.numpy()
+    with eng.create_execution_context() as ctx:
+        with pytest.raises(RuntimeError):
+            ctx.set_tensor_address("output", bindings[1])                  # this engine's bindings are image / depth / sky
+        depth, sky = common.do_inference(ctx, engine=eng, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        depth, sky = depth.reshape(518, 518).copy(), sky.reshape(518, 518).copy()
+    common.free_buffers(inputs, outputs, stream)
+    eng.close()
+    m = R.compare_depth(depth_ref[0].numpy(), depth)
+    print("da3 depth", m)
+    assert m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= GATE["max_rel"], m
+    # the sky map is a rectified logit: absolute error against the logit's unit spread (a relative measure is meaningless at 0)
+    err = np.abs(sky - sky_ref[0].numpy())
+    print("da3 sky max abs err", float(err.max()), "mean", float(err.mean()))
+    assert float(err.max()) <= 1e-2 and float(err.mean()) <= 1e-3 and (sky >= 0).all()
+
+
+def test_depth_anything_ac_input_contract_bit_exact(lib):
+    """The fused uint8 input binding with scale_dtype="float32" (MDE_FLAG_SCALE_F32): the patch rows the trunk sees equal
+    im2col of core/preprocess.py's depth_anything_ac tensor bit for bit, and differ from depth_anything_v2's in the last bits.
+    Also the model's native, non-square size from its keep-ratio rule (4:3 -> 518 x 700) builds and runs."""
+    from oracle import preprocess_np as PP
+    sd, _, _, _ = R.reference("vits")
+    img = R.synthetic_image(3, 480, 640)
+    cols = {}
+    for sdt in ("float32", "float64"):
+        meta = W.describe("vits", 518, 518, 20.0)
+        eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1, input_mode="u8_hwc", max_src_hw=(480, 640), scale_dtype=sdt), meta)
+        eng.load_state_dict(sd)
+        eng.finalize()
+        out = torch.empty(1, 518, 518, device="cuda")
+        src = torch.from_numpy(img).cuda()
+        ctx = eng.create_execution_context()
+        ctx.set_input_shape("input", (1, 480, 640, 3))
+        ctx.set_tensor_address("input", src.data_ptr())
+        ctx.set_tensor_address("output", out.data_ptr())
+        ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        cols[sdt] = fetch(ctx, "cols", (1369, 640), "fp16")
+        ref = torch.from_numpy(PP.im2col(PP.preprocess_stretch_imagenet(img, 518, 518, sdt), 14, 640)).half().float()
+        assert torch.equal(cols[sdt], ref), sdt
+        ctx.close(); eng.close()
+    h, w = W.keep_ratio_size(480, 640, 518, 14, "ceil")
+    assert (h, w) == (518, 700)
+    meta = W.describe("vits", h, w, None)
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1, input_mode="u8_hwc", max_src_hw=(480, 640), scale_dtype="float32"), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    out = torch.full((1, h, w), float("nan"), device="cuda")
+    with eng.create_execution_context() as ctx:
+        ctx.set_input_shape("input", (1, 480, 640, 3))
+        ctx.set_tensor_address("input", torch.from_numpy(img).cuda().data_ptr())
+        ctx.set_tensor_address("output", out.data_ptr())
+        ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    eng.close()

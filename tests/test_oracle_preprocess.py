@@ -195,3 +195,25 @@ def test_vggt_preprocessing_against_live_reference_module():
             cv2.ipp.setUseIPP(was)
     finally:
         sys.path.remove("/root/reference")
+
+
+# ------------------------------------------------------------------------------------------------ Depth-Anything-AC
+def test_depth_anything_ac_contract_against_reference_golden_vectors():
+    """core/preprocess.py:470-476 `da_ac`: depth_anything_v2's stretch with the division by 255 in float32 (the last bits
+    differ), and the "ceil" keep-ratio rule for the network size (4:3 -> 518 x 700 where depth_anything_v2 gets 518 x 686)."""
+    import hashlib
+    g = np.load(GOLDEN)
+    keys = [k for k in g.files if k.startswith("ac_full_")]
+    assert len(keys) == 5
+    for k in keys:
+        seed, src = int(k.split("seed")[1].split("_")[0]), tuple(int(v) for v in k.split("_")[3].split("x"))
+        img = np.random.default_rng(seed).integers(0, 256, (*src, 3), dtype=np.uint8)
+        assert np.array_equal(P.preprocess_stretch_imagenet(img, 56, 56, "float32"), g[k]), k
+        big = P.preprocess_stretch_imagenet(img, 518, 518, "float32")
+        assert hashlib.sha256(big.tobytes()).digest() == g[f"ac_sha_seed{seed}_{src[0]}x{src[1]}_to_518x518"].tobytes()
+        assert not np.array_equal(big, P.preprocess_stretch_imagenet(img, 518, 518))          # float64 division: other last bits
+        want = g[f"ac_keep_ratio_seed{seed}_{src[0]}x{src[1]}"]
+        assert P.keep_ratio_size(*src, 518, 14, "ceil") == tuple(want[:2]) and P.keep_ratio_size(*src, 518, 14, "constrain") == tuple(want[2:])
+        from monocular_depth_estimation_trt_b200 import weights as W
+        assert W.keep_ratio_size(*src, 518, 14, "ceil") == tuple(want[:2]) and W.keep_ratio_size(*src, 518, 14, "constrain") == tuple(want[2:])
+    assert P.keep_ratio_size(480, 640) == (518, 700) and P.keep_ratio_size(480, 640, rounding="constrain") == (518, 686)
