@@ -65,6 +65,9 @@ extern "C" {
                              * L2's fp32 adds in arrival order, i.e. results are no longer bitwise reproducible run to run */
 #define MDE_FLAG_NO_PDL 2   /* launch without programmatic dependent launch (default: on for GEMM / attention / LayerNorm) */
 #define MDE_FLAG_NO_GRAPH 4 /* always launch kernel by kernel instead of replaying the captured CUDA graph */
+#define MDE_FLAG_NORMALISE_F32 16 /* MDE_INPUT_F32_NCHW: the graph's own first op (x - norm_mean) / norm_std, in the units of the binding
+                                  * (VGGT: 0..1 images, reports/profile/vggt.json layer 2; Metric3D V2: 0..255, metric3d_v2.json layers
+                                  * 0-2), applied in fp32 before the 16-bit rounding of the patch rows */
 #define MDE_FLAG_SCALE_F32 8 /* MDE_INPUT_U8_HWC: v / 255 evaluated in float32 before the float64 (v - mean) / std -- depth_anything_ac's
                               * input contract (core/preprocess.py:294-305, :470-476); default: float64 throughout (depth_anything_v2) */
 

@@ -12,7 +12,7 @@ MDE_INPUT_F32_NCHW, MDE_INPUT_U8_HWC = 0, 1
 MDE_DT_F32, MDE_DT_U8, MDE_DT_F16, MDE_DT_BF16 = 0, 1, 2, 3
 MDE_HEAD_DPT, MDE_HEAD_ENCODER_TAPS, MDE_HEAD_DPT_EXP_SKY = 0, 1, 2
 MDE_OUTPUT_MODEL_GRID, MDE_OUTPUT_SOURCE_GRID = 0, 1
-MDE_FLAG_SPLIT_K, MDE_FLAG_NO_PDL, MDE_FLAG_NO_GRAPH, MDE_FLAG_SCALE_F32 = 1, 2, 4, 8
+MDE_FLAG_SPLIT_K, MDE_FLAG_NO_PDL, MDE_FLAG_NO_GRAPH, MDE_FLAG_SCALE_F32, MDE_FLAG_NORMALISE_F32 = 1, 2, 4, 8, 16
 MDE_ABI_VERSION = 2
 PRECISIONS = {"fp16": MDE_FP16, "bf16": MDE_BF16}
 

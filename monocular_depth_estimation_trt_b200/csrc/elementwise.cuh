@@ -132,6 +132,7 @@ struct Im2colParams {
   const float* nchw;
   void* cols;
   int H, W, patch, kpad;
+  float mean[3], inv_std[3];   // (v - mean_c) * inv_std_c before the 16-bit rounding; 0 / 1 = the tensor is used as is
 };
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_f32_kernel(const Im2colParams p) {
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) im2col_f32_kernel(const Im2colParams p) {
   for (int i = threadIdx.x; i < 3 * per_c; i += blockDim.x) {
     const int c = i / per_c, rem = i % per_c, ky = rem / p.W, x = rem % p.W;
     const float v = p.nchw[((static_cast<long long>(b) * 3 + c) * p.H + gy * p.patch + ky) * p.W + x];
-    tile[(x / p.patch) * p.kpad + c * pp2 + ky * p.patch + x % p.patch] = F16Traits<T>::from_f(v);
+    tile[(x / p.patch) * p.kpad + c * pp2 + ky * p.patch + x % p.patch] = F16Traits<T>::from_f((v - p.mean[c]) * p.inv_std[c]);
   }
   __syncthreads();
   const int n16 = gw * p.kpad / 8;

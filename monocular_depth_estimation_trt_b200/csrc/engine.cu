@@ -259,9 +259,14 @@ static int validate_desc(const mde_engine_desc* d) {
     if (d->taps[i] < 0 || d->taps[i] >= d->depth || (i > 0 && d->taps[i] <= d->taps[i - 1]))
       return fail(MDE_ERR_INVALID, "taps must be increasing block indices below depth");
   }
-  if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH | MDE_FLAG_SCALE_F32)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
+  if (d->flags & ~(MDE_FLAG_SPLIT_K | MDE_FLAG_NO_PDL | MDE_FLAG_NO_GRAPH | MDE_FLAG_SCALE_F32 | MDE_FLAG_NORMALISE_F32)) return fail(MDE_ERR_INVALID, "unknown bits in flags 0x%x", d->flags);
   if (d->num_registers < 0 || d->num_registers > 16) return fail(MDE_ERR_INVALID, "num_registers must be 0..16");
   if (d->attn_poly < -1 || d->attn_poly > 4) return fail(MDE_ERR_INVALID, "attn_poly must be -1 (default) or 0..4 eighths");
+  if (d->flags & MDE_FLAG_NORMALISE_F32) {
+    if (d->input_mode != MDE_INPUT_F32_NCHW) return fail(MDE_ERR_INVALID, "MDE_FLAG_NORMALISE_F32 belongs to the float32 input binding");
+    for (int c = 0; c < 3; ++c)
+      if (!(d->norm_std[c] > 0.0)) return fail(MDE_ERR_INVALID, "norm_std must be positive");
+  }
   if (d->input_mode == MDE_INPUT_U8_HWC) {
     if (d->max_src_h <= 0 || d->max_src_w <= 0) return fail(MDE_ERR_INVALID, "max_src_h/max_src_w are required for the uint8 input");
     for (int c = 0; c < 3; ++c)
@@ -882,7 +887,8 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
                                      op.out, nullptr, s));
         break;
       case Op::IM2COL_F32:
-        MDE_TRY(launch_im2col_f32(prec, static_cast<const float*>(c->d_input), d.batch, d.input_h, d.input_w, d.patch_size, e->kpad, op.out, s));
+        MDE_TRY(launch_im2col_f32(prec, static_cast<const float*>(c->d_input), d.batch, d.input_h, d.input_w, d.patch_size, e->kpad, op.out, s,
+                                  (d.flags & MDE_FLAG_NORMALISE_F32) ? d.norm_mean : nullptr, (d.flags & MDE_FLAG_NORMALISE_F32) ? d.norm_std : nullptr));
         break;
       case Op::CLS_ROW:
         MDE_TRY(launch_cls_row(static_cast<float*>(op.out), e->cls, e->pos, e->reg, d.num_registers, d.batch, e->ntok, d.embed_dim, s));

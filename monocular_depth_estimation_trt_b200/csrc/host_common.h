@@ -82,7 +82,7 @@ int launch_bilinear(int precision, const void* d_in, void* d_out, int batch, int
                     cudaStream_t s, const float* d_addend = nullptr);
 int launch_im2col_s2(int precision, const void* d_in, void* d_out, int batch, int h, int w, int c, cudaStream_t s);
 int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int w, int patch, int kpad, void* d_cols,
-                      cudaStream_t s);
+                      cudaStream_t s, const double* mean3 = nullptr, const double* std3 = nullptr);
 int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batch_stride, int batch, int src_h,
                          int src_w, int dst_h, int dst_w, int patch, int kpad, int swap_rb, const float* d_lut,
                          void* d_cols, float* d_nchw, cudaStream_t s, int keep_ratio_pad = 0, const double* pad_rgb = nullptr);

@@ -646,10 +646,14 @@ static int check_patch_geometry(int h, int w, int patch, int kpad) {
 }
 
 int launch_im2col_f32(int precision, const float* d_nchw, int batch, int h, int w, int patch, int kpad, void* d_cols,
-                      cudaStream_t s) {
+                      cudaStream_t s, const double* mean3, const double* std3) {
   MDE_TRY(check_patch_geometry(h, w, patch, kpad));
   Im2colParams p;
   p.nchw = d_nchw; p.cols = d_cols; p.H = h; p.W = w; p.patch = patch; p.kpad = kpad;
+  for (int c = 0; c < 3; ++c) {
+    p.mean[c] = mean3 ? static_cast<float>(mean3[c]) : 0.f;
+    p.inv_std[c] = std3 ? static_cast<float>(1.0 / std3[c]) : 1.f;
+  }
   const int smem = (w / patch) * kpad * 2;
   dim3 grid(h / patch, batch);
   if (precision == MDE_BF16) {

@@ -39,7 +39,7 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
               mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
               device: int = 0, head: str = "dpt", tap_norm_mask: int = 0xF, output: str = "model_grid",
               split_k: bool = False, pdl: bool = True, graph: bool = True, attn_poly: int = -1,
-              registers: int = 0, scale_dtype: str = "float64") -> _lib.EngineDesc:
+              registers: int = 0, scale_dtype: str = "float64", normalise_f32: bool = False) -> _lib.EngineDesc:
     """`split_k`, `pdl`, `graph` and `attn_poly` are the engine's tuning surface (mde_engine_desc.flags / attn_poly): they are
     part of the description -- and of the fingerprint `get_engine` records -- not environment variables."""
     if precision not in _lib.PRECISIONS:
@@ -75,7 +75,10 @@ def make_desc(meta: Mapping, precision: str = "fp16", batch: int = 1, input_mode
     if scale_dtype not in ("float64", "float32"):
         raise ValueError(f"[MDET] scale_dtype {scale_dtype!r}: float64 (depth_anything_v2) or float32 (depth_anything_ac)")
     d.flags = ((_lib.MDE_FLAG_SPLIT_K if split_k else 0) | (0 if pdl else _lib.MDE_FLAG_NO_PDL) |
-               (0 if graph else _lib.MDE_FLAG_NO_GRAPH) | (_lib.MDE_FLAG_SCALE_F32 if scale_dtype == "float32" else 0))
+               (0 if graph else _lib.MDE_FLAG_NO_GRAPH) | (_lib.MDE_FLAG_SCALE_F32 if scale_dtype == "float32" else 0) |
+               (_lib.MDE_FLAG_NORMALISE_F32 if normalise_f32 else 0))
+    if normalise_f32 and input_mode != "f32_nchw":
+        raise ValueError("[MDET] normalise_f32 applies to the float32 input binding (the uint8 binding normalises through its table)")
     d.attn_poly = int(attn_poly)
     d.num_registers = int(registers if registers else meta.get("registers", 0))
     return d
@@ -203,12 +206,14 @@ class Engine:
                    f"set_weight({name})")
 
     def load_state_dict(self, state_dict: Mapping) -> None:
+        """`meta["pos_interp"]` ("dinov2" | "bilinear") picks the rule the position embedding is resized with for a grid other
+        than the trained one (Metric3D V2's export uses bilinear, weights.resize_pos_embed)."""
         gh = self._desc.input_h // self._desc.patch_size
         gw = self._desc.input_w // self._desc.patch_size
         for k, v in state_dict.items():
             a = v.detach().cpu().float().numpy() if hasattr(v, "detach") else np.asarray(v, dtype=np.float32)
             if k == "pretrained.pos_embed":
-                a = W.resize_pos_embed(a, gh, gw)
+                a = W.resize_pos_embed(a, gh, gw, self.meta.get("pos_interp", "dinov2"))
             self.set_weight(k, a)
 
     def load_weights_file(self, path: str) -> None:
@@ -219,7 +224,7 @@ class Engine:
         # only that one tensor is read again, and only when this engine's grid differs from it
         pos = W.load_tensor(path, "pretrained.pos_embed")
         if pos.shape[1] != gh * gw + 1 or gh != gw:
-            self.set_weight("pretrained.pos_embed", W.resize_pos_embed(pos, gh, gw))
+            self.set_weight("pretrained.pos_embed", W.resize_pos_embed(pos, gh, gw, self.meta.get("pos_interp", "dinov2")))
 
     def finalize(self) -> "Engine":
         _lib.check(self._lib.mde_engine_finalize(self._h), "mde_engine_finalize")

@@ -15,8 +15,8 @@ epilogue), LayerNorm, FC1 GEMM (+GELU), FC2 GEMM (LayerScale + residual).  torch
 
 `VGGTEngine` is the whole exported model (models/vggt/onnx_export.py:38-52 `VGGTDepthOnlyWrapper`; spec.json: images float32
 [1, S, 3, 518, 518] scaled by 1/255, output `depth`) behind the engine / context surface `allocate_buffers` / `do_inference`
-drive: the DINOv2-with-registers trunk (a trunk-only C-ABI engine with four register tokens, the ImageNet normalisation folded
-into its patch-embed weights), camera / register tokens (`mde_k_assemble_tokens`), the aggregator above, and the depth head --
+drive: the DINOv2-with-registers trunk (a trunk-only C-ABI engine with four register tokens and the graph's ImageNet normalisation
+in its input stage), camera / register tokens (`mde_k_assemble_tokens`), the aggregator above, and the depth head --
 LayerNorm over the 2D-wide [frame | global] taps, DPT reassemble with the head's sin / cos position embedding added after each
 projection and again after the final up-sampling, RefineNets, `exp` -- composed from the GEMM / conv kernels.
 """
@@ -296,20 +296,16 @@ class VGGTEngine:
         self.trunk = None
         self.agg = None
         try:
-            # ---- trunk: DINOv2 with four registers; (x - mean) / std folded into the patch embedding (two linear maps, one rounding)
+            # ---- trunk: DINOv2 with four registers; the graph's (x - mean) / std (profile layer 2) applied where the patch rows are formed
             sd = {"pretrained." + k[len(TRUNK):]: _t(v) for k, v in state_dict.items() if k.startswith(TRUNK)}
             if not sd:
                 raise ValueError(f"[MDET] the state dict holds no '{TRUNK}*' tensors")
-            w = sd["pretrained.patch_embed.proj.weight"].double()
-            mean, std = torch.tensor(RESNET_MEAN, dtype=torch.float64), torch.tensor(RESNET_STD, dtype=torch.float64)
-            sd["pretrained.patch_embed.proj.bias"] = (sd["pretrained.patch_embed.proj.bias"].double()
-                                                      - (w * (mean / std).view(1, 3, 1, 1)).sum(dim=(1, 2, 3))).float()
-            sd["pretrained.patch_embed.proj.weight"] = (w / std.view(1, 3, 1, 1)).float()
             L = cfg["depth"]
             meta = W.describe(encoder, H, Wd, None)
             meta["taps"] = [L - 4, L - 3, L - 2, L - 1]
             meta["registers"] = int(sd["pretrained.register_tokens"].shape[1])
-            self.trunk = E.Engine(E.make_desc(meta, precision=precision, batch=self.S, head="encoder_taps", tap_norm_mask=0x8, device=device), meta)
+            self.trunk = E.Engine(E.make_desc(meta, precision=precision, batch=self.S, head="encoder_taps", tap_norm_mask=0x8, device=device,
+                                                  normalise_f32=True, mean=RESNET_MEAN, std=RESNET_STD), meta)
             self.trunk.load_state_dict(sd)
             self.trunk.finalize()
             # ---- aggregator + head

@@ -82,10 +82,11 @@ def keep_ratio_size(src_h: int, src_w: int, target: int = 518, multiple: int = 1
     return snap(src_h * scale), snap(src_w * scale)
 
 
-def resize_pos_embed(pos_embed: np.ndarray, gh: int, gw: int) -> np.ndarray:
+def resize_pos_embed(pos_embed: np.ndarray, gh: int, gw: int, mode: str = "dinov2") -> np.ndarray:
     """DINOv2's position-embedding rule for a grid other than the trained square one: bicubic
     resize of the patch part with scale (g + 0.1) / m, cls part untouched.  At the trained grid
-    (37 x 37 for 518 / 14) the table is used as is."""
+    (37 x 37 for 518 / 14) the table is used as is.  mode="bilinear": what the reference's Metric3D V2 export does instead
+    (reports/profile/metric3d_v2.json layer 6 `/depth_model/encoder/Resize`: LINEAR, half-pixel, to the 44 x 76 grid by size)."""
     n = pos_embed.shape[1] - 1
     m = int(round(math.sqrt(n)))
     if gh * gw == n and gh == gw:
@@ -94,8 +95,13 @@ def resize_pos_embed(pos_embed: np.ndarray, gh: int, gw: int) -> np.ndarray:
     import torch.nn.functional as F
     pe = torch.from_numpy(np.asarray(pos_embed, dtype=np.float32))
     d = pe.shape[-1]
-    patch = F.interpolate(pe[:, 1:].reshape(1, m, m, d).permute(0, 3, 1, 2),
-                          scale_factor=((gh + 0.1) / m, (gw + 0.1) / m), mode="bicubic", antialias=False)
+    if mode == "bilinear":
+        patch = F.interpolate(pe[:, 1:].reshape(1, m, m, d).permute(0, 3, 1, 2), size=(gh, gw), mode="bilinear", align_corners=False)
+    elif mode == "dinov2":
+        patch = F.interpolate(pe[:, 1:].reshape(1, m, m, d).permute(0, 3, 1, 2),
+                              scale_factor=((gh + 0.1) / m, (gw + 0.1) / m), mode="bicubic", antialias=False)
+    else:
+        raise ValueError(f"[MDET] unknown position-embedding resize mode {mode!r}")
     if tuple(patch.shape[-2:]) != (gh, gw):
         raise ValueError(f"position embedding resize produced {tuple(patch.shape[-2:])}, wanted {(gh, gw)}")
     patch = patch.permute(0, 2, 3, 1).reshape(1, gh * gw, d)

@@ -520,3 +520,38 @@ def test_depth_anything_ac_input_contract_bit_exact(lib):
         torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     eng.close()
+
+
+def test_metric3d_v2_trunk_with_registers_and_bilinear_pos_embed(lib):
+    """Metric3D V2's encoder as the reference exports it (reports/profile/metric3d_v2.json layers 0-131): 0..255 input with the
+    in-graph (x - mean) / std applied where the patch rows are formed (MDE_FLAG_NORMALISE_F32), DINOv2 with four registers (1 + 4 + 44 * 76 = 3349 tokens, layer
+    10), position embedding resized to 44 x 76 with a half-pixel BILINEAR resize (layer 6), final LayerNorm (layer 131).
+    Trunk-only engine, batch 2, against the oracle's trunk (pinned on transformers' Dinov2WithRegistersModel).  The RAFT-style
+    decoder behind it is not built."""
+    from oracle import dav2_torch as O, preprocess_np as PP
+    enc, H, Wd = "vits", 616, 1064
+    cfg = dict(O.MODEL_CONFIGS[enc])
+    L = cfg["depth"]
+    cfg["taps"] = [L - 4, L - 3, L - 2, L - 1]
+    sd = {k: v for k, v in O.init_state_dict(enc, seed=9, registers=4).items() if k.startswith("pretrained.")}
+    x = torch.cat([torch.from_numpy(PP.preprocess_pad_none(R.synthetic_image(i, 480, 640), H, Wd)) for i in range(2)])   # 0..255, padded
+    mean, std = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1), torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
+    taps = O.encoder_taps(sd, (x - mean) / std, cfg, norm_mask=0x8, pos_interp="bilinear")
+    meta = W.describe(enc, H, Wd, None)
+    meta.update(taps=cfg["taps"], registers=4, pos_interp="bilinear")
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=2, head="encoder_taps", tap_norm_mask=0x8, normalise_f32=True,
+                               mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    T = 44 * 76
+    out = torch.zeros(4, 2, T, 384, dtype=torch.float16, device="cuda")
+    with eng.create_execution_context() as ctx:
+        ctx.set_tensor_address("input", x.cuda().data_ptr())
+        ctx.set_tensor_address("output", out.data_ptr())
+        ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        xres = fetch(ctx, "x", (2, 1 + 4 + T, 384), "fp16")
+    eng.close()
+    for i in range(4):
+        assert rms_rel(out[i].float().cpu(), taps[i]) < INTER["fp16"], i
+    assert xres.shape[1] == 3349
