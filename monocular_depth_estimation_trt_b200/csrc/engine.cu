@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <string>
@@ -103,6 +104,7 @@ struct Op {
 struct mde_context {
   mde_engine* e = nullptr;
   std::vector<void*> allocs;
+  char* arena = nullptr;
   std::vector<Op> plan;
   std::map<std::string, std::pair<void*, int64_t>> named;   // debug buffers
   std::map<std::string, int> named_dtype;
@@ -512,20 +514,24 @@ struct Planner {
   bool dry;            // dry run: only add up the workspace bytes
   int64_t bytes = 0;
 
+  // One arena per context, bump-allocated with LIFO scopes: a tensor lives from its alloc() to the release() of the scope it
+  // was allocated in, so the encoder's temporaries, the reassemble stage, each RefineNet level and the tail share memory
+  // (ViT-L, batch 64: 12.8 GiB instead of 19.8 GiB with one allocation per tensor).  The dry run makes the same calls with a
+  // null arena and only records the high-water mark; named buffers (mde_context_get_buffer) live outside every scope.
+  char* arena = nullptr;
+  int64_t top = 0;
   void* alloc(int64_t n, const char* name = nullptr, int dtype = 1) {
     n = (n + 255) / 256 * 256;
-    bytes += n;
+    const int64_t at = top;
+    top += n;
+    if (top > bytes) bytes = top;
     if (dry || rc != MDE_OK) return nullptr;
-    void* p = nullptr;
-    cudaError_t err = cudaMalloc(&p, static_cast<size_t>(n));
-    if (err != cudaSuccess) {
-      rc = fail(MDE_ERR_CUDA, "cudaMalloc of %lld workspace bytes failed: %s", static_cast<long long>(n), cudaGetErrorString(err));
-      return nullptr;
-    }
-    c->allocs.push_back(p);
+    void* p = arena + at;
     if (name) { c->named[name] = {p, n}; c->named_dtype[name] = dtype; }
     return p;
   }
+  int64_t mark() const { return top; }
+  void release(int64_t m) { top = m; }
   void* alloc16(int64_t elems, const char* name = nullptr) { return alloc(elems * 2, name, 1); }
 
   void gemm(const char* what, const void* a, long long m, int k, int lda, const void* b, int n, int ldb,
@@ -583,6 +589,7 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   const mde_engine_desc& d = e->d;
   Planner pl{c, e, d.precision};
   pl.dry = dry;
+  pl.arena = (c && !dry) ? c->arena : nullptr;
   const int B = d.batch, D = d.embed_dim, T = e->T, NT = e->ntok, F = d.features;
   const long long rows = static_cast<long long>(B) * NT;
   const long long prow = static_cast<long long>(B) * T;
@@ -592,15 +599,32 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   void* cols = pl.alloc16(prow * e->kpad, "cols");
   float* x = static_cast<float*>(pl.alloc(rows * D * 4, "x", 0));
   float* xs = static_cast<float*>(pl.alloc(rows * D * 4, "x_snapshot", 0));
-  void* ln = pl.alloc16(rows * D);
-  void* qkv = pl.alloc16(rows * 3 * D);
-  void* att = pl.alloc16(rows * D);
-  void* hid = pl.alloc16(rows * 4 * D);
   const bool taps_only = d.head_mode == MDE_HEAD_ENCODER_TAPS;   // the taps go straight to the output binding / the gather buffers
   void* tap[4] = {nullptr, nullptr, nullptr, nullptr};
   const char* tap_names[4] = {"tap0", "tap1", "tap2", "tap3"};
   if (!taps_only)
     for (int i = 0; i < 4; ++i) tap[i] = pl.alloc16(prow * D, tap_names[i]);
+  // head tensors that outlive their producers' scopes: the four layer_rn maps (and their ReLU copies) and the two fusion
+  // outputs that alternate between the RefineNet levels (level 3 and 1 write A, level 2 and 0 write B = "path_1")
+  const int F0 = d.features;
+  void *r[4] = {nullptr, nullptr, nullptr, nullptr}, *r_relu[4] = {nullptr, nullptr, nullptr, nullptr};
+  void *path_a = nullptr, *path_b = nullptr;
+  if (!taps_only) {
+    const char* r_names[4] = {"r0", "r1", "r2", "r3"};
+    for (int i = 0; i < 4; ++i) {
+      const long long px = static_cast<long long>(B) * e->lvl_h[i] * e->lvl_w[i];
+      r[i] = pl.alloc16(px * F0, r_names[i]);
+      r_relu[i] = pl.alloc16(px * F0);
+    }
+    auto out_px = [&](int i) { return static_cast<long long>(B) * (i > 0 ? e->lvl_h[i - 1] : 2 * e->lvl_h[0]) * (i > 0 ? e->lvl_w[i - 1] : 2 * e->lvl_w[0]); };
+    path_a = pl.alloc16(std::max(out_px(3), out_px(1)) * F0);
+    path_b = pl.alloc16(std::max(out_px(2), out_px(0)) * F0, "path_1");
+  }
+  const int64_t encoder_scope = pl.mark();
+  void* ln = pl.alloc16(rows * D);
+  void* qkv = pl.alloc16(rows * 3 * D);
+  void* att = pl.alloc16(rows * D);
+  void* hid = pl.alloc16(rows * 4 * D);
   if (!dry) { c->x = x; c->x_snapshot = xs; c->x_bytes = rows * D * 4; }
 
   // ---- embed
@@ -653,8 +677,10 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     if (bytes_out) *bytes_out = pl.bytes;
     return pl.rc;
   }
+  pl.release(encoder_scope);
   // ---- DPT reassemble
   const int gh = e->gh, gw = e->gw;
+  const int64_t reassemble_scope = pl.mark();     // projections, resized maps and the stride-2 gather die with the layer_rn convs
   void* l[4];
   for (int i = 0; i < 4; ++i) {
     void* pr = pl.alloc16(prow * oc[i]);
@@ -679,21 +705,18 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     }
   }
   // ---- layer_rn: raw r_i (residual of the first RCU) and relu(r_i) (input of its first conv)
-  void *r[4], *r_relu[4];
-  const char* r_names[4] = {"r0", "r1", "r2", "r3"};
   for (int i = 0; i < 4; ++i) {
-    const long long px = static_cast<long long>(B) * e->lvl_h[i] * e->lvl_w[i];
-    r[i] = pl.alloc16(px * F, r_names[i]);
-    r_relu[i] = pl.alloc16(px * F);
     mde_epilogue ep = ep_zero(); ep.d_out = r[i]; ep.d_out_relu = r_relu[i]; ep.ld_out = F;
     pl.conv("layer_rn", l[i], B, e->lvl_h[i], e->lvl_w[i], oc[i], e->rn_w[i], F, ep);
   }
+  pl.release(reassemble_scope);
   // ---- RefineNets 4 -> 1
   void* path = nullptr;   // output of the previous fusion block, already at this level's resolution
   for (int i = 3; i >= 0; --i) {
     const int H = e->lvl_h[i], W = e->lvl_w[i];
     const long long px = static_cast<long long>(B) * H * W;
     const Refine& rf = e->refine[i];
+    const int64_t level_scope = pl.mark();
     void* a = pl.alloc16(px * F);
     const void* s_relu = r_relu[i];
     const void* s_raw = r[i];
@@ -720,9 +743,10 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     { mde_epilogue ep = ep_zero(); ep.d_bias = rf.out_b; ep.d_out = q; ep.ld_out = F;
       pl.gemm("out_conv1x1", u, px, F, F, rf.out_w, F, F, ep); }
     const int Ho = i > 0 ? e->lvl_h[i - 1] : 2 * H, Wo = i > 0 ? e->lvl_w[i - 1] : 2 * W;
-    path = pl.alloc16(static_cast<long long>(B) * Ho * Wo * F, i == 0 ? "path_1" : nullptr);
+    path = (i == 3 || i == 1) ? path_a : path_b;           // the level's input `path` is the OTHER buffer
     Op bl; bl.kind = Op::BILINEAR; bl.in = q; bl.out = path; bl.i0 = H; bl.i1 = W; bl.i2 = Ho; bl.i3 = Wo; bl.i4 = F;
     pl.push(bl, "bilinear", 2.0 * F * (px + static_cast<double>(B) * Ho * Wo));
+    pl.release(level_scope);
   }
   // ---- output convs + fused depth head
   {
@@ -779,7 +803,14 @@ extern "C" int mde_context_create(mde_engine* e, mde_context** out) {
   mde_context* c = new mde_context();
   c->e = e;
   int64_t bytes = 0;
-  int rc = build_plan(c, e, false, &bytes);
+  int rc = build_plan(nullptr, e, true, &bytes);           // sizes the arena: the same alloc / release sequence without memory
+  if (rc == MDE_OK) {
+    void* arena = nullptr;
+    cudaError_t err = cudaMalloc(&arena, static_cast<size_t>(std::max<int64_t>(bytes, 256)));
+    if (err != cudaSuccess) rc = fail(MDE_ERR_CUDA, "cudaMalloc of %lld workspace bytes failed: %s", static_cast<long long>(bytes), cudaGetErrorString(err));
+    else { c->allocs.push_back(arena); c->arena = static_cast<char*>(arena); }
+  }
+  if (rc == MDE_OK) rc = build_plan(c, e, false, &bytes);
   if (rc != MDE_OK) {
     std::string msg = mde_last_error();
     mde_context_destroy(c);

@@ -378,7 +378,8 @@ class DepthProContext:
         z16 = lambda *shape: torch.zeros(*shape, dtype=dt, device=dev)
         self.crops_in = torch.zeros(e.per_rank, 3, CROP, CROP, dtype=torch.float32, device=dev)
         self.low_in = torch.zeros(1, 3, CROP, CROP, dtype=torch.float32, device=dev)
-        self.patch = S.ShardedPatchEncoder(e.trunks[0], n_items=e.n_crops, world=e.world, rank=e.rank, mode=e.gather_mode)
+        self.patch = S.ShardedPatchEncoder(e.trunks[0], n_items=e.n_crops, world=e.world, rank=e.rank, mode=e.gather_mode,
+                                           external_sync=True)      # the PeerSync hand-shake below orders the rounds on the stream
         self.sync = S.PeerSync(e.world, e.rank) if (e.world > 1 and e.gather_mode == "fused") else None
         self.ctx_img, self.ctx_fov = e.trunks[1].create_execution_context(), e.trunks[2].create_execution_context()
         self.img_taps, self.fov_taps = z16(4, 1, GRID * GRID, D), z16(4, 1, GRID * GRID, D)

@@ -202,11 +202,16 @@ class ShardedPatchEncoder:
     """Runs a trunk-only engine (head "encoder_taps", batch = per_rank) on this rank's crops and leaves ALL crops'
     taps in ``gathered()``.  ``engine`` must have been built with batch == shard_bounds(n_items, world)[0]."""
 
-    def __init__(self, engine, n_items: int, world: int, rank: int, mode: str = "fused"):
+    def __init__(self, engine, n_items: int, world: int, rank: int, mode: str = "fused", external_sync: bool = False):
+        """`external_sync`: the caller orders the ranks itself (DepthProContext wraps every round in a `PeerSync`
+        wait_acks / signal_ready / wait_ready / signal_acks hand-shake on the stream).  Otherwise the class does: `finish()`
+        ends a round with a barrier, and the next fused `enqueue()` first waits -- stream drained, barrier -- until every rank
+        has released the previous round (`release()`), so that no rank's stores can land in a buffer a peer still reads."""
         import torch
         if mode not in ("fused", "nccl"):
             raise ValueError(f"[MDET] unknown gather mode {mode!r}")
         self.engine, self.world, self.rank, self.mode, self.n_items = engine, world, rank, mode, n_items
+        self.external_sync, self._round_open = bool(external_sync), False
         self.per_rank, self.bounds = shard_bounds(n_items, world)
         shape = engine.get_tensor_shape("output")              # [4, per_rank, T, D]
         if shape[1] != self.per_rank:
@@ -228,8 +233,11 @@ class ShardedPatchEncoder:
         collective.  Asynchronous: call `finish()` before reading `gathered()`."""
         import torch
         import torch.distributed as dist
+        if self.mode == "fused" and self.world > 1 and not self.external_sync and self._round_open:
+            self.release()
         self.ctx.set_tensor_address("input", input_ptr)
         self.ctx.execute_async_v3(stream_handle)
+        self._round_open = True
         if self.mode == "nccl" and self.world > 1:
             g = self.buffers.view()
             # per tap: the ranks' [per_rank, T, D] slabs are contiguous in the gathered layout.  The collective is ordered
@@ -247,6 +255,16 @@ class ShardedPatchEncoder:
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
+
+    def release(self) -> None:
+        """This rank is done reading `gathered()` of the current round (its consumers have been enqueued): drain them and meet
+        the other ranks, after which anyone may overwrite the buffers.  Called by the next `enqueue()` if the caller did not."""
+        import torch
+        import torch.distributed as dist
+        if self._round_open and self.world > 1 and not self.external_sync:
+            torch.cuda.synchronize()
+            dist.barrier()
+        self._round_open = False
 
     def gathered(self):
         """[4, n_items, T, D]: the padded slots of the last rank(s) are cut off."""
