@@ -277,7 +277,9 @@ def run_ours(args):
             traffic = json.load(f).get(dom_key, {}).get("dram_bytes_per_launch")
 
     def kernel_roofline(key, g):
-        tensor = g[1] > 0
+        # tensor-core kernels (GEMMs, implicit-GEMM convs, attention) are held to the bf16/fp16 dense peak, everything else
+        # -- including the DPT tail's CUDA-core interpolate + taps + head kernel -- to the HBM copy bandwidth
+        tensor = g[1] > 0 and key.split(" ")[0].startswith(("gemm", "conv", "attention"))
         ach = (g[1] / (g[0] / 1000.0) / 1e12) if tensor else (g[2] / (g[0] / 1000.0) / 1e9)
         peak = pk["tflops"] if tensor else pk["hbm"]
         return {"kernel": key, "launches_per_step": g[3], "ms_per_launch": g[0] / g[3], "bound": "tensor" if tensor else "hbm",

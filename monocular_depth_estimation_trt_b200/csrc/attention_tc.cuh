@@ -101,7 +101,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y, img = blockIdx.z;
+  // images from the last one down: the QKV GEMM swept the rows front to back, its last ~100 MB are still in the L2; and the
+  // projection GEMM behind this kernel starts at row 0, which is then what was written last
+  const int head = blockIdx.y, img = gridDim.z - 1 - blockIdx.z;
   const int q0 = blockIdx.x * 128;
   const int nkv = (p.ntok + 127) / 128;
   const int last_chunks = (p.ntok - (nkv - 1) * 128 + 31) / 32;   // 32-key chunks of the last key tile that hold real keys (1..4)

@@ -183,8 +183,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
   constexpr int V = D / 128;   // float4 per lane
   griddep_launch_dependents();
   griddep_wait();
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  // Rows are walked from the LAST one down: the GEMM that has just updated the residual stream swept it front to back, so its
+  // most recent ~100 MB are still in the 126 MB L2, and the GEMM that follows starts at row 0 -- the rows written last here.
+  const long long row = p.rows - 1 - (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5));
+  if (row < 0) return;
   const int lane = threadIdx.x & 31;
   long long orow = row;
   if (p.drop_cls) {       // number of leading tokens of every image that are skipped: cls (1), cls + registers (5), ...
@@ -342,12 +344,17 @@ __global__ void __launch_bounds__(256) bilinear_nhwc_kernel(const BilinearParams
       const float4 a0 = __ldg(ad), a1 = __ldg(ad + 1);
       add[0] = a0.x; add[1] = a0.y; add[2] = a0.z; add[3] = a0.w; add[4] = a1.x; add[5] = a1.y; add[6] = a1.z; add[7] = a1.w;
     }
+    // a + w * (b - a) on packed fp32 pairs: the same arithmetic (subtract, multiply-add; torch's own form), half the issue slots
+    const f32x2 wx2 = f2_splat(wx), wy2 = f2_splat(wy), neg1 = f2_splat(-1.0f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 v00 = Tr::unpack2(a[k]), v01 = Tr::unpack2(bb[k]), v10 = Tr::unpack2(cc[k]), v11 = Tr::unpack2(d[k]);
-      const float tx0 = v00.x + wx * (v01.x - v00.x), tx1 = v00.y + wx * (v01.y - v00.y);
-      const float bx0 = v10.x + wx * (v11.x - v10.x), bx1 = v10.y + wx * (v11.y - v10.y);
-      ro[k] = Tr::pack2(tx0 + wy * (bx0 - tx0) + add[2 * k], tx1 + wy * (bx1 - tx1) + add[2 * k + 1]);
+      const f32x2 p00 = f2_pack(v00.x, v00.y), p10 = f2_pack(v10.x, v10.y);
+      const f32x2 top = f2_fma(wx2, f2_fma(p00, neg1, f2_pack(v01.x, v01.y)), p00);
+      const f32x2 bot = f2_fma(wx2, f2_fma(p10, neg1, f2_pack(v11.x, v11.y)), p10);
+      float r0, r1;
+      f2_unpack(f2_fma(wy2, f2_fma(top, neg1, bot), top), r0, r1);
+      ro[k] = Tr::pack2(r0 + add[2 * k], r1 + add[2 * k + 1]);
     }
     *reinterpret_cast<uint4*>(orow + static_cast<long long>(i) * 8) = r;
   }

@@ -754,12 +754,13 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     void* o1 = pl.alloc16(static_cast<long long>(B) * H1 * W1 * (F / 2));
     { mde_epilogue ep = ep_zero(); ep.d_bias = e->oc1_b; ep.d_out = o1; ep.ld_out = F / 2;
       pl.conv("output_conv1", path, B, H1, W1, F, e->oc1_w, F / 2, ep); }
-    // output_conv2[0]'s channel contraction at THIS resolution (nine taps x 32 channels = 288 columns, padded to 384),
+    // output_conv2[0]'s channel contraction at THIS resolution (nine taps x 32 channels = 288 columns: two full 128-wide tiles
+    // and a quarter-filled third one whose store boxes the tensor map clips),
     // then one kernel interpolates z to the input size, sums the taps, applies bias/ReLU and the 1x1 head.
     const long long px1 = static_cast<long long>(B) * H1 * W1;
-    void* z = pl.alloc16(px1 * 384, "z_taps");
-    { mde_epilogue ep = ep_zero(); ep.d_out = z; ep.ld_out = 384;
-      pl.gemm("output_conv2 taps", o1, px1, F / 2, F / 2, e->oc2_w, 384, F / 2, ep, 0, 288); }
+    void* z = pl.alloc16(px1 * 288, "z_taps");
+    { mde_epilogue ep = ep_zero(); ep.d_out = z; ep.ld_out = 288;
+      pl.gemm("output_conv2 taps", o1, px1, F / 2, F / 2, e->oc2_w, 288, F / 2, ep); }
     Op uh; uh.kind = Op::UPCONV_HEAD; uh.in = z; uh.i0 = H1; uh.i1 = W1; uh.i2 = d.input_h; uh.i3 = d.input_w;
     const double opx = static_cast<double>(B) * d.input_h * d.input_w;
     if (d.output_mode == MDE_OUTPUT_SOURCE_GRID) {
@@ -773,8 +774,8 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     if (d.head_mode == MDE_HEAD_DPT_EXP_SKY) {
       // the sky branch on the same o1: its own tap contraction into the same z buffer (the depth branch has consumed it), then
       // the same interpolate + sum + ReLU + 1x1 kernel with a ReLU at the end, into the second output binding
-      { mde_epilogue ep = ep_zero(); ep.d_out = z; ep.ld_out = 384;
-        pl.gemm("sky_output_conv2 taps", o1, px1, F / 2, F / 2, e->sky2_w, 384, F / 2, ep, 0, 288); }
+      { mde_epilogue ep = ep_zero(); ep.d_out = z; ep.ld_out = 288;
+        pl.gemm("sky_output_conv2 taps", o1, px1, F / 2, F / 2, e->sky2_w, 288, F / 2, ep); }
       Op us = uh; us.i4 = 1;      // i4 == 1: the sky variant (weights, activation, destination)
       pl.push(us, "upconv_head sky interpolate+taps+head", 2.0 * 288 * px1 + 4.0 * opx, 2.0 * (9 * 4 * 32 + 32) * opx);
     }
@@ -954,10 +955,10 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
         break;
       case Op::UPCONV_HEAD:
         if (op.i4 == 1)
-          MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->sky2_b, e->sky_head_w, e->sky_head_b, 0.f,
+          MDE_TRY(launch_upconv_head(prec, op.in, 288, d.batch, op.i0, op.i1, op.i2, op.i3, e->sky2_b, e->sky_head_w, e->sky_head_b, 0.f,
                                      static_cast<float*>(c->d_output2), s));
         else
-          MDE_TRY(launch_upconv_head(prec, op.in, 384, d.batch, op.i0, op.i1, op.i2, op.i3, e->oc2_b, e->head_w, e->head_b,
+          MDE_TRY(launch_upconv_head(prec, op.in, 288, d.batch, op.i0, op.i1, op.i2, op.i3, e->oc2_b, e->head_w, e->head_b,
                                      d.max_depth > 0.f ? d.max_depth : 0.f, static_cast<float*>(op.out ? op.out : c->d_output), s,
                                      d.head_mode == MDE_HEAD_DPT_EXP_SKY));
         break;

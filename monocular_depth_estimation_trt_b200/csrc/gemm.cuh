@@ -330,7 +330,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = m_block(tile);
         const int n_tile = (tile % p.n_tiles) * BLOCK_N;
-        constexpr int kPerWarp = BLOCK_N / 64;             // chunks per warp; the host guarantees N % BLOCK_N == 0, BLOCK_N >= 128
+        constexpr int kPerWarp = BLOCK_N / 64;             // chunks per warp; the host guarantees N % 32 == 0, BLOCK_N >= 128 (a last tile
+                                                           // that N does not fill: B rows read as zeros, store boxes clipped)
         const int ch_begin = half * kPerWarp;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -343,7 +344,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           float4 bia[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            bia[g] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n_base) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bia[g] = (p.bias && n_base < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n_base) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_ld_wait();
           float v[32];
 #pragma unroll

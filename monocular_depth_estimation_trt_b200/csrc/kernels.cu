@@ -117,8 +117,11 @@ static int maybe_tma_out(GemmOp* op, int precision, const mde_epilogue* ep, long
     p.tma_x = 1;
     return MDE_OK;
   }
+  // N need not fill the last tile: B rows beyond N are zero-filled by the tensor map, store boxes beyond N are clipped (whole
+  // 32-column chunks only, so that the per-chunk bias loads stay inside the vector)
   if (!ep->d_out || ep->d_x || ep->d_res1 || ep->d_res2 || ep->d_out_relu || ep->d_gamma || ep->d_head_w || p.conv ||
-      p.row_map != ROW_IDENTITY || op->block_n < 128 || n % op->block_n || (reinterpret_cast<uintptr_t>(ep->d_out) & 15))
+      p.row_map != ROW_IDENTITY || op->block_n < 128 || n % 32 || (n % op->block_n && ep->gather_n > 0) ||
+      (reinterpret_cast<uintptr_t>(ep->d_out) & 15))
     return MDE_OK;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(ep->ld_out) * 2};
@@ -156,11 +159,14 @@ static int encode_map(CUtensorMap* map, int precision, const void* base, int ran
 }
 
 static int pick_block_n(int n) {
-  // smallest padded N wins; ties go to the wider tile (fewer A re-reads, longer MMA bursts)
+  // smallest padded N wins; ties go to the wider tile (fewer A re-reads, longer MMA bursts).  From 128 columns on only the
+  // wide tiles compete: a narrow tile re-reads its 128-wide A operand per 32 / 64 columns and has no bulk-store epilogue, which
+  // costs more than the zero columns of a partly filled wide tile (N = 288: 128-wide tiles, the third one a quarter full).
   const int cands[4] = {256, 128, 64, 32};
   int best = 32;
   long long best_pad = 1LL << 60;
   for (int bn : cands) {
+    if (n >= 128 && bn < 128) continue;
     const long long pad = static_cast<long long>((n + bn - 1) / bn) * bn;
     if (pad < best_pad) { best_pad = pad; best = bn; }
   }
