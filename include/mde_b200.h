@@ -249,10 +249,14 @@ int mde_k_attention(int32_t precision, const void* d_qkv, void* d_out, int32_t b
  * V at v_col0; d_out: [batch*ntok_q][heads*64]. */
 int mde_k_attention_kv(int32_t precision, const void* d_q, int32_t ldq, const void* d_kv, int32_t ldkv, int32_t k_col0,
                        int32_t v_col0, void* d_out, int32_t batch, int32_t ntok_q, int32_t ntok_kv, int32_t heads, void* stream);
-/* mde_k_attention with an explicit share of polynomial exponentials (poly_eighths 0..4, -1: the library default;
- * tools/attn_sweep.py sweeps it). */
+/* The same op forced onto the one-query-tile-per-CTA kernel (csrc/attention_tc.cuh) with an explicit share of polynomial
+ * exponentials (poly_eighths 0..4, -1: the library default; tools/attn_sweep.py sweeps it). */
 int mde_k_attention_poly(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
                          int32_t poly_eighths, void* stream);
+/* The same op forced onto the three-query-tiles-per-CTA persistent kernel (csrc/attention_q3.cuh) whatever the problem size;
+ * mde_k_attention picks between the two by the number of work items.  poly_eighths as above. */
+int mde_k_attention_q3(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       int32_t poly_eighths, void* stream);
 /* The default attention kernel with clock64 stamps of the softmax warps' phases (profiling aid, tools/attn_trace.py):
  * d_trace int64 [2048 CTAs][4 warps][64 slots], zero-initialised by the caller; slot 0 kernel entry, 1 after the prologue sync,
  * then per key tile: S available, S in registers, exponentials done, previous P V done, P stored; then O available, stored. */

@@ -22,6 +22,7 @@ struct AttnParams {
   // the queries are this rank's tokens, the keys/values every rank's, gathered into one [ntok, 2D] k|v buffer)
   int ntok_q;        // queries per image
   int k_col0, v_col0;// first column of K / V of head 0 in the key/value tensor (D and 2D in a packed q|k|v tensor)
+  int batch;         // images (the persistent tcgen05 kernel decodes its work items itself)
   long long* trace;  // trace instantiation only (tools/attn_trace.py): clock64 stamps of the softmax warps' phases, else NULL
 };
 

@@ -119,6 +119,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     }
   };
   stamp();
+  if (kTrace && lane == 0 && warp < 4 && cta_lin < kAtcTraceCtas) {      // which SM: the last slot of the warp's record
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[(static_cast<long long>(cta_lin) * 4 + warp) * kAtcTraceSlots + kAtcTraceSlots - 1] = smid;
+  }
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&map_qkv);
@@ -178,18 +183,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     }
   } else if (warp == 5) {
     // ===================================================== MMA issuer
+    // The whole warp runs the loop (every lane waits on the barriers) and one elected lane issues.  Descriptors and addresses
+    // are computed from warp-uniform values, so the compiler keeps them in uniform registers, where tcgen05.mma wants them, and
+    // issues the MMAs of a product back to back; under `if (lane == 0)` it wrapped every MMA in an elect loop with register ->
+    // uniform-register moves, ~110 clk per MMA (profiles/r02_attention_q3_traces.txt).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_o = umma_idesc_f16(Tr::kFmt, 128, 64) | (1u << 16);   // B (= V) is MN-major
+      const uint32_t smem0 = smem_u32(atc_smem);
+      const uint64_t qa = umma_desc_k_sw128(smem0);
       // the last key tile only spans the 32-key chunks that hold real keys: fewer S columns, fewer P V steps
       auto issue_s = [&](int st, int j) {
         const uint32_t idesc_s = umma_idesc_f16(Tr::kFmt, 128, j == nkv - 1 ? last_chunks * 32 : 128);
-        const uint64_t a = umma_desc_k_sw128(smem_u32(sQ));
-        const uint64_t b = umma_desc_k_sw128(smem_u32(sK + st * kAtcQBytes));
+        const uint64_t b = umma_desc_k_sw128(smem0 + kAtcQBytes + st * kAtcQBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base, a + 2 * k, b + 2 * k, idesc_s, k != 0);
-        tc_commit(s_full);
-        tc_commit(&k_empty[st]);
+          for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base, qa + 2 * k, b + 2 * k, idesc_s, k != 0);
+          tc_commit(s_full);
+          tc_commit(&k_empty[st]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -208,13 +221,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         mbar_wait(&v_full[st], (j / kAtcStages) & 1);
         mbar_wait(p_ready, j & 1);                 // P(j) in TMEM, O rescaled
         tc_fence_after();
-        const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV + st * kAtcQBytes));
+        const uint64_t vb = umma_desc_mn_sw128(smem0 + (1 + kAtcStages + st) * kAtcQBytes);
         const int ksteps = j == nkv - 1 ? 2 * last_chunks : 8;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed P columns, two 8-row groups of V (2048 bytes)
-          if (k < ksteps) tc_mma_f16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
-        tc_commit(o_full);
-        tc_commit(&v_empty[st]);
+          for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed P columns, two 8-row groups of V (2048 bytes)
+            if (k < ksteps) tc_mma_f16_ts(tmem_base + 128, tmem_base + 192 + 8 * k, vb + 128 * k, idesc_o, (j | k) != 0);
+          tc_commit(o_full);
+          tc_commit(&v_empty[st]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 6) {

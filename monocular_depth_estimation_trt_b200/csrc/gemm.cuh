@@ -260,8 +260,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop and one elected lane issues: with the descriptors computed from warp-uniform values the
+    // compiler keeps them in uniform registers and issues the four MMAs of a k block back to back.  Under `if (lane == 0)` it
+    // wrapped every tcgen05.mma in an elect loop with register -> uniform-register moves, ~110 clk per MMA -- more than the
+    // 64 clk a 128 x 128 x 16 MMA takes, so the single-CTA N = 128 tiles were issue-bound (profiles/r02_attention_q3_traces.txt).
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(Tr::kFmt, 128 * kCtas, BLOCK_N);
+      const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -275,21 +280,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int nsub = min(kKSub, kb_end - kb0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          for (int sub = 0; sub < nsub; ++sub) {
-            const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + (stage * kKSub + sub) * Cfg::kABytes));
-            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + (stage * kKSub + sub) * Cfg::kBBytes));
+          if (elect_one()) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint64_t a_desc = umma_desc_k_sw128(smem_a0 + (stage * kKSub + sub) * Cfg::kABytes);
+              const uint64_t b_desc = umma_desc_k_sw128(smem_b0 + (stage * kKSub + sub) * Cfg::kBBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-              const uint32_t accumulate = ((kb0 + sub - kb_begin) | k) != 0;
-              if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
-              else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+              for (int k = 0; k < 4; ++k) {
+                // +32 bytes per UMMA_K=16 step inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                const uint32_t accumulate = ((kb0 + sub - kb_begin) | k) != 0;
+                if (kCtas == 2) tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                else tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+              }
             }
+            if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           }
-          if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (kCtas == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
+        if (elect_one()) {
+          if (kCtas == 2) tc_commit_pair(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

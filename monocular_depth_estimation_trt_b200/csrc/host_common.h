@@ -62,10 +62,14 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream);
 struct AttnOp {
   alignas(64) CUtensorMap map_qkv;   // 128-row boxes: query tiles
   alignas(64) CUtensorMap map_kv128; // key/value source with 128-row boxes (the same tensor as map_qkv for self-attention)
+  alignas(64) CUtensorMap map_kv96;  // the same source with 96-row boxes (attention_q3.cuh)
   const void* qkv;
   void* out;
   int batch, ntok, heads, precision;
   int ntok_q, k_col0, v_col0;        // queries per image; first K / V column of head 0 in the key/value source
+  unsigned int* counters;            // {next item, CTAs done} of the persistent kernel (a slot of a per-device slab)
+  int kind;                          // 0: two CTAs per SM, one query tile each (attention_tc.cuh); 1: one persistent CTA per SM, three query
+                                     // tiles (attention_q3.cuh); make_* picks by the number of work items
   int poly;                          // eighths of the exponentials evaluated on the FMA pipe (0..4; make_* sets the default, 2)
 };
 int make_attention_op(AttnOp* op, int precision, const void* d_qkv, void* d_out, int batch, int ntok, int heads);

@@ -13,6 +13,7 @@
 
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
+#include "attention_q3.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "host_common.h"
@@ -398,6 +399,25 @@ int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batc
                                : launch_attention_t<__half>(d_qkv, d_out, batch, ntok, heads, s);
 }
 
+// Work counter of the persistent kernel: {next item, CTAs done}, rearmed by the last CTA of every launch.  One pair per launch
+// out of a per-device slab, handed out round-robin, so that launches running side by side on different streams never share one.
+static int attention_counters(unsigned int** out) {
+  constexpr int kSlots = 1024;
+  static std::mutex mu;
+  static unsigned int* slab[64];
+  static unsigned int next[64];
+  int dev = 0;
+  MDE_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(MDE_ERR_INVALID, "attention: device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!slab[dev]) {
+    MDE_CUDA_TRY(cudaMalloc(&slab[dev], kSlots * 2 * sizeof(unsigned int)));
+    MDE_CUDA_TRY(cudaMemset(slab[dev], 0, kSlots * 2 * sizeof(unsigned int)));
+  }
+  *out = slab[dev] + 2 * (next[dev]++ % kSlots);
+  return MDE_OK;
+}
+
 int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, const void* d_kv, int ldkv, int k_col0, int v_col0,
                          void* d_out, int batch, int ntok_q, int ntok_kv, int heads) {
   if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
@@ -421,7 +441,18 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(ldkv), static_cast<cuuint64_t>(rows_kv)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(ldkv) * 2};
   cuuint32_t box128[2] = {64, 128};
+  cuuint32_t box96[2] = {64, kAq3Keys};
   op->poly = 2;      // the measured optimum (tools/attn_sweep.py); engines override it from mde_engine_desc.attn_poly
+  // Three query tiles per persistent CTA when there is work for every SM several times over (items = image x head x group of
+  // three query tiles); below that the one-query-tile kernel spreads a small problem over more SMs.  At the batch-64 ViT-L
+  // shape the two take the same time stand-alone and the persistent one 7 % less energy per launch (K / V tiles read once
+  // for three query tiles), which is what counts inside the power-capped step (profiles/r02_energy_per_kernel.txt).
+  {
+    const long long items = static_cast<long long>(batch) * heads * (((ntok_q + 127) / 128 + 2) / 3);
+    op->kind = items >= 4LL * num_sms() ? 1 : 0;
+  }
+  MDE_TRY(attention_counters(&op->counters));
+  MDE_TRY(encode_map(&op->map_kv96, precision, d_kv, 2, dims, str, box96));
   return encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128);
 }
 
@@ -435,7 +466,7 @@ static int launch_attention_tc_t(const AttnOp& op, cudaStream_t s) {
   auto kern = attention_tc_kernel<T, kPoly>;
   MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAtcSmemBytes, true));
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr; p.batch = op.batch;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
@@ -461,7 +492,7 @@ static int launch_attention_trace_t(const AttnOp& op, long long* d_trace, cudaSt
   auto kern = attention_tc_kernel<T, 2, true>;
   MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAtcSmemBytes, true));
   AttnParams p;
-  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = d_trace;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = d_trace; p.batch = op.batch;
   p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   dim3 grid((op.ntok_q + 127) / 128, op.heads, op.batch);
@@ -470,7 +501,50 @@ static int launch_attention_trace_t(const AttnOp& op, long long* d_trace, cudaSt
   return MDE_OK;
 }
 
+template <typename T, int kPoly>
+static int launch_attention_q3_t(const AttnOp& op, cudaStream_t s) {
+  auto kern = attention_q3_kernel<T, kPoly>;
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAq3SmemBytes, true));
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = nullptr;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0; p.batch = op.batch;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  const int q_tiles = (op.ntok_q + 127) / 128;
+  const long long items = static_cast<long long>(op.batch) * op.heads * ((q_tiles + 2) / 3);
+  if (items > 0x3fffffffLL) return fail(MDE_ERR_INVALID, "attention: too many work items");
+  dim3 grid(static_cast<unsigned>(std::min<long long>(items, num_sms())));
+  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAq3Threads), kAq3SmemBytes, s, 1, op.map_qkv, op.map_kv96, p, op.counters));
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+template <typename T>
+static int launch_attention_q3_trace_t(const AttnOp& op, long long* d_trace, cudaStream_t s) {
+  auto kern = attention_q3_kernel<T, 2, true>;
+  MDE_TRY(ensure_func_attrs(reinterpret_cast<const void*>(kern), kAq3SmemBytes, true));
+  AttnParams p;
+  p.qkv = op.qkv; p.out = op.out; p.ntok = op.ntok; p.heads = op.heads; p.D = op.heads * 64; p.trace = d_trace; p.batch = op.batch;
+  p.ntok_q = op.ntok_q; p.k_col0 = op.k_col0; p.v_col0 = op.v_col0;
+  p.scale_log2 = 0.125f * 1.44269504088896340736f;
+  const int q_tiles = (op.ntok_q + 127) / 128;
+  const long long items = static_cast<long long>(op.batch) * op.heads * ((q_tiles + 2) / 3);
+  kern<<<static_cast<unsigned>(std::min<long long>(items, num_sms())), kAq3Threads, kAq3SmemBytes, s>>>(op.map_qkv, op.map_kv96, p, op.counters);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+template <typename T>
+static int launch_attention_q3_p(const AttnOp& op, cudaStream_t s) {
+  switch (op.poly) {
+    case 0: return launch_attention_q3_t<T, 0>(op, s);
+    case 1: return launch_attention_q3_t<T, 1>(op, s);
+    case 2: return launch_attention_q3_t<T, 2>(op, s);
+    case 3: return launch_attention_q3_t<T, 3>(op, s);
+    case 4: return launch_attention_q3_t<T, 4>(op, s);
+  }
+  return fail(MDE_ERR_INVALID, "attention: the polynomial share is 0..4 eighths, not %d", op.poly);
+}
+
 int launch_attention_op(const AttnOp& op, cudaStream_t s) {
+  if (op.kind == 1) return op.precision == MDE_BF16 ? launch_attention_q3_p<__nv_bfloat16>(op, s) : launch_attention_q3_p<__half>(op, s);
   return op.precision == MDE_BF16 ? launch_attention_tc_p<__nv_bfloat16>(op, s) : launch_attention_tc_p<__half>(op, s);
 }
 
@@ -820,6 +894,17 @@ int mde_k_attention_poly(int32_t precision, const void* d_qkv, void* d_out, int3
   AttnOp op;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
   if (poly_eighths >= 0) op.poly = poly_eighths;
+  op.kind = 0;
+  return launch_attention_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_attention_q3(int32_t precision, const void* d_qkv, void* d_out, int32_t batch, int32_t ntok, int32_t heads,
+                       int32_t poly_eighths, void* stream) {
+  clear_error();
+  AttnOp op;
+  MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  if (poly_eighths >= 0) op.poly = poly_eighths;
+  op.kind = 1;
   return launch_attention_op(op, static_cast<cudaStream_t>(stream));
 }
 
@@ -836,7 +921,12 @@ int mde_k_attention_trace(int32_t precision, const void* d_qkv, void* d_out, int
   clear_error();
   if (!d_trace) return fail(MDE_ERR_INVALID, "attention_trace: the trace buffer is required");
   AttnOp op;
+  const bool q3 = precision >= 16;   // profiling aid: precision + 16 traces the three-query-tile kernel ([CTAs][16 rows][256 slots], attention_q3.cuh)
+  if (q3) precision -= 16;
   MDE_TRY(make_attention_op(&op, precision, d_qkv, d_out, batch, ntok, heads));
+  if (q3)
+    return precision == MDE_BF16 ? launch_attention_q3_trace_t<__nv_bfloat16>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream))
+                                      : launch_attention_q3_trace_t<__half>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream));
   return precision == MDE_BF16 ? launch_attention_trace_t<__nv_bfloat16>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream))
                                : launch_attention_trace_t<__half>(op, reinterpret_cast<long long*>(d_trace), static_cast<cudaStream_t>(stream));
 }

@@ -66,10 +66,15 @@ def pack_conv3x3(w, dtype):
 
 
 def attention(precision, qkv, batch, ntok, heads, variant="tc"):
-    """variant: "tc" (the engine's kernel), "tc:<n>" (the same with n/8 of the exponentials on the FMA pipe), "mma" (the
-    independent mma.sync cross-check)."""
+    """variant: "tc" (whatever the library picks), "tc:<n>" (the one-query-tile kernel with n/8 of the exponentials on the FMA
+    pipe), "q3" / "q3:<n>" (the three-query-tile persistent kernel), "mma" (the independent mma.sync cross-check)."""
     lib = _lib.load()
     out = torch.empty(batch * ntok, heads * 64, dtype=qkv.dtype, device=qkv.device)
+    if variant.startswith("q3"):
+        poly = int(variant[3:]) if variant.startswith("q3:") else -1
+        _lib.check(lib.mde_k_attention_q3(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, poly, stream()),
+                   "mde_k_attention_q3")
+        return out
     if variant.startswith("tc:"):
         _lib.check(lib.mde_k_attention_poly(_lib.PRECISIONS[precision], ptr(qkv), ptr(out), batch, ntok, heads, int(variant[3:]), stream()),
                    "mde_k_attention_poly")

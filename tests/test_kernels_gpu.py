@@ -168,7 +168,7 @@ def test_conv3x3_fused_depth_head(lib, prec, max_depth):
 
 
 # ------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("variant", ["tc", "tc:0", "tc:4", "mma"])
+@pytest.mark.parametrize("variant", ["tc", "tc:0", "tc:4", "q3", "q3:0", "q3:4", "mma"])
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,ntok,heads", [(2, 1370, 6), (1, 577, 16), (3, 64, 2), (1, 129, 1), (1, 3349, 2),
                                           (2, 256, 3), (1, 257, 2), (2, 128, 1)])
@@ -363,7 +363,7 @@ def test_preprocess_keep_ratio_pad_bit_exact(lib, src, dst):
 
 
 # ------------------------------------------------------------------------------------------ edge cases
-@pytest.mark.parametrize("variant", ["tc", "tc:0", "tc:3"])
+@pytest.mark.parametrize("variant", ["tc", "tc:0", "tc:3", "q3", "q3:3"])
 @pytest.mark.parametrize("B,ntok,heads", [(1, 1, 1), (2, 5, 2), (1, 31, 1), (1, 32, 1), (1, 33, 3), (1, 127, 1), (1, 128, 2), (3, 255, 1), (1, 256, 1), (1, 257, 1)])
 def test_attention_ragged_token_counts(lib, variant, B, ntok, heads):
     """One token, tile boundaries and every +-1 around them: masking of the ragged last key tile, clipped query rows,

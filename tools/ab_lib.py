@@ -7,6 +7,18 @@ CHILD = r'''
 import sys, os, json
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
+import ctypes
+class _Tolerant(ctypes.CDLL):          # an older build may lack a per-kernel test entry point the current _lib declares
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if not name.startswith("mde_k_"):
+                raise
+            f = ctypes.CFUNCTYPE(ctypes.c_int)(lambda *a: -1)
+            setattr(self, name, f)
+            return f
+ctypes.CDLL = _Tolerant
 from monocular_depth_estimation_trt_b200 import _lib
 _lib.LIB_PATH = LIB
 from monocular_depth_estimation_trt_b200 import engine as E, weights as W
