@@ -180,6 +180,49 @@ static void pick_ctas(GemmOp* op) {
   const bool wide = op->block_n == 256 || (op->block_n == 128 && op->p.num_k_blocks >= 8);
   op->ctas = (wide && op->p.m_tiles >= 2 && op->p.num_k_blocks >= 4) ? 2 : 1;
 }
+
+// Tile width and CTA pairing.  A problem that fills the chip several times over takes the widest tile (fewest operand
+// re-reads, longest MMA bursts: pick_block_n / pick_ctas).  A SMALL problem -- batch 1: 11 row tiles -- is latency-bound: with
+// 256-wide pair tiles FC2 (N = 1024) runs on 48 of 148 SMs for 64 k-blocks.  There the candidates are scored by
+//     waves x (k-blocks x 4 MMAs x BLOCK_N / 2 clk  +  epilogue  +  fixed cost per tile)
+// and narrower tiles win when they put more SMs to work or cut the last partial wave (FC1: 96 pair tiles on 74 pairs).
+// p.m_tiles and p.num_k_blocks are set; sets op->block_n, op->ctas, p.n_tiles.
+static void pick_tiling(GemmOp* op, int n, bool fused_head, bool whole_wide_tiles = false) {
+  GemmParams& p = op->p;
+  op->block_n = fused_head ? 32 : pick_block_n(n);
+  p.n_tiles = (n + op->block_n - 1) / op->block_n;
+  pick_ctas(op);
+  const int sms = num_sms();
+  if (fused_head || n < 128 || sms <= 0 || g_opts.split_k) return;    // split-K engines keep the wide tiles and split those
+  {
+    const int units = op->ctas == 2 ? sms / 2 : sms;
+    const long long tiles = op->ctas == 2 ? static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles : static_cast<long long>(p.m_tiles) * p.n_tiles;
+    if (tiles >= 2LL * units) return;
+  }
+  long long best_cost = 1LL << 60, best_work = 1LL << 60;
+  int best_bn = op->block_n, best_ctas = op->ctas;
+  const int bns[3] = {256, 128, 64};
+  for (int bn : bns) {
+    for (int ctas = 2; ctas >= 1; --ctas) {
+      if (ctas == 2 && (bn < 128 || p.m_tiles < 2 || p.num_k_blocks < 4)) continue;
+      if (whole_wide_tiles && (bn < 128 || n % bn)) continue;     // the fused gather stores whole 128- / 256-column tiles
+      const int n_tiles = (n + bn - 1) / bn;
+      const long long m_units = ctas == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+      const long long tiles = m_units * n_tiles;
+      const int units = sms / ctas;
+      const long long waves = (tiles + units - 1) / units;
+      const long long per_tile = static_cast<long long>(p.num_k_blocks) * 2 * bn + (bn >= 128 ? 10 : 30) * bn + 1500;
+      const long long cost = waves * per_tile;
+      const long long work = m_units * ctas * n_tiles * bn;       // padded rows x columns (in 128-row units)
+      if (cost < best_cost || (cost == best_cost && work < best_work)) {
+        best_cost = cost; best_work = work; best_bn = bn; best_ctas = ctas;
+      }
+    }
+  }
+  op->block_n = best_bn;
+  op->ctas = best_ctas;
+  p.n_tiles = (n + best_bn - 1) / best_bn;
+}
 static int pick_grid(GemmOp* op) {
   const int sms = num_sms();
   if (sms <= 0) return fail(MDE_ERR_CUDA, "no CUDA device");
@@ -235,10 +278,9 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
   p.M = static_cast<int>(m); p.N = n; p.K = k;
   if (m > 0x7fffffffLL) return fail(MDE_ERR_INVALID, "gemm: m too large");
   p.num_k_blocks = (k + 63) / 64;
-  op->block_n = ep->d_head_w ? 32 : pick_block_n(n);
   if (ep->d_head_w && n != 32) return fail(MDE_ERR_INVALID, "fused depth head needs n == 32");
   p.m_tiles = static_cast<int>((m + 127) / 128);
-  p.n_tiles = (n + op->block_n - 1) / op->block_n;
+  pick_tiling(op, n, ep->d_head_w != nullptr, ep->gather_n > 0);
   p.conv = 0;
   if (ep->tokens > 0) {
     p.row_map = ROW_TOKENS; p.tokens = ep->tokens; p.tok_skip = tok_skip;
@@ -251,7 +293,6 @@ int make_gemm_op(GemmOp* op, int precision, const void* d_a, long long m, int k,
       return fail(MDE_ERR_INVALID, "gemm: inconsistent pixel-shuffle description");
   }
   op->precision = precision;
-  pick_ctas(op);
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(m)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(lda) * 2};
@@ -296,12 +337,10 @@ int make_conv_op(GemmOp* op, int precision, const void* d_in, int batch, int h, 
       best_eff = eff; p.tile_w = tw; p.tile_h = th; p.tiles_x = tx; p.tiles_y = ty;
     }
   }
-  op->block_n = ep->d_head_w ? 32 : pick_block_n(cout);
   if (ep->d_head_w && cout != 32) return fail(MDE_ERR_INVALID, "fused depth head needs cout == 32");
   p.m_tiles = batch * p.tiles_x * p.tiles_y;
-  p.n_tiles = (cout + op->block_n - 1) / op->block_n;
+  pick_tiling(op, cout, ep->d_head_w != nullptr);
   op->precision = precision;
-  pick_ctas(op);
   {
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
                           static_cast<cuuint64_t>(batch)};
