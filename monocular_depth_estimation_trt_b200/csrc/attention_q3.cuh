@@ -9,13 +9,19 @@
 //     query tile t:  S_t [160 t, 160 t + 96)   fp32 scores of a 96-key tile; P (16-bit, 48 columns) is stored over its own S
 //                    O_t [160 t + 96, 160 t + 160)
 //   warps 0-11  three softmax groups (thread = query row = TMEM lane)
-//   warp 12     TMA producer: fetches work items from an atomic counter, loads the Q tiles of an item and streams K / V
+//   warp 12     TMA producer: walks this CTA's work items, loads the Q tiles of an item and streams K / V
 //               tiles (96 keys) through a 4-stage ring that the three query tiles SHARE (one third of the L2 reads)
 //   warps 13-15 MMA issuers, one thread each: warp 13 + t owns query tile t and issues, per key tile, strictly
 //               wait P_t(j);  O_t += P_t(j) V(j);  S_t(j + 1) = Q_t K(j + 1)^T      (S(j + 1) overwrites P(j), so it follows
 //               P V(j) in issue order; the tensor pipe executes one thread's MMAs in order)
 // A work item is (image, head, group of three consecutive query tiles); the last group of a row may hold fewer tiles.
-// The CTAs pull items from a global counter until it runs out (the last CTA to finish resets it for the next launch).
+// Items are handed out by a work counter when the op owns one (`counters` = {next item, CTAs done}, zero before the first
+// launch; the last CTA through rearms it), else CTA b takes items b, b + gridDim.x, ...  The counter keeps the CTAs in one
+// compact window of items however their speeds differ and is ~5 % faster (0.64 vs 0.67 ms at the batch-64 shape), but it is
+// state that outlives the launch: two launches that may run side by side must not share one.  Engine contexts own a counter
+// per attention op of their plan; the per-kernel entry points (mde_k_attention*), whose ops live for one call and may be
+// frozen into the caller's CUDA graphs, take the static schedule.  Either way neighbouring CTAs work on neighbouring groups
+// of the same (image, head): its K / V tiles are read from HBM once and from the L2 by the others.
 #pragma once
 #include <cuda/std/type_traits>
 
@@ -75,10 +81,13 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int q_tiles = (p.ntok_q + 127) / 128;
   const int n_groups = (q_tiles + 2) / 3;
   const int n_items = p.batch * p.heads * n_groups;
-  // item -> (image, head, group); images from the last one down (see attention_tc.cuh)
+  // item -> (image, head, group); images from the last one down (see attention_tc.cuh).  The group index is skewed by the
+  // (image, head) index: a row's last group may hold fewer query tiles than the others, and with gridDim.x a multiple of
+  // n_groups (148 SMs, 4 groups at 1370 tokens) a CTA would otherwise meet the same group index in every round -- a quarter
+  // of the CTAs all short items, the rest all long ones (measured: 0.70 instead of 0.64 ms).
   auto decode = [&](int item, int& img, int& head, int& g) {
-    g = item % n_groups;
     const int ih = item / n_groups;
+    g = (item - ih * n_groups + ih) % n_groups;
     head = ih % p.heads;
     img = p.batch - 1 - ih / p.heads;
   };
@@ -115,7 +124,7 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int n = 0;; ++n) {
         const int slot = n & 3;
         if (n >= 4) mbar_wait(&it_empty[slot], ((n >> 2) - 1) & 1);
-        int item = static_cast<int>(atomicAdd(&counters[0], 1u));
+        int item = counters ? static_cast<int>(atomicAdd(&counters[0], 1u)) : static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
         if (item >= n_items) item = -1;
         item_ring[slot] = item;
         mbar_arrive(&it_full[slot]);
@@ -151,8 +160,8 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int j = 1; j < nkv; ++j) load_kv(j);
         stamp(15, 0);
       }
-      // every CTA has made its last fetch once all of them have been here: the last one rearms the counter
-      if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
+      // every CTA has made its last fetch once all of them have been here: the last one rearms the counter for the next launch
+      if (counters && atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
         counters[0] = 0;
         counters[1] = 0;
         __threadfence();
@@ -353,7 +362,9 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&it_empty[slot]);
         if (item < 0) break;
-        const int nq = min(3, q_tiles - 3 * (item % n_groups));
+        int img_i, head_i, g_i;
+        decode(item, img_i, head_i, g_i);
+        const int nq = min(3, q_tiles - 3 * g_i);
         const int c0 = n * nkv;
         if (t >= nq) {
           for (int j = 0; j < nkv; ++j) {

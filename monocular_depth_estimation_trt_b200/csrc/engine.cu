@@ -116,6 +116,7 @@ struct mde_context {
   int gather_ranks = 0, gather_rank = 0;       // mde_context_set_gather
   // The launch sequence is captured into a CUDA graph the first time it runs with a given set of bindings and replayed
   // afterwards: one cudaGraphLaunch instead of ~165 kernel launches (what dominates a batch-1 forward on the host side).
+  unsigned int* attn_counters = nullptr;   // [depth][2], see mde_context_create
   cudaGraphExec_t graph_exec = nullptr;
   unsigned long long graph_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool graph_failed = false;
@@ -654,6 +655,7 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
     { Op a; a.kind = Op::ATTENTION; a.in = qkv; a.out = att;
       if (!dry && pl.rc == MDE_OK) pl.rc = make_attention_op(&a.attn, d.precision, qkv, att, B, NT, d.num_heads);
       if (d.attn_poly >= 0) a.attn.poly = d.attn_poly;
+      if (!dry && c && c->attn_counters) a.attn.counters = c->attn_counters + 2 * i;   // this context's op alone uses the pair
       pl.push(a, "attention", 8.0 * rows * D, 4.0 * static_cast<double>(B) * NT * NT * D); }
     { mde_epilogue ep = ep_zero(); ep.d_bias = b.proj_b; ep.d_gamma = b.ls1; ep.d_x = x; ep.accumulate_x = 1; ep.ld_out = D;
       pl.gemm("proj+ls+res", att, rows, D, D, b.proj_w, D, D, ep); }
@@ -810,6 +812,15 @@ extern "C" int mde_context_create(mde_engine* e, mde_context** out) {
     cudaError_t err = cudaMalloc(&arena, static_cast<size_t>(std::max<int64_t>(bytes, 256)));
     if (err != cudaSuccess) rc = fail(MDE_ERR_CUDA, "cudaMalloc of %lld workspace bytes failed: %s", static_cast<long long>(bytes), cudaGetErrorString(err));
     else { c->allocs.push_back(arena); c->arena = static_cast<char*>(arena); }
+  }
+  if (rc == MDE_OK && e->d.depth > 0) {
+    // work counters of the persistent attention kernel, one {next item, CTAs done} pair per block (attention_q3.cuh)
+    void* cnt = nullptr;
+    const size_t cnt_bytes = static_cast<size_t>(e->d.depth) * 2 * sizeof(unsigned int);
+    cudaError_t err = cudaMalloc(&cnt, cnt_bytes);
+    if (err == cudaSuccess) { c->allocs.push_back(cnt); err = cudaMemset(cnt, 0, cnt_bytes); }
+    if (err != cudaSuccess) rc = fail(MDE_ERR_CUDA, "attention work counters: %s", cudaGetErrorString(err));
+    else c->attn_counters = static_cast<unsigned int*>(cnt);
   }
   if (rc == MDE_OK) rc = build_plan(c, e, false, &bytes);
   if (rc != MDE_OK) {
@@ -988,6 +999,13 @@ extern "C" int mde_context_enqueue(mde_context* c, void* stream) {
   const bool no_graph = (c->e->d.flags & MDE_FLAG_NO_GRAPH) != 0 || profile_mode();
   // the legacy default stream cannot be captured; a failed capture falls back to plain launches for good
   if (no_graph || c->graph_failed || s == nullptr || s == cudaStreamLegacy) return enqueue_impl(c, s, false);
+  {
+    // the caller is recording its own graph (depth_pro.py captures the three trunks, the decoder and both heads in one): the
+    // launches go straight into that capture
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) return enqueue_impl(c, s, false);
+    cudaGetLastError();
+  }
   if (!c->d_input || (!c->d_output && c->gather_ranks == 0)) return fail(MDE_ERR_STATE, "set_tensor_address must be called for 'input' and 'output' before enqueue");
   unsigned long long key[8] = {reinterpret_cast<unsigned long long>(c->d_input), reinterpret_cast<unsigned long long>(c->d_output),
                                static_cast<unsigned long long>(c->src_h), static_cast<unsigned long long>(c->src_w),

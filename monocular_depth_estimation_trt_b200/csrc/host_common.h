@@ -67,7 +67,8 @@ struct AttnOp {
   void* out;
   int batch, ntok, heads, precision;
   int ntok_q, k_col0, v_col0;        // queries per image; first K / V column of head 0 in the key/value source
-  unsigned int* counters;            // {next item, CTAs done} of the persistent kernel (a slot of a per-device slab)
+  unsigned int* counters;            // attention_q3 only: {next item, CTAs done}, zero-initialised and owned by whoever owns the op (an
+                                     // engine context: one per attention op of its plan); NULL = static round-robin over the CTAs
   int kind;                          // 0: two CTAs per SM, one query tile each (attention_tc.cuh); 1: one persistent CTA per SM, three query
                                      // tiles (attention_q3.cuh); make_* picks by the number of work items
   int poly;                          // eighths of the exponentials evaluated on the FMA pipe (0..4; make_* sets the default, 2)

@@ -438,25 +438,6 @@ int launch_attention_mma(int precision, const void* d_qkv, void* d_out, int batc
                                : launch_attention_t<__half>(d_qkv, d_out, batch, ntok, heads, s);
 }
 
-// Work counter of the persistent kernel: {next item, CTAs done}, rearmed by the last CTA of every launch.  One pair per launch
-// out of a per-device slab, handed out round-robin, so that launches running side by side on different streams never share one.
-static int attention_counters(unsigned int** out) {
-  constexpr int kSlots = 1024;
-  static std::mutex mu;
-  static unsigned int* slab[64];
-  static unsigned int next[64];
-  int dev = 0;
-  MDE_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(MDE_ERR_INVALID, "attention: device ordinal %d out of range", dev);
-  std::lock_guard<std::mutex> lock(mu);
-  if (!slab[dev]) {
-    MDE_CUDA_TRY(cudaMalloc(&slab[dev], kSlots * 2 * sizeof(unsigned int)));
-    MDE_CUDA_TRY(cudaMemset(slab[dev], 0, kSlots * 2 * sizeof(unsigned int)));
-  }
-  *out = slab[dev] + 2 * (next[dev]++ % kSlots);
-  return MDE_OK;
-}
-
 int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, const void* d_kv, int ldkv, int k_col0, int v_col0,
                          void* d_out, int batch, int ntok_q, int ntok_kv, int heads) {
   if (precision != MDE_FP16 && precision != MDE_BF16) return fail(MDE_ERR_INVALID, "precision must be MDE_FP16 or MDE_BF16");
@@ -490,7 +471,7 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
     const long long items = static_cast<long long>(batch) * heads * (((ntok_q + 127) / 128 + 2) / 3);
     op->kind = items >= 4LL * num_sms() ? 1 : 0;
   }
-  MDE_TRY(attention_counters(&op->counters));
+  op->counters = nullptr;     // static item schedule unless the owner of the op gives it a work counter (engine.cu)
   MDE_TRY(encode_map(&op->map_kv96, precision, d_kv, 2, dims, str, box96));
   return encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128);
 }

@@ -424,6 +424,10 @@ class DepthProContext:
         self.overlap_trunks = True
         self.profile_stages = False       # True: CUDA events at the stage boundaries of the next execute (see stage_times())
         self._marks = []
+        self.use_graph = True
+        self._graph_exec = None
+        self._graph_key = None
+        self._graph_failed = False
 
     # -- IExecutionContext surface
     def set_tensor_address(self, name: str, ptr: int) -> bool:
@@ -437,13 +441,51 @@ class DepthProContext:
         return True
 
     def execute_async_v3(self, stream_handle) -> bool:
-        import torch
+        """One forward on `stream_handle`.  The ~585 launches (three trunks on three streams, neck, decoder, two heads) are
+        recorded into ONE CUDA graph the first time they run with a given set of bindings and replayed afterwards, like the
+        C-ABI engine does for its own plan (csrc/engine.cu `mde_context_enqueue`): issuing them through ctypes costs the host
+        more than the device needs to run them.  Not for the NCCL baseline on several ranks, the legacy stream, or while
+        `profile_stages` wants events between the stages; `use_graph = False` turns it off."""
         missing = [n for n, _ in self.e.IO if not self.addr.get(n)]
         if missing:
             raise RuntimeError(f"[MDET] execute before set_tensor_address for {missing}")
+        sh = int(stream_handle)
+        graphable = (self.use_graph and not self.profile_stages and sh != 0 and not self._graph_failed
+                     and self.e.gather_mode == "fused")      # the NCCL baseline issues collectives / copies on torch's stream
+        if not graphable:
+            return self._enqueue(sh)
+        from .common_runtime import cuda_call, cudart
+        key = tuple(sorted(self.addr.items())) + (self.overlap_trunks,)
+        if self._graph_exec is None or key != self._graph_key:
+            self.release_graph()
+            cuda_call(cudart.cudaStreamBeginCapture(sh, cudart.cudaStreamCaptureMode.cudaStreamCaptureModeThreadLocal))
+            ok = False
+            try:
+                self._enqueue(sh)
+                ok = True
+            finally:
+                err, graph = cudart.cudaStreamEndCapture(sh)
+                if not ok or int(err) != 0:
+                    cudart.cudaGetLastError()
+                    self._graph_failed = True           # a forward that cannot be recorded runs launch by launch from now on
+            if self._graph_failed:
+                return self._enqueue(sh)
+            self._graph_exec = cuda_call(cudart.cudaGraphInstantiate(graph, 0))
+            cuda_call(cudart.cudaGraphDestroy(graph))
+            self._graph_key = key
+        cuda_call(cudart.cudaGraphLaunch(self._graph_exec, sh))
+        return True
+
+    def release_graph(self) -> None:
+        from .common_runtime import cudart
+        if getattr(self, "_graph_exec", None) is not None:
+            cudart.cudaGraphExecDestroy(self._graph_exec)
+        self._graph_exec = None
+        self._graph_key = None
+
+    def _enqueue(self, sh: int) -> bool:
         e, o, b, w, n = self.e, self.ops, self.b, self.e.weights, self.n
         D, Fd, side = e.D, e.features, self.side
-        sh = int(stream_handle)
         o.stream = C.c_void_p(sh)
         o.launches = 0
         from .common_runtime import cuda_call, cudart
@@ -587,6 +629,7 @@ class DepthProContext:
         return self.b[name]
 
     def close(self) -> None:
+        self.release_graph()
         for c in (getattr(self, "ctx_img", None), getattr(self, "ctx_fov", None)):
             if c is not None:
                 c.close()
