@@ -150,6 +150,34 @@ def get_engine(
                                                 dynamic_input_shapes, 1, input_mode, extra))
         print(f"[MDET] Engine build done! ({time.time() - begin:.2f} [sec])")
         return engine
+    if meta.get("family") in ("vggt", "streamvggt"):
+        # models/vggt/onnx2trt.py / models/streamvggt/onnx2trt.py: bindings `images` [1, S, 3, H, W] -> `depth` [1, S, H, W, 1].
+        # `world` / `rank` shard the frames of a scene (VGGT only); a StreamVGGT file written with stream_frames > 0 builds the
+        # streaming engine (one frame per execute against cached keys / values, `context.reset_stream()` between streams).
+        from .vggt import VGGTEngine
+        if batch != 1 or input_mode != "f32_nchw" or output != "model_grid":
+            raise ValueError("[MDET] the VGGT engines take one scene of float32 frames, as their spec.json says")
+        print(f"[MDET] Build engine ({engine_file_path or model_path})")
+        sd, _ = W.load(model_path)
+        engine = VGGTEngine(sd, encoder=meta["encoder"], depth=meta["aggregator_depth"], features=meta["features"],
+                            out_channels=tuple(meta["out_channels"]), taps=tuple(meta["taps"]), frames=meta["frames"],
+                            image_hw=(meta["input_h"], meta["input_w"]), precision=precision, world=world, rank=rank, gather=gather,
+                            device=device, causal=meta["family"] == "streamvggt", stream_frames=meta.get("stream_frames", 0))
+        for i in range(engine.num_io_tensors):
+            name = engine.get_tensor_name(i)
+            kind = "input" if engine.get_tensor_mode(name) == TensorIOMode.INPUT else "output"
+            print(f"[MDET] {kind}({i}) name: {name}, shape= {engine.get_tensor_shape(name)}")
+        if engine_file_path:
+            os.makedirs(os.path.dirname(engine_file_path) or ".", exist_ok=True)
+            with open(engine_file_path, "w", encoding="utf-8") as f:
+                json.dump({"backend": "mde_b200", "abi": _lib.load().mde_abi_version(), "meta": meta, "precision": precision,
+                           "batch": 1, "input_mode": input_mode, "world": world}, f, indent=2)
+            if check_fingerprint:
+                with open(os.path.splitext(engine_file_path)[0] + ".fingerprint", "w", encoding="utf-8") as f:
+                    f.write(_engine_fingerprint(model_path, precision, workspace_gib, opt_level, obey_precision_constraints,
+                                                dynamic_input_shapes, 1, input_mode, extra))
+        print(f"[MDET] Engine build done! ({time.time() - begin:.2f} [sec])")
+        return engine
     desc = make_desc(meta, precision=precision, batch=batch, input_mode=input_mode,
                      max_src_hw=max_src_hw, swap_rb=swap_rb, device=device, output=output,
                      split_k=split_k, pdl=pdl, graph=graph, attn_poly=attn_poly)

@@ -71,8 +71,17 @@ class Aggregator:
 
     def __init__(self, state_dict: Mapping, dim: int, depth: int, num_heads: int, gh: int, gw: int, frames_total: int,
                  precision: str = "bf16", n_special: int = 5, world: int = 1, rank: int = 0, gather: str = "fused",
-                 taps: Sequence[int] = (), device: int = 0):
+                 taps: Sequence[int] = (), device: int = 0, causal: bool = False, cache_frames: int = 0):
+        """causal: StreamVGGT's temporal causal attention -- in a global block the tokens of frame i see the tokens of frames
+        <= i (oracle/vggt_torch.py `aggregate`).  cache_frames > 0 (with frames_total == 1): the streaming form of the same
+        model -- `forward(tokens, stream, frame_index=t)` takes ONE frame, appends its keys / values to a per-block cache
+        ([cache_frames * N, 2D] 16-bit, written by the qk-norm + RoPE kernel) and attends to the t + 1 frames held there; frame t
+        of a stream then equals frame t of the causal forward over the whole sequence."""
         import torch
+        if causal and world > 1:
+            raise ValueError("[MDET] the causal (StreamVGGT) aggregator is single-GPU: a frame only needs its predecessors' keys")
+        if cache_frames and (frames_total != 1 or not causal):
+            raise ValueError("[MDET] the key / value cache belongs to the causal aggregator fed one frame at a time")
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"[MDET] precision {precision!r} is not supported; use one of {sorted(_lib.PRECISIONS)}")
         if dim != num_heads * 64:
@@ -100,6 +109,8 @@ class Aggregator:
         self.x = z(self.rows, D, dt=torch.float32)
         self.ln, self.qkv, self.att, self.hid = z(self.rows, D), z(self.rows, 3 * D), z(self.rows, D), z(self.rows, 4 * D)
         self.tap_out = {t: z(self.rows, 2 * D, dt=torch.float32) for t in self.taps}      # [frame | global] residual streams
+        self.causal, self.cache_frames, self.frame_index = bool(causal), int(cache_frames), 0
+        self.cache = [z(self.cache_frames * self.N, 2 * D) for _ in range(depth)] if cache_frames else None
         self.kv = self.sync = None
         if world > 1:
             self.kv = S.PeerBuffers(world, rank, (self.rows_total, 2 * D), precision)
@@ -107,17 +118,29 @@ class Aggregator:
             if gather == "fused":
                 self.sync = S.PeerSync(world, rank)
 
-    def _block(self, w: _BlockWeights, global_block: bool, sh: int) -> None:
+    def _block(self, w: _BlockWeights, global_block: bool, sh: int, layer: int = 0) -> None:
         o, D, rows = self.ops, self.D, self.rows
+        streaming = global_block and self.cache is not None
+        t, N = self.frame_index, self.N
         o.layernorm(self.x, w.n1w, w.n1b, self.ln, rows, D, LN_EPS)
         o.gemm(self.ln, rows, D, D, w.qkv, 3 * D, o.ep(bias=w.qkv_b, out=self.qkv, ld_out=3 * D))
         sharded = global_block and self.world > 1
         if sharded and self.sync is not None:
             self.sync.wait_acks(sh)                                # every peer has finished reading the previous layer's K|V
+        if streaming:       # this frame's finished K rows and its V rows go to rows [t * N, (t + 1) * N) of the block's cache
+            gather = (self.cache[layer].data_ptr() + t * N * 2 * D * 2,)
+        else:
+            gather = self.mine if (sharded and self.sync is not None) else ()
         o.qknorm_rope(self.qkv, rows, self.heads, w.qw, w.qb, w.kw, w.kb, QK_EPS, self.pos, self.cos_sin, self.max_pos,
-                      gather=self.mine if (sharded and self.sync is not None) else (), gather_ld=2 * D)
+                      gather=gather, gather_ld=2 * D)
         if not global_block:
             o.attention(self.qkv, self.att, self.S_local, self.N, self.heads)
+        elif streaming:
+            o.attention_kv(self.qkv, 3 * D, self.cache[layer], 2 * D, 0, D, self.att, 1, N, (t + 1) * N, self.heads)
+        elif self.causal and self.S_local > 1:
+            # frame f's queries against the keys / values of frames 0..f, read in place from the packed q|k|v rows
+            for f in range(self.S_local):
+                o.attention_kv(self.qkv[f * N:], 3 * D, self.qkv[:, D:], 3 * D, 0, D, self.att[f * N:], 1, N, (f + 1) * N, self.heads)
         elif not sharded:
             o.attention(self.qkv, self.att, 1, rows, self.heads)
         else:
@@ -143,20 +166,25 @@ class Aggregator:
         cuda_call(cudart.cudaMemcpy2DAsync(dst.data_ptr() + half * self.D * 4, 2 * self.D * 4, self.x.data_ptr(), self.D * 4,
                                            self.D * 4, self.rows, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, sh))
 
-    def forward(self, tokens_ptr: int, stream_handle) -> None:
+    def forward(self, tokens_ptr: int, stream_handle, frame_index: int = None) -> None:
         """tokens: float32 [frames_local, N, D] on the device (special tokens first).  Asynchronous on `stream_handle`;
-        afterwards `x` holds the last global block's output and `tap_out[layer]` the [frame | global] pair of each tap."""
+        afterwards `x` holds the last global block's output and `tap_out[layer]` the [frame | global] pair of each tap.
+        frame_index (streaming aggregators only): the position of this frame in its stream, 0 starts a new one."""
         from .common_runtime import cuda_call, cudart
         sh = int(stream_handle)
+        if self.cache is not None:
+            if frame_index is None or not 0 <= int(frame_index) < self.cache_frames:
+                raise ValueError(f"[MDET] streaming forward needs frame_index in [0, {self.cache_frames}), got {frame_index}")
+            self.frame_index = int(frame_index)
         self.ops.stream = C.c_void_p(sh)
         self.ops.launches = 0
         cuda_call(cudart.cudaMemcpyAsync(self.x.data_ptr(), int(tokens_ptr), self.rows * self.D * 4,
                                          cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, sh))
         for i, (fw, gw_) in enumerate(self.blocks):
-            self._block(fw, False, sh)
+            self._block(fw, False, sh, i)
             if i in self.tap_out:
                 self._tap(i, 0, sh)
-            self._block(gw_, True, sh)
+            self._block(gw_, True, sh, i)
             if i in self.tap_out:
                 self._tap(i, 1, sh)
 
@@ -167,6 +195,8 @@ class Aggregator:
         from .common_runtime import cuda_call, cudart
         if self.world > 1 and self.sync is None:
             raise RuntimeError("[MDET] the NCCL baseline is not captured; use gather='fused'")
+        if self.cache is not None:
+            raise RuntimeError("[MDET] a streaming step changes its cache offsets from frame to frame: not captured")
         sh = int(stream_handle)
         if sh == 0:
             raise ValueError("[MDET] capture needs a non-default stream")
@@ -278,8 +308,18 @@ class VGGTEngine:
 
     def __init__(self, state_dict: Mapping, encoder: str = "vitl", depth: int = 24, features: int = 256,
                  out_channels: Sequence[int] = (256, 512, 1024, 1024), taps: Sequence[int] = (4, 11, 17, 23), frames: int = 16,
-                 image_hw=(518, 518), precision: str = "fp16", world: int = 1, rank: int = 0, gather: str = "fused", device: int = 0):
+                 image_hw=(518, 518), precision: str = "fp16", world: int = 1, rank: int = 0, gather: str = "fused", device: int = 0,
+                 causal: bool = False, stream_frames: int = 0):
+        """causal=True: StreamVGGT (models/streamvggt/onnx_export.py:35-53: the same aggregator -> depth head pair with temporal
+        causal attention in the global blocks; identical to VGGT at the one frame the reference exports).  stream_frames > 0
+        (needs frames == 1): the streaming form -- every `execute_async_v3` takes the NEXT frame of a stream of up to
+        `stream_frames` frames and attends to the cached keys / values of its predecessors; `context.reset_stream()` starts a
+        new stream.  Frame t of a stream equals frame t of the causal forward over the sequence (tests/test_vggt_gpu.py)."""
         import torch
+        if stream_frames and (int(frames) != 1 or world != 1):
+            raise ValueError("[MDET] a streaming engine takes one frame per call on one GPU (frames=1, world=1)")
+        causal = bool(causal or stream_frames)
+        self.causal, self.stream_frames = causal, int(stream_frames)
         cfg = W.ENCODERS[encoder]
         H, Wd = int(image_hw[0]), int(image_hw[1])
         if H % 14 or Wd % 14:
@@ -310,7 +350,8 @@ class VGGTEngine:
             self.trunk.finalize()
             # ---- aggregator + head
             self.agg = Aggregator(state_dict, self.D, self.depth, self.heads, self.gh, self.gw, frames_total=self.S_total, precision=precision,
-                                  world=world, rank=rank, gather=gather, taps=self.taps, device=device)
+                                  world=world, rank=rank, gather=gather, taps=self.taps, device=device, causal=causal,
+                                  cache_frames=self.stream_frames)
             self.special = torch.cat([_t(state_dict["aggregator.camera_token"])[0], _t(state_dict["aggregator.register_token"])[0]],
                                      dim=1).contiguous().to(self.device)                      # [2, 5, D]
             self.head = _HeadWeights(state_dict, self.D, self.F, self.oc, self.gh, self.gw, H, Wd, self.S, self.dtype, self.device)
@@ -390,6 +431,11 @@ class VGGTContext:
         self.b = b
         self.launches_per_enqueue = 0
         self._captured = False
+        self.stream_index = 0              # streaming engines: position of the next frame in its stream
+
+    def reset_stream(self) -> None:
+        """Streaming engines: the next `execute_async_v3` starts a new stream (its frame sees only itself)."""
+        self.stream_index = 0
 
     def set_tensor_address(self, name: str, ptr: int) -> bool:
         self.e.get_tensor_shape(name)
@@ -418,9 +464,16 @@ class VGGTContext:
         o.stream = C.c_void_p(sh)
         o.launches = 0
         # 2. camera + register tokens in front
-        o.assemble_tokens(self.trunk_out[3], e.special, S_, T, N_SPECIAL, D, e.rank * S_, self.tokens)
+        streaming = e.stream_frames > 0
+        if streaming and self.stream_index >= e.stream_frames:
+            raise RuntimeError(f"[MDET] the stream is {e.stream_frames} frames long (the size of the key / value cache): reset_stream() first")
+        o.assemble_tokens(self.trunk_out[3], e.special, S_, T, N_SPECIAL, D, self.stream_index if streaming else e.rank * S_, self.tokens)
         # 3. aggregator (graph replay after the first call on a capturable stream)
-        if sh != 0 and (e.world == 1 or e.agg.sync is not None):
+        if streaming:
+            e.agg.forward(self.tokens.data_ptr(), sh, frame_index=self.stream_index)
+            self._agg_launches = o.launches
+            self.stream_index += 1
+        elif sh != 0 and (e.world == 1 or e.agg.sync is not None):
             if not self._captured:
                 e.agg.forward(self.tokens.data_ptr(), sh)              # warm run: every kernel's attributes are set outside the capture
                 self._agg_launches = o.launches

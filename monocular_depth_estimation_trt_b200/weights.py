@@ -60,6 +60,25 @@ def describe_depth_pro(encoder: str = "vitl", features: int = 256, hook_blocks=(
                 input_h=int(image_size), input_w=int(image_size))
 
 
+def describe_vggt(encoder: str = "vitl", depth: int = 24, features: int = 256, out_channels=(256, 512, 1024, 1024),
+                  taps=(4, 11, 17, 23), frames: int = 1, image_hw=(518, 518), family: str = "vggt", stream_frames: int = 0) -> dict:
+    """Description stored next to a VGGT (`family="vggt"`, models/vggt/onnx_export.py:38-52) or StreamVGGT (`"streamvggt"`,
+    models/streamvggt/onnx_export.py:35-53: temporal causal attention in the global blocks) state dict: trunk, aggregator depth,
+    DPT widths, tapped layers, frames per execute (the reference exports S = 1: spec.json rank-5 [1, 1, 3, 518, 518]).
+    stream_frames > 0 (StreamVGGT only): the streaming engine -- one frame per execute against a key / value cache that long."""
+    if encoder not in ENCODERS:
+        raise KeyError(f"unknown encoder {encoder!r}; available: {sorted(ENCODERS)}")
+    if family not in ("vggt", "streamvggt"):
+        raise ValueError(f"unknown family {family!r}")
+    if stream_frames and family != "streamvggt":
+        raise ValueError("only StreamVGGT has a streaming form")
+    c = ENCODERS[encoder]
+    return dict(family=family, encoder=encoder, embed_dim=c["embed_dim"], num_heads=c["num_heads"], patch_size=14,
+                aggregator_depth=int(depth), features=int(features), out_channels=[int(x) for x in out_channels],
+                taps=[int(t) for t in taps], frames=int(frames), input_h=int(image_hw[0]), input_w=int(image_hw[1]),
+                stream_frames=int(stream_frames))
+
+
 def keep_ratio_size(src_h: int, src_w: int, target: int = 518, multiple: int = 14, rounding: str = "ceil") -> Tuple[int, int]:
     """The engine size for a source frame under the keep-ratio rule of the Depth Anything family (core/preprocess.py:157-171
     `resize_keep_ratio`, bound "lower", with :112-137 `_round_to_multiple`): short side to `target`, both sides snapped to

@@ -103,9 +103,9 @@ def init_aggregator(dim: int, depth: int, seed: int = 0) -> Dict[str, torch.Tens
     return sd
 
 
-def block(sd, prefix: str, t: torch.Tensor, pos: torch.Tensor, num_heads: int) -> torch.Tensor:
+def block(sd, prefix: str, t: torch.Tensor, pos: torch.Tensor, num_heads: int, mask: torch.Tensor = None) -> torch.Tensor:
     """t [B, N, D], pos [N, 2] -> the block's output (norm1 -> attention with qk-norm + RoPE -> LayerScale -> residual;
-    norm2 -> MLP (exact-erf GELU) -> LayerScale -> residual)."""
+    norm2 -> MLP (exact-erf GELU) -> LayerScale -> residual).  mask: bool [N, N], True where a query may see a key (None: all)."""
     B, N, D = t.shape
     hd = D // num_heads
     y = F.layer_norm(t, (D,), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], LN_EPS)
@@ -114,7 +114,10 @@ def block(sd, prefix: str, t: torch.Tensor, pos: torch.Tensor, num_heads: int) -
     q = F.layer_norm(q, (hd,), sd[prefix + "attn.q_norm.weight"], sd[prefix + "attn.q_norm.bias"], QK_EPS)
     k = F.layer_norm(k, (hd,), sd[prefix + "attn.k_norm.weight"], sd[prefix + "attn.k_norm.bias"], QK_EPS)
     q, k = rope_2d(q, pos), rope_2d(k, pos)
-    a = torch.softmax((q * hd ** -0.5) @ k.transpose(-2, -1), dim=-1) @ v
+    scores = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    if mask is not None:
+        scores = scores.masked_fill(~mask, float("-inf"))
+    a = torch.softmax(scores, dim=-1) @ v
     a = a.transpose(1, 2).reshape(B, N, D)
     t = t + sd[prefix + "ls1.gamma"] * F.linear(a, sd[prefix + "attn.proj.weight"], sd[prefix + "attn.proj.bias"])
     y = F.layer_norm(t, (D,), sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], LN_EPS)
@@ -123,17 +126,25 @@ def block(sd, prefix: str, t: torch.Tensor, pos: torch.Tensor, num_heads: int) -
 
 
 @torch.no_grad()
-def aggregate(sd, tokens: torch.Tensor, gh: int, gw: int, num_heads: int, depth: int) -> List[torch.Tensor]:
+def aggregate(sd, tokens: torch.Tensor, gh: int, gw: int, num_heads: int, depth: int, causal: bool = False) -> List[torch.Tensor]:
     """tokens [S, N, D] (one scene: S frames of N = 5 + gh*gw tokens, special tokens first) -> per layer the concatenation
-    [S, N, 2D] of the frame block's and the global block's output, as the aggregator hands them to the heads."""
+    [S, N, 2D] of the frame block's and the global block's output, as the aggregator hands them to the heads.
+    causal: StreamVGGT's temporal causal attention (models/streamvggt/onnx_export.py:35-53 exports the same aggregator / depth
+    head pair as VGGT's; upstream streamvggt/models/aggregator.py masks the global blocks so that the tokens of frame i see the
+    tokens of frames <= i, which is what lets a stream be processed frame by frame against cached keys / values).  With one
+    frame -- all the reference ever exports -- the two coincide."""
     S, N, D = tokens.shape
     pos = positions(gh, gw, N - gh * gw)
+    mask = None
+    if causal and S > 1:
+        frame_of = torch.arange(S).repeat_interleave(N)
+        mask = frame_of[:, None] >= frame_of[None, :]
     out = []
     t = tokens
     for i in range(depth):
         t = block(sd, f"aggregator.frame_blocks.{i}.", t, pos, num_heads)                          # S sequences of N tokens
         frame = t
-        t = block(sd, f"aggregator.global_blocks.{i}.", t.reshape(1, S * N, D), pos.repeat(S, 1), num_heads).reshape(S, N, D)
+        t = block(sd, f"aggregator.global_blocks.{i}.", t.reshape(1, S * N, D), pos.repeat(S, 1), num_heads, mask).reshape(S, N, D)
         out.append(torch.cat([frame, t], dim=-1))
     return out
 
@@ -311,16 +322,18 @@ def depth_head(sd, taps: List[torch.Tensor], gh: int, gw: int, image_h: int, ima
 
 
 @torch.no_grad()
-def vggt_depth(sd, images: torch.Tensor, encoder: str = "vitl", depth: int = 24, taps=(4, 11, 17, 23), trace=None) -> torch.Tensor:
+def vggt_depth(sd, images: torch.Tensor, encoder: str = "vitl", depth: int = 24, taps=(4, 11, 17, 23), trace=None,
+               causal: bool = False) -> torch.Tensor:
     """images float32 [S, 3, H, W] in 0..1 (one scene) -> depth [S, H, W] = exp(channel 0 of the head)  (`activate_head`,
-    activation "exp"; the confidence channel is computed by the graph but not returned by the reference's wrapper)."""
+    activation "exp"; the confidence channel is computed by the graph but not returned by the reference's wrapper).
+    causal=True: StreamVGGT (see `aggregate`)."""
     from oracle import dav2_torch as O
     S, _, H, W = images.shape
     gh, gw = H // 14, W // 14
     tok = frame_tokens(sd, images, encoder)
     if trace is not None:
         trace["tokens"] = tok
-    layers = aggregate(sd, tok, gh, gw, O.MODEL_CONFIGS[encoder]["num_heads"], depth)
+    layers = aggregate(sd, tok, gh, gw, O.MODEL_CONFIGS[encoder]["num_heads"], depth, causal)
     if trace is not None:
         trace["aggregated"] = [layers[t] for t in taps]
     logits = depth_head(sd, [layers[t] for t in taps], gh, gw, H, W, trace)

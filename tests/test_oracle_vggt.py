@@ -76,6 +76,28 @@ def test_block_attention_agrees_with_sdpa_and_global_mixes_frames():
     assert not torch.allclose(layers[0][:2, :, D:], layers2[0][:2, :, D:])
 
 
+def test_causal_aggregator_is_the_streaming_model():
+    """StreamVGGT (models/streamvggt/onnx_export.py:35-53): with temporal causal attention a frame does not see its successors
+    -- frame i of the causal forward over S frames equals frame i of the forward over the first i + 1 frames (what a key / value
+    cache computes frame by frame); with one frame it IS the VGGT aggregator; the last frame sees everything in both."""
+    torch.manual_seed(2)
+    D, H, S, gh, gw, depth = 128, 2, 3, 2, 3, 2
+    sd = V.init_aggregator(D, depth, seed=5)
+    tok = torch.randn(S, 5 + gh * gw, D)
+    full = V.aggregate(sd, tok, gh, gw, H, depth)
+    causal = V.aggregate(sd, tok, gh, gw, H, depth, causal=True)
+    for i in range(S):
+        prefix = V.aggregate(sd, tok[:i + 1], gh, gw, H, depth, causal=True)
+        for layer in range(depth):
+            assert torch.allclose(causal[layer][i], prefix[layer][i], atol=1e-5)
+    one = V.aggregate(sd, tok[:1], gh, gw, H, depth)
+    assert torch.allclose(causal[0][0], one[0][0], atol=1e-5)                      # frame 0 never sees the others
+    assert not torch.allclose(causal[1][0], full[1][0], atol=1e-3)                 # ... which it does without the mask
+    tok2 = tok.clone(); tok2[2] += 1.0                                              # a later frame changes nothing before it
+    causal2 = V.aggregate(sd, tok2, gh, gw, H, depth, causal=True)
+    assert torch.equal(causal[1][:2], causal2[1][:2]) and not torch.allclose(causal[1][2], causal2[1][2])
+
+
 def test_product_tables_equal_the_oracle_tables():
     from monocular_depth_estimation_trt_b200 import vggt as P
     assert torch.equal(torch.from_numpy(P.token_positions(37, 37)).long(), V.positions(37, 37))

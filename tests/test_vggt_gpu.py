@@ -85,6 +85,48 @@ def test_aggregator_against_the_oracle(lib, prec):
     agg.close()
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_causal_aggregator_and_its_streaming_form(lib, prec):
+    """StreamVGGT: (a) the causal aggregator over S frames against the oracle's masked forward; (b) the same frames fed ONE AT A
+    TIME through an aggregator with a key / value cache: frame t of the stream is frame t of (a), bit for bit (same kernels,
+    same key order; only where the keys live differs)."""
+    torch.manual_seed(7)
+    D, H, S, depth, gh, gw = 384, 6, 3, 2, 9, 11
+    sd = V.init_aggregator(D, depth, seed=6)
+    N = 5 + gh * gw
+    tok = torch.randn(S, N, D)
+    ref = V.aggregate(sd, tok, gh, gw, H, depth, causal=True)
+    x = tok.cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    agg = P.Aggregator(sd, D, depth, H, gh, gw, frames_total=S, precision=prec, taps=(0, 1), causal=True)
+    agg.forward(x.data_ptr(), stream)
+    torch.cuda.synchronize()
+    whole = {t: agg.tap_out[t].clone().reshape(S, N, 2 * D) for t in (0, 1)}
+    for t in (0, 1):
+        got = whole[t].cpu()
+        e_frame, e_global = rms_rel(got[..., :D], ref[t][..., :D]), rms_rel(got[..., D:], ref[t][..., D:])
+        print(prec, "causal layer", t, "frame", e_frame, "global", e_global)
+        assert e_frame < INTER[prec] * (t + 1) and e_global < INTER[prec] * (t + 1)
+    assert agg.ops.launches == depth * (8 + 8 + S - 1)                  # a global block: one attention launch per frame
+    agg.close()
+    full = V.aggregate(sd, tok, gh, gw, H, depth)                        # the unmasked model is a different function
+    assert rms_rel(whole[1][0, :, D:].cpu(), full[1][0, :, D:]) > 3 * INTER[prec]
+    step = P.Aggregator(sd, D, depth, H, gh, gw, frames_total=1, precision=prec, taps=(0, 1), causal=True, cache_frames=S)
+    for rnd in range(2):                                                 # a second stream over the same cache
+        for f in range(S):
+            step.forward(x[f].data_ptr(), stream, frame_index=f)
+            torch.cuda.synchronize()
+            for t in (0, 1):
+                assert torch.equal(step.tap_out[t].reshape(N, 2 * D), whole[t][f]), (rnd, f, t)
+    with pytest.raises(ValueError):
+        step.forward(x[0].data_ptr(), stream, frame_index=S)             # beyond the cache
+    with pytest.raises(ValueError):
+        step.forward(x[0].data_ptr(), stream)                            # a streaming step needs its position
+    step.close()
+    with pytest.raises(ValueError):
+        P.Aggregator(sd, D, depth, H, gh, gw, frames_total=2, precision=prec, causal=True, world=2)
+
+
 def test_aggregator_graph_replay_equals_eager(lib):
     """The forward captured into a CUDA graph (one host launch per forward) gives the eager launches' result bit for bit."""
     torch.manual_seed(6)
@@ -222,3 +264,81 @@ def test_whole_model_against_the_oracle(lib, prec):
             pytest.xfail(f"bf16 operands miss north_star's gate on the fp32 oracle: {worst}")
     else:
         assert worst["abs_rel"] <= 2e-3 and worst["max_rel"] <= 1e-2, worst
+
+
+def test_streamvggt_whole_model_stream_equals_causal_forward(lib):
+    """models/streamvggt as an engine: (a) `causal=True` over the S frames of a scene against the oracle's causal forward
+    (north_star's gate); (b) the streaming engine (one frame per execute, cached keys / values): depth map t of the stream is
+    depth map t of (a) bit for bit, a reset starts a new stream, and a stream cannot outgrow its cache."""
+    from monocular_depth_estimation_trt_b200 import common
+    import refsetup as R
+    sd, imgs, _, _, taps = vggt_reference()
+    S = imgs.shape[0]
+    ref = V.vggt_depth(sd, imgs, encoder="vits", depth=4, taps=taps, causal=True)
+    kw = dict(encoder="vits", depth=4, features=64, out_channels=(48, 96, 192, 384), taps=taps, precision="fp16")
+    with P.VGGTEngine(sd, frames=S, causal=True, **kw) as engine, engine.create_execution_context() as context:
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+        inputs[0].host = imgs.numpy()
+        out = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        whole = out[0].reshape(S, 518, 518).copy()
+        common.free_buffers(inputs, outputs, stream)
+    worst = {"abs_rel": 0.0, "max_rel": 0.0}
+    for s in range(S):
+        m = R.compare_depth(ref[s].numpy(), whole[s])
+        worst = {k: max(worst[k], m[k]) for k in worst}
+    print("streamvggt causal", worst)
+    assert worst["abs_rel"] <= 2e-3 and worst["max_rel"] <= 1e-2, worst
+    with P.VGGTEngine(sd, frames=1, stream_frames=S, **kw) as engine, engine.create_execution_context() as context:
+        assert engine.get_tensor_shape("images") == (1, 1, 3, 518, 518)
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+        for rnd in range(2):
+            for f in range(S):
+                inputs[0].host = imgs[f:f + 1].numpy()
+                out = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+                assert np.array_equal(out[0].reshape(518, 518), whole[f]), (rnd, f)
+            with pytest.raises(RuntimeError):
+                common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+            context.reset_stream()
+        common.free_buffers(inputs, outputs, stream)
+    with pytest.raises(ValueError):
+        P.VGGTEngine(sd, frames=2, stream_frames=4, **kw)
+
+
+def test_get_engine_builds_vggt_and_streamvggt_from_exported_files(lib, tmp_path):
+    """models/{vggt,streamvggt}/onnx2trt.py's build call: export file -> get_engine -> allocate_buffers -> do_inference; the
+    family in the file picks the attention mask, `stream_frames` the streaming engine; results equal the directly built
+    engines' bit for bit and the fingerprint record is written."""
+    from monocular_depth_estimation_trt_b200 import common, weights as W
+    sd, imgs, _, _, taps = vggt_reference()
+    S = imgs.shape[0]
+    kw = dict(encoder="vits", depth=4, features=64, out_channels=(48, 96, 192, 384), taps=taps)
+
+    def run(engine, frames):
+        with engine, engine.create_execution_context() as context:
+            inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+            outs = []
+            for f in frames:
+                inputs[0].host = f.numpy()
+                outs.append(common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)[0].copy())
+            common.free_buffers(inputs, outputs, stream)
+        return outs
+
+    got = {}
+    for family in ("vggt", "streamvggt"):
+        path = str(tmp_path / f"{family}_518x518.mdew")
+        W.save(path, sd, W.describe_vggt(frames=S, family=family, **kw))
+        got[family] = run(common.get_engine(path, str(tmp_path / "engine" / f"{family}_fp16.engine"), "fp16"), [imgs])[0]
+        direct = run(P.VGGTEngine(sd, frames=S, precision="fp16", causal=family == "streamvggt", **kw), [imgs])[0]
+        assert np.array_equal(got[family], direct)
+        assert (tmp_path / "engine" / f"{family}_fp16.fingerprint").exists()
+    whole = got["streamvggt"].reshape(S, 518, 518)
+    assert not np.array_equal(got["vggt"].reshape(S, 518, 518)[0], whole[0])      # frame 0 sees / does not see the other frames
+    path = str(tmp_path / "streamvggt_stream.mdew")
+    W.save(path, sd, W.describe_vggt(frames=1, family="streamvggt", stream_frames=S, **kw))
+    steps = run(common.get_engine(path, "", "fp16"), [imgs[f:f + 1] for f in range(S)])
+    for f in range(S):
+        assert np.array_equal(steps[f].reshape(518, 518), whole[f]), f
+    with pytest.raises(ValueError):
+        W.describe_vggt(family="vggt", stream_frames=4, **kw)
+    with pytest.raises(ValueError):
+        common.get_engine(path, "", "fp16", batch=2)
