@@ -463,13 +463,22 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
   cuuint32_t box128[2] = {64, 128};
   cuuint32_t box96[2] = {64, kAq3Keys};
   op->poly = 2;      // the measured optimum (tools/attn_sweep.py); engines override it from mde_engine_desc.attn_poly
-  // Three query tiles per persistent CTA when there is work for every SM several times over (items = image x head x group of
-  // three query tiles); below that the one-query-tile kernel spreads a small problem over more SMs.  At the batch-64 ViT-L
-  // shape the two take the same time stand-alone and the persistent one 7 % less energy per launch (K / V tiles read once
-  // for three query tiles), which is what counts inside the power-capped step (profiles/r02_energy_per_kernel.txt).
+  // Which kernel: one query tile per CTA, two CTAs per SM (attention_tc.cuh), or three query tiles per persistent CTA
+  // (attention_q3.cuh).  At the batch-64 ViT-L shape the two take the same time; the persistent one reads each K / V tile
+  // once for three query tiles (7 % less energy per launch in the first measurement, profiles/r02_energy_per_kernel.txt) and
+  // has no wave structure.  What decides for small and medium problems is the tail: an item of the persistent kernel (three
+  // query tiles over all keys) takes ~1.37x as long as one wave of the other (16.8 vs 23 us at 1370 tokens), so compare
+  //     ceil(CTAs / (2 SMs))   against   1.37 x ceil(items / SMs).
+  // Batch 1 (176 CTAs, 64 items): one wave of small CTAs wins.  VGGT sharded over 8 GPUs (2 frames per rank: 352 CTAs = a
+  // full wave and a 19 %-full one; 128 items = one round): the persistent kernel wins by a third.
   {
-    const long long items = static_cast<long long>(batch) * heads * (((ntok_q + 127) / 128 + 2) / 3);
-    op->kind = items >= 4LL * num_sms() ? 1 : 0;
+    const int sms = std::max(1, num_sms());
+    const long long q_tiles = (ntok_q + 127) / 128;
+    const long long ctas = static_cast<long long>(batch) * heads * q_tiles;
+    const long long items = static_cast<long long>(batch) * heads * ((q_tiles + 2) / 3);
+    const double t_tc = static_cast<double>((ctas + 2 * sms - 1) / (2 * sms));
+    const double t_q3 = 1.37 * static_cast<double>((items + sms - 1) / sms);
+    op->kind = t_q3 <= t_tc ? 1 : 0;
   }
   op->counters = nullptr;     // static item schedule unless the owner of the op gives it a work counter (engine.cu)
   MDE_TRY(encode_map(&op->map_kv96, precision, d_kv, 2, dims, str, box96));

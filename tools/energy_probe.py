@@ -86,9 +86,9 @@ for case in cases:
         ep = K.epilogue(bias=bias, gamma=gamma, act=kw.get("act", 0), x=x, accumulate_x=bool(kw.get("x")), out=out, ld_out=n)
         measure(f"gemm {case} {M}x{n}x{k}", lambda: K.gemm(a.precision, A, Bm, ep), 2.0 * M * n * k, 24)
         del A, Bm, x, out
-    elif case in ("attn", "attn_q3", "attn_p0", "attn_p4"):
+    elif case.startswith("attn"):
         qkv = torch.randn(M, 3 * D, device=dev).to(dt)
-        v = {"attn": "tc:2", "attn_q3": "q3:2", "attn_p0": "tc:0", "attn_p4": "tc:4"}[case]
+        v = {"attn": "tc:2", "attn_q3": "q3:2", "attn_p0": "tc:0", "attn_p4": "tc:4"}.get(case) or case.split("=")[1]   # attn=q3:1
         measure(f"attention[{v}]", lambda: K.attention(a.precision, qkv, B, N, H, v), 4.0 * B * H * N * N * 64, 24)
         del qkv
     elif case == "ln":

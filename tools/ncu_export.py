@@ -7,16 +7,19 @@ import argparse, csv, io, subprocess
 
 ap = argparse.ArgumentParser()
 ap.add_argument("report"); ap.add_argument("out"); ap.add_argument("--top", type=int, default=30)
+ap.add_argument("--kernel", default="", help="regex on the kernel name (reports holding several kernels)")
 a = ap.parse_args()
-raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+sel = ["--kernel-name", "regex:" + a.kernel] if a.kernel else []
+raw = subprocess.run(["ncu", "-i", a.report, *sel, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 with open(a.out + "_raw.csv", "w") as f:
     w = csv.writer(f)
     for k, unit, v in zip(rows[0], rows[1], rows[2]):
         w.writerow([k, v, unit])
-src = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True, check=True).stdout
+src = subprocess.run(["ncu", "-i", a.report, *sel, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-name, hdr, data = rows[0][1], rows[1], rows[2:]
+name, hdr = rows[0][1], rows[1]
+data = [r for r in rows[2:] if len(r) >= len(hdr) and r[0].startswith("0x")]
 ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 S = lambda r: int(r[ix["# Samples"]])

@@ -7,7 +7,9 @@ range, so that one `ncu --set full --profile-from-start off` run captures them a
 
 Order of the profiled launches (the report's launch index): 0 layernorm, 1 preprocess_u8 (kernel 1), 2 proj GEMM (+LayerScale
 + residual reduction), 3 conv256 (refinenet1 RCU conv at 148 x 148), 4 conv128 (output_conv1 at 296 x 296), 5 convT 4x4 +
-pixel shuffle, 6 convT 2x2 + pixel shuffle, 7 output_conv2 taps GEMM (N = 384), 8 upconv_head, 9 bilinear 148 -> 296, 10 attention.
+pixel shuffle, 6 convT 2x2 + pixel shuffle, 7 output_conv2 taps GEMM (N = 384), 8 upconv_head, 9 bilinear 148 -> 296, 10 attention (the kernel the library
+picks at this size: three query tiles per persistent CTA, attention_q3.cuh), 11 attention, one query tile per CTA
+(attention_tc.cuh), 12 QKV GEMM, 13 FC1 + GELU GEMM, 14 FC2 (+ LayerScale + residual reduction) GEMM.
 """
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -37,6 +39,9 @@ p1 = rn(T, 512).to(dt); wct1 = rn(4 * 512, 512, scale=1 / 22.0).to(dt); bct1 = 0
 wz = rn(384, 128, scale=1 / 11.0).to(dt); z = torch.empty(B, 296, 296, 384, dtype=dt, device=dev)
 hb, hw = 0.1 * rn(32), rn(32, scale=0.2)
 qkv = rn(rows, 3 * D).to(dt)
+ln16 = rn(rows, D).to(dt); wqkv = rn(3 * D, D, scale=D ** -0.5).to(dt); bqkv = 0.1 * rn(3 * D); qkv_out = torch.empty(rows, 3 * D, dtype=dt, device=dev)
+wfc1 = rn(4 * D, D, scale=D ** -0.5).to(dt); bfc1 = 0.1 * rn(4 * D); hid = torch.empty(rows, 4 * D, dtype=dt, device=dev)
+wfc2 = rn(D, 4 * D, scale=(4 * D) ** -0.5).to(dt); bfc2 = 0.1 * rn(D)
 
 
 def run():
@@ -51,6 +56,10 @@ def run():
     K.upconv_head(pr, z, 518, 518, hb, hw, 0.1, 20.0)
     K.bilinear(pr, f148, 296, 296)
     K.attention(pr, qkv, B, 1370, 16)
+    K.attention(pr, qkv, B, 1370, 16, "tc:2")
+    K.gemm(pr, ln16, wqkv, K.epilogue(bias=bqkv, out=qkv_out, ld_out=3 * D))
+    K.gemm(pr, ln16, wfc1, K.epilogue(bias=bfc1, act=1, out=hid, ld_out=4 * D))
+    K.gemm(pr, hid, wfc2, K.epilogue(bias=bfc2, gamma=ls, x=x, accumulate_x=True, ld_out=D))
 
 
 run(); run()
@@ -60,7 +69,8 @@ run()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 # plain timing of the same launches (CUDA events) for the record printed next to the capture
-names = ["layernorm", "preprocess_u8", "proj gemm", "conv256 148^2", "conv128 296^2", "convT4+shuffle", "convT2+shuffle", "taps gemm", "upconv_head", "bilinear 148->296", "attention"]
+names = ["layernorm", "preprocess_u8", "proj gemm", "conv256 148^2", "conv128 296^2", "convT4+shuffle", "convT2+shuffle", "taps gemm", "upconv_head", "bilinear 148->296", "attention (q3)",
+         "attention (tc)", "qkv gemm", "fc1+gelu gemm", "fc2+ls+res gemm"]
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
 fns = [lambda: K.layernorm(pr, x, lw, lb), lambda: K.preprocess_u8(pr, src, 518, 518, want_nchw=False),
        lambda: K.gemm(pr, att, wproj, K.epilogue(bias=bproj, gamma=ls, x=x, accumulate_x=True, ld_out=D)),
@@ -70,7 +80,10 @@ fns = [lambda: K.layernorm(pr, x, lw, lb), lambda: K.preprocess_u8(pr, src, 518,
        lambda: K.gemm(pr, p1, wct1, K.epilogue(bias=bct1, out=l1, ld_out=512, shuffle=(2, 512, 37, 37))),
        lambda: K.gemm(pr, o296.reshape(-1, 128), wz, K.epilogue(out=z, ld_out=384)),
        lambda: K.upconv_head(pr, z, 518, 518, hb, hw, 0.1, 20.0), lambda: K.bilinear(pr, f148, 296, 296),
-       lambda: K.attention(pr, qkv, B, 1370, 16)]
+       lambda: K.attention(pr, qkv, B, 1370, 16), lambda: K.attention(pr, qkv, B, 1370, 16, "tc:2"),
+       lambda: K.gemm(pr, ln16, wqkv, K.epilogue(bias=bqkv, out=qkv_out, ld_out=3 * D)),
+       lambda: K.gemm(pr, ln16, wfc1, K.epilogue(bias=bfc1, act=1, out=hid, ld_out=4 * D)),
+       lambda: K.gemm(pr, hid, wfc2, K.epilogue(bias=bfc2, gamma=ls, x=x, accumulate_x=True, ld_out=D))]
 for i, f in enumerate(fns):
     evs[i].record(); f()
 evs[-1].record(); torch.cuda.synchronize()
