@@ -236,6 +236,10 @@ typedef struct mde_epilogue {
  * lda, ldb multiples of 8; N multiple of 8. */
 int mde_k_gemm(int32_t precision, const void* d_a, int64_t m, int32_t k, int32_t lda, const void* d_b, int32_t n,
                int32_t ldb, const mde_epilogue* ep, void* stream);
+/* Tuning probe (tools/gemm_tiling_probe.py): mde_k_gemm with the tile width (32 / 64 / 128 / 256 columns), the CTA pairing
+ * (1 / 2) and the split-K count (1..16; only residual-reduction epilogues split) forced instead of picked. */
+int mde_k_gemm_tiled(int32_t precision, const void* d_a, int64_t m, int32_t k, int32_t lda, const void* d_b, int32_t n,
+                     int32_t ldb, const mde_epilogue* ep, int32_t block_n, int32_t ctas, int32_t splits, void* stream);
 /* 3x3 / stride 1 / pad 1 convolution, NHWC.  d_in: [B][H][W][cin] 16-bit (cin multiple of 8);
  * d_w: [cout][9*cin_pad] 16-bit with cin_pad = cin rounded up to 64 and K index = (ky*3+kx)*cin_pad + c. */
 int mde_k_conv3x3(int32_t precision, const void* d_in, int32_t batch, int32_t h, int32_t w, int32_t cin,

@@ -187,8 +187,19 @@ static void pick_ctas(GemmOp* op) {
 //     waves x (k-blocks x 4 MMAs x BLOCK_N / 2 clk  +  epilogue  +  fixed cost per tile)
 // and narrower tiles win when they put more SMs to work or cut the last partial wave (FC1: 96 pair tiles on 74 pairs).
 // p.m_tiles and p.num_k_blocks are set; sets op->block_n, op->ctas, p.n_tiles.
+// mde_k_gemm_tiled (a tuning probe, tools/gemm_tiling_probe.py): the next GEMM op of this thread takes the given tile width,
+// pairing and split count instead of the picked ones
+struct TilingOverride { int block_n = 0, ctas = 0, splits = 0; };
+static thread_local TilingOverride g_tiling;
+
 static void pick_tiling(GemmOp* op, int n, bool fused_head, bool whole_wide_tiles = false) {
   GemmParams& p = op->p;
+  if (g_tiling.block_n > 0 && !fused_head) {
+    op->block_n = g_tiling.block_n;
+    op->ctas = g_tiling.ctas == 2 && g_tiling.block_n >= 128 && p.m_tiles >= 2 ? 2 : 1;
+    p.n_tiles = (n + op->block_n - 1) / op->block_n;
+    return;
+  }
   op->block_n = fused_head ? 32 : pick_block_n(n);
   p.n_tiles = (n + op->block_n - 1) / op->block_n;
   pick_ctas(op);
@@ -232,7 +243,10 @@ static int pick_grid(GemmOp* op) {
   pw.kb_per_split = p.num_k_blocks;
   const int units = op->ctas == 2 ? sms / 2 : sms;                                        // CTAs or CTA pairs that can run at once
   const int tiles = op->ctas == 2 ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
-  if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && g_opts.split_k) {
+  if (g_tiling.splits > 1 && p.tma_x) {
+    pw.kb_per_split = (p.num_k_blocks + g_tiling.splits - 1) / g_tiling.splits;
+    pw.splits = (p.num_k_blocks + pw.kb_per_split - 1) / pw.kb_per_split;
+  } else if (p.tma_x && tiles * 2 <= units && p.num_k_blocks >= 16 && g_opts.split_k) {
     // small batch: a handful of tiles on 148 SMs.  Split K so that every SM gets a piece (at least 8 k-blocks each);
     // the reduction epilogue adds the partial products in the L2.  Opt-in (MDE_FLAG_SPLIT_K in mde_engine_desc.flags, part
     // of the engine fingerprint): the fp32 adds happen in arrival order, so results are no longer reproducible bit for bit.
@@ -897,6 +911,20 @@ int mde_k_gemm(int32_t precision, const void* d_a, int64_t m, int32_t k, int32_t
   if (!ep) return fail(MDE_ERR_INVALID, "epilogue description is required");
   GemmOp op;
   MDE_TRY(make_gemm_op(&op, precision, d_a, m, k, lda, d_b, n, ldb, ep));
+  return launch_gemm(op, static_cast<cudaStream_t>(stream));
+}
+
+int mde_k_gemm_tiled(int32_t precision, const void* d_a, int64_t m, int32_t k, int32_t lda, const void* d_b, int32_t n,
+                     int32_t ldb, const mde_epilogue* ep, int32_t block_n, int32_t ctas, int32_t splits, void* stream) {
+  clear_error();
+  if (!ep) return fail(MDE_ERR_INVALID, "epilogue description is required");
+  if ((block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256) || ctas < 1 || ctas > 2 || splits < 1 || splits > 16)
+    return fail(MDE_ERR_INVALID, "gemm_tiled: block_n 32/64/128/256, ctas 1/2, splits 1..16");
+  GemmOp op;
+  g_tiling.block_n = block_n; g_tiling.ctas = ctas; g_tiling.splits = splits;
+  const int rc = make_gemm_op(&op, precision, d_a, m, k, lda, d_b, n, ldb, ep);
+  g_tiling = TilingOverride{};
+  MDE_TRY(rc);
   return launch_gemm(op, static_cast<cudaStream_t>(stream));
 }
 
