@@ -479,20 +479,15 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
   op->poly = 2;      // the measured optimum (tools/attn_sweep.py); engines override it from mde_engine_desc.attn_poly
   // Which kernel: one query tile per CTA, two CTAs per SM (attention_tc.cuh), or three query tiles per persistent CTA
   // (attention_q3.cuh).  At the batch-64 ViT-L shape the two take the same time; the persistent one reads each K / V tile
-  // once for three query tiles (7 % less energy per launch in the first measurement, profiles/r02_energy_per_kernel.txt) and
-  // has no wave structure.  What decides for small and medium problems is the tail: an item of the persistent kernel (three
-  // query tiles over all keys) takes ~1.37x as long as one wave of the other (16.8 vs 23 us at 1370 tokens), so compare
-  //     ceil(CTAs / (2 SMs))   against   1.37 x ceil(items / SMs).
-  // Batch 1 (176 CTAs, 64 items): one wave of small CTAs wins.  VGGT sharded over 8 GPUs (2 frames per rank: 352 CTAs = a
-  // full wave and a 19 %-full one; 128 items = one round): the persistent kernel wins by a third.
+  // once for three query tiles (7 % less energy per launch, profiles/r02_energy_per_kernel.txt), which is what counts inside
+  // the power-capped step.  Its work items are coarse, though (three query tiles over all keys, ~25 us at 1374 tokens), and a
+  // launch takes whole rounds of them: measured at 1374 tokens and 16 heads (profiles/r02b_attention_small_batch.txt) the
+  // one-tile kernel grows smoothly with the batch (48 / 56 / 65 / 108 / 188 us at batch 2 / 3 / 4 / 8 / 16) while the
+  // persistent one steps at every multiple of 148 items (48 / 74 / 76 / 124 / 198 us).  So: the persistent kernel from eight
+  // rounds on, where its last, partly filled round costs less than its shared K / V reads save.
   {
-    const int sms = std::max(1, num_sms());
-    const long long q_tiles = (ntok_q + 127) / 128;
-    const long long ctas = static_cast<long long>(batch) * heads * q_tiles;
-    const long long items = static_cast<long long>(batch) * heads * ((q_tiles + 2) / 3);
-    const double t_tc = static_cast<double>((ctas + 2 * sms - 1) / (2 * sms));
-    const double t_q3 = 1.37 * static_cast<double>((items + sms - 1) / sms);
-    op->kind = t_q3 <= t_tc ? 1 : 0;
+    const long long items = static_cast<long long>(batch) * heads * (((ntok_q + 127) / 128 + 2) / 3);
+    op->kind = items >= 8LL * std::max(1, num_sms()) ? 1 : 0;
   }
   op->counters = nullptr;     // static item schedule unless the owner of the op gives it a work counter (engine.cu)
   MDE_TRY(encode_map(&op->map_kv96, precision, d_kv, 2, dims, str, box96));

@@ -307,9 +307,12 @@ def test_resize_depth_matches_the_scripts_postprocessing(lib, B, h, w, ho, wo):
 
 # ------------------------------------------------------------------------------------------ sharded global attention pieces (one GPU)
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("B,nq,nkv,heads", [(1, 700, 2748, 6), (2, 130, 517, 2), (1, 1374, 1374, 16)])
+@pytest.mark.parametrize("B,nq,nkv,heads", [(1, 700, 2748, 6), (2, 130, 517, 2), (1, 1374, 1374, 16),
+                                            (1, 2748, 21984, 16), (20, 1374, 2748, 16), (24, 1300, 1501, 16)])
 def test_attention_queries_and_keys_from_different_row_sets(lib, prec, B, nq, nkv, heads):
-    """Queries = a rank's tokens, keys/values = everybody's tokens in a gathered [nkv, 2D] k|v buffer."""
+    """Queries = a rank's tokens, keys/values = everybody's tokens in a gathered [nkv, 2D] k|v buffer.  Then 2 of VGGT's
+    16 frames per rank against all 16 (the 8-GPU shape), and two shapes large enough (>= 8 rounds of work items) for the library
+    to pick the persistent three-query-tile kernel with keys from another row set, the second one ragged on both sides."""
     dt = K.TORCH_DT[prec]
     D = heads * 64
     qkv = rnd((B * nq, 3 * D), dt, seed=51)
