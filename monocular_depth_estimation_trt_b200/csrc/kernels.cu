@@ -805,6 +805,7 @@ int launch_preprocess_u8(int precision, const uint8_t* d_src, long long src_batc
                          int src_w, int dst_h, int dst_w, int patch, int kpad, int swap_rb, const float* d_lut,
                          void* d_cols, float* d_nchw, cudaStream_t s, int keep_ratio_pad, const double* pad_rgb) {
   MDE_TRY(check_patch_geometry(dst_h, dst_w, patch, kpad));
+  if (patch > 16) return fail(MDE_ERR_INVALID, "preprocess_u8: patch sizes up to 16, not %d", patch);
   if (src_h < 1 || src_w < 1) return fail(MDE_ERR_INVALID, "preprocess: empty source image");
   PreprocParams p;
   p.src = d_src; p.src_batch_stride = src_batch_stride; p.src_h = src_h; p.src_w = src_w;
