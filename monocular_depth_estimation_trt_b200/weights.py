@@ -230,17 +230,78 @@ def _shape(v):
     return tuple(v.shape)
 
 
+def from_hf_depth_anything(hf_sd: Mapping[str, object]) -> Dict[str, object]:
+    """transformers' `DepthAnythingForDepthEstimation` key set (the `*-hf` checkpoints on the hub, e.g.
+    depth-anything/Depth-Anything-V2-Small-hf) -> the upstream key names models/depth_anything_v2/infer.py:62-63 loads and
+    the engine takes: separate query / key / value projections are stacked into `attn.qkv`, `neck.fusion_stage.layers.k` is
+    `refinenet{4-k}`, `neck.reassemble_stage.layers.i` the `projects` / `resize_layers` pair, `head.conv1..3` the output convs.
+    Tensors are passed through untouched (torch or numpy); tests/test_weights.py pins the mapping on transformers' own forward."""
+    import numpy as np
+
+    def cat(parts):
+        if hasattr(parts[0], "detach"):
+            import torch
+            return torch.cat(list(parts), dim=0)
+        return np.concatenate([np.asarray(p_) for p_ in parts], axis=0)
+
+    g = hf_sd.__getitem__
+    o = {}
+    e = "backbone.embeddings."
+    o["pretrained.cls_token"], o["pretrained.pos_embed"] = g(e + "cls_token"), g(e + "position_embeddings")
+    if e + "mask_token" in hf_sd:
+        o["pretrained.mask_token"] = g(e + "mask_token")
+    o["pretrained.patch_embed.proj.weight"], o["pretrained.patch_embed.proj.bias"] = g(e + "patch_embeddings.projection.weight"), g(e + "patch_embeddings.projection.bias")
+    layers = sorted({int(k.split(".")[3]) for k in hf_sd if k.startswith("backbone.encoder.layer.")})
+    if not layers:
+        raise ValueError("[MDET] not a transformers DepthAnything state dict: no 'backbone.encoder.layer.*' tensors")
+    for i in layers:
+        p_, q = f"pretrained.blocks.{i}.", f"backbone.encoder.layer.{i}."
+        for n in ("norm1", "norm2"):
+            o[p_ + n + ".weight"], o[p_ + n + ".bias"] = g(q + n + ".weight"), g(q + n + ".bias")
+        o[p_ + "attn.qkv.weight"] = cat([g(q + f"attention.attention.{n}.weight") for n in ("query", "key", "value")])
+        o[p_ + "attn.qkv.bias"] = cat([g(q + f"attention.attention.{n}.bias") for n in ("query", "key", "value")])
+        o[p_ + "attn.proj.weight"], o[p_ + "attn.proj.bias"] = g(q + "attention.output.dense.weight"), g(q + "attention.output.dense.bias")
+        o[p_ + "ls1.gamma"], o[p_ + "ls2.gamma"] = g(q + "layer_scale1.lambda1"), g(q + "layer_scale2.lambda1")
+        for n in ("fc1", "fc2"):
+            o[p_ + f"mlp.{n}.weight"], o[p_ + f"mlp.{n}.bias"] = g(q + f"mlp.{n}.weight"), g(q + f"mlp.{n}.bias")
+    o["pretrained.norm.weight"], o["pretrained.norm.bias"] = g("backbone.layernorm.weight"), g("backbone.layernorm.bias")
+    h = "depth_head."
+    for i in range(4):
+        o[h + f"projects.{i}.weight"] = g(f"neck.reassemble_stage.layers.{i}.projection.weight")
+        o[h + f"projects.{i}.bias"] = g(f"neck.reassemble_stage.layers.{i}.projection.bias")
+        if i != 2:
+            o[h + f"resize_layers.{i}.weight"] = g(f"neck.reassemble_stage.layers.{i}.resize.weight")
+            o[h + f"resize_layers.{i}.bias"] = g(f"neck.reassemble_stage.layers.{i}.resize.bias")
+        o[h + f"scratch.layer{i + 1}_rn.weight"] = g(f"neck.convs.{i}.weight")
+        r, f = h + f"scratch.refinenet{i + 1}.", f"neck.fusion_stage.layers.{3 - i}."
+        o[r + "out_conv.weight"], o[r + "out_conv.bias"] = g(f + "projection.weight"), g(f + "projection.bias")
+        for u, hu in (("resConfUnit1", "residual_layer1"), ("resConfUnit2", "residual_layer2")):
+            for cv, hc in (("conv1", "convolution1"), ("conv2", "convolution2")):
+                o[r + f"{u}.{cv}.weight"], o[r + f"{u}.{cv}.bias"] = g(f + f"{hu}.{hc}.weight"), g(f + f"{hu}.{hc}.bias")
+    o[h + "scratch.output_conv1.weight"], o[h + "scratch.output_conv1.bias"] = g("head.conv1.weight"), g("head.conv1.bias")
+    o[h + "scratch.output_conv2.0.weight"], o[h + "scratch.output_conv2.0.bias"] = g("head.conv2.weight"), g("head.conv2.bias")
+    o[h + "scratch.output_conv2.2.weight"], o[h + "scratch.output_conv2.2.bias"] = g("head.conv3.weight"), g("head.conv3.bias")
+    return o
+
+
 def export_checkpoint(checkpoint_path: str, out_path: str, input_h: int = 518, input_w: int = 518,
                       max_depth: float | None = None) -> dict:
     """Stage `export` for an upstream checkpoint (models/depth_anything_v2/infer.py:62-63:
-    `model.load_state_dict(torch.load(f"checkpoints/depth_anything_v2_{encoder}.pth"))`): read the .pth, keep the
-    tensors the engine needs under their upstream key names, write the .mdew file.  `max_depth` None = the relative
+    `model.load_state_dict(torch.load(f"checkpoints/depth_anything_v2_{encoder}.pth"))`) or its transformers twin
+    (`model.safetensors` / `pytorch_model.bin` of a `*-hf` repository, key names mapped by `from_hf_depth_anything`): read the
+    file, keep the tensors the engine needs under their upstream key names, write the .mdew file.  `max_depth` None = the relative
     model, 20 / 80 = the metric Hypersim / VKITTI heads (infer_metric.py:61-65).  Returns the stored description."""
     import torch
-    sd = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+    if checkpoint_path.endswith(".safetensors"):          # the hub's `*-hf` repositories ship model.safetensors
+        from safetensors.torch import load_file
+        sd = load_file(checkpoint_path, device="cpu")
+    else:
+        sd = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
     if isinstance(sd, dict) and "state_dict" in sd and "pretrained.cls_token" not in sd:
         sd = sd["state_dict"]
     sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    if "backbone.embeddings.cls_token" in sd:             # transformers' key names
+        sd = from_hf_depth_anything(sd)
     enc = encoder_of(sd)
     keep = {k: v for k, v in sd.items() if k.startswith(("pretrained.", "depth_head."))}
     meta = describe(enc, input_h, input_w, max_depth)

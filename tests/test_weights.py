@@ -72,3 +72,46 @@ def test_export_from_an_upstream_style_checkpoint(tmp_path, lib):
     assert W.encoder_of(O.init_state_dict("vitb", seed=1)) == "vitb"
     with pytest.raises(ValueError):
         W.encoder_of({"foo": torch.zeros(1)})
+
+
+def test_export_from_a_transformers_checkpoint(tmp_path, lib):
+    """SURVEY 8 f-2 on a REAL key set: transformers' DepthAnythingForDepthEstimation (what the hub's `*-hf` repositories
+    hold) with its own random init, saved the way `save_pretrained` does (model.safetensors) -> `export_checkpoint` ->
+    .mdew under upstream's key names -> the oracle's forward of THOSE tensors equals transformers' forward of the model
+    they came from (the key mapping, the q|k|v stacking and the refinenet order are pinned by an independent
+    implementation), and the engine description / native loader accept the file."""
+    pytest.importorskip("transformers")
+    from safetensors.torch import save_file
+    import hf_bridge as H
+    torch.manual_seed(11)
+    m = H.hf_model("vits", 20.0)
+    with torch.no_grad():                      # a fresh init leaves LayerScale at 1 and biases at 0: make every tensor matter
+        for k, v in m.state_dict().items():
+            if v.dtype.is_floating_point and ("lambda1" in k or k.endswith(".bias")):
+                v.add_(0.05 * torch.randn_like(v))
+    hf_sd = {k: v.contiguous() for k, v in m.state_dict().items()}
+    ck = tmp_path / "model.safetensors"
+    save_file(hf_sd, str(ck))
+    out = str(tmp_path / "hf.mdew")
+    meta = W.export_checkpoint(str(ck), out, 518, 518, max_depth=20.0)
+    assert meta["encoder"] == "vits" and meta["max_depth"] == 20.0
+    back, meta2 = W.load(out)
+    assert set(back) - {"pretrained.mask_token"} == set(O.init_state_dict("vits", seed=0)) - {"pretrained.mask_token"}
+    sd = {k: torch.from_numpy(v) for k, v in back.items()}
+    x = torch.randn(1, 3, 518, 518, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = m(pixel_values=x).predicted_depth
+    got = O.forward(sd, x, "vits", max_depth=20.0)
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-6)).max().item()
+    assert rel < 5e-5, rel
+    # the inverse of the test helper that pins the oracle: to_hf(from_hf(x)) is the identity on the tensors the model uses
+    again = H.to_hf(W.from_hf_depth_anything(hf_sd), "vits")
+    assert all(torch.equal(again[k], hf_sd[k]) for k in again) and set(again) <= set(hf_sd)
+    eng = E.Engine(E.make_desc(meta2), meta2)
+    eng.load_weights_file(out)
+    eng.close()
+    with pytest.raises(ValueError):
+        W.from_hf_depth_anything({"backbone.embeddings.cls_token": torch.zeros(1, 1, 384),
+                                  "backbone.embeddings.position_embeddings": torch.zeros(1, 1370, 384),
+                                  "backbone.embeddings.patch_embeddings.projection.weight": torch.zeros(1),
+                                  "backbone.embeddings.patch_embeddings.projection.bias": torch.zeros(1)})
