@@ -266,6 +266,34 @@ def test_whole_model_against_the_oracle(lib, prec):
         assert worst["abs_rel"] <= 2e-3 and worst["max_rel"] <= 1e-2, worst
 
 
+def test_whole_model_at_the_released_width(lib):
+    """BASELINE.json configs[4] at the model's own widths -- ViT-L trunk with registers, 24 + 24 aggregator blocks, 256-feature
+    DPT head on the (4, 11, 17, 23) taps -- on TWO frames (the oracle's fp32 forward takes ~20 s on the host cores; 16 frames
+    would take minutes), seeded init as it is: the log-depth head of the uncalibrated model spreads the depths over 0.07 .. 4."""
+    from monocular_depth_estimation_trt_b200 import common
+    import refsetup as R
+    from oracle import preprocess_np as PP
+    taps = (4, 11, 17, 23)
+    sd = V.init_vggt("vitl", depth=24, features=256, out_channels=(256, 512, 1024, 1024), seed=0)
+    imgs = torch.cat([torch.from_numpy(PP.preprocess_square_pad_cubic(
+        np.random.default_rng(i).integers(0, 256, (480, 640, 3), dtype=np.uint8), 518, 518))[0] for i in range(2)])
+    ref = V.vggt_depth(sd, imgs, "vitl", 24, taps)
+    assert float(ref.min()) > 0.01 and float(ref.std() / ref.mean()) > 0.2          # a non-degenerate map
+    with P.VGGTEngine(sd, encoder="vitl", depth=24, features=256, out_channels=(256, 512, 1024, 1024), taps=taps, frames=2,
+                      precision="fp16") as engine, engine.create_execution_context() as context:
+        inputs, outputs, bindings, stream = common.allocate_buffers(engine)
+        inputs[0].host = imgs.numpy()
+        out = common.do_inference(context, engine=engine, bindings=bindings, inputs=inputs, outputs=outputs, stream=stream)
+        got = out[0].reshape(2, 518, 518).copy()
+        common.free_buffers(inputs, outputs, stream)
+    worst = {"abs_rel": 0.0, "max_rel": 0.0}
+    for s_ in range(2):
+        m = R.compare_depth(ref[s_].numpy(), got[s_])
+        worst = {k: max(worst[k], m[k]) for k in worst}
+    print("vggt ViT-L 24+24 fp16", worst)
+    assert worst["abs_rel"] <= 2e-3 and worst["max_rel"] <= 1e-2, worst
+
+
 def test_streamvggt_whole_model_stream_equals_causal_forward(lib):
     """models/streamvggt as an engine: (a) `causal=True` over the S frames of a scene against the oracle's causal forward
     (north_star's gate); (b) the streaming engine (one frame per execute, cached keys / values): depth map t of the stream is
