@@ -84,7 +84,7 @@ struct mde_engine {
 namespace {
 
 struct Op {
-  enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, UPCONV_HEAD, RESIZE_DEPTH, SNAPSHOT } kind;
+  enum Kind { PREPROC_U8, IM2COL_F32, CLS_ROW, GEMM, LAYERNORM, ATTENTION, BILINEAR, IM2COL_S2, UPCONV_HEAD, RESIZE_DEPTH, SNAPSHOT, JOIN } kind;
   GemmOp g;
   AttnOp attn;
   // generic scalar/pointer slots for the small kernels
@@ -94,6 +94,8 @@ struct Op {
   long long rows = 0;
   int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
   int block = -1;   // encoder block this op belongs to (SNAPSHOT ops)
+  int branch = 0;   // 0: the caller's stream; 1..3: a side stream forked from it (small batches: the DPT reassemble stage's four
+                    // independent project -> resize -> layer_rn chains run side by side, see enqueue_impl)
   std::string label;   // what the launch is, for per-op timing reports
   double flops = 0.0;  // algorithmic FLOPs (2*MACs, logical sizes, no padding)
   double bytes = 0.0;  // algorithmic bytes (operands read once + result written once)
@@ -117,6 +119,8 @@ struct mde_context {
   // The launch sequence is captured into a CUDA graph the first time it runs with a given set of bindings and replayed
   // afterwards: one cudaGraphLaunch instead of ~165 kernel launches (what dominates a batch-1 forward on the host side).
   unsigned int* attn_counters = nullptr;   // [depth][2], see mde_context_create
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // forked branches of the plan (Op::branch 1..3)
+  cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
   cudaGraphExec_t graph_exec = nullptr;
   unsigned long long graph_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool graph_failed = false;
@@ -514,6 +518,7 @@ struct Planner {
   int rc = MDE_OK;
   bool dry;            // dry run: only add up the workspace bytes
   int64_t bytes = 0;
+  int branch = 0;      // stamped on every op pushed while it is set
 
   // One arena per context, bump-allocated with LIFO scopes: a tensor lives from its alloc() to the release() of the scope it
   // was allocated in, so the encoder's temporaries, the reassemble stage, each RefineNet level and the tail share memory
@@ -547,6 +552,7 @@ struct Planner {
     op.label = buf;
     op.flops = 2.0 * static_cast<double>(m) * n_real * k_real;
     op.bytes = 2.0 * (static_cast<double>(m) * k_real + static_cast<double>(n_real) * k_real) + epilogue_bytes(ep, static_cast<double>(m) * n_real);
+    op.branch = branch;
     if (rc == MDE_OK) c->plan.push_back(op);
   }
   void conv(const char* what, const void* in, int B, int H, int W, int cin, const void* w, int cout, const mde_epilogue& ep) {
@@ -559,6 +565,7 @@ struct Planner {
     const double px = static_cast<double>(B) * H * W;
     op.flops = 2.0 * px * cout * 9.0 * cin + (ep.d_head_w ? 2.0 * px * 32 : 0.0);
     op.bytes = 2.0 * (px * cin + 9.0 * cin * cout) + (ep.d_head_w ? 4.0 * px : epilogue_bytes(ep, px * cout));
+    op.branch = branch;
     if (rc == MDE_OK) c->plan.push_back(op);
   }
   static double epilogue_bytes(const mde_epilogue& ep, double elems) {
@@ -576,6 +583,7 @@ struct Planner {
     c->plan.back().label = label;
     c->plan.back().bytes = bytes;
     c->plan.back().flops = flops;
+    c->plan.back().branch = branch;
   }
 };
 
@@ -683,8 +691,14 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   // ---- DPT reassemble
   const int gh = e->gh, gw = e->gw;
   const int64_t reassemble_scope = pl.mark();     // projections, resized maps and the stride-2 gather die with the layer_rn convs
+  // Small batches: the four chains project -> resize -> layer_rn share nothing but their inputs' producer (every temporary
+  // below has its own arena range until the scope is released) and each fills a fraction of the SMs, so they run side by
+  // side: chain 3 (stride-2 gather + K = 9 * oc[3] GEMM, the longest) on the caller's stream, chains 0-2 on side streams.
+  const bool fork = rows <= 4LL * NT;
+  auto branch_of = [&](int i) { return fork && i < 3 ? i + 1 : 0; };
   void* l[4];
   for (int i = 0; i < 4; ++i) {
+    pl.branch = branch_of(i);
     void* pr = pl.alloc16(prow * oc[i]);
     mde_epilogue ep = ep_zero(); ep.d_bias = e->proj_b[i]; ep.d_out = pr; ep.ld_out = oc[i];
     pl.gemm("projects", tap[i], prow, D, D, e->proj_w[i], oc[i], D, ep);
@@ -708,11 +722,28 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
   }
   // ---- layer_rn: raw r_i (residual of the first RCU) and relu(r_i) (input of its first conv)
   for (int i = 0; i < 4; ++i) {
+    pl.branch = branch_of(i);
     mde_epilogue ep = ep_zero(); ep.d_out = r[i]; ep.d_out_relu = r_relu[i]; ep.ld_out = F;
     pl.conv("layer_rn", l[i], B, e->lvl_h[i], e->lvl_w[i], oc[i], e->rn_w[i], F, ep);
   }
+  pl.branch = 0;
+  if (fork) { Op j; j.kind = Op::JOIN; pl.push(j, "join"); }
   pl.release(reassemble_scope);
   // ---- RefineNets 4 -> 1
+  // Small batches: the first convolution of levels 2, 1 and 0 (RCU1.conv1 on relu(r_i)) needs nothing from the level above
+  // it; the three run on the side streams beside level 3's chain and rejoin before level 2 adds `path`.  Their outputs then
+  // live outside the per-level scopes (which alias one another).
+  void* a_early[3] = {nullptr, nullptr, nullptr};
+  if (fork) {
+    for (int i = 2; i >= 0; --i) {
+      const long long px = static_cast<long long>(B) * e->lvl_h[i] * e->lvl_w[i];
+      a_early[i] = pl.alloc16(px * F);
+      pl.branch = i + 1;
+      mde_epilogue ep = ep_zero(); ep.d_bias = e->refine[i].rcu1.b1; ep.act = 2; ep.d_out = a_early[i]; ep.ld_out = F;
+      pl.conv("rcu1.conv1", r_relu[i], B, e->lvl_h[i], e->lvl_w[i], F, e->refine[i].rcu1.w1, F, ep);
+    }
+    pl.branch = 0;
+  }
   void* path = nullptr;   // output of the previous fusion block, already at this level's resolution
   for (int i = 3; i >= 0; --i) {
     const int H = e->lvl_h[i], W = e->lvl_w[i];
@@ -726,10 +757,16 @@ int build_plan(mde_context* c, mde_engine* e, bool dry, int64_t* bytes_out) {
       // s = path + RCU1(r_i) = conv2(relu(conv1(relu(r_i)))) + r_i + path
       void* s = pl.alloc16(px * F);
       void* sr = pl.alloc16(px * F);
-      { mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu1.b1; ep.act = 2; ep.d_out = a; ep.ld_out = F;
-        pl.conv("rcu1.conv1", r_relu[i], B, H, W, F, rf.rcu1.w1, F, ep); }
+      const void* a1 = a;
+      if (fork) {
+        a1 = a_early[i];
+        if (i == 2) { Op j; j.kind = Op::JOIN; pl.push(j, "join"); }
+      } else {
+        mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu1.b1; ep.act = 2; ep.d_out = a; ep.ld_out = F;
+        pl.conv("rcu1.conv1", r_relu[i], B, H, W, F, rf.rcu1.w1, F, ep);
+      }
       { mde_epilogue ep = ep_zero(); ep.d_bias = rf.rcu1.b2; ep.d_res1 = r[i]; ep.d_res2 = path; ep.d_out = s; ep.d_out_relu = sr; ep.ld_out = F;
-        pl.conv("rcu1.conv2+res", a, B, H, W, F, rf.rcu1.w2, F, ep); }
+        pl.conv("rcu1.conv2+res", a1, B, H, W, F, rf.rcu1.w2, F, ep); }
       s_relu = sr; s_raw = s;
     }
     // u = RCU2(s)
@@ -823,6 +860,18 @@ extern "C" int mde_context_create(mde_engine* e, mde_context** out) {
     else c->attn_counters = static_cast<unsigned int*>(cnt);
   }
   if (rc == MDE_OK) rc = build_plan(c, e, false, &bytes);
+  if (rc == MDE_OK) {
+    bool any = false;
+    for (const Op& op : c->plan) any = any || op.branch > 0;
+    if (any) {       // side streams + events of the forked branches (non-blocking: they only ever synchronise through the events)
+      cudaError_t err = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming);
+      for (int b = 0; b < 3 && err == cudaSuccess; ++b) {
+        err = cudaStreamCreateWithFlags(&c->side[b], cudaStreamNonBlocking);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->join_ev[b], cudaEventDisableTiming);
+      }
+      if (err != cudaSuccess) rc = fail(MDE_ERR_CUDA, "side streams of the plan: %s", cudaGetErrorString(err));
+    }
+  }
   if (rc != MDE_OK) {
     std::string msg = mde_last_error();
     mde_context_destroy(c);
@@ -839,6 +888,11 @@ extern "C" void mde_context_destroy(mde_context* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   for (void* p : c->allocs) cudaFree(p);
   for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
+  for (int b = 0; b < 3; ++b) {
+    if (c->side[b]) cudaStreamDestroy(c->side[b]);
+    if (c->join_ev[b]) cudaEventDestroy(c->join_ev[b]);
+  }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   delete c;
 }
 
@@ -884,7 +938,7 @@ extern "C" int mde_context_snapshot_block(mde_context* c, int32_t block) {
 extern "C" int mde_context_launches_per_enqueue(const mde_context* c) {
   if (!c) return 0;
   int n = 0;
-  for (const Op& op : c->plan) n += op.kind != Op::SNAPSHOT;
+  for (const Op& op : c->plan) n += op.kind != Op::SNAPSHOT && op.kind != Op::JOIN;
   return n;
 }
 
@@ -921,9 +975,39 @@ static int enqueue_impl(mde_context* c, cudaStream_t s, bool timed) {
   const mde_engine_desc& d = e->d;
   const int prec = d.precision;
   size_t ev = 0;
+  cudaStream_t main_stream = s;
+  bool forked = false;
+  bool used[3] = {false, false, false};
   for (Op& op : c->plan) {
+    s = main_stream;
+    // per-op timing keeps everything on one stream (the events bracket single launches); so does a context without side streams
+    const bool branches = !timed && c->side[0] != nullptr;
+    if (op.kind == Op::JOIN) {          // the side branches rejoin the caller's stream: what follows reads their results
+      if (branches && forked) {
+        for (int b = 0; b < 3; ++b) {
+          if (!used[b]) continue;
+          MDE_CUDA_TRY(cudaEventRecord(c->join_ev[b], c->side[b]));
+          MDE_CUDA_TRY(cudaStreamWaitEvent(main_stream, c->join_ev[b], 0));
+          used[b] = false;
+        }
+        forked = false;
+      }
+      continue;
+    }
+    if (branches && op.branch > 0) {
+      if (!forked) {       // everything enqueued so far happens before the branches
+        MDE_CUDA_TRY(cudaEventRecord(c->fork_ev, main_stream));
+        forked = true;
+      }
+      if (!used[op.branch - 1]) {
+        MDE_CUDA_TRY(cudaStreamWaitEvent(c->side[op.branch - 1], c->fork_ev, 0));
+        used[op.branch - 1] = true;
+      }
+      s = c->side[op.branch - 1];
+    }
     if (timed && op.kind != Op::SNAPSHOT) MDE_CUDA_TRY(cudaEventRecord(c->events[ev++], s));
     switch (op.kind) {
+      case Op::JOIN: break;
       case Op::PREPROC_U8:
         MDE_TRY(launch_preprocess_u8(prec, static_cast<const uint8_t*>(c->d_input), static_cast<long long>(c->src_h) * c->src_w * 3,
                                      d.batch, c->src_h, c->src_w, d.input_h, d.input_w, d.patch_size, e->kpad, d.swap_rb, e->lut,
@@ -1076,7 +1160,7 @@ extern "C" int mde_context_op_info(const mde_context* c, int32_t i, char* label,
   if (!c || !label || label_capacity < 1 || !flops || !bytes) return fail(MDE_ERR_INVALID, "bad argument to mde_context_op_info");
   int k = 0;
   for (const Op& op : c->plan) {
-    if (op.kind == Op::SNAPSHOT) continue;
+    if (op.kind == Op::SNAPSHOT || op.kind == Op::JOIN) continue;
     if (k++ == i) {
       snprintf(label, static_cast<size_t>(label_capacity), "%s", op.label.c_str());
       *flops = op.flops;
