@@ -35,23 +35,25 @@ constexpr int kAq3QBytes = 128 * 64 * 2;
 constexpr int kAq3KvBytes = kAq3Keys * 64 * 2;
 constexpr int kAq3Stages = 4;
 constexpr int kAq3TileCols = 160;
-constexpr int kAq3SmemBytes = 3 * kAq3QBytes + 2 * kAq3Stages * kAq3KvBytes + 512;   // 147 968 B
+constexpr int kAq3OutBytes = 12 * 32 * 128;       // per softmax warp: 32 output rows of 128 bytes, staged for coalesced stores
+constexpr int kAq3SmemBytes = 3 * kAq3QBytes + 2 * kAq3Stages * kAq3KvBytes + kAq3OutBytes + 512;   // 197 120 B
 
 // kTrace: clock64 stamps into p.trace [CTA][16 rows][256 slots] (tools/attn_q3_trace.py): rows 0-11 the softmax warps (per key
-// tile: S available, S in registers, exponentials done, P announced; per item: O available, O stored), rows 12-14 the MMA
+// tile: S available, S in registers, exponentials done, P announced; per item: O available, O in registers, O staged, O stored), rows 12-14 the MMA
 // threads' issue times of query tile 0-2 (S(0), PV(0), S(1), ...), row 15 the producer (per item: fetched, Q requested, K/V done).
 constexpr int kAq3TraceRows = 16, kAq3TraceSlots = 256;
 template <typename T, int kPoly, bool kTrace = false>
 __global__ void __launch_bounds__(kAq3Threads, 1)
-attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttnParams p,
-                    unsigned int* __restrict__ counters) {
+attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                    const __grid_constant__ CUtensorMap map_out, const AttnParams p, unsigned int* __restrict__ counters) {
   using Tr = F16Traits<T>;
   extern __shared__ __align__(1024) uint8_t aq3_smem[];
   if ((smem_u32(aq3_smem) & 1023u) != 0) __trap();
   uint8_t* sQ = aq3_smem;
   uint8_t* sK = sQ + 3 * kAq3QBytes;
   uint8_t* sV = sK + kAq3Stages * kAq3KvBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAq3Stages * kAq3KvBytes);
+  uint8_t* sO = sV + kAq3Stages * kAq3KvBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + kAq3OutBytes);
   uint64_t* q_full = bars;                        // [3]  Q tile of the item loaded
   uint64_t* q_empty = q_full + 3;                 // [3]  every S of the item computed: Q may be replaced
   uint64_t* k_full = q_empty + 3;                 // [stages]
@@ -95,6 +97,7 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 12 && lane == 0) {
     prefetch_tmap(&map_q);
     prefetch_tmap(&map_kv);
+    prefetch_tmap(&map_out);
     for (int t = 0; t < 3; ++t) {
       mbar_init(&q_full[t], 1); mbar_init(&q_empty[t], 1); mbar_init(&s_full[t], 1); mbar_init(&p_ready[t], 128);
       mbar_init(&o_full[t], 1); mbar_init(&o_free[t], 128);
@@ -301,21 +304,36 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&o_free[t]);
+      if (lane == 0) stamp(warp, 0);
+      // Thread = row: a warp-wide 16-byte global store touches 32 rows 2 KB apart, and even regrouped into whole rows the
+      // eight stores of a warp took ~2000 clk in which the softmax warp issued nothing and the next item's first S waited
+      // (clock64 trace, profiles/r02_attention_q3_traces.txt).  Instead: the 32 rows go into a 4 KB stage in the 128-byte
+      // swizzle of the output's tensor map ({D, queries of the image, image}, 64 x 32 boxes: rows past the image's last
+      // query are clipped by the copy engine) and ONE bulk tensor store takes them from there, asynchronously.
       const float inv = 1.0f / l_run;
-      const int qrow = (3 * g + t) * 128 + r;
-      if (qrow < p.ntok_q) {
-        T* gout = static_cast<T*>(p.out) + (static_cast<long long>(img) * p.ntok_q + qrow) * p.D + head * 64;
+      uint8_t* stage = sO + warp * (32 * 128);
+      if (na > 1) {                           // the previous item's store has finished READING the stage
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 v;
-            v.x = Tr::pack2(__uint_as_float(o[h][c * 8 + 0]) * inv, __uint_as_float(o[h][c * 8 + 1]) * inv);
-            v.y = Tr::pack2(__uint_as_float(o[h][c * 8 + 2]) * inv, __uint_as_float(o[h][c * 8 + 3]) * inv);
-            v.z = Tr::pack2(__uint_as_float(o[h][c * 8 + 4]) * inv, __uint_as_float(o[h][c * 8 + 5]) * inv);
-            v.w = Tr::pack2(__uint_as_float(o[h][c * 8 + 6]) * inv, __uint_as_float(o[h][c * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(gout + h * 32 + c * 8) = v;
-          }
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = Tr::pack2(__uint_as_float(o[h][c * 8 + 0]) * inv, __uint_as_float(o[h][c * 8 + 1]) * inv);
+          v.y = Tr::pack2(__uint_as_float(o[h][c * 8 + 2]) * inv, __uint_as_float(o[h][c * 8 + 3]) * inv);
+          v.z = Tr::pack2(__uint_as_float(o[h][c * 8 + 4]) * inv, __uint_as_float(o[h][c * 8 + 5]) * inv);
+          v.w = Tr::pack2(__uint_as_float(o[h][c * 8 + 6]) * inv, __uint_as_float(o[h][c * 8 + 7]) * inv);
+          const int chunk = h * 4 + c;                                   // 16-byte chunk of this thread's row
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
+        }
+      fence_proxy_async_smem();               // the generic-proxy writes above are visible to the bulk copy
+      __syncwarp();
+      if (lane == 0) stamp(warp, 0);
+      if (lane == 0) {
+        tma_store_3d(&map_out, stage, head * 64, (3 * g + t) * 128 + wq * 32, img);
+        bulk_commit();
       }
       if (lane == 0) stamp(warp, 0);
     }
@@ -415,6 +433,7 @@ attention_q3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     else issuer(integral_constant<int, 2>{});
   }
 
+  if (warp < 12 && lane == 0) bulk_wait0();    // this warp's output stores have landed before its shared memory goes away
   tc_fence_before();
   __syncthreads();
   if (warp == 13) {

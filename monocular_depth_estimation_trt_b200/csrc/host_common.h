@@ -63,6 +63,7 @@ struct AttnOp {
   alignas(64) CUtensorMap map_qkv;   // 128-row boxes: query tiles
   alignas(64) CUtensorMap map_kv128; // key/value source with 128-row boxes (the same tensor as map_qkv for self-attention)
   alignas(64) CUtensorMap map_kv96;  // the same source with 96-row boxes (attention_q3.cuh)
+  alignas(64) CUtensorMap map_out3;  // the output as {D, queries per image, images} with 64 x 32 x 1 boxes (attention_q3.cuh's bulk stores)
   const void* qkv;
   void* out;
   int batch, ntok, heads, precision;

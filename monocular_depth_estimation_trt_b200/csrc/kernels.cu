@@ -491,6 +491,13 @@ int make_attention_op_kv(AttnOp* op, int precision, const void* d_q, int ldq, co
   }
   op->counters = nullptr;     // static item schedule unless the owner of the op gives it a work counter (engine.cu)
   MDE_TRY(encode_map(&op->map_kv96, precision, d_kv, 2, dims, str, box96));
+  {
+    const int D = heads * 64;
+    cuuint64_t odims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(ntok_q), static_cast<cuuint64_t>(batch)};
+    cuuint64_t ostr[2] = {static_cast<cuuint64_t>(D) * 2, static_cast<cuuint64_t>(ntok_q) * D * 2};
+    cuuint32_t obox[3] = {64, 32, 1};
+    MDE_TRY(encode_map(&op->map_out3, precision, d_out, 3, odims, ostr, obox));
+  }
   return encode_map(&op->map_kv128, precision, d_kv, 2, dims, str, box128);
 }
 
@@ -551,7 +558,7 @@ static int launch_attention_q3_t(const AttnOp& op, cudaStream_t s) {
   const long long items = static_cast<long long>(op.batch) * op.heads * ((q_tiles + 2) / 3);
   if (items > 0x3fffffffLL) return fail(MDE_ERR_INVALID, "attention: too many work items");
   dim3 grid(static_cast<unsigned>(std::min<long long>(items, num_sms())));
-  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAq3Threads), kAq3SmemBytes, s, 1, op.map_qkv, op.map_kv96, p, op.counters));
+  MDE_CUDA_TRY(launch_pdl(kern, grid, dim3(kAq3Threads), kAq3SmemBytes, s, 1, op.map_qkv, op.map_kv96, op.map_out3, p, op.counters));
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
@@ -565,7 +572,7 @@ static int launch_attention_q3_trace_t(const AttnOp& op, long long* d_trace, cud
   p.scale_log2 = 0.125f * 1.44269504088896340736f;
   const int q_tiles = (op.ntok_q + 127) / 128;
   const long long items = static_cast<long long>(op.batch) * op.heads * ((q_tiles + 2) / 3);
-  kern<<<static_cast<unsigned>(std::min<long long>(items, num_sms())), kAq3Threads, kAq3SmemBytes, s>>>(op.map_qkv, op.map_kv96, p, op.counters);
+  kern<<<static_cast<unsigned>(std::min<long long>(items, num_sms())), kAq3Threads, kAq3SmemBytes, s>>>(op.map_qkv, op.map_kv96, op.map_out3, p, op.counters);
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }

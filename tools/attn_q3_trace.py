@@ -32,7 +32,7 @@ for cta in (0, 77):
         print(f"  softmax warp {w} (per key tile: S available, S in regs, exps done, P announced):")
         for j in range(6):
             print("     ", r[4 * j:4 * j + 4].tolist())
-    per_item = 4 * nkv + 2
+    per_item = 4 * nkv + 4
     w0 = tr[cta, 0]
     n_items = int((w0 > 0).sum()) // per_item
     ends = [int(w0[(i + 1) * per_item - 1] - t0) for i in range(min(n_items, 4))]

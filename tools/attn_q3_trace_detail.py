@@ -7,7 +7,7 @@ cta = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 it = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 t0 = tr[cta, 15, 0]
 nkv = 15
-per = 4 * nkv + 2
+per = 4 * nkv + 4
 m = [tr[cta, 12 + t, it * 2 * nkv:(it + 1) * 2 * nkv] - t0 for t in range(3)]
 for j in range(3, 6):
     print('j', j, 'S issued', [int(m[t][2 * j]) for t in range(3)], 'PV issued', [int(m[t][2 * j + 1]) for t in range(3)])
