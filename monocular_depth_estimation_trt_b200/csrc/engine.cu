@@ -522,7 +522,7 @@ struct Planner {
 
   // One arena per context, bump-allocated with LIFO scopes: a tensor lives from its alloc() to the release() of the scope it
   // was allocated in, so the encoder's temporaries, the reassemble stage, each RefineNet level and the tail share memory
-  // (ViT-L, batch 64: 12.8 GiB instead of 19.8 GiB with one allocation per tensor).  The dry run makes the same calls with a
+  // (ViT-L, batch 64: 10.9 GiB instead of 19.8 GiB with one allocation per tensor).  The dry run makes the same calls with a
   // null arena and only records the high-water mark; named buffers (mde_context_get_buffer) live outside every scope.
   char* arena = nullptr;
   int64_t top = 0;
