@@ -192,6 +192,13 @@ int mde_k_preprocess_u8_pad(int32_t precision, const uint8_t* d_src, int32_t bat
  * binding [1, S, 3, H, W] of models/vggt/spec.json with B = S frames). */
 int mde_k_preprocess_u8_square_pad_cubic(const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w,
                                          int32_t swap_rb, int32_t pad_value, float* d_nchw, void* stream);
+/* Depth-Anything-AC `native` profile (core/preprocess.py:470-476 `da_ac(h, w, stretch=False)`, models/depth_anything_ac/
+ * onnx2trt.py:50-75): no uint8 resize; float32 / 255; cv2's FLOAT INTER_CUBIC (OpenCV's own path, bit-exact:
+ * oracle/preprocess_np.py `resize_cubic_f32`) to dst_h x dst_w -- the keep-ratio "ceil" size, 480 x 640 -> 518 x 700 --
+ * then (x - mean) / std in float64 (mean3 / std3 of the OUTPUT channels; both NULL: the resized 0..1 image).
+ * d_src: uint8 [B][src_h][src_w][3]; d_nchw: float32 [B][3][dst_h][dst_w]. */
+int mde_k_preprocess_u8_cubic_f32(const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w,
+                                  int32_t swap_rb, const double* mean3, const double* std3, float* d_nchw, void* stream);
 int mde_k_im2col_f32(int32_t precision, const float* d_nchw, int32_t batch, int32_t h, int32_t w, int32_t patch,
                      int32_t kpad, void* d_cols, void* stream);
 

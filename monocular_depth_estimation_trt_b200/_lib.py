@@ -25,7 +25,7 @@ SYMBOLS = [
     "mde_context_create", "mde_context_destroy", "mde_context_set_tensor_address",
     "mde_context_set_input_shape", "mde_context_enqueue", "mde_context_set_gather", "mde_context_launches_per_enqueue",
     "mde_context_get_buffer", "mde_context_snapshot_block", "mde_context_enqueue_timed", "mde_context_op_info",
-    "mde_k_preprocess_u8", "mde_k_preprocess_u8_pad", "mde_k_preprocess_u8_square_pad_cubic", "mde_k_im2col_f32", "mde_k_gemm", "mde_k_gemm_tiled", "mde_k_conv3x3", "mde_k_attention", "mde_k_attention_poly", "mde_k_attention_q3", "mde_k_attention_trace", "mde_k_attention_kv", "mde_k_attention_mma",
+    "mde_k_preprocess_u8", "mde_k_preprocess_u8_pad", "mde_k_preprocess_u8_square_pad_cubic", "mde_k_preprocess_u8_cubic_f32", "mde_k_im2col_f32", "mde_k_gemm", "mde_k_gemm_tiled", "mde_k_conv3x3", "mde_k_attention", "mde_k_attention_poly", "mde_k_attention_q3", "mde_k_attention_trace", "mde_k_attention_kv", "mde_k_attention_mma",
     "mde_k_layernorm", "mde_k_bilinear", "mde_k_bilinear_add", "mde_k_assemble_tokens", "mde_k_im2col_s2", "mde_k_upconv_head", "mde_k_resize_depth", "mde_k_merge_patches", "mde_k_peer_signal", "mde_k_peer_wait",
     "mde_k_resize_crops", "mde_k_depth_pro_post", "mde_k_resize_depth_halfpixel", "mde_k_resize_depth_halfpixel_nan", "mde_k_qknorm_rope", "mde_k_peer_signal_counter", "mde_k_peer_wait_counter",
 ]
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
         "mde_k_preprocess_u8_pad": (C.c_int, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32,
                                               P(C.c_double), P(C.c_double), P(C.c_double), vp, vp, vp]),
         "mde_k_preprocess_u8_square_pad_cubic": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "mde_k_preprocess_u8_cubic_f32": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, P(C.c_double), P(C.c_double), vp, vp]),
         "mde_k_im2col_f32": (C.c_int, [i32, vp, i32, i32, i32, i32, i32, vp, vp]),
         "mde_k_gemm": (C.c_int, [i32, vp, i64, i32, i32, vp, i32, i32, P(Epilogue), vp]),
         "mde_k_gemm_tiled": (C.c_int, [i32, vp, i64, i32, i32, vp, i32, i32, P(Epilogue), i32, i32, i32, vp]),

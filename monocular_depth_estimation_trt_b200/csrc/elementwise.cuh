@@ -843,4 +843,61 @@ __global__ void __launch_bounds__(256) preprocess_cubic_pad_kernel(const CubicPa
   p.out[((static_cast<long long>(b) * 3 + c) * p.dst_h + dy) * p.dst_w + dx] = __fdiv_rn(static_cast<float>(level), 255.f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Depth-Anything-AC `native` profile (core/preprocess.py:470-476 `da_ac(h, w, stretch=False)`, models/depth_anything_ac/
+// onnx2trt.py:50-75): the uint8 frame is NOT resized; it becomes float32 / 255 (RGB), is resized with cv2's FLOAT
+// INTER_CUBIC to the keep-ratio size and standardised in float64.  OpenCV's own float cubic (oracle/preprocess_np.py
+// `resize_cubic_f32`, bit-exact with cv2 when IPP is off): Keys coefficients (A = -0.75) in fp32 in `interpolateCubic`'s order,
+// horizontal taps with replicated borders added left to right, vertical taps added right to left in the 4-lane vector loop
+// and left to right for the last (W * 3) % 4 interleaved elements of a row, every product and sum rounded separately.
+// ---------------------------------------------------------------------------------------------
+struct CubicF32Params {
+  const unsigned char* src;   // [B][src_h][src_w][3]
+  float* out;                 // [B][3][dst_h][dst_w]
+  int B, src_h, src_w, dst_h, dst_w, swap_rb, tail;
+  double scale_y, scale_x;
+  double mean[3], std[3];     // of the OUTPUT channels (RGB)
+};
+__device__ __forceinline__ void cubic_taps_f32(int d, double scale, int* s, float (&co)[4]) {
+  const float fx = static_cast<float>((d + 0.5) * scale - 0.5);
+  const float fl = floorf(fx);
+  *s = static_cast<int>(fl);
+  const float x = __fsub_rn(fx, fl), A = -0.75f;
+  const float x1 = __fadd_rn(x, 1.f), xm = __fsub_rn(1.f, x);
+  co[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), -3.75f), x1), -6.f), x1), -3.f);
+  co[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(1.25f, x), 2.25f), x), x), 1.f);
+  co[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(1.25f, xm), 2.25f), xm), xm), 1.f);
+  co[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, co[0]), co[1]), co[2]);
+}
+__global__ void __launch_bounds__(256) preprocess_cubic_f32_kernel(const CubicF32Params p) {
+  const int dx = blockIdx.x * 256 + threadIdx.x, dy = blockIdx.y;
+  const int b = blockIdx.z / 3, c = blockIdx.z % 3;
+  if (dx >= p.dst_w) return;
+  int sy, sx;
+  float ya[4], xa[4];
+  cubic_taps_f32(dy, p.scale_y, &sy, ya);
+  cubic_taps_f32(dx, p.scale_x, &sx, xa);
+  const unsigned char* img = p.src + static_cast<long long>(b) * p.src_h * p.src_w * 3;
+  const int sc = p.swap_rb ? 2 - c : c;
+  float r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int y = min(max(sy + k - 1, 0), p.src_h - 1);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = min(max(sx + j - 1, 0), p.src_w - 1);
+      const float v = __fdiv_rn(static_cast<float>(img[(static_cast<long long>(y) * p.src_w + x) * 3 + sc]), 255.f);
+      const float t = __fmul_rn(v, xa[j]);
+      acc = j == 0 ? t : __fadd_rn(acc, t);
+    }
+    r[k] = __fmul_rn(acc, ya[k]);
+  }
+  float v;
+  if (dx * 3 + c >= p.dst_w * 3 - p.tail) v = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), r[2]), r[3]);
+  else v = __fadd_rn(r[0], __fadd_rn(r[1], __fadd_rn(r[2], r[3])));
+  const double z = __ddiv_rn(__dsub_rn(static_cast<double>(v), p.mean[c]), p.std[c]);
+  p.out[((static_cast<long long>(b) * 3 + c) * p.dst_h + dy) * p.dst_w + dx] = __double2float_rn(z);
+}
+
 }  // namespace mde

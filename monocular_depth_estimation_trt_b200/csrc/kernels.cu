@@ -1130,6 +1130,27 @@ int mde_k_preprocess_u8_square_pad_cubic(const uint8_t* d_src, int32_t batch, in
   return MDE_OK;
 }
 
+int mde_k_preprocess_u8_cubic_f32(const uint8_t* d_src, int32_t batch, int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w,
+                                  int32_t swap_rb, const double* mean3, const double* std3, float* d_nchw, void* stream) {
+  clear_error();
+  if (!d_src || !d_nchw) return fail(MDE_ERR_INVALID, "preprocess_cubic_f32: null pointer");
+  if (batch < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return fail(MDE_ERR_INVALID, "preprocess_cubic_f32: empty problem");
+  if (dst_h > 65535 || batch * 3 > 65535) return fail(MDE_ERR_INVALID, "preprocess_cubic_f32: output exceeds grid limits");
+  if ((mean3 == nullptr) != (std3 == nullptr)) return fail(MDE_ERR_INVALID, "preprocess_cubic_f32: mean and std go together (both NULL: the 0..1 image as it is)");
+  CubicF32Params p;
+  p.src = d_src; p.out = d_nchw; p.B = batch; p.src_h = src_h; p.src_w = src_w; p.dst_h = dst_h; p.dst_w = dst_w;
+  p.swap_rb = swap_rb ? 1 : 0; p.tail = (dst_w * 3) % 4;
+  p.scale_y = static_cast<double>(src_h) / dst_h; p.scale_x = static_cast<double>(src_w) / dst_w;
+  for (int c = 0; c < 3; ++c) {
+    p.mean[c] = mean3 ? mean3[c] : 0.0; p.std[c] = std3 ? std3[c] : 1.0;
+    if (!(p.std[c] > 0.0)) return fail(MDE_ERR_INVALID, "preprocess_cubic_f32: std must be positive");
+  }
+  dim3 grid((dst_w + 255) / 256, dst_h, batch * 3);
+  preprocess_cubic_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
 int mde_k_resize_crops(const void* d_src, int32_t src_is_u8_hwc, int32_t swap_rb, int32_t src_h, int32_t src_w,
                        const mde_crop* crops, int32_t n_crops, int32_t out_h, int32_t out_w, const float* mean3,
                        const float* std3, float* d_out, void* stream) {

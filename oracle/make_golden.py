@@ -8,7 +8,8 @@ preprocess_golden.npz  outputs of the REFERENCE module itself (imported from /ro
                        full tensors at small target sizes, sha256 of the float32 bytes at 518x518; the same for
                        'metric3d_v2' (keep-ratio + pad, 616x1064) together with the geometry it reports, and for 'vggt'
                        (white square pad + cubic resize, IPP switched off: see oracle/preprocess_np.py resize_cubic_u8), and for
-                       'depth_anything_ac' (float32 division by 255) with its keep-ratio network sizes.
+                       'depth_anything_ac' (float32 division by 255) with its keep-ratio network sizes, and its
+                       `native` profile (stretch=False: float32 cubic resize to the keep-ratio size, IPP off).
 dav2_vits_golden.npz   the oracle's own ViT-S 518x518 batch-1 forward (BASELINE config 1) with the
                        seeded, calibrated init: a 7x-strided subsample of the depth map and summary
                        statistics.  It pins the oracle against drift between hosts; the oracle
@@ -88,6 +89,18 @@ def main():
             sc = 518 / min(h, w)
             sizes += [ref._round_to_multiple(h * sc, 14, rounding, **kw), ref._round_to_multiple(w * sc, 14, rounding, **kw)]
         blob[f"ac_keep_ratio_seed{i}_{h}x{w}"] = np.array(sizes, dtype=np.int64)        # [ceil h, ceil w, constrain h, constrain w]
+    # Depth-Anything-AC `native` profile (stretch=False): float32 / 255, cv2 float INTER_CUBIC to the keep-ratio "ceil" size,
+    # ImageNet statistics in float64.  IPP off for the same reason as above (float cubic goes through IPP in the wheel).
+    cv2.ipp.setUseIPP(False)
+    for i, (h, w) in enumerate(SOURCES + [(37, 53)]):
+        img = synthetic(i, h, w)
+        t, geom = ref.preprocess_for(img, "depth_anything_ac", (56, 56), stretch=False)
+        blob[f"acn_full_seed{i}_{h}x{w}_target56"] = t
+        t, geom = ref.preprocess_for(img, "depth_anything_ac", (518, 518), stretch=False)
+        digest = hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+        blob[f"acn_sha_seed{i}_{h}x{w}_target518"] = np.frombuffer(bytes.fromhex(digest), dtype=np.uint8)
+        blob[f"acn_size_seed{i}_{h}x{w}_target518"] = np.array([geom.dst_h, geom.dst_w], dtype=np.int64)
+    cv2.ipp.setUseIPP(True)
     np.savez_compressed(os.path.join(OUT, "preprocess_golden.npz"), **blob)
     print("wrote preprocess_golden.npz", len(blob), "entries")
 

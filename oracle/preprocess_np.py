@@ -219,6 +219,64 @@ def resize_cubic_u8(img: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
     return out
 
 
+# ------------------------------------------------------------------ Depth-Anything-AC `native` profile: float32 INTER_CUBIC
+def _cubic_tables_f32(ssize: int, dsize: int):
+    """Source index of the second tap and the four float32 Keys coefficients (A = -0.75) per destination index, as cv2 computes
+    them for 32-bit data (imgproc/resize.cpp `interpolateCubic`, no fixed-point rounding)."""
+    f32 = np.float32
+    A, one = f32(-0.75), f32(1)
+    d = np.arange(dsize, dtype=np.float64)
+    fx = ((d + 0.5) * (ssize / dsize) - 0.5).astype(f32)
+    s = np.floor(fx).astype(np.int64)
+    x = (fx - s.astype(f32)).astype(f32)
+    c0 = ((A * (x + one) - f32(5) * A) * (x + one) + f32(8) * A) * (x + one) - f32(4) * A
+    c1 = ((A + f32(2)) * x - (A + f32(3))) * x * x + one
+    c2 = ((A + f32(2)) * (one - x) - (A + f32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    return s, np.stack([c0, c1, c2, c3], axis=1).astype(f32)
+
+
+def resize_cubic_f32(img: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+    """cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_CUBIC) for HxWxC float32 (imgproc/resize.cpp
+    `HResizeCubic<float>` then `VResizeCubic<float>`): four-tap horizontal sums with replicated borders, taps added left to
+    right; four-tap vertical sums, added right to left in the 4-lane vector loop and left to right in the scalar loop that
+    finishes a row ((W * C) % 4 elements); every product and sum rounded to float32, nothing fused.  Bit-exact
+    with cv2 4.x when IPP is off (`cv2.ipp.setUseIPP(False)`); opencv-python wheels route float cubic through Intel IPP by
+    default, whose closed implementation differs from this by up to 5e-5 on 0..1 data (tests/test_oracle_preprocess.py)."""
+    assert img.dtype == np.float32 and img.ndim == 3
+    src_h, src_w, _ = img.shape
+    if (src_h, src_w) == (dst_h, dst_w):
+        return img.copy()
+    xi, xa = _cubic_tables_f32(src_w, dst_w)
+    yi, ya = _cubic_tables_f32(src_h, dst_h)
+    H = None
+    for k in range(4):
+        term = img[:, np.clip(xi + k - 1, 0, src_w - 1), :] * xa[:, k][None, :, None]
+        H = term if H is None else (H + term)
+    R = [H[np.clip(yi + k - 1, 0, src_h - 1)] * ya[:, k][:, None, None] for k in range(4)]
+    out = (R[0] + (R[1] + (R[2] + R[3]))).astype(np.float32)          # `VResizeCubicVec_32f`: four products added right to left
+    tail = (dst_w * img.shape[2]) % 4                                 # elements past the last full 4-lane vector of a row: the
+    if tail:                                                          # scalar loop, which adds them left to right
+        flat = out.reshape(dst_h, -1)
+        ltr = (((R[0] + R[1]) + R[2]) + R[3]).astype(np.float32).reshape(dst_h, -1)
+        flat[:, -tail:] = ltr[:, -tail:]
+    return out
+
+
+def preprocess_keep_ratio_cubic_f32(img_bgr: np.ndarray, target: int = 518, multiple: int = 14, mean=IMAGENET_MEAN,
+                                    std=IMAGENET_STD) -> np.ndarray:
+    """depth_anything_ac's `native` profile (core/preprocess.py:470-476 `da_ac(h, w, stretch=False)`, models/depth_anything_ac/
+    onnx2trt.py:50-75): no uint8 resize; BGR -> RGB; float32 / 255; cv2 float INTER_CUBIC to the keep-ratio "ceil" size (short
+    side `target`, both sides rounded up to `multiple`: 480 x 640 -> 518 x 700); (x - mean) / std in float64; float32
+    [1, 3, H, W]."""
+    assert img_bgr.dtype == np.uint8 and img_bgr.ndim == 3
+    h, w = keep_ratio_size(img_bgr.shape[0], img_bgr.shape[1], target, multiple, "ceil")
+    x = img_bgr[:, :, ::-1].astype(np.float32) / np.float32(255.0)
+    x = resize_cubic_f32(np.ascontiguousarray(x), h, w)
+    x = (x.astype(np.float64) - np.asarray(mean, np.float64)) / np.asarray(std, np.float64)
+    return np.ascontiguousarray(x.astype(np.float32).transpose(2, 0, 1)[None])
+
+
 def square_pad_geometry(src_h: int, src_w: int):
     """core/preprocess.py:222-265 `resize_square_pad` with symmetric=True: (top, left) and the padded size -- the SAME count on
     both sides, so an odd difference leaves the canvas one pixel short of square, as upstream does."""

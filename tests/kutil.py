@@ -210,3 +210,15 @@ def preprocess_u8_square_pad_cubic(src_u8, dst_h, dst_w, swap_rb=True, pad_value
     _lib.check(lib.mde_k_preprocess_u8_square_pad_cubic(ptr(src_u8), B, H, W_, dst_h, dst_w, int(swap_rb), pad_value, ptr(out), stream()),
                "mde_k_preprocess_u8_square_pad_cubic")
     return out
+
+
+def preprocess_u8_cubic_f32(src_u8, dst_h, dst_w, swap_rb=True, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """Depth-Anything-AC's `native` profile: src_u8 [B, H, W, 3] uint8 cuda tensor -> float32 [B, 3, dst_h, dst_w]."""
+    lib = _lib.load()
+    B, H, W_, _ = src_u8.shape
+    out = torch.full((B, 3, dst_h, dst_w), float("nan"), dtype=torch.float32, device=src_u8.device)
+    m3 = (C.c_double * 3)(*mean) if mean is not None else None
+    s3 = (C.c_double * 3)(*std) if std is not None else None
+    _lib.check(lib.mde_k_preprocess_u8_cubic_f32(ptr(src_u8), B, H, W_, dst_h, dst_w, int(swap_rb), m3, s3, ptr(out), stream()),
+               "mde_k_preprocess_u8_cubic_f32")
+    return out

@@ -522,6 +522,58 @@ def test_depth_anything_ac_input_contract_bit_exact(lib):
     eng.close()
 
 
+@pytest.mark.parametrize("src", [(480, 640), (769, 1025), (500, 500), (37, 53), (1036, 720)])
+def test_depth_anything_ac_native_preprocessing_kernel_is_bit_exact(lib, src):
+    """Depth-Anything-AC's `native` profile on the device (`mde_k_preprocess_u8_cubic_f32`): uint8 frames -> float32 / 255 ->
+    cv2's float INTER_CUBIC to the keep-ratio "ceil" size -> ImageNet statistics in float64, against the oracle (byte-exact with
+    the reference module's tensors and with cv2's own cubic path), two frames per call, every bit; also a small target and the
+    plain resized image without statistics."""
+    import kutil as K
+    from oracle import preprocess_np as PP
+    frames = np.stack([np.random.default_rng(s).integers(0, 256, (*src, 3), dtype=np.uint8) for s in (5, 6)])
+    d = torch.from_numpy(frames).cuda()
+    for target in (518, 56):
+        h, w = PP.keep_ratio_size(*src, target, 14, "ceil")
+        ref = np.concatenate([PP.preprocess_keep_ratio_cubic_f32(f, target) for f in frames])
+        got = K.preprocess_u8_cubic_f32(d, h, w)
+        torch.cuda.synchronize()
+        assert got.shape == ref.shape and np.array_equal(got.cpu().numpy(), ref), (src, target)
+    h, w = PP.keep_ratio_size(*src, 56, 14, "ceil")
+    plain = K.preprocess_u8_cubic_f32(d, h, w, mean=None, std=None)
+    x0 = np.ascontiguousarray(frames[0][:, :, ::-1].astype(np.float32) / np.float32(255.0))
+    assert np.array_equal(plain[0].cpu().numpy(), PP.resize_cubic_f32(x0, h, w).transpose(2, 0, 1))
+
+
+def test_depth_anything_ac_native_profile_end_to_end(lib):
+    """models/depth_anything_ac/onnx2trt.py with `profile = 'native'`: the frame is preprocessed on the device at its own
+    aspect (480 x 640 -> 518 x 700), the engine built for that size takes the float32 tensor, and the map goes through the gate
+    against the oracle's forward of the reference-exact tensor."""
+    import kutil as K
+    from oracle import dav2_torch as O, preprocess_np as PP
+    sd, _, _, _ = R.reference("vits")
+    img = R.synthetic_image(4, 480, 640)
+    x_ref = torch.from_numpy(PP.preprocess_keep_ratio_cubic_f32(img))
+    h, w = x_ref.shape[2:]
+    assert (h, w) == (518, 700)
+    want = O.forward(sd, x_ref, "vits", max_depth=20.0)[0].numpy()
+    meta = W.describe("vits", h, w, 20.0)
+    eng = E.Engine(E.make_desc(meta, precision="fp16", batch=1), meta)
+    eng.load_state_dict(sd)
+    eng.finalize()
+    x_dev = K.preprocess_u8_cubic_f32(torch.from_numpy(img[None]).cuda(), h, w)
+    assert torch.equal(x_dev.cpu(), x_ref)
+    out = torch.full((1, h, w), float("nan"), device="cuda")
+    with eng.create_execution_context() as ctx:
+        ctx.set_tensor_address("input", x_dev.data_ptr())
+        ctx.set_tensor_address("output", out.data_ptr())
+        ctx.execute_async_v3(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    eng.close()
+    m = R.compare_depth(want, out[0].cpu().numpy())
+    print("depth_anything_ac native 518x700 fp16", m["abs_rel"], m["max_rel"])
+    assert m["abs_rel"] <= GATE["abs_rel"] and m["max_rel"] <= GATE["max_rel"], m
+
+
 def test_metric3d_v2_trunk_with_registers_and_bilinear_pos_embed(lib):
     """Metric3D V2's encoder as the reference exports it (reports/profile/metric3d_v2.json layers 0-131): 0..255 input with the
     in-graph (x - mean) / std applied where the patch rows are formed (MDE_FLAG_NORMALISE_F32), DINOv2 with four registers (1 + 4 + 44 * 76 = 3349 tokens, layer

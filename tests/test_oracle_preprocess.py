@@ -217,3 +217,43 @@ def test_depth_anything_ac_contract_against_reference_golden_vectors():
         from monocular_depth_estimation_trt_b200 import weights as W
         assert W.keep_ratio_size(*src, 518, 14, "ceil") == tuple(want[:2]) and W.keep_ratio_size(*src, 518, 14, "constrain") == tuple(want[2:])
     assert P.keep_ratio_size(480, 640) == (518, 700) and P.keep_ratio_size(480, 640, rounding="constrain") == (518, 686)
+
+
+def test_depth_anything_ac_native_profile_against_reference_golden_vectors():
+    """models/depth_anything_ac/onnx2trt.py:50-75 `profile = 'native'` (core/preprocess.py:470-476 `da_ac(h, w, stretch=False)`):
+    no uint8 resize, float32 / 255, cv2 float INTER_CUBIC to the keep-ratio "ceil" size, ImageNet statistics in float64 --
+    byte-exact against tensors the reference module produced (IPP off, see `resize_cubic_f32`)."""
+    import hashlib
+    g = np.load(GOLDEN)
+    keys = [k for k in g.files if k.startswith("acn_full_")]
+    assert len(keys) == 6
+    for k in keys:
+        seed, src = int(k.split("seed")[1].split("_")[0]), tuple(int(v) for v in k.split("_")[3].split("x"))
+        img = np.random.default_rng(seed).integers(0, 256, (*src, 3), dtype=np.uint8)
+        small = P.preprocess_keep_ratio_cubic_f32(img, 56)
+        assert small.shape == g[k].shape and np.array_equal(small, g[k]), k
+        big = P.preprocess_keep_ratio_cubic_f32(img, 518)
+        assert tuple(g[f"acn_size_seed{seed}_{src[0]}x{src[1]}_target518"]) == big.shape[2:]
+        assert hashlib.sha256(big.tobytes()).digest() == g[f"acn_sha_seed{seed}_{src[0]}x{src[1]}_target518"].tobytes()
+    assert P.preprocess_keep_ratio_cubic_f32(synthetic(0, 480, 640)).shape == (1, 3, 518, 700)
+
+
+@pytest.mark.parametrize("src", [(480, 640), (769, 1025), (500, 500), (37, 53), (1036, 720), (518, 518), (123, 457), (5, 4)])
+@pytest.mark.parametrize("dst", [(518, 700), (518, 518), (70, 98), (56, 57)])
+def test_float_cubic_restatement_bit_exact_vs_cv2_own_path(src, dst):
+    """`resize_cubic_f32` against cv2's own float INTER_CUBIC (IPP off): taps left to right horizontally, right to left in the
+    vertical vector loop, left to right in the scalar loop that finishes a row -- bit for bit, up- and down-scaling, borders.
+    With IPP on (the wheel's default) cv2 differs from its own path by up to ~5e-5 on 0..1 data."""
+    cv2 = pytest.importorskip("cv2")
+    x = np.ascontiguousarray(synthetic(11, *src).astype(np.float32) / np.float32(255.0))
+    was = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        ref = cv2.resize(x, (dst[1], dst[0]), interpolation=cv2.INTER_CUBIC)
+        assert np.array_equal(P.resize_cubic_f32(x, *dst), ref)
+        if was and src != dst:
+            cv2.ipp.setUseIPP(True)
+            ipp = cv2.resize(x, (dst[1], dst[0]), interpolation=cv2.INTER_CUBIC)
+            assert float(np.abs(ipp - ref).max()) < 2e-4
+    finally:
+        cv2.ipp.setUseIPP(was)
