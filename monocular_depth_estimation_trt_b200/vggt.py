@@ -266,6 +266,92 @@ def pack_deconv(w, s: int, dtype):
     return w.permute(2, 3, 1, 0).reshape(s * s * cout, cin).to(dtype).contiguous()
 
 
+def required_tensors(encoder: str = "vitl", depth: int = 24, features: int = 256, out_channels: Sequence[int] = (256, 512, 1024, 1024),
+                     trunk_grid: int = 37) -> dict:
+    """Name -> shape of every tensor the engine reads from a VGGT / StreamVGGT state dict, under upstream's module tree (the model
+    models/vggt/onnx_export.py:38-52 and models/streamvggt/onnx_export.py:35-53 load their checkpoints into): the DINOv2 trunk with
+    four registers under `aggregator.patch_embed.`, the two-variant camera / register tokens, `depth` frame and global blocks with
+    q / k LayerNorms, and the depth head (LayerNorm over 2D, projections, resize layers, layer_rn, RefineNets -- refinenet4
+    without its first residual unit -- and the output convolutions with two channels: log depth and confidence).
+    `export_checkpoint` checks a checkpoint against it before anything is written."""
+    c = W.ENCODERS[encoder]
+    D, L, F = c["embed_dim"], c["depth"], int(features)
+    oc = [int(x) for x in out_channels]
+    s = {}
+    t = TRUNK
+    s[t + "cls_token"] = (1, 1, D); s[t + "register_tokens"] = (1, 4, D); s[t + "pos_embed"] = (1, 1 + trunk_grid * trunk_grid, D)
+    s[t + "patch_embed.proj.weight"] = (D, 3, 14, 14); s[t + "patch_embed.proj.bias"] = (D,)
+    s[t + "norm.weight"] = (D,); s[t + "norm.bias"] = (D,)
+
+    def block(b, qk_norm):
+        for n in ("norm1", "norm2"):
+            s[b + n + ".weight"] = (D,); s[b + n + ".bias"] = (D,)
+        s[b + "attn.qkv.weight"] = (3 * D, D); s[b + "attn.qkv.bias"] = (3 * D,)
+        s[b + "attn.proj.weight"] = (D, D); s[b + "attn.proj.bias"] = (D,)
+        if qk_norm:
+            for n in ("q_norm", "k_norm"):
+                s[b + f"attn.{n}.weight"] = (64,); s[b + f"attn.{n}.bias"] = (64,)
+        s[b + "ls1.gamma"] = (D,); s[b + "ls2.gamma"] = (D,)
+        s[b + "mlp.fc1.weight"] = (4 * D, D); s[b + "mlp.fc1.bias"] = (4 * D,)
+        s[b + "mlp.fc2.weight"] = (D, 4 * D); s[b + "mlp.fc2.bias"] = (D,)
+
+    for i in range(L):
+        block(f"{t}blocks.{i}.", False)
+    s["aggregator.camera_token"] = (1, 2, 1, D); s["aggregator.register_token"] = (1, 2, 4, D)
+    for i in range(int(depth)):
+        block(f"aggregator.frame_blocks.{i}.", True)
+        block(f"aggregator.global_blocks.{i}.", True)
+    h = "depth_head."
+    s[h + "norm.weight"] = (2 * D,); s[h + "norm.bias"] = (2 * D,)
+    for i in range(4):
+        s[h + f"projects.{i}.weight"] = (oc[i], 2 * D, 1, 1); s[h + f"projects.{i}.bias"] = (oc[i],)
+        s[h + f"scratch.layer{i + 1}_rn.weight"] = (F, oc[i], 3, 3)
+        r = h + f"scratch.refinenet{i + 1}."
+        s[r + "out_conv.weight"] = (F, F, 1, 1); s[r + "out_conv.bias"] = (F,)
+        for u in (("resConfUnit2",) if i == 3 else ("resConfUnit1", "resConfUnit2")):
+            for cv in ("conv1", "conv2"):
+                s[r + f"{u}.{cv}.weight"] = (F, F, 3, 3); s[r + f"{u}.{cv}.bias"] = (F,)
+    s[h + "resize_layers.0.weight"] = (oc[0], oc[0], 4, 4); s[h + "resize_layers.0.bias"] = (oc[0],)
+    s[h + "resize_layers.1.weight"] = (oc[1], oc[1], 2, 2); s[h + "resize_layers.1.bias"] = (oc[1],)
+    s[h + "resize_layers.3.weight"] = (oc[3], oc[3], 3, 3); s[h + "resize_layers.3.bias"] = (oc[3],)
+    s[h + "scratch.output_conv1.weight"] = (F // 2, F, 3, 3); s[h + "scratch.output_conv1.bias"] = (F // 2,)
+    s[h + "scratch.output_conv2.0.weight"] = (32, F // 2, 3, 3); s[h + "scratch.output_conv2.0.bias"] = (32,)
+    s[h + "scratch.output_conv2.2.weight"] = (2, 32, 1, 1); s[h + "scratch.output_conv2.2.bias"] = (2,)
+    return s
+
+
+def export_checkpoint(checkpoint_path: str, out_path: str, encoder: str = "vitl", depth: int = 24, features: int = 256,
+                      out_channels: Sequence[int] = (256, 512, 1024, 1024), taps: Sequence[int] = (4, 11, 17, 23), frames: int = 1,
+                      image_hw=(518, 518), family: str = "vggt", stream_frames: int = 0) -> dict:
+    """Stage `export` for an upstream VGGT (`family="vggt"`, models/vggt/onnx_export.py:60-75) or StreamVGGT (`"streamvggt"`,
+    models/streamvggt/onnx_export.py:70-78: `ckpt = torch.load(...); model.load_state_dict(ckpt)`) checkpoint, .pt / .pth or
+    .safetensors: read the state dict, check it against `required_tensors` (the camera / point / track heads the reference's
+    wrappers never run are dropped), write the .mdew file `common.get_engine` builds the engine from."""
+    import torch
+    if checkpoint_path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        sd = load_file(checkpoint_path, device="cpu")
+    else:
+        sd = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+    if isinstance(sd, dict) and "state_dict" in sd and "aggregator.camera_token" not in sd:
+        sd = sd["state_dict"]
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    grid = 37
+    if TRUNK + "pos_embed" in sd:
+        n = int(sd[TRUNK + "pos_embed"].shape[1]) - 1
+        grid = int(round(n ** 0.5))
+    need = required_tensors(encoder, depth, features, out_channels, trunk_grid=grid)
+    missing = [k for k in need if k not in sd]
+    wrong = [f"{k}: {tuple(sd[k].shape)} != {shape}" for k, shape in need.items() if k in sd and tuple(sd[k].shape) != shape]
+    if missing or wrong:
+        raise ValueError(f"[MDET] {checkpoint_path} is not a {family} ({encoder}, {depth} + {depth} blocks, {features} head features) "
+                         f"checkpoint: {len(missing)} tensors missing (first: {missing[:3]}), {len(wrong)} with another shape (first: {wrong[:3]})")
+    meta = W.describe_vggt(encoder, depth, features, out_channels, taps, frames, image_hw, family, stream_frames)
+    meta["source_checkpoint_sha256"] = W.file_sha256(checkpoint_path)
+    W.save(out_path, {k: sd[k] for k in need}, meta)
+    return meta
+
+
 class _HeadWeights:
     def __init__(self, sd: Mapping, D: int, F: int, oc, gh: int, gw: int, H: int, Wd: int, frames: int, dtype, device):
         import torch

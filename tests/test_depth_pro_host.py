@@ -106,3 +106,32 @@ def test_required_tensors_are_exactly_what_the_oracle_model_holds(tmp_path):
     torch.save({k: v for k, v in sd.items() if not k.startswith("fov.")}, ckpt)
     with pytest.raises(ValueError, match="tensors missing"):
         DPE.export_checkpoint(ckpt, str(tmp_path / "x.mdew"), encoder="vits", features=64)
+
+
+def test_vggt_required_tensors_and_export_stage(tmp_path):
+    """The VGGT / StreamVGGT checkpoint contract against the oracle's parameter list, and the export stage: a state dict
+    saved the way upstream's checkpoints are (extra heads the wrappers never run, a `module.` prefix) comes back as an .mdew
+    file with the family in its description; a file without the depth head is refused by name."""
+    from oracle import vggt_torch as V
+    from monocular_depth_estimation_trt_b200 import vggt as P, weights as W
+    for enc, depth, feat, oc in (("vits", 2, 64, (48, 96, 192, 384)), ("vitl", 24, 256, (256, 512, 1024, 1024))):
+        need = P.required_tensors(enc, depth, feat, oc)
+        if enc == "vits":
+            sd = V.init_vggt(enc, depth=depth, features=feat, out_channels=oc, seed=3)
+            have = {k: tuple(v.shape) for k, v in sd.items() if not k.endswith("mask_token")}
+            assert need == have, (sorted(set(need) ^ set(have))[:6])
+        else:
+            # trunk 7 + 24 x 14, two token sets, 48 aggregator blocks x 18, head: norm 2, per level 5, 7 residual units x 4, 6 + 6
+            assert len(need) == 7 + 24 * 14 + 2 + 48 * 18 + 2 + 4 * 5 + 7 * 4 + 6 + 6
+    ckpt = str(tmp_path / "model.pt")
+    extra = {"camera_head.trunk.0.weight": torch.zeros(3, 3), "point_head.norm.weight": torch.zeros(8)}
+    torch.save({"module." + k: v for k, v in {**sd, **extra}.items()}, ckpt)
+    kw = dict(encoder="vits", depth=2, features=64, out_channels=(48, 96, 192, 384), taps=(0, 0, 1, 1), frames=3)
+    meta = P.export_checkpoint(ckpt, str(tmp_path / "v.mdew"), family="streamvggt", **kw)
+    back, meta2 = W.load(str(tmp_path / "v.mdew"))
+    assert meta2 == meta and meta["family"] == "streamvggt" and meta["frames"] == 3 and len(meta["source_checkpoint_sha256"]) == 64
+    assert set(back) == set(P.required_tensors("vits", 2, 64, (48, 96, 192, 384)))
+    assert np.array_equal(back["aggregator.camera_token"], sd["aggregator.camera_token"].numpy())
+    torch.save({k: v for k, v in sd.items() if not k.startswith("depth_head.")}, ckpt)
+    with pytest.raises(ValueError, match="tensors missing"):
+        P.export_checkpoint(ckpt, str(tmp_path / "x.mdew"), **kw)
